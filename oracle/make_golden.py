@@ -1,0 +1,135 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference Python (TEST INFRASTRUCTURE).
+
+Run in the build container only (needs /root/reference):   python -m oracle.make_golden
+
+What is pinned:
+  * golden/hashgrid_naive.npz  -- wisp.ops.grid.hashgrid_naive (ops/grid.py:16-75), the reference's own
+    pure-torch statement of the hash index + trilinear blend.  Depends on NO oracle code (only a 3-line
+    points_to_corners stub), so it pins oracle/wisp_oracle.c:wo_hashgrid_* independently.
+  * golden/rf_trace_*.npz      -- wisp.models.Pipeline(NeuralRadianceField(HashGrid), PackedRFTracer)
+    forward + backward, executed by the reference's own classes on CPU.  Kaolin / wisp._C native calls are
+    answered by the oracle (oracle/ref_import.py), torch.rand is replaced by a recorded jitter tensor.
+    Pins every piece of wisp-side glue: sample generation and culling (octree_as.py:247-309), the 'cat'
+    zeroing / 'sum' reduction (hash_grid.py:224-233), decoder + embedder wiring (nerf.py:219-264),
+    tau/integration/background blend and buffer scatter (packed_rf_tracer.py:130-165).
+"""
+from __future__ import annotations
+
+import os
+import warnings
+
+import numpy as np
+import torch
+
+from . import oracle as O
+from . import ref_import
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _mlp_params(m):
+    Ws = [l.weight.detach().numpy().copy() for l in m.layers] + [m.lout.weight.detach().numpy().copy()]
+    if m.lout.bias is None:
+        return Ws, None
+    bs = [l.bias.detach().numpy().copy() for l in m.layers] + [m.lout.bias.detach().numpy().copy()]
+    return Ws, bs
+
+
+def _mlp_grads(m):
+    parts = []
+    for l in list(m.layers) + [m.lout]:
+        parts.append(l.weight.grad.reshape(-1).numpy())
+        if l.bias is not None:
+            parts.append(l.bias.grad.reshape(-1).numpy())
+    return np.concatenate(parts)
+
+
+def gen_hashgrid_naive():
+    from wisp.ops.grid import hashgrid_naive
+    rng = np.random.default_rng(7)
+    resolutions = [4, 7, 13, 24, 40]
+    bw = 9                       # T=512: levels 4,7 dense (res^3<T), others hashed; no res^3 == T case
+    T = 2 ** bw
+    begin = O.table_layout(resolutions, bw)
+    sizes = np.diff(begin)
+    F = 2
+    table = rng.standard_normal((int(begin[-1]), F)).astype(np.float32)
+    coords = rng.uniform(-0.999, 0.999, (257, 3)).astype(np.float32)
+    feats = hashgrid_naive(torch.from_numpy(coords), torch.tensor(resolutions), bw, len(resolutions) - 1,
+                           torch.from_numpy(table), torch.from_numpy(sizes), torch.from_numpy(begin[:-1]))
+    np.savez_compressed(os.path.join(OUT, "hashgrid_naive.npz"), coords=coords, table=table, resolutions=np.asarray(resolutions),
+                        codebook_bitwidth=bw, feats=feats.numpy())
+    print("hashgrid_naive", feats.shape, "T", T)
+
+
+def gen_rf_trace(name, *, level, res, hw, n_steps, num_lods, bw, min_res, max_res, hidden, num_layers, bias, multiscale,
+                 view_embedder, near, far, bg, feature_std=0.5, sparse=True, loss="huber", seed=0):
+    from wisp.models import Pipeline
+    from wisp.tracers import PackedRFTracer
+    from wisp.accelstructs import OctreeAS
+    from wisp.models.grids import HashGrid
+    from wisp.models.nefs import NeuralRadianceField
+    from wisp.core import Rays
+    torch.manual_seed(seed)
+    oct_np = O.points_to_octree(O.lego_like_points(level), level) if sparse else O.dense_octree(level)
+    blas = OctreeAS(torch.from_numpy(oct_np))
+    grid = HashGrid.from_geometric(blas, feature_dim=2, num_lods=num_lods, multiscale_type=multiscale, feature_std=feature_std,
+                                   codebook_bitwidth=bw, min_grid_res=min_res, max_grid_res=max_res)
+    nef = NeuralRadianceField(grid, view_embedder=view_embedder, view_multires=4, hidden_dim=hidden, num_layers=num_layers, bias=bias)
+    tracer = PackedRFTracer(raymarch_type='ray', num_steps=n_steps, bg_color=bg)
+    pipe = Pipeline(nef, tracer)
+    o, d = O.look_at_rays([-3.0, 0.65, -3.0], [0, 0, 0], hw, hw, 30.0)
+    R = o.shape[0]
+    jit = np.random.default_rng(seed + 1).random((R, n_steps), dtype=np.float32)
+    rays = Rays(torch.from_numpy(o), torch.from_numpy(d), dist_min=near, dist_max=far)
+    orig = torch.rand
+    torch.rand = lambda *a, **k: torch.from_numpy(jit)
+    try:
+        mr = grid.raymarch(rays, level=grid.active_lods[-1], num_samples=n_steps, raymarch_type='ray')
+        rb = pipe(rays=rays, channels=["rgb", "depth", "alpha", "hit"])
+    finally:
+        torch.rand = orig
+    target = torch.sigmoid(torch.from_numpy(np.random.default_rng(seed + 2).standard_normal((R, 3)).astype(np.float32)))
+    lossv = {"huber": torch.nn.functional.smooth_l1_loss(rb.rgb, target, reduction='none').mean(),
+             "l2": torch.nn.functional.mse_loss(rb.rgb, target, reduction='none').mean(),
+             "l1": torch.abs(rb.rgb - target).mean()}[loss]
+    lossv.backward()
+    dW, db = _mlp_params(nef.decoder_density)
+    cW, cb = _mlp_params(nef.decoder_color)
+    vm = {"positional": 3, "none": 1, "identity": 1}[view_embedder]   # nerf.py:105-106,116-119: include_input=True makes "none" an identity
+    onef = O.Nef([int(r) for r in grid.resolutions], 2, bw, grid.codebook.feats.detach().numpy(), dW, db, cW, cb,
+                 multiscale=multiscale, view_mode=vm, view_freq=4)
+    icfg, resa, begin, table, pd, pc = onef.pack()
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        octree=oct_np, level=level, origins=o, dirs=d, near=near, far=far, n_steps=n_steps, jitter=jit, bg=np.asarray(bg, np.float32),
+        icfg=icfg, res=resa, begin=begin, table=table, dens_params=pd, col_params=pc, target=target.numpy(), loss_type=loss,
+        # reference outputs
+        mr_ridx=mr.ridx.numpy(), mr_samples=mr.samples.numpy(), mr_depth=mr.depth_samples.numpy(), mr_deltas=mr.deltas.numpy(),
+        mr_boundary=mr.boundary.numpy(),
+        rgb=rb.rgb.detach().numpy(), depth=rb.depth.detach().numpy(), alpha=rb.alpha.detach().numpy(), hit=rb.hit.numpy(),
+        num_samples=tracer.get_prev_num_samples(), loss=float(lossv),
+        g_table=grid.codebook.feats.grad.numpy(), g_dens=_mlp_grads(nef.decoder_density), g_col=_mlp_grads(nef.decoder_color))
+    print(name, "R", R, "S", tracer.get_prev_num_samples(), "hit", int(rb.hit.sum()), "loss", float(lossv))
+
+
+def main():
+    warnings.filterwarnings("ignore")
+    ref_import.install()
+    os.makedirs(OUT, exist_ok=True)
+    gen_hashgrid_naive()
+    # A: miniature of BASELINE config 2 (cat, bias, positional view embedding, sparse lego-like octree)
+    gen_rf_trace("rf_trace_cat", level=5, res=None, hw=24, n_steps=96, num_lods=6, bw=11, min_res=4, max_res=48, hidden=32,
+                 num_layers=1, bias=True, multiscale="cat", view_embedder="positional", near=0.0, far=10.0, bg=(1.0, 1.0, 1.0))
+    # B: 'sum' aggregation, no bias, 2 hidden layers, dense octree, black background, l2 loss, training-style near/far
+    gen_rf_trace("rf_trace_sum", level=3, res=None, hw=16, n_steps=48, num_lods=4, bw=10, min_res=4, max_res=32, hidden=16,
+                 num_layers=2, bias=False, multiscale="sum", view_embedder="positional", near=1.0, far=6.0, bg=(0.0, 0.0, 0.0),
+                 sparse=False, loss="l2", seed=3)
+    # C: view_embedder="none" (which nerf.py:105-106,116-119 turns into an identity embedding of ray_d), l1 loss
+    gen_rf_trace("rf_trace_noview", level=4, res=None, hw=16, n_steps=64, num_lods=4, bw=10, min_res=4, max_res=32, hidden=16,
+                 num_layers=1, bias=True, multiscale="cat", view_embedder="none", near=0.0, far=10.0, bg=(0.2, 0.5, 0.9),
+                 loss="l1", seed=5)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,98 @@
+"""CPU tests: the oracle (oracle/wisp_oracle.c) against the fixtures produced by the UNMODIFIED reference
+Python (oracle/make_golden.py).  These pin the oracle before it is used to judge the CUDA path."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from golden_util import load_case
+
+CASES = ["rf_trace_cat", "rf_trace_sum", "rf_trace_noview"]
+
+
+def test_hashgrid_against_reference_naive(golden_dir):
+    """wisp.ops.grid.hashgrid_naive (ops/grid.py:16-75) vs wo_hashgrid_fwd.  fp32 tolerance of the reference's own
+    unit test for one trilinear blend (tests/core/test_grid_interpolation.py:50-53): atol 1e-6 / rtol 1e-4
+    (atol widened to 2e-6: the naive version clamps in float, the kernel in double)."""
+    g = np.load(os.path.join(golden_dir, "hashgrid_naive.npz"))
+    feats = O.hashgrid_fwd(g["coords"], g["table"], [int(r) for r in g["resolutions"]], int(g["codebook_bitwidth"]))
+    np.testing.assert_allclose(feats, g["feats"], atol=2e-6, rtol=1e-4)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_raymarch_bit_exact(golden_dir, name):
+    """OctreeAS._raymarch_ray executed by the reference Python: indices bit-exact, floats bit-exact."""
+    g, nef, spc = load_case(os.path.join(golden_dir, name + ".npz"))
+    mr = O.raymarch_ray(spc, g["origins"], g["dirs"], float(g["near"]), float(g["far"]), int(g["n_steps"]), jitter_arr=g["jitter"])
+    assert np.array_equal(mr["ridx"], g["mr_ridx"])
+    assert np.array_equal(mr["boundary"], g["mr_boundary"])
+    assert np.array_equal(mr["samples"], g["mr_samples"])
+    assert np.array_equal(mr["depth_samples"], g["mr_depth"])
+    assert np.array_equal(mr["deltas"], g["mr_deltas"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_trace_forward(golden_dir, name):
+    g, nef, spc = load_case(os.path.join(golden_dir, name + ".npz"))
+    f = O.rf_trace_fwd(spc, nef, g["origins"], g["dirs"], float(g["near"]), float(g["far"]), int(g["n_steps"]), bg=g["bg"], jitter_arr=g["jitter"])
+    assert f["num_samples"] == int(g["num_samples"])
+    assert np.array_equal(f["hit"], g["hit"])
+    np.testing.assert_allclose(f["rgb"], g["rgb"], atol=1e-5, rtol=0)
+    np.testing.assert_allclose(f["alpha"], g["alpha"], atol=1e-5, rtol=0)
+    np.testing.assert_allclose(f["depth"], g["depth"], atol=5e-5, rtol=0)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_trace_backward(golden_dir, name):
+    """Gradients: reference autograd (torch) through the reference glue vs the oracle's hand-written backward."""
+    g, nef, spc = load_case(os.path.join(golden_dir, name + ".npz"))
+    st = O.rf_step(spc, nef, g["origins"], g["dirs"], float(g["near"]), float(g["far"]), int(g["n_steps"]), g["target"],
+                   loss=str(g["loss_type"]), bg=g["bg"], jitter_arr=g["jitter"])
+    assert abs(st["loss"] - float(g["loss"])) < 1e-6
+    for key, ref in (("table", g["g_table"]), ("dens", g["g_dens"]), ("col", g["g_col"])):
+        scale = max(np.abs(ref).max(), 1e-12)
+        assert np.abs(st[key] - ref).max() <= 1e-4 * scale + 1e-9, key
+
+
+def test_backward_api_matches_step(golden_dir):
+    g, nef, spc = load_case(os.path.join(golden_dir, "rf_trace_cat.npz"))
+    R = g["origins"].shape[0]
+    st = O.rf_step(spc, nef, g["origins"], g["dirs"], 0.0, 10.0, int(g["n_steps"]), g["target"], bg=g["bg"], jitter_arr=g["jitter"])
+    grgb = (st["rgb"] - g["target"]) / (3 * R)
+    b = O.rf_trace_bwd(spc, nef, g["origins"], g["dirs"], 0.0, 10.0, int(g["n_steps"]), grgb, bg=g["bg"], jitter_arr=g["jitter"])
+    np.testing.assert_allclose(b["table"], st["table"], atol=1e-9)
+    np.testing.assert_allclose(b["col"], st["col"], atol=1e-8)
+
+
+def test_spc_dense_and_points():
+    spc = O.octree_to_spc(O.dense_octree(3))
+    assert spc.max_level == 3
+    assert spc.pyramid[0].tolist() == [1, 8, 64, 512, 0]
+    assert spc.pyramid[1].tolist() == [0, 1, 9, 73, 585]
+    # Morton order, child c = 4x+2y+z
+    assert spc.points[1:9].tolist() == [[0, 0, 0], [0, 0, 1], [0, 1, 0], [0, 1, 1], [1, 0, 0], [1, 0, 1], [1, 1, 0], [1, 1, 1]]
+    pts = O.lego_like_points(5)
+    s2 = O.octree_to_spc(O.points_to_octree(pts, 5))
+    lvl = s2.points[s2.pyramid[1, 5]: s2.pyramid[1, 5] + s2.pyramid[0, 5]]
+    assert set(map(tuple, lvl.tolist())) == set(map(tuple, pts.tolist()))
+
+
+def test_query_edges():
+    spc = O.octree_to_spc(O.dense_octree(2))
+    c = np.array([[-1.0, -1.0, -1.0], [1.0, 0.0, 0.0], [0.999999, 0.0, 0.0], [-1.0000001, 0, 0], [0.0, 0.0, 0.0],
+                  [np.nextafter(np.float32(0), np.float32(-1)), 0, 0]], dtype=np.float32)
+    p = O.query(spc, c)
+    assert p[0] >= 0 and p[1] == -1 and p[2] >= 0 and p[3] == -1 and p[4] >= 0
+    wp = O.query(spc, c, with_parents=True)
+    assert wp.shape == (6, 3) and wp[0, 0] == 0 and wp[1].tolist() == [-1, -1, -1]
+    # the cell just below 0 differs from the cell at 0 along x
+    assert p[5] != p[4]
+
+
+def test_jitter_stream_properties():
+    v = np.array([O.jitter(3, r, s) for r in range(8) for s in range(64)], dtype=np.float32)
+    assert v.min() >= 0.0 and v.max() < 1.0
+    assert abs(v.mean() - 0.5) < 0.06
+    assert len(np.unique(v)) > 500
