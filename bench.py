@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- rays/s (fwd+bwd) of the volumetric render hot path on BASELINE.json's config 2.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--res 1024] [--scene lego|dense]
+
+One "step" = one pass of the hot path over one 1024x1024 frame of synthetic rays:
+    Pipeline(NeuralRadianceField(HashGrid L=16,F=2,T=2^19; decoders 32-64-16 / 42-64-64-3), PackedRFTracer('ray', 2048))
+    forward -> huber loss vs a synthetic target image -> backward -> (N>1: NCCL all-reduce of the gradients) -> fused Adam step.
+`value`  : whole-job rays/s with rays and target already resident in HBM.
+`e2e`    : the same step driven from HOST buffers: rays + target copied H2D from pinned memory and the loss read back
+           D2H inside the timed region, through the public Pipeline call.
+`--impl reference`: the CPU restatement of the reference path (oracle, OpenMP, all host cores) on a bounded ray sample.
+Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rays/sec (fwd+bwd) 1024^2 Lego NeRF HashGrid"
+CAM_ORIGIN, CAM_LOOKAT, CAM_FOV, NEAR, FAR = [-3.0, 0.65, -3.0], [0.0, 0.0, 0.0], 30.0, 0.0, 10.0   # nerf_hash.yaml:111-118
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--res", type=int, default=1024)
+    ap.add_argument("--num-steps", type=int, default=2048)
+    ap.add_argument("--scene", default="lego", choices=["lego", "dense"])
+    ap.add_argument("--precision", type=int, default=0)
+    ap.add_argument("--cpu-sample-rays", type=int, default=0, help="rays in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args):
+    return {"workload": f"app/nerf HashGrid 16-level F=2 T=2^19, 2-layer-64 MLP, {args.res}^2 rays x {args.num_steps} steps ('ray'), "
+                        f"{'lego-like level-7 octree' if args.scene == 'lego' else 'dense level-7 octree'}, fwd+bwd+Adam",
+            "rays_per_step_per_gpu": args.res * args.res, "num_steps": args.num_steps, "scene": args.scene,
+            "camera": {"origin": CAM_ORIGIN, "lookat": CAM_LOOKAT, "fov": CAM_FOV, "near": NEAR, "far": FAR},
+            "loss": "huber/rays", "optimizer": "Adam(fused, torch) on table + decoders",
+            "l2": "per-step working set (hit masks + sample records, >1 GB) exceeds the 126 MB L2; a different camera every step",
+            "parallelism": f"dp{args.gpus} (one view per GPU per step, NCCL all-reduce of gradients)" if args.gpus > 1 else "single GPU"}
+
+
+def orbit_origin(i: int):
+    """Camera i of the orbit: the reference camera rotated about the y axis."""
+    a = 2.0 * np.pi * (i % 360) / 360.0 * 7.0
+    x, z = CAM_ORIGIN[0], CAM_ORIGIN[2]
+    return [float(x * np.cos(a) - z * np.sin(a)), CAM_ORIGIN[1], float(x * np.sin(a) + z * np.cos(a))]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm (oracle): cpu_baseline of the GPU line and the whole `--impl reference` run
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_scene(args):
+    from oracle import oracle as O
+    onef = O.make_nef(feature_std=1e-4, seed=0)                       # config 2 shapes
+    pts = O.lego_like_points(7)
+    spc = O.octree_to_spc(O.points_to_octree(pts, 7) if args.scene == "lego" else O.dense_octree(7))
+    return O, onef, spc
+
+
+def cpu_time_step(O, onef, spc, args, nrays, cam_i, seed):
+    """One bounded sample: `nrays` rays strided uniformly over the res^2 frame of camera cam_i, full config."""
+    o, d = O.look_at_rays(orbit_origin(cam_i), CAM_LOOKAT, args.res, args.res, CAM_FOV)
+    R = o.shape[0]
+    sel = (np.arange(nrays, dtype=np.int64) * R) // nrays
+    o, d = np.ascontiguousarray(o[sel]), np.ascontiguousarray(d[sel])
+    tgt = (1.0 / (1.0 + np.exp(-np.random.default_rng(2).standard_normal((nrays, 3))))).astype(np.float32)
+    t0 = time.perf_counter()
+    st = O.rf_step(spc, onef, o, d, NEAR, FAR, args.num_steps, tgt, loss="huber", bg=(0, 0, 0), seed=seed)
+    dt = time.perf_counter() - t0
+    return dt, st["num_samples"]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    O, onef, spc = cpu_scene(args)
+    cores = O.num_threads()
+    nrays = args.cpu_sample_rays or 16384
+    for i in range(args.warmup):
+        cpu_time_step(O, onef, spc, args, max(256, nrays // 8), i, i)
+    tot, samples = 0.0, 0
+    for i in range(args.steps):
+        dt, ns = cpu_time_step(O, onef, spc, args, nrays, args.warmup + i, args.warmup + i)
+        tot += dt; samples += ns
+    value = nrays * args.steps / tot
+    sample = f"{nrays} rays strided over the {args.res}^2 frame per step, full config (n={args.num_steps}); {samples // max(args.steps, 1)} hit samples/step"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * tot / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args),
+            "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "reference has no CPU tracer and cannot be built here (kaolin un-vendored); this is the oracle port, OpenMP"}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[j] for r in self.rows if len(r) >= 7 for j in range(4) if r[3 + j].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import wisp_b200 as W
+    from oracle import oracle as O           # scene description + CPU baseline only; never on the measured GPU path
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, (world, args.gpus)
+
+    # ---- model: identical random init on every rank ----
+    torch.manual_seed(0)
+    pts = torch.from_numpy(O.lego_like_points(7))
+    blas = W.OctreeAS.from_quantized_points(pts.to(dev), 7) if args.scene == "lego" else W.OctreeAS.make_dense(7, device=dev)
+    grid = W.HashGrid.from_geometric(blas, feature_dim=2, num_lods=16, multiscale_type='cat', feature_std=1e-4, codebook_bitwidth=19,
+                                     min_grid_res=16, max_grid_res=512)
+    nef = W.NeuralRadianceField(grid, view_embedder='positional', view_multires=4, hidden_dim=64, num_layers=1, bias=True).to(dev)
+    tracer = W.PackedRFTracer(raymarch_type='ray', num_steps=args.num_steps, bg_color=(0.0, 0.0, 0.0))
+    tracer.precision = args.precision
+    pipe = W.Pipeline(nef, tracer)
+    params = [p for p in nef.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-3, eps=1e-15, fused=True)
+
+    R = args.res * args.res
+    nsteps_total = args.warmup + args.steps
+    # ---- inputs: one camera per (step, rank); host copies pinned for the e2e leg ----
+    host_rays, host_tgt = [], []
+    g = torch.Generator().manual_seed(2)
+    for i in range(nsteps_total):
+        o, d = O.look_at_rays(orbit_origin(i * world + rank), CAM_LOOKAT, args.res, args.res, CAM_FOV)
+        host_rays.append((torch.from_numpy(o).pin_memory(), torch.from_numpy(d).pin_memory()))
+        host_tgt.append(torch.sigmoid(torch.randn(R, 3, generator=g)).pin_memory())
+    dev_rays = [(o.to(dev), d.to(dev)) for o, d in host_rays]
+    dev_tgt = [t.to(dev) for t in host_tgt]
+
+    def step(i, origins, dirs, target):
+        opt.zero_grad(set_to_none=False)
+        tracer.seed = 1000 + i * world + rank
+        rb = pipe(rays=W.Rays(origins, dirs, dist_min=NEAR, dist_max=FAR), lod_idx=None, channels=["rgb"])
+        loss = torch.nn.functional.smooth_l1_loss(rb.rgb, target, reduction='none').mean()       # multiview_trainer.py:144-154
+        loss.backward()
+        if world > 1:
+            for p in params:
+                dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
+                p.grad.div_(world)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ----
+    for i in range(args.warmup):
+        step(i, *dev_rays[i], dev_tgt[i])
+    barrier()
+
+    # ---- timed: device-resident inputs ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    W.ops.PROFILE = []
+    launches0 = W._cabi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    total_samples = 0
+    for k in range(args.steps):
+        i = args.warmup + k
+        step(i, *dev_rays[i], dev_tgt[i])
+        total_samples += tracer.get_prev_num_samples()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = W._cabi.launch_count() - launches0
+    prof = W.ops.PROFILE
+    W.ops.PROFILE = None
+    stage_ms = {}
+    for name, a, b in prof:
+        stage_ms.setdefault(name, []).append(a.elapsed_time(b))
+
+    # ---- timed: end to end from host buffers through the public API ----
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e2.record()
+    for k in range(args.steps):
+        i = args.warmup + k
+        o = host_rays[i][0].to(dev, non_blocking=True); d = host_rays[i][1].to(dev, non_blocking=True)
+        t = host_tgt[i].to(dev, non_blocking=True)
+        loss = step(i, o, d, t)
+        loss_host = float(loss.item())
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    tms = torch.tensor([ms, ms_e2e, float(total_samples)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = tms.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tms.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, ms_e2e, total_samples = float(mx[0]), float(mx[1]), float(sm[2])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    rays_total = R * args.steps * world
+    value = rays_total / (ms * 1e-3)
+    e2e_value = rays_total / (ms_e2e * 1e-3)
+    S_step = total_samples / (args.steps * world)
+
+    # ---- roofline of the dominant kernel (algorithmic bytes per hit sample) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    e = 4                                                      # fp32 table and fp32 gradients
+    L_eff = 15                                                 # 'cat' zeroes the last LOD (hash_grid.py:228): 15 of 16 levels are read
+    per_sample = {"shade_fwd": L_eff * 8 * 2 * e, "shade_bwd": 2 * L_eff * 8 * 2 * e}
+    mean_ms = {k: float(np.mean(v)) for k, v in stage_ms.items()}
+    dom = max((k for k in mean_ms if k in per_sample), key=lambda k: mean_ms[k])
+    algo_bytes = S_step * per_sample[dom]
+    achieved = algo_bytes / (mean_ms[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "wb_" + dom + "_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                "algorithmic_bytes_per_sample": per_sample[dom], "samples_per_launch": S_step, "kernel_ms": mean_ms[dom],
+                "note": "table (40 MB) is L2 resident: this is HBM-equivalent gather bandwidth, see DESIGN.md"}
+
+    line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == 0 else "f16(tensor)+f32 accumulate", "data": "synthetic", "config": workload_config(args),
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": R * (24 + 12), "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                    "last_loss": loss_host},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "samples_per_step_per_gpu": S_step, "samples_per_sec": total_samples / (ms * 1e-3), "stage_ms": mean_ms}
+
+    if not args.no_cpu_baseline:
+        Oc, onef, spc = cpu_scene(args)
+        nr = args.cpu_sample_rays or 32768
+        cpu_time_step(Oc, onef, spc, args, 256, 0, 0)
+        dt, ns = cpu_time_step(Oc, onef, spc, args, nr, args.warmup, 1000 + args.warmup)
+        line["cpu_baseline"] = {"value": nr / dt, "unit": "rays/s", "cores": Oc.num_threads(), "kind": "port",
+                                "sample": f"{nr} rays strided over the {args.res}^2 frame, full config, {ns} hit samples, {dt:.1f} s"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,175 @@
+/*
+ * wispb200.h -- C ABI of libwispb200.so: the B200 (sm_100a) volumetric render path that drops in behind
+ * kaolin-wisp's Pipeline / BaseTracer / BLASGrid / BaseNeuralField API.
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch owns all tensors; the library borrows
+ *     them for the duration of the call and allocates nothing persistent);
+ *   - every entry point takes the cudaStream_t to launch on (as void*), never synchronises the host,
+ *     and returns 0 on success or a negative wb_status; wb_last_error() describes the last failure of the
+ *     calling thread.  The reference raises from AT_ERROR/AT_CUDA_CHECK instead
+ *     (wisp/csrc/ops/hashgrid_interpolate.cpp:66-68, uniform_sample_cuda.cu:95);
+ *   - layouts are the reference's: row-major, float32 unless stated, int64 ridx, bool(u8) masks.
+ *
+ * Each group cites the reference interface it replaces (paths relative to the kaolin-wisp checkout).
+ */
+#ifndef WISPB200_H_
+#define WISPB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* wb_stream;            /* cudaStream_t */
+
+enum wb_status {
+    WB_OK = 0,
+    WB_ERR_INVALID = -1,            /* bad argument / unsupported configuration */
+    WB_ERR_CUDA = -2,               /* a CUDA runtime call failed (message has the cudaError string) */
+    WB_ERR_NODEVICE = -3            /* no sm_100 device: there is NO CPU fallback */
+};
+
+const char* wb_last_error(void);
+int wb_version(void);
+/* Device check used by the host shim at import: WB_OK only on compute capability 10.x. */
+int wb_device_check(int device);
+/* Number of kernels this library launched since load (bench.py's gpu_launches). */
+int64_t wb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Neural field descriptor (NeuralRadianceField + HashGrid + BasicDecoder x2 + PositionalEmbedder)
+ *   wisp/models/nefs/nerf.py:30-173, wisp/models/grids/hash_grid.py:27-89, wisp/models/grids/utils.py:13-63
+ * Plain C struct, passed by pointer (host memory); the pointers inside are device pointers.
+ * ---------------------------------------------------------------------------------------------- */
+#define WB_MAX_LODS 32
+#define WB_MAX_LAYERS 8
+
+typedef struct wb_nef_desc {
+    /* hash grid */
+    int32_t num_lods;                       /* L                                                     */
+    int32_t feature_dim;                    /* F (even, ops/grid.py:83-84)                           */
+    int32_t codebook_size;                  /* T = 2^codebook_bitwidth (hashgrid_interpolate.cpp:59) */
+    int32_t multiscale;                     /* 0 'cat', 1 'sum' (hash_grid.py:226-231)               */
+    int32_t lod_idx;                        /* 'cat': features of LODs >= lod_idx are zeroed         */
+    int32_t resolutions[WB_MAX_LODS];       /* MultiTable.resolutions                                */
+    int64_t begin_idxes[WB_MAX_LODS + 1];   /* MultiTable.begin_idxes (rows)                         */
+    const float* table;                     /* MultiTable.feats [rows, F] fp32 master                */
+    /* embedders: 0 none, 1 identity, 2 positional (no input), 3 positional + input                   */
+    int32_t pos_mode, pos_freq;             /* nerf.py:103-104                                       */
+    int32_t view_mode, view_freq;           /* nerf.py:105-106 (include_input=True => never 0/2)     */
+    /* decoders: packed parameters [W0 (out x in, row-major like nn.Linear.weight), b0?, W1, b1?, ...] */
+    int32_t has_bias;
+    int32_t dens_layers;                    /* linear layers of decoder_density = num_layers + 1     */
+    int32_t dens_dims[WB_MAX_LAYERS + 1];
+    int32_t col_layers;                     /* linear layers of decoder_color   = num_layers + 2     */
+    int32_t col_dims[WB_MAX_LAYERS + 1];
+    const float* dens_params;
+    const float* col_params;
+} wb_nef_desc;
+
+/* Rays (wisp/core/rays.py:19-36).  near/far: scalars, or per-ray arrays when near_v != NULL. */
+typedef struct wb_rays {
+    const float* origins;                   /* [R,3] */
+    const float* dirs;                      /* [R,3] */
+    int64_t num_rays;
+    float dist_min, dist_max;
+    const float* near_v;                    /* optional [R] */
+    const float* far_v;                     /* optional [R] */
+} wb_rays;
+
+/* Occupancy structure (wisp/accelstructs/octree_as.py:43-62): the SPC tensors the reference keeps. */
+typedef struct wb_octree {
+    const uint8_t* octree;                  /* [nbytes] one byte per non-leaf node, breadth first   */
+    const int32_t* prefix;                  /* [nbytes+1] exclusive sum of popcounts ("exsum")      */
+    int64_t nbytes;
+    int32_t max_level;
+    const uint32_t* bits;                   /* optional dense bitmask of `bits_level` built by       */
+    int32_t bits_level;                     /*   wb_octree_build_bits; NULL -> descend the bytes     */
+} wb_octree;
+
+/* ------------------------------------------------------------------------------------------------
+ * SPC helpers  -- replace kaolin.ops.spc.{scan_octrees, generate_points, unbatched_query}
+ *   call sites: wisp/ops/spc/conversions.py:84-87, wisp/accelstructs/octree_as.py:146-163
+ * ---------------------------------------------------------------------------------------------- */
+/* points: int16 [total,3] (generate_points); pyramid on the host. */
+int wb_octree_generate_points(const uint8_t* octree, const int32_t* prefix, int64_t nbytes,
+                              int16_t* points, int64_t total, wb_stream s);
+/* bits: zero-initialised uint32 [(8^level + 31)/32]; bit (x<<2L | y<<L | z) set iff the level-L cell is occupied. */
+int wb_octree_build_bits(const int16_t* level_points, int64_t num_points, int32_t level, uint32_t* bits, wb_stream s);
+/* OctreeAS.query (octree_as.py:146-163): out int32 [N] or [N, level+1] (with_parents). */
+int wb_query(const wb_octree* oct, const float* coords, int64_t N, int32_t level, int32_t with_parents,
+             int32_t* out, wb_stream s);
+
+/* ------------------------------------------------------------------------------------------------
+ * OctreeAS._raymarch_ray  (wisp/accelstructs/octree_as.py:247-309)
+ *   count -> (caller scans counts into offsets, reads the total) -> fill.
+ *   jitter: explicit [R, n] tensor (the reference's torch.rand draw) or NULL for the counter-based stream
+ *   keyed by (seed, ray, step) (see DESIGN.md "Jitter contract").
+ *   hitmask: uint32 [R, (n+31)/32] written by count and consumed by fill.
+ * ---------------------------------------------------------------------------------------------- */
+int wb_raymarch_ray_count(const wb_octree* oct, int32_t level, const wb_rays* rays, int32_t num_samples,
+                          const float* jitter, uint32_t seed, uint32_t* hitmask, int32_t* counts, wb_stream s);
+/* exclusive scan of counts -> offsets (int64 [R+1], offsets[R] = total).  workspace >= wb_scan_workspace_bytes(R). */
+int64_t wb_scan_workspace_bytes(int64_t R);
+int wb_scan_counts(const int32_t* counts, int64_t R, int64_t* offsets, void* workspace, int64_t workspace_bytes, wb_stream s);
+/* ASRaymarchResults layout (base_as.py:57-84): ridx i64[S], samples f32[S,3], depth f32[S,1], deltas f32[S,1],
+ * boundary u8[S].  Any output pointer may be NULL. */
+int wb_raymarch_ray_fill(const wb_rays* rays, int32_t num_samples, const float* jitter, uint32_t seed,
+                         const uint32_t* hitmask, const int64_t* offsets,
+                         int64_t* ridx, float* samples, float* depth, float* deltas, uint8_t* boundary, wb_stream s);
+
+/* ------------------------------------------------------------------------------------------------
+ * HashGrid.interpolate kernels -- replace wisp._C.ops.hashgrid_interpolate_cuda / _backward_cuda
+ *   (wisp/csrc/ops/hashgrid_interpolate.h:18-33, hashgrid_interpolate.cpp:46-105): all LODs in ONE launch.
+ *   feats/grad_feats: [N, L*F] raw kernel output (the 'cat' zeroing / 'sum' reduction of hash_grid.py:224-233
+ *   is applied by the host shim, as in the reference).  grad_table must be zero-initialised (cpp:85).
+ * ---------------------------------------------------------------------------------------------- */
+int wb_hashgrid_fwd(const float* coords, int64_t N, const wb_nef_desc* grid, float* feats, wb_stream s);
+int wb_hashgrid_bwd(const float* coords, int64_t N, const wb_nef_desc* grid, const float* grad_feats,
+                    float* grad_table, wb_stream s);
+
+/* ------------------------------------------------------------------------------------------------
+ * Packed compositing -- replaces kaolin.render.spc.{exponential_integration, sum_reduce} + the buffer
+ *   scatter of PackedRFTracer.trace (wisp/tracers/packed_rf_tracer.py:136-165).
+ *   shaded: float4 [S] = (r, g, b, sigma); offsets int64 [R+1]; depth/deltas [S].
+ *   bg: HOST pointer to 3 floats (tracer.bg_color; a launch parameter, not a tensor).
+ *   outputs: rgb [R,3], depth_out [R] (may be NULL), alpha [R], hit u8[R].
+ * ---------------------------------------------------------------------------------------------- */
+int wb_composite_fwd(const float* shaded, const float* depth, const float* deltas, const int64_t* offsets, int64_t R,
+                     const float* bg, float* rgb, float* depth_out, float* alpha, uint8_t* hit, wb_stream s);
+/* g_shaded float4 [S] = dL/d(r,g,b,sigma).  g_depth / g_alpha may be NULL. */
+int wb_composite_bwd(const float* shaded, const float* depth, const float* deltas, const int64_t* offsets, int64_t R,
+                     const float* bg, const float* g_rgb, const float* g_depth, const float* g_alpha,
+                     float* g_shaded, wb_stream s);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused render path -- replaces PackedRFTracer.trace + NeuralRadianceField.rgba + HashGrid.interpolate
+ *   (wisp/tracers/packed_rf_tracer.py:84-181, wisp/models/nefs/nerf.py:219-264).
+ *   1. wb_raymarch_ray_count + wb_scan_counts            (sample culling, bit-exact with the reference)
+ *   2. wb_rf_march_fill   : compact sample records (t, delta, ray) -- 12 B/sample instead of 29 B
+ *   3. wb_rf_shade_fwd    : gather + decoders fused, one pass, (r,g,b,sigma) per sample
+ *   4. wb_composite_fwd
+ *   backward: wb_composite_bwd -> wb_rf_shade_bwd (recomputes the decoders, scatters table gradients).
+ *   precision: 0 = fp32 SIMT decoders (reference autocast-off numerics),
+ *              1 = fp16 tensor-core decoders with fp32 accumulation (reference autocast-on numerics).
+ * ---------------------------------------------------------------------------------------------- */
+int wb_rf_march_fill(const wb_rays* rays, int32_t num_samples, const float* jitter, uint32_t seed,
+                     const uint32_t* hitmask, const int64_t* offsets,
+                     float* rec_t, float* rec_delta, int32_t* rec_ray, wb_stream s);
+/* Packs decoder parameters into the shared-memory image the shade kernels stage with one bulk (TMA) copy.
+ * blob: float [wb_rf_param_blob_floats(nef)]. */
+int64_t wb_rf_param_blob_floats(const wb_nef_desc* nef, int32_t precision);
+int wb_rf_pack_params(const wb_nef_desc* nef, int32_t precision, float* blob, wb_stream s);
+int wb_rf_shade_fwd(const wb_nef_desc* nef, const float* blob, int32_t precision, const wb_rays* rays,
+                    const float* rec_t, const int32_t* rec_ray, int64_t S, float* shaded, wb_stream s);
+/* grad_table [rows,F], grad_dens / grad_col (packed like the params) are ACCUMULATED into (caller zeroes). */
+int wb_rf_shade_bwd(const wb_nef_desc* nef, const float* blob, int32_t precision, const wb_rays* rays,
+                    const float* rec_t, const int32_t* rec_ray, int64_t S, const float* g_shaded,
+                    float* grad_table, float* grad_dens, float* grad_col, wb_stream s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WISPB200_H_ */

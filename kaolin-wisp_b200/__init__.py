@@ -1,0 +1,15 @@
+"""wisp_b200 -- Blackwell (sm_100a) volumetric render path behind the kaolin-wisp API.
+
+Import as `wisp_b200` (the directory is named kaolin-wisp_b200 per the repo layout; the top-level `wisp_b200`
+package aliases it).  Host-side classes mirror the reference's names and arguments; all compute goes through
+libwispb200.so (hand-written CUDA behind a C ABI, include/wispb200.h).  There is no CPU fallback.
+"""
+from . import _cabi, ops, spc                                                   # noqa: F401
+from .core import Rays, RenderBuffer                                            # noqa: F401
+from .accelstructs import OctreeAS, ASQueryResults, ASRaymarchResults, ASRaytraceResults   # noqa: F401
+from .grids import HashGrid, MultiTable                                         # noqa: F401
+from .nefs import NeuralRadianceField, BasicDecoder, PositionalEmbedder, get_positional_embedder   # noqa: F401
+from .tracers import PackedRFTracer                                             # noqa: F401
+from .pipeline import Pipeline                                                  # noqa: F401
+
+__version__ = "0.1.0"

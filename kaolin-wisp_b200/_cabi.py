@@ -1,0 +1,158 @@
+"""ctypes binding of libwispb200.so -- the only place the host shim touches native code.
+
+The C ABI (include/wispb200.h) takes raw device pointers, sizes and a cudaStream_t; PyTorch is used here only
+as the owner of device memory and streams.  There is NO CPU or eager fallback: if the library is missing, or
+the device is not sm_100, every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libwispb200.so")
+
+WB_MAX_LODS = 32
+WB_MAX_LAYERS = 8
+
+
+class NefDesc(C.Structure):
+    """struct wb_nef_desc (include/wispb200.h)."""
+    _fields_ = [
+        ("num_lods", C.c_int32), ("feature_dim", C.c_int32), ("codebook_size", C.c_int32),
+        ("multiscale", C.c_int32), ("lod_idx", C.c_int32),
+        ("resolutions", C.c_int32 * WB_MAX_LODS),
+        ("begin_idxes", C.c_int64 * (WB_MAX_LODS + 1)),
+        ("table", C.c_void_p),
+        ("pos_mode", C.c_int32), ("pos_freq", C.c_int32), ("view_mode", C.c_int32), ("view_freq", C.c_int32),
+        ("has_bias", C.c_int32),
+        ("dens_layers", C.c_int32), ("dens_dims", C.c_int32 * (WB_MAX_LAYERS + 1)),
+        ("col_layers", C.c_int32), ("col_dims", C.c_int32 * (WB_MAX_LAYERS + 1)),
+        ("dens_params", C.c_void_p), ("col_params", C.c_void_p),
+    ]
+
+
+class RaysDesc(C.Structure):
+    """struct wb_rays."""
+    _fields_ = [("origins", C.c_void_p), ("dirs", C.c_void_p), ("num_rays", C.c_int64),
+                ("dist_min", C.c_float), ("dist_max", C.c_float), ("near_v", C.c_void_p), ("far_v", C.c_void_p)]
+
+
+class OctreeDesc(C.Structure):
+    """struct wb_octree."""
+    _fields_ = [("octree", C.c_void_p), ("prefix", C.c_void_p), ("nbytes", C.c_int64), ("max_level", C.c_int32),
+                ("bits", C.c_void_p), ("bits_level", C.c_int32)]
+
+
+EXPORTS = [
+    "wb_last_error", "wb_version", "wb_device_check", "wb_launch_count",
+    "wb_octree_generate_points", "wb_octree_build_bits", "wb_query",
+    "wb_raymarch_ray_count", "wb_scan_workspace_bytes", "wb_scan_counts", "wb_raymarch_ray_fill",
+    "wb_hashgrid_fwd", "wb_hashgrid_bwd", "wb_composite_fwd", "wb_composite_bwd",
+    "wb_rf_march_fill", "wb_rf_param_blob_floats", "wb_rf_pack_params", "wb_rf_shade_fwd", "wb_rf_shade_bwd",
+]
+
+_lib: Optional[C.CDLL] = None
+_checked_devices = set()
+
+
+class WispB200Error(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load libwispb200.so; raise loudly if it was not built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise WispB200Error(
+                f"{LIB_PATH} not found: build it with `python kaolin-wisp_b200/build.py` (or __graft_entry__.build()). "
+                "wisp_b200 has no CPU/eager fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.wb_last_error.restype = C.c_char_p
+        L.wb_launch_count.restype = C.c_int64
+        L.wb_scan_workspace_bytes.restype = C.c_int64
+        L.wb_scan_workspace_bytes.argtypes = [C.c_int64]
+        L.wb_rf_param_blob_floats.restype = C.c_int64
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise WispB200Error(f"libwispb200 error {rc}: {lib().wb_last_error().decode()}")
+
+
+def require_device(t: torch.Tensor) -> None:
+    """Every compute call requires a CUDA tensor on an sm_100 device."""
+    if not t.is_cuda:
+        raise WispB200Error("wisp_b200 kernels need CUDA tensors on a B200 (sm_100a); there is no CPU fallback")
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if idx not in _checked_devices:
+        check(lib().wb_device_check(C.c_int(idx)))
+        _checked_devices.add(idx)
+
+
+def launch_count() -> int:
+    return int(lib().wb_launch_count())
+
+
+def ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _per_ray(v, R: int, device) -> torch.Tensor:
+    t = torch.as_tensor(v, dtype=torch.float32, device=device).reshape(-1)
+    if t.numel() == 1:
+        t = t.expand(R)
+    if t.numel() != R:
+        raise WispB200Error(f"per-ray dist_min/dist_max must have {R} entries, got {t.numel()}")
+    return t.contiguous()
+
+
+def make_rays(origins: torch.Tensor, dirs: torch.Tensor, dist_min, dist_max):
+    """-> (RaysDesc, keepalive).  dist_min/dist_max: python floats or per-ray tensors (wisp/core/rays.py:31-35)."""
+    o, d = f32c(origins), f32c(dirs)
+    keep = [o, d]
+    r = RaysDesc()
+    r.origins, r.dirs, r.num_rays = o.data_ptr(), d.data_ptr(), o.shape[0]
+    if torch.is_tensor(dist_min) or torch.is_tensor(dist_max):
+        nv, fv = _per_ray(dist_min, o.shape[0], o.device), _per_ray(dist_max, o.shape[0], o.device)
+        keep += [nv, fv]
+        r.near_v, r.far_v, r.dist_min, r.dist_max = nv.data_ptr(), fv.data_ptr(), 0.0, 0.0
+    else:
+        r.near_v, r.far_v = None, None
+        r.dist_min, r.dist_max = float(dist_min), float(dist_max)
+    return r, keep
+
+
+def make_grid_desc(table: torch.Tensor, resolutions: Sequence[int], begin_idxes: Sequence[int], codebook_size: int,
+                   multiscale: str = "cat", lod_idx: Optional[int] = None) -> NefDesc:
+    d = NefDesc()
+    L = len(resolutions)
+    if L > WB_MAX_LODS:
+        raise WispB200Error(f"num_lods {L} > {WB_MAX_LODS}")
+    d.num_lods, d.feature_dim, d.codebook_size = L, table.shape[1], int(codebook_size)
+    d.multiscale = 0 if multiscale == "cat" else 1
+    d.lod_idx = L - 1 if lod_idx is None else int(lod_idx)
+    for i, r in enumerate(resolutions):
+        d.resolutions[i] = int(r)
+    for i, b in enumerate(begin_idxes):
+        d.begin_idxes[i] = int(b)
+    d.table = table.data_ptr()
+    return d

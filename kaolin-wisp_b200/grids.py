@@ -1,0 +1,120 @@
+"""HashGrid / MultiTable: host-side mirrors of wisp.models.grids.HashGrid (wisp/models/grids/hash_grid.py:20-265)
+and wisp.models.grids.utils.MultiTable (wisp/models/grids/utils.py:13-71).  Parameter names are the reference's
+(`codebook.feats`, `codebook.begin_idxes`) so state_dicts and the trainer's name-based optimiser groups
+(base_trainer.py:216-235) carry over."""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .accelstructs import ASRaymarchResults, OctreeAS
+
+
+class MultiTable(nn.Module):
+    def __init__(self, resolutions: Tuple[int, ...], coord_dim: int, feature_dim: int, std: float = 0.01, max_feats: Optional[int] = None):
+        super().__init__()
+        self.num_lods = len(resolutions)
+        self.max_feats = max_feats
+        self.register_buffer("begin_idxes", torch.zeros(self.num_lods + 1, dtype=torch.int64))
+        self.register_buffer("num_feats", torch.zeros(self.num_lods, dtype=torch.int64))
+        self.coord_dim = coord_dim
+        self.feature_dim = feature_dim
+        self.resolutions = torch.zeros([self.num_lods, 1], dtype=torch.int64)
+        num_so_far = 0
+        for i in range(self.num_lods):
+            self.resolutions[i] = resolutions[i]
+            n = int(resolutions[i]) ** coord_dim
+            if max_feats:
+                n = min(max_feats, n)
+            self.begin_idxes[i] = num_so_far
+            self.num_feats[i] = n
+            num_so_far += n
+        self.begin_idxes[self.num_lods] = num_so_far
+        self.total_feats = num_so_far
+        self.feats = nn.Parameter(torch.randn(self.total_feats, feature_dim) * std)
+
+    def get_level(self, idx):
+        return self.feats[self.begin_idxes[idx]:self.begin_idxes[idx + 1]]
+
+
+class HashGrid(nn.Module):
+    """Multi-resolution hash grid (hash_grid.py:27-89)."""
+
+    def __init__(self, blas: OctreeAS, feature_dim: int, resolutions: List[int], multiscale_type: str = 'sum',
+                 feature_std: float = 0.0, feature_bias: float = 0.0, codebook_bitwidth: int = 8, coord_dim: int = 3):
+        super().__init__()
+        assert coord_dim == 3, "the accelerated path covers the 3D hash grid"
+        self.blas = blas
+        if blas is not None:
+            lvl = blas.max_level
+            s, c = int(blas.pyramid[1, lvl]), int(blas.pyramid[0, lvl])
+            self.dense_points = blas.points[s:s + c].clone()
+            self.num_cells = self.dense_points.shape[0]
+            self.occupancy = torch.zeros(self.num_cells)
+        self.feature_dim = feature_dim
+        self.multiscale_type = multiscale_type
+        self.feature_std = feature_std
+        self.feature_bias = feature_bias
+        self.codebook_bitwidth = codebook_bitwidth
+        self.resolutions = [int(r) for r in resolutions]
+        self.num_lods = len(resolutions)
+        self.active_lods = [x for x in range(self.num_lods)]
+        self.max_lod = self.num_lods - 1
+        self.codebook_size = 2 ** codebook_bitwidth
+        self.coord_dim = coord_dim
+        self.codebook = MultiTable(self.resolutions, coord_dim, feature_dim, feature_std, self.codebook_size)
+
+    @classmethod
+    def from_octree(cls, blas, feature_dim, base_lod=2, num_lods=1, multiscale_type='sum', feature_std=0.0, feature_bias=0.0,
+                    codebook_bitwidth=8, coord_dim=3):
+        resolutions = [2 ** (base_lod + x) for x in range(num_lods)]
+        return cls(blas, feature_dim, resolutions, multiscale_type, feature_std, feature_bias, codebook_bitwidth, coord_dim)
+
+    @classmethod
+    def from_geometric(cls, blas, feature_dim, num_lods, multiscale_type='sum', feature_std=0.0, feature_bias=0.0,
+                       codebook_bitwidth=8, min_grid_res=16, max_grid_res=None, coord_dim=3):
+        b = np.exp((np.log(max_grid_res) - np.log(min_grid_res)) / (num_lods - 1))          # hash_grid.py:160-161
+        resolutions = [int(np.floor(min_grid_res * (b ** l))) for l in range(num_lods)]
+        return cls(blas, feature_dim, resolutions, multiscale_type, feature_std, feature_bias, codebook_bitwidth, coord_dim)
+
+    @classmethod
+    def from_resolutions(cls, blas, feature_dim, resolutions=None, multiscale_type='sum', feature_std=0.0, feature_bias=0.0,
+                         codebook_bitwidth=8, coord_dim=3):
+        assert resolutions is not None, 'HashGrid.from_resolutions() constructor cannot accept a None resolutions arg.'
+        return cls(blas, feature_dim, resolutions, multiscale_type, feature_std, feature_bias, codebook_bitwidth, coord_dim)
+
+    def freeze(self):
+        self.codebook.requires_grad_(False)
+
+    def interpolate(self, coords, lod_idx):
+        """hash_grid.py:205-233 (including the 'cat' zeroing of LODs >= lod_idx)."""
+        output_shape = coords.shape[:-1]
+        if coords.ndim == 3:
+            batch, num_samples, coords_dim = coords.shape
+            coords = coords.reshape(batch * num_samples, coords_dim)
+        feats = ops.hashgrid(coords, self.codebook_bitwidth, lod_idx, self.codebook)
+        if self.multiscale_type == 'cat':
+            feats = feats.reshape(*output_shape, feats.shape[-1])
+            mask = torch.ones(feats.shape[-1], device=feats.device, dtype=feats.dtype)
+            mask[lod_idx * self.feature_dim:] = 0       # reference writes zeros in place (hash_grid.py:228)
+            return feats * mask
+        elif self.multiscale_type == 'sum':
+            return feats.reshape(*output_shape, len(self.resolutions), feats.shape[-1] // len(self.resolutions)).sum(-2)
+        else:
+            raise NotImplementedError
+
+    def raymarch(self, rays, raymarch_type, num_samples, level=None, **kw) -> ASRaymarchResults:
+        return self.blas.raymarch(rays, raymarch_type=raymarch_type, num_samples=num_samples, level=self.blas.max_level, **kw)
+
+    def raytrace(self, rays, level=None, with_exit=False):
+        return self.blas.raytrace(rays, level=level, with_exit=with_exit)
+
+    def query(self, coords, level=None, with_parents=False):
+        return self.blas.query(coords, level=level, with_parents=with_parents)
+
+    def name(self) -> str:
+        return "Hash Grid"

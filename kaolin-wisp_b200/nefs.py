@@ -1,0 +1,214 @@
+"""NeuralRadianceField and its parts: host-side mirrors of
+  wisp.models.nefs.NeuralRadianceField   (wisp/models/nefs/nerf.py:25-295)
+  wisp.models.nefs.BaseNeuralField       (wisp/models/nefs/base_nef.py:120-202, channel dispatch)
+  wisp.models.decoders.BasicDecoder      (wisp/models/decoders/basic_decoders.py:16-101)
+  wisp.models.embedders.PositionalEmbedder / get_positional_embedder (positional_embedder.py:15-100)
+Module / parameter names are the reference's (decoder_density.layers.N.weight, decoder_color.lout.bias,
+grid.codebook.feats ...).  `rgba()` is the unfused route (our hash-grid kernel + torch Linear); the tracer uses
+`fused_spec()` to hand the whole field to the fused native pipeline instead.
+"""
+from __future__ import annotations
+
+import inspect
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .grids import HashGrid
+
+
+class PositionalEmbedder(nn.Module):
+    def __init__(self, num_freq, max_freq_log2, log_sampling=True, include_input=True, input_dim=3):
+        super().__init__()
+        self.num_freq, self.max_freq_log2, self.log_sampling, self.include_input = num_freq, max_freq_log2, log_sampling, include_input
+        self.out_dim = input_dim if include_input else 0
+        if log_sampling:
+            bands = 2.0 ** torch.linspace(0.0, max_freq_log2, steps=num_freq)
+        else:
+            bands = torch.linspace(1, 2.0 ** max_freq_log2, steps=num_freq)
+        self.out_dim += bands.shape[0] * input_dim * 2
+        self.bands = nn.Parameter(bands).requires_grad_(False)
+
+    def forward(self, coords):
+        N = coords.shape[0]
+        winded = (coords[:, None] * self.bands[None, :, None]).reshape(N, coords.shape[1] * self.num_freq)
+        encoded = torch.cat([torch.sin(winded), torch.cos(winded)], dim=-1)
+        if self.include_input:
+            encoded = torch.cat([coords, encoded], dim=-1)
+        return encoded
+
+
+def get_positional_embedder(frequencies, input_dim=3, include_input=True):
+    enc = PositionalEmbedder(frequencies, frequencies - 1, input_dim=input_dim, include_input=include_input)
+    return enc, enc.out_dim
+
+
+class BasicDecoder(nn.Module):
+    """Linear/activation stack (basic_decoders.py:59-101); only layer=nn.Linear, activation=relu, no skips."""
+
+    def __init__(self, input_dim, output_dim, activation=torch.relu, bias=True, layer=nn.Linear, num_layers=1, hidden_dim=128, skip=None):
+        super().__init__()
+        self.input_dim, self.output_dim, self.activation, self.bias = input_dim, output_dim, activation, bias
+        self.layer, self.num_layers, self.hidden_dim, self.skip = layer, num_layers, hidden_dim, skip or []
+        layers = []
+        for i in range(num_layers):
+            layers.append(layer(input_dim if i == 0 else hidden_dim, hidden_dim, bias=bias))
+        self.layers = nn.ModuleList(layers)
+        self.lout = layer(hidden_dim, output_dim, bias=bias)
+
+    def forward(self, x, return_h=False):
+        h = x
+        for l in self.layers:
+            h = self.activation(l(h))
+        out = self.lout(h)
+        return (out, h) if return_h else out
+
+    def packed_params(self):
+        """[W0, b0?, W1, b1?, ...] -- the order the C ABI expects (include/wispb200.h)."""
+        out = []
+        for l in list(self.layers) + [self.lout]:
+            out.append(l.weight)
+            if l.bias is not None:
+                out.append(l.bias)
+        return out
+
+    def dims(self):
+        return [self.input_dim] + [self.hidden_dim] * self.num_layers + [self.output_dim]
+
+
+class BaseNeuralField(nn.Module):
+    """Channel dispatch of base_nef.py:120-202."""
+
+    def __init__(self):
+        super().__init__()
+        self._forward_functions = {}
+        self.register_forward_functions()
+
+    def _register_forward_function(self, fn, channels):
+        if isinstance(channels, str):
+            channels = [channels]
+        self._forward_functions[fn] = set(channels)
+
+    def get_supported_channels(self):
+        out = set()
+        for v in self._forward_functions.values():
+            out |= v
+        return out
+
+    def forward(self, channels=None, **kwargs):
+        if not (isinstance(channels, (str, list, set)) or channels is None):
+            raise Exception(f"Channels type invalid, got {type(channels)}."
+                            "Make sure your arguments for the nef are provided as keyword arguments.")
+        requested = self.get_supported_channels() if channels is None else {channels} if isinstance(channels, str) else set(channels)
+        unsupported = requested - self.get_supported_channels()
+        if unsupported:
+            raise Exception(f"Channels {unsupported} are not supported in {self.__class__.__name__}")
+        fns = sorted(((len(ch & requested), fn) for fn, ch in self._forward_functions.items() if ch & requested), key=lambda x: x[0], reverse=True)
+        ret = {}
+        for _, fn in fns:
+            supported = self._forward_functions[fn] & requested
+            requested = requested - supported
+            if supported:
+                spec = inspect.getfullargspec(fn)
+                nreq = len(spec.args) - (len(spec.defaults) if spec.defaults else 0)
+                args = {}
+                for a in spec.args[1:nreq]:
+                    if a not in kwargs:
+                        raise Exception(f"Argument {a} not found as input to in {self.__class__.__name__}.{fn.__name__}()")
+                    args[a] = kwargs[a]
+                for a in spec.args[nreq:]:
+                    if a in kwargs:
+                        args[a] = kwargs[a]
+                out = fn(**args)
+                for c in supported:
+                    ret[c] = out[c]
+        if isinstance(channels, str):
+            return ret.get(channels)
+        if isinstance(channels, list):
+            return [ret[c] for c in channels]
+        return ret
+
+
+class NeuralRadianceField(BaseNeuralField):
+    def __init__(self, grid, pos_embedder='none', view_embedder='none', pos_multires=10, view_multires=4, position_input=False,
+                 activation_type='relu', layer_type='linear', hidden_dim=128, num_layers=1, bias=False,
+                 prune_density_decay: Optional[float] = (0.01 * 512) / np.sqrt(3), prune_min_density: Optional[float] = 0.6):
+        super().__init__()
+        self.grid = grid
+        if activation_type != 'relu' or layer_type not in ('linear', 'none'):
+            raise NotImplementedError("wisp_b200 covers activation_type='relu', layer_type='linear' (the shipped NeRF configs)")
+        self.pos_embedder_type, self.view_embedder_type = pos_embedder, view_embedder
+        self.pos_multires, self.view_multires, self.position_input = pos_multires, view_multires, position_input
+        self.pos_embedder, self.pos_embed_dim = self.init_embedder(pos_embedder, pos_multires, include_input=position_input)
+        self.view_embedder, self.view_embed_dim = self.init_embedder(view_embedder, view_multires, include_input=True)
+        self.activation_type, self.layer_type, self.hidden_dim, self.num_layers, self.bias = activation_type, layer_type, hidden_dim, num_layers, bias
+        self.decoder_density = BasicDecoder(self.density_net_input_dim(), 16, torch.relu, bias, nn.Linear, num_layers, hidden_dim)
+        if self.decoder_density.lout.bias is not None:
+            self.decoder_density.lout.bias.data[0] = 1.0                        # nerf.py:162-163
+        self.decoder_color = BasicDecoder(self.color_net_input_dim(), 3, torch.relu, bias, nn.Linear, num_layers + 1, hidden_dim)
+        self.prune_density_decay, self.prune_min_density = prune_density_decay, prune_min_density
+
+    def init_embedder(self, embedder_type, frequencies=None, include_input=False):
+        """nerf.py:110-141."""
+        if embedder_type == 'none' and not include_input:
+            return None, 0
+        if embedder_type == 'identity' or (embedder_type == 'none' and include_input):
+            return nn.Identity(), 3
+        if embedder_type == 'positional':
+            return get_positional_embedder(frequencies=frequencies, include_input=include_input)
+        raise NotImplementedError(f'Unsupported embedder type for NeuralRadianceField: {embedder_type}')
+
+    def register_forward_functions(self):
+        self._register_forward_function(self.rgba, ["density", "rgb"])
+
+    def rgba(self, coords, ray_d, lod_idx=None):
+        """nerf.py:219-264, unfused: hash-grid kernel + torch decoders."""
+        if lod_idx is None:
+            lod_idx = len(self.grid.active_lods) - 1
+        batch, _ = coords.shape
+        feats = self.grid.interpolate(coords, lod_idx).reshape(batch, self.effective_feature_dim())
+        if self.pos_embedder is not None:
+            feats = torch.cat([feats, self.pos_embedder(coords).view(batch, self.pos_embed_dim)], dim=-1)
+        density_feats = self.decoder_density(feats)
+        if self.view_embedder is not None:
+            fdir = torch.cat([density_feats, self.view_embedder(ray_d).view(batch, self.view_embed_dim)], dim=-1)
+        else:
+            fdir = density_feats
+        colors = torch.sigmoid(self.decoder_color(fdir[..., 1:]))
+        density = torch.relu(density_feats[..., 0:1])
+        return dict(rgb=colors, density=density)
+
+    def effective_feature_dim(self):
+        return self.grid.feature_dim * self.grid.num_lods if self.grid.multiscale_type == 'cat' else self.grid.feature_dim
+
+    def density_net_input_dim(self):
+        return self.effective_feature_dim() + self.pos_embed_dim
+
+    def color_net_input_dim(self):
+        return 15 + self.view_embed_dim
+
+    # ---- fused path ----------------------------------------------------------------------------------------
+    @staticmethod
+    def _embed_mode(kind: str, include_input: bool, freq: int):
+        if kind == 'none' and not include_input:
+            return 0, 0
+        if kind == 'identity' or (kind == 'none' and include_input):
+            return 1, 0
+        return (3 if include_input else 2), freq
+
+    def fused_spec(self, lod_idx: Optional[int] = None) -> Optional[ops.NefSpec]:
+        """Description of this field for wb_rf_*; None when the configuration is outside the fused path."""
+        g = self.grid
+        if not isinstance(g, HashGrid) or g.feature_dim > 8:
+            return None
+        if lod_idx is None:
+            lod_idx = len(g.active_lods) - 1
+        pm, pf = self._embed_mode(self.pos_embedder_type, self.position_input, self.pos_multires)
+        vm, vf = self._embed_mode(self.view_embedder_type, True, self.view_multires)
+        return ops.NefSpec(resolutions=list(g.resolutions), begin_idxes=[int(b) for b in g.codebook.begin_idxes.tolist()],
+                           codebook_size=g.codebook_size, feature_dim=g.feature_dim, multiscale=g.multiscale_type, lod_idx=int(lod_idx),
+                           pos_mode=pm, pos_freq=pf, view_mode=vm, view_freq=vf, has_bias=bool(self.bias),
+                           dens_dims=self.decoder_density.dims(), col_dims=self.decoder_color.dims())

@@ -1,0 +1,350 @@
+"""Tensor-level operators over the C ABI: the functions the wisp-facing classes (and wisp itself, once patched by
+wisp_b200.install()) call.  Each one names the reference operator it stands in for.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _cabi as A
+
+# Optional per-stage device timing (bench.py): when PROFILE is a list, every native stage appends
+# (name, start_event, end_event) recorded on the launching (current torch) stream.
+PROFILE: Optional[list] = None
+
+
+class _stage:
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True); self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.name, self.e0, self.e1))
+        return False
+
+
+# --------------------------------------------------------------------------------------------------------------
+# octree handle: the SPC tensors the reference's OctreeAS keeps (octree_as.py:58-62) + the optional dense bitmask
+# --------------------------------------------------------------------------------------------------------------
+@dataclass
+class OctreeTensors:
+    octree: torch.Tensor          # uint8 [nbytes]
+    prefix: torch.Tensor          # int32 [nbytes+1]
+    points: torch.Tensor          # int16 [total,3]
+    pyramid: torch.Tensor         # int32 [2, max_level+2] (CPU)
+    max_level: int
+    bits: Optional[torch.Tensor] = None
+    bits_level: int = -1
+
+    def desc(self) -> A.OctreeDesc:
+        d = A.OctreeDesc()
+        d.octree, d.prefix, d.nbytes, d.max_level = self.octree.data_ptr(), self.prefix.data_ptr(), self.octree.shape[0], self.max_level
+        d.bits = self.bits.data_ptr() if self.bits is not None else None
+        d.bits_level = self.bits_level
+        return d
+
+    def ensure_bits(self, level: int) -> None:
+        """Dense occupancy bitmask of `level` (<= 10): 8^level bits, built once per octree by wb_octree_build_bits."""
+        if level > 10 or (self.bits is not None and self.bits_level == level):
+            return
+        A.require_device(self.octree)
+        words = (8 ** level + 31) // 32
+        bits = torch.zeros(words, dtype=torch.int32, device=self.octree.device)
+        start, cnt = int(self.pyramid[1, level]), int(self.pyramid[0, level])
+        lvl = self.points[start:start + cnt].contiguous()
+        A.check(A.lib().wb_octree_build_bits(A.ptr(lvl), C.c_int64(cnt), C.c_int32(level), A.ptr(bits), A.stream()))
+        self.bits, self.bits_level = bits, level
+
+
+def query(oct: OctreeTensors, coords: torch.Tensor, level: int, with_parents: bool = False) -> torch.Tensor:
+    """spc_ops.unbatched_query(octree, prefix, coords, level, with_parents)  (octree_as.py:162)."""
+    A.require_device(coords)
+    c = A.f32c(coords)
+    N = c.shape[0]
+    out = torch.empty((N, level + 1) if with_parents else (N,), dtype=torch.int32, device=c.device)
+    d = oct.desc()
+    A.check(A.lib().wb_query(C.byref(d), A.ptr(c), C.c_int64(N), C.c_int32(level), C.c_int32(int(with_parents)), A.ptr(out), A.stream()))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# raymarch 'ray'
+# --------------------------------------------------------------------------------------------------------------
+@dataclass
+class MarchState:
+    """Intermediate state of one raymarch: per-ray hit bitmask, counts and offsets (device), total (host)."""
+    rays: A.RaysDesc
+    keep: list
+    n: int
+    jitter: Optional[torch.Tensor]
+    seed: int
+    hitmask: torch.Tensor
+    counts: torch.Tensor
+    offsets: torch.Tensor
+    total: int
+
+
+def march_count(oct: OctreeTensors, origins, dirs, dist_min, dist_max, num_samples: int, level: int,
+                jitter: Optional[torch.Tensor] = None, seed: int = 0) -> MarchState:
+    """Sample culling of OctreeAS._raymarch_ray (octree_as.py:272-288) without materialising candidates."""
+    A.require_device(origins)
+    oct.ensure_bits(level)
+    rays, keep = A.make_rays(origins, dirs, dist_min, dist_max)
+    R = rays.num_rays
+    dev = origins.device
+    nw = (num_samples + 31) // 32
+    hitmask = torch.empty((R, nw), dtype=torch.int32, device=dev)
+    counts = torch.empty(R, dtype=torch.int32, device=dev)
+    offsets = torch.empty(R + 1, dtype=torch.int64, device=dev)
+    jit = None if jitter is None else A.f32c(jitter)
+    if jit is not None and tuple(jit.shape) != (R, num_samples):
+        raise A.WispB200Error(f"jitter must be [{R}, {num_samples}]")
+    od = oct.desc()
+    L = A.lib()
+    with _stage("march_count"):
+        A.check(L.wb_raymarch_ray_count(C.byref(od), C.c_int32(level), C.byref(rays), C.c_int32(num_samples), A.ptr(jit),
+                                        C.c_uint32(seed & 0xFFFFFFFF), A.ptr(hitmask), A.ptr(counts), A.stream()))
+    wsb = int(L.wb_scan_workspace_bytes(C.c_int64(R)))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    with _stage("scan"):
+        A.check(L.wb_scan_counts(A.ptr(counts), C.c_int64(R), A.ptr(offsets), A.ptr(ws), C.c_int64(wsb), A.stream()))
+    total = int(offsets[-1].item())       # the one host sync of the path (the reference syncs in torch.nonzero, octree_as.py:288)
+    return MarchState(rays, keep + [jit], num_samples, jit, seed & 0xFFFFFFFF, hitmask, counts, offsets, total)
+
+
+def march_fill_reference_layout(ms: MarchState, device):
+    """ASRaymarchResults tensors (base_as.py:57-84)."""
+    S = ms.total
+    ridx = torch.empty(S, dtype=torch.int64, device=device)
+    samples = torch.empty((S, 3), dtype=torch.float32, device=device)
+    depth = torch.empty((S, 1), dtype=torch.float32, device=device)
+    deltas = torch.empty((S, 1), dtype=torch.float32, device=device)
+    boundary = torch.empty(S, dtype=torch.bool, device=device)
+    if S > 0:
+        A.check(A.lib().wb_raymarch_ray_fill(C.byref(ms.rays), C.c_int32(ms.n), A.ptr(ms.jitter), C.c_uint32(ms.seed), A.ptr(ms.hitmask),
+                                             A.ptr(ms.offsets), A.ptr(ridx), A.ptr(samples), A.ptr(depth), A.ptr(deltas), A.ptr(boundary), A.stream()))
+    return ridx, samples, depth, deltas, boundary
+
+
+def march_fill_records(ms: MarchState, device):
+    """Fused-path sample records: depth t, delta, ray index (12 B/sample)."""
+    S = ms.total
+    rec_t = torch.empty(S, dtype=torch.float32, device=device)
+    rec_delta = torch.empty(S, dtype=torch.float32, device=device)
+    rec_ray = torch.empty(S, dtype=torch.int32, device=device)
+    if S > 0:
+        with _stage("march_fill"):
+            A.check(A.lib().wb_rf_march_fill(C.byref(ms.rays), C.c_int32(ms.n), A.ptr(ms.jitter), C.c_uint32(ms.seed), A.ptr(ms.hitmask),
+                                             A.ptr(ms.offsets), A.ptr(rec_t), A.ptr(rec_delta), A.ptr(rec_ray), A.stream()))
+    return rec_t, rec_delta, rec_ray
+
+
+# --------------------------------------------------------------------------------------------------------------
+# hash grid interpolate (unfused drop-in for wisp.ops.grid.hashgrid)
+# --------------------------------------------------------------------------------------------------------------
+class HashGridInterpolate(torch.autograd.Function):
+    """wisp.ops.grid.HashGridInterpolate (ops/grid.py:77-126) over wb_hashgrid_fwd / wb_hashgrid_bwd.
+    Differences by design: all LODs in one launch; the table is read as fp32 master (no per-call .half() copy,
+    ops/grid.py:88-89) and gradients accumulate in fp32."""
+
+    @staticmethod
+    def forward(ctx, coords, resolutions, codebook_bitwidth, lod_idx, codebook, codebook_first_idx):
+        if codebook.shape[-1] % 2 == 1:
+            raise Exception("The codebook feature dimension needs to be a multiple of 2.")   # ops/grid.py:83-84
+        assert coords.shape[-1] == 3, "only the 3D hash grid is on the accelerated path"
+        A.require_device(codebook)
+        c = A.f32c(coords)
+        res = [int(r) for r in torch.as_tensor(resolutions).reshape(-1).tolist()]
+        begin = [int(b) for b in codebook_first_idx.tolist()] if torch.is_tensor(codebook_first_idx) else list(codebook_first_idx)
+        table = A.f32c(codebook.detach())
+        desc = A.make_grid_desc(table, res, begin, 2 ** codebook_bitwidth)
+        feats = torch.empty((c.shape[0], len(res) * table.shape[1]), dtype=torch.float32, device=c.device)
+        A.check(A.lib().wb_hashgrid_fwd(A.ptr(c), C.c_int64(c.shape[0]), C.byref(desc), A.ptr(feats), A.stream()))
+        ctx.save_for_backward(c, table)
+        ctx.meta = (res, begin, codebook_bitwidth)
+        return feats
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        c, table = ctx.saved_tensors
+        res, begin, bw = ctx.meta
+        desc = A.make_grid_desc(table, res, begin, 2 ** bw)
+        g = A.f32c(grad_output)
+        gt = torch.zeros_like(table)                      # hashgrid_interpolate.cpp:85
+        A.check(A.lib().wb_hashgrid_bwd(A.ptr(c), C.c_int64(c.shape[0]), C.byref(desc), A.ptr(g), A.ptr(gt), A.stream()))
+        return None, None, None, None, gt, None
+
+
+def hashgrid(coords, codebook_bitwidth, lod_idx, codebook):
+    """wisp.ops.grid.hashgrid (ops/grid.py:128-144); `codebook` is a MultiTable."""
+    batch, dim = coords.shape
+    feats = HashGridInterpolate.apply(coords.contiguous(), codebook.resolutions, codebook_bitwidth, lod_idx,
+                                      codebook.feats, codebook.begin_idxes)
+    feature_dim = codebook.feats.shape[1] * len(codebook.resolutions)
+    return feats.reshape(batch, feature_dim)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# packed compositing
+# --------------------------------------------------------------------------------------------------------------
+def _bg3(bg) -> "C.Array":
+    v = [float(x) for x in (bg.detach().cpu().reshape(-1).tolist() if torch.is_tensor(bg) else bg)]
+    return (C.c_float * 3)(*v[:3])
+
+
+class CompositeFn(torch.autograd.Function):
+    """exponential_integration + sum_reduce + per-ray scatter of PackedRFTracer.trace (packed_rf_tracer.py:136-165).
+    shaded [S,4] = (r,g,b,sigma); returns rgb [R,3], depth [R,1], alpha [R,1], hit [R] (bool)."""
+
+    @staticmethod
+    def forward(ctx, shaded, depth, deltas, offsets, bg):
+        A.require_device(shaded)
+        R = offsets.shape[0] - 1
+        dev = shaded.device
+        sh, dp, dl = A.f32c(shaded), A.f32c(depth).reshape(-1), A.f32c(deltas).reshape(-1)
+        rgb = torch.empty((R, 3), dtype=torch.float32, device=dev)
+        dout = torch.empty((R, 1), dtype=torch.float32, device=dev)
+        alpha = torch.empty((R, 1), dtype=torch.float32, device=dev)
+        hit = torch.empty(R, dtype=torch.bool, device=dev)
+        bgv = _bg3(bg)
+        A.check(A.lib().wb_composite_fwd(A.ptr(sh), A.ptr(dp), A.ptr(dl), A.ptr(offsets), C.c_int64(R), bgv,
+                                         A.ptr(rgb), A.ptr(dout), A.ptr(alpha), A.ptr(hit), A.stream()))
+        ctx.save_for_backward(sh, dp, dl, offsets)
+        ctx.bg = bgv
+        ctx.mark_non_differentiable(hit)
+        return rgb, dout, alpha, hit
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_alpha, _g_hit):
+        sh, dp, dl, offsets = ctx.saved_tensors
+        R = offsets.shape[0] - 1
+        g_sh = torch.zeros_like(sh)
+        A.check(A.lib().wb_composite_bwd(A.ptr(sh), A.ptr(dp), A.ptr(dl), A.ptr(offsets), C.c_int64(R), ctx.bg,
+                                         A.ptr(A.f32c(g_rgb)), A.ptr(A.f32c(g_depth).reshape(-1)) if g_depth is not None else None,
+                                         A.ptr(A.f32c(g_alpha).reshape(-1)) if g_alpha is not None else None, A.ptr(g_sh), A.stream()))
+        return g_sh, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------------------------
+# fused render path
+# --------------------------------------------------------------------------------------------------------------
+@dataclass
+class NefSpec:
+    """Static description of a NeuralRadianceField(HashGrid) that the fused path supports."""
+    resolutions: List[int]
+    begin_idxes: List[int]
+    codebook_size: int
+    feature_dim: int
+    multiscale: str
+    lod_idx: int
+    pos_mode: int
+    pos_freq: int
+    view_mode: int
+    view_freq: int
+    has_bias: bool
+    dens_dims: List[int]
+    col_dims: List[int]
+
+    def desc(self, table: torch.Tensor, dens_flat: torch.Tensor, col_flat: torch.Tensor) -> A.NefDesc:
+        d = A.make_grid_desc(table, self.resolutions, self.begin_idxes, self.codebook_size, self.multiscale, self.lod_idx)
+        d.pos_mode, d.pos_freq, d.view_mode, d.view_freq = self.pos_mode, self.pos_freq, self.view_mode, self.view_freq
+        d.has_bias = int(self.has_bias)
+        d.dens_layers = len(self.dens_dims) - 1
+        d.col_layers = len(self.col_dims) - 1
+        if d.dens_layers > A.WB_MAX_LAYERS or d.col_layers > A.WB_MAX_LAYERS:
+            raise A.WispB200Error("decoder too deep for the fused path")
+        for i, v in enumerate(self.dens_dims):
+            d.dens_dims[i] = v
+        for i, v in enumerate(self.col_dims):
+            d.col_dims[i] = v
+        d.dens_params, d.col_params = dens_flat.data_ptr(), col_flat.data_ptr()
+        return d
+
+
+def _flatten(params: Sequence[torch.Tensor]) -> torch.Tensor:
+    return torch.cat([p.detach().reshape(-1).float() for p in params]) if params else torch.zeros(0)
+
+
+class RFTraceFn(torch.autograd.Function):
+    """PackedRFTracer.trace + NeuralRadianceField.rgba + HashGrid.interpolate as one native pipeline:
+         march(count/scan/fill) -> shade (gather + decoders fused) -> composite        (forward)
+         composite_bwd -> shade_bwd (decoder recompute, table scatter)                  (backward)
+    Inputs: table, then the decoder parameters in packing order [W0, b0?, W1, b1?, ...] for density then colour.
+    """
+
+    @staticmethod
+    def forward(ctx, ms: MarchState, spec: NefSpec, n_dens: int, bg, precision: int, want_depth: bool, table, *params):
+        A.require_device(table)
+        L = A.lib()
+        dev = table.device
+        tb = A.f32c(table.detach())
+        dens_flat, col_flat = _flatten(params[:n_dens]), _flatten(params[n_dens:])
+        desc = spec.desc(tb, dens_flat, col_flat)
+        nblob = int(L.wb_rf_param_blob_floats(C.byref(desc), C.c_int32(precision)))
+        if nblob < 0:
+            raise A.WispB200Error(L.wb_last_error().decode())
+        blob = torch.empty(nblob, dtype=torch.float32, device=dev)
+        A.check(L.wb_rf_pack_params(C.byref(desc), C.c_int32(precision), A.ptr(blob), A.stream()))
+        rec_t, rec_delta, rec_ray = march_fill_records(ms, dev)
+        S, R = ms.total, ms.rays.num_rays
+        shaded = torch.empty((S, 4), dtype=torch.float32, device=dev)
+        with _stage("shade_fwd"):
+            A.check(L.wb_rf_shade_fwd(C.byref(desc), A.ptr(blob), C.c_int32(precision), C.byref(ms.rays), A.ptr(rec_t), A.ptr(rec_ray),
+                                      C.c_int64(S), A.ptr(shaded), A.stream()))
+        rgb = torch.empty((R, 3), dtype=torch.float32, device=dev)
+        depth = torch.empty((R, 1), dtype=torch.float32, device=dev)
+        alpha = torch.empty((R, 1), dtype=torch.float32, device=dev)
+        hit = torch.empty(R, dtype=torch.bool, device=dev)
+        bgv = _bg3(bg)
+        with _stage("composite_fwd"):
+            A.check(L.wb_composite_fwd(A.ptr(shaded), A.ptr(rec_t), A.ptr(rec_delta), A.ptr(ms.offsets), C.c_int64(R), bgv,
+                                       A.ptr(rgb), A.ptr(depth), A.ptr(alpha), A.ptr(hit), A.stream()))
+        ctx.ms, ctx.spec, ctx.n_dens, ctx.bg, ctx.precision = ms, spec, n_dens, bgv, precision
+        ctx.param_shapes = [p.shape for p in params]
+        ctx.save_for_backward(tb, dens_flat, col_flat, blob, rec_t, rec_delta, rec_ray, shaded)
+        ctx.mark_non_differentiable(hit)
+        return rgb, depth, alpha, hit
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_alpha, _g_hit):
+        tb, dens_flat, col_flat, blob, rec_t, rec_delta, rec_ray, shaded = ctx.saved_tensors
+        ms, spec = ctx.ms, ctx.spec
+        L = A.lib()
+        S, R = ms.total, ms.rays.num_rays
+        desc = spec.desc(tb, dens_flat, col_flat)
+        g_sh = torch.empty_like(shaded)
+        gd = A.f32c(g_depth).reshape(-1) if g_depth is not None else None
+        ga = A.f32c(g_alpha).reshape(-1) if g_alpha is not None else None
+        grgb = A.f32c(g_rgb)
+        with _stage("composite_bwd"):
+            A.check(L.wb_composite_bwd(A.ptr(shaded), A.ptr(rec_t), A.ptr(rec_delta), A.ptr(ms.offsets), C.c_int64(R), ctx.bg,
+                                       A.ptr(grgb), A.ptr(gd), A.ptr(ga), A.ptr(g_sh), A.stream()))
+        g_table = torch.zeros_like(tb)
+        g_dens = torch.zeros_like(dens_flat)
+        g_col = torch.zeros_like(col_flat)
+        with _stage("shade_bwd"):
+            A.check(L.wb_rf_shade_bwd(C.byref(desc), A.ptr(blob), C.c_int32(ctx.precision), C.byref(ms.rays), A.ptr(rec_t), A.ptr(rec_ray),
+                                      C.c_int64(S), A.ptr(g_sh), A.ptr(g_table), A.ptr(g_dens), A.ptr(g_col), A.stream()))
+        grads = []
+        for flat, shapes in ((g_dens, ctx.param_shapes[:ctx.n_dens]), (g_col, ctx.param_shapes[ctx.n_dens:])):
+            o = 0
+            for shp in shapes:
+                n = int(torch.Size(shp).numel())
+                grads.append(flat[o:o + n].reshape(shp)); o += n
+        return (None, None, None, None, None, None, g_table, *grads)
+
+
+def rf_trace(ms: MarchState, spec: NefSpec, table: torch.Tensor, dens_params: Sequence[torch.Tensor],
+             col_params: Sequence[torch.Tensor], bg, precision: int = 0):
+    """-> rgb [R,3], depth [R,1], alpha [R,1], hit [R]."""
+    return RFTraceFn.apply(ms, spec, len(dens_params), bg, precision, True, table, *dens_params, *col_params)

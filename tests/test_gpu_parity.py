@@ -1,0 +1,278 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the product package / C ABI, against
+  (1) the golden fixtures produced by the unmodified reference Python, and
+  (2) the CPU oracle on seeded inputs.
+Tolerances: indices and sample floats bit-exact; fp32 decoders: rgb/alpha 1e-4 abs, depth 5e-4 abs (depth sums
+weights times distances up to 10); gradients rtol 1e-3 of the largest entry (atomic summation order)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O
+from golden_util import load_case
+
+CASES = ["rf_trace_cat", "rf_trace_sum", "rf_trace_noview"]
+
+
+@pytest.fixture(scope="module")
+def W():
+    import wisp_b200
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return wisp_b200
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def test_library_is_native_and_device_ok(W):
+    assert W._cabi.lib().wb_version() >= 100
+    W._cabi.require_device(torch.zeros(1, device="cuda"))
+    assert os.path.exists(W._cabi.LIB_PATH)
+
+
+def test_torch_cuda_contract():
+    """The bit-exact contract for sample generation restates what the reference's torch CUDA kernels compute:
+    addcmul == fma(dir, t, origin); linspace lower/upper halves FMA-contracted (see wb_common.cuh)."""
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.randn(1 << 16, generator=g), torch.randn(1 << 16, generator=g)
+    c = torch.rand(1 << 16, generator=g) * 10
+    t = torch.addcmul(a.cuda(), b.cuda(), c.cuda()).cpu().numpy()
+    fma = (a.double() + b.double() * c.double()).float().numpy()          # fused: one rounding
+    unf = (a + (b * c)).numpy()
+    frac_fma, frac_unf = float((t == fma).mean()), float((t == unf).mean())
+    print("addcmul cuda: ==fma", frac_fma, "==unfused", frac_unf)
+    n = 2048
+    ls = torch.linspace(0, 1, n, device="cuda").cpu().numpy()
+    step = np.float32(1.0) / np.float32(n - 1)
+    i = np.arange(n)
+    lo = (np.float64(step) * i).astype(np.float32)
+    hi = (1.0 - np.float64(step) * (n - 1 - i)).astype(np.float32)
+    ref = np.where(i < n // 2, lo, hi)
+    frac_ls = float((ls == ref).mean())
+    print("linspace cuda == contract", frac_ls)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/contract.txt", "w") as f:
+        f.write(f"addcmul_eq_fma {frac_fma}\naddcmul_eq_unfused {frac_unf}\nlinspace_eq_contract {frac_ls}\n")
+    assert frac_fma == 1.0
+    assert frac_ls == 1.0
+
+
+def test_query_bit_exact(W):
+    rng = np.random.default_rng(0)
+    spc = O.octree_to_spc(O.points_to_octree(O.lego_like_points(6), 6))
+    coords = rng.uniform(-1.05, 1.05, (200000, 3)).astype(np.float32)
+    # exact cell faces and the +/-1 borders
+    k = (rng.integers(0, 65, (4096, 3)) / 32.0 - 1.0).astype(np.float32)
+    coords = np.concatenate([coords, k, np.nextafter(k, np.float32(-2)), np.nextafter(k, np.float32(2))])
+    blas = W.OctreeAS(dev(spc.octree))
+    for level in (6, 4):
+        got = blas.query(dev(coords), level=level).pidx.cpu().numpy()
+        assert np.array_equal(got, O.query(spc, coords, level))
+    gp = blas.query(dev(coords), with_parents=True).pidx.cpu().numpy()
+    assert np.array_equal(gp, O.query(spc, coords, with_parents=True))
+    # the product's own host-side SPC builder agrees with the oracle's
+    assert np.array_equal(blas.points.cpu().numpy(), spc.points)
+    assert np.array_equal(blas.prefix.cpu().numpy(), spc.prefix)
+    assert np.array_equal(blas.pyramid.cpu().numpy(), spc.pyramid)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_raymarch_golden_bit_exact(W, golden_dir, name):
+    g, onef, spc = load_case(os.path.join(golden_dir, name + ".npz"))
+    blas = W.OctreeAS(dev(spc.octree))
+    rays = W.Rays(dev(g["origins"]), dev(g["dirs"]), dist_min=float(g["near"]), dist_max=float(g["far"]))
+    mr = blas.raymarch(rays, 'ray', int(g["n_steps"]), jitter=dev(g["jitter"]))
+    assert np.array_equal(mr.ridx.cpu().numpy(), g["mr_ridx"])
+    assert np.array_equal(mr.boundary.cpu().numpy(), g["mr_boundary"])
+    assert np.array_equal(mr.samples.cpu().numpy(), g["mr_samples"])
+    assert np.array_equal(mr.depth_samples.cpu().numpy(), g["mr_depth"])
+    assert np.array_equal(mr.deltas.cpu().numpy(), g["mr_deltas"])
+    assert mr.ridx.dtype == torch.int64 and mr.boundary.dtype == torch.bool and mr.pack_info is None
+
+
+@pytest.mark.parametrize("n,level,pernear", [(2048, 7, False), (100, 5, False), (33, 5, True), (1, 4, False)])
+def test_raymarch_seeded_vs_oracle(W, n, level, pernear):
+    """Counter-based jitter stream, non power-of-two n, per-ray near/far, n == 1; bit-exact vs the oracle."""
+    spc = O.octree_to_spc(O.points_to_octree(O.lego_like_points(level), level))
+    o, d = O.look_at_rays([-3.0, 0.65, -3.0], [0, 0, 0], 48, 48, 30.0)
+    blas = W.OctreeAS(dev(spc.octree))
+    if pernear:
+        rng = np.random.default_rng(1)
+        near = rng.uniform(0.0, 2.0, o.shape[0]).astype(np.float32); far = (near + rng.uniform(3.0, 8.0, o.shape[0])).astype(np.float32)
+        rays = W.Rays(dev(o), dev(d), dist_min=dev(near)[:, None], dist_max=dev(far)[:, None])
+    else:
+        near, far = 0.0, 10.0
+        rays = W.Rays(dev(o), dev(d), dist_min=near, dist_max=far)
+    mr = blas.raymarch(rays, 'ray', n, seed=1234)
+    ref = O.raymarch_ray(spc, o, d, near, far, n, seed=1234)
+    assert np.array_equal(mr.ridx.cpu().numpy(), ref["ridx"])
+    assert np.array_equal(mr.samples.cpu().numpy(), ref["samples"])
+    assert np.array_equal(mr.depth_samples.cpu().numpy(), ref["depth_samples"])
+    assert np.array_equal(mr.deltas.cpu().numpy(), ref["deltas"])
+    assert np.array_equal(mr.boundary.cpu().numpy(), ref["boundary"])
+
+
+def test_raymarch_empty_and_errors(W):
+    spc = O.octree_to_spc(O.points_to_octree(np.array([[0, 0, 0]], dtype=np.int16), 4))
+    blas = W.OctreeAS(dev(spc.octree))
+    o = np.tile(np.array([[5.0, 5.0, 5.0]], np.float32), (7, 1)); d = np.tile(np.array([[1.0, 0, 0]], np.float32), (7, 1))
+    mr = blas.raymarch(W.Rays(dev(o), dev(d), 0.0, 1.0), 'ray', 16)
+    assert mr.ridx.shape[0] == 0 and mr.samples.shape == (0, 3)
+    with pytest.raises(TypeError):
+        blas.raymarch(W.Rays(dev(o), dev(d), 0.0, 1.0), 'bogus', 16)          # octree_as.py:427
+    mr0 = blas.raymarch(W.Rays(dev(o[:0]), dev(d[:0]), 0.0, 1.0), 'ray', 16)
+    assert mr0.ridx.shape[0] == 0
+
+
+def test_hashgrid_golden_naive(W, golden_dir):
+    g = np.load(os.path.join(golden_dir, "hashgrid_naive.npz"))
+    res = [int(r) for r in g["resolutions"]]; bw = int(g["codebook_bitwidth"])
+    table = dev(g["table"]).requires_grad_(True)
+    begin = torch.from_numpy(O.table_layout(res, bw))
+    feats = W.ops.HashGridInterpolate.apply(dev(g["coords"]), torch.tensor(res), bw, len(res) - 1, table, begin)
+    np.testing.assert_allclose(feats.detach().cpu().numpy(), g["feats"], atol=2e-6, rtol=1e-4)
+
+
+@pytest.mark.parametrize("bw,F", [(19, 2), (12, 4), (14, 8)])
+def test_hashgrid_fwd_bwd_vs_oracle(W, bw, F):
+    rng = np.random.default_rng(3)
+    res = O.geometric_resolutions(16, 16, 512)
+    begin = O.table_layout(res, bw)
+    table = rng.standard_normal((int(begin[-1]), F)).astype(np.float32)
+    coords = rng.uniform(-1.0, 1.0, (30000, 3)).astype(np.float32)
+    coords[:64] = np.sign(coords[:64])                       # corners / faces of the volume: clamp path
+    t = dev(table).requires_grad_(True)
+    feats = W.ops.HashGridInterpolate.apply(dev(coords), torch.tensor(res), bw, 15, t, torch.from_numpy(begin))
+    ref = O.hashgrid_fwd(coords, table, res, bw)
+    np.testing.assert_allclose(feats.detach().cpu().numpy(), ref, atol=1e-6, rtol=1e-5)
+    go = rng.standard_normal(ref.shape).astype(np.float32)
+    feats.backward(dev(go))
+    gref = O.hashgrid_bwd(coords, go, table.shape[0], res, bw)
+    scale = np.abs(gref).max()
+    assert np.abs(t.grad.cpu().numpy() - gref).max() <= 1e-4 * scale
+
+
+def test_composite_vs_oracle(W):
+    rng = np.random.default_rng(5)
+    R = 300
+    counts = rng.integers(0, 90, R); counts[::7] = 0
+    offsets = np.zeros(R + 1, np.int64); offsets[1:] = np.cumsum(counts)
+    S = int(offsets[-1])
+    shaded = np.concatenate([rng.random((S, 3)), rng.random((S, 1)) * 30], -1).astype(np.float32)
+    deltas = (rng.random(S) * 0.01).astype(np.float32)
+    depth = np.concatenate([np.sort(rng.random(c) * 10) for c in counts]).astype(np.float32)
+    boundary = np.zeros(S, np.uint8); boundary[offsets[:-1][counts > 0]] = 1
+    bg = (0.3, 0.6, 0.9)
+    sh = dev(shaded).requires_grad_(True)
+    rgb, dout, alpha, hit = W.ops.CompositeFn.apply(sh, dev(depth), dev(deltas), dev(offsets), bg)
+    tau = shaded[:, 3] * deltas
+    cols, w = O.exponential_integration(shaded[:, :3], tau, boundary)
+    a = O.sum_reduce(w, boundary); dd = O.sum_reduce(w * depth[:, None], boundary)
+    has = counts > 0
+    exp_rgb = np.tile(np.array(bg, np.float32), (R, 1)); exp_rgb[has] = np.array(bg, np.float32) * (1 - a) + cols
+    exp_a = np.zeros((R, 1), np.float32); exp_a[has] = a
+    exp_d = np.zeros((R, 1), np.float32); exp_d[has] = dd
+    np.testing.assert_allclose(rgb.detach().cpu().numpy(), exp_rgb, atol=2e-6)
+    np.testing.assert_allclose(alpha.detach().cpu().numpy(), exp_a, atol=2e-6)
+    np.testing.assert_allclose(dout.detach().cpu().numpy(), exp_d, atol=2e-5)
+    assert np.array_equal(hit.cpu().numpy(), exp_a[:, 0] > 0)
+    # backward against torch autograd of the twin formulas (CPU)
+    from oracle import torch_twin as TW
+    g1, g2, g3 = rng.standard_normal((R, 3)).astype(np.float32), rng.standard_normal((R, 1)).astype(np.float32), rng.standard_normal((R, 1)).astype(np.float32)
+    (rgb * dev(g1)).sum().add((dout * dev(g2)).sum()).add((alpha * dev(g3)).sum()).backward()
+    st = torch.from_numpy(shaded).requires_grad_(True)
+    b = torch.from_numpy(boundary.astype(bool))
+    c2, w2 = TW.exponential_integration(st[:, :3], st[:, 3:4] * torch.from_numpy(deltas)[:, None], b)
+    a2 = TW.sum_reduce(w2, b); d2 = TW.sum_reduce(w2 * torch.from_numpy(depth)[:, None], b)
+    rgb2 = torch.tensor(bg) * (1 - a2) + c2
+    hs = torch.from_numpy(has)
+    ((rgb2 * torch.from_numpy(g1)[hs]).sum() + (d2 * torch.from_numpy(g2)[hs]).sum() + (a2 * torch.from_numpy(g3)[hs]).sum()).backward()
+    gref = st.grad.numpy()
+    assert np.abs(sh.grad.cpu().numpy() - gref).max() <= 2e-5 * max(1.0, np.abs(gref).max())
+
+
+def _run_fused(W, g, onef, spc, fused=True):
+    from gpu_util import nef_from_oracle, packed_grads
+    nef, blas = nef_from_oracle(onef, spc)
+    tracer = W.PackedRFTracer(raymarch_type='ray', num_steps=int(g["n_steps"]), bg_color=tuple(float(x) for x in g["bg"]))
+    tracer.jitter = dev(g["jitter"])
+    pipe = W.Pipeline(nef, tracer)
+    rays = W.Rays(dev(g["origins"]), dev(g["dirs"]), dist_min=float(g["near"]), dist_max=float(g["far"]))
+    if not fused:
+        nef.fused_spec = lambda lod_idx=None: None           # force the unfused route
+    rb = pipe(rays=rays, channels=["rgb", "depth", "alpha", "hit"])
+    return nef, tracer, rb
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("name", CASES)
+def test_trace_golden(W, golden_dir, name, fused):
+    """Pipeline(nef, PackedRFTracer) forward + backward against what the reference's own classes produced."""
+    from gpu_util import packed_grads
+    g, onef, spc = load_case(os.path.join(golden_dir, name + ".npz"))
+    nef, tracer, rb = _run_fused(W, g, onef, spc, fused)
+    assert tracer.get_prev_num_samples() == int(g["num_samples"])
+    assert np.array_equal(rb.hit.cpu().numpy(), g["hit"])
+    np.testing.assert_allclose(rb.rgb.detach().cpu().numpy(), g["rgb"], atol=1e-4, rtol=0)
+    np.testing.assert_allclose(rb.alpha.detach().cpu().numpy(), g["alpha"], atol=1e-4, rtol=0)
+    np.testing.assert_allclose(rb.depth.detach().cpu().numpy(), g["depth"], atol=5e-4, rtol=0)
+    target = dev(g["target"])
+    lt = str(g["loss_type"])
+    loss = {"huber": lambda: torch.nn.functional.smooth_l1_loss(rb.rgb, target), "l2": lambda: torch.nn.functional.mse_loss(rb.rgb, target),
+            "l1": lambda: torch.abs(rb.rgb - target).mean()}[lt]()
+    assert abs(float(loss) - float(g["loss"])) < 1e-5
+    loss.backward()
+    gt, gd, gc = packed_grads(nef)
+    for got, ref, nm in ((gt, g["g_table"], "table"), (gd, g["g_dens"], "dens"), (gc, g["g_col"], "col")):
+        scale = max(np.abs(ref).max(), 1e-12)
+        assert np.abs(got - ref).max() <= 1e-3 * scale, (nm, np.abs(got - ref).max(), scale)
+
+
+def test_trace_config2_slice_vs_oracle(W):
+    """BASELINE config 2 shapes (L=16, F=2, T=2^19, 64-wide decoders, n=2048, level-7 lego-like octree) on a
+    32x32-ray slice of the 1024^2 frame; counter-based jitter; fwd + bwd vs the oracle."""
+    from gpu_util import nef_from_oracle, packed_grads
+    onef = O.make_nef(feature_std=0.2, seed=3)
+    spc = O.octree_to_spc(O.points_to_octree(O.lego_like_points(7), 7))
+    o, d = O.look_at_rays([-3.0, 0.65, -3.0], [0, 0, 0], 1024, 1024, 30.0)
+    sel = (np.arange(496, 528)[:, None] * 1024 + np.arange(500, 532)[None]).reshape(-1)
+    o, d = o[sel], d[sel]
+    nef, blas = nef_from_oracle(onef, spc)
+    tracer = W.PackedRFTracer('ray', 2048, bg_color=(0.0, 0.0, 0.0)); tracer.seed = 77
+    rays = W.Rays(dev(o), dev(d), 0.0, 10.0)
+    rb = W.Pipeline(nef, tracer)(rays=rays, channels=["rgb", "depth", "alpha", "hit"])
+    f = O.rf_trace_fwd(spc, onef, o, d, 0.0, 10.0, 2048, bg=(0, 0, 0), seed=77)
+    assert tracer.get_prev_num_samples() == f["num_samples"] and f["num_samples"] > 10000
+    np.testing.assert_allclose(rb.rgb.detach().cpu().numpy(), f["rgb"], atol=1e-4)
+    np.testing.assert_allclose(rb.alpha.detach().cpu().numpy(), f["alpha"], atol=1e-4)
+    np.testing.assert_allclose(rb.depth.detach().cpu().numpy(), f["depth"], atol=1e-3)
+    assert np.array_equal(rb.hit.cpu().numpy(), f["hit"])
+    tgt = torch.sigmoid(torch.randn(o.shape[0], 3, generator=torch.Generator().manual_seed(2)))
+    torch.nn.functional.smooth_l1_loss(rb.rgb, tgt.cuda()).backward()
+    st = O.rf_step(spc, onef, o, d, 0.0, 10.0, 2048, tgt.numpy(), bg=(0, 0, 0), seed=77)
+    gt, gd, gc = packed_grads(nef)
+    for got, ref, nm in ((gt, st["table"], "table"), (gd, st["dens"], "dens"), (gc, st["col"], "col")):
+        scale = np.abs(ref).max()
+        assert np.abs(got - ref).max() <= 2e-3 * scale, (nm, np.abs(got - ref).max(), scale)
+
+
+def test_no_rays_and_no_hits(W):
+    from gpu_util import nef_from_oracle
+    onef = O.make_nef(num_lods=4, codebook_bitwidth=10, min_res=4, max_res=32, hidden_dim=16, feature_std=0.5, seed=1)
+    spc = O.octree_to_spc(O.points_to_octree(O.lego_like_points(4), 4))
+    nef, blas = nef_from_oracle(onef, spc)
+    tracer = W.PackedRFTracer('ray', 32, bg_color=(0.1, 0.2, 0.3))
+    o = np.tile(np.array([[5.0, 5.0, 5.0]], np.float32), (5, 1)); d = np.tile(np.array([[1.0, 0, 0]], np.float32), (5, 1))
+    rb = tracer(nef, rays=W.Rays(dev(o), dev(d), 0.0, 1.0))
+    assert tracer.get_prev_num_samples() == 0
+    np.testing.assert_allclose(rb.rgb.cpu().numpy(), np.tile(np.array([[0.1, 0.2, 0.3]], np.float32), (5, 1)))
+    assert not rb.hit.any() and float(rb.alpha.abs().sum()) == 0.0
+    rb0 = tracer(nef, rays=W.Rays(dev(o[:0]), dev(d[:0]), 0.0, 1.0))
+    assert rb0.rgb.shape == (0, 3)

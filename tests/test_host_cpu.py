@@ -1,0 +1,101 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every symbol include/wispb200.h declares,
+the ctypes struct layouts match the header, the host-side SPC builder matches the oracle, and compute entry points
+refuse to run without a B200 (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import wisp_b200 as W
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "wispb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(wb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = W._cabi.lib()
+    names = header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"libwispb200.so does not export {n}"
+    assert sorted(W._cabi.EXPORTS) == names
+
+
+def test_struct_layouts_match_header(tmp_path):
+    """Compile include/wispb200.h with the C compiler and compare sizeof/offsetof with the ctypes mirrors."""
+    import subprocess
+    src = tmp_path / "lay.c"
+    src.write_text('''#include <stdio.h>
+#include <stddef.h>
+#include "wispb200.h"
+int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(wb_nef_desc), offsetof(wb_nef_desc, begin_idxes), offsetof(wb_nef_desc, table),
+  offsetof(wb_nef_desc, dens_dims), offsetof(wb_nef_desc, col_params), sizeof(wb_rays), offsetof(wb_rays, near_v), sizeof(wb_octree), offsetof(wb_octree, bits_level)); return 0; }''')
+    exe = tmp_path / "lay"
+    subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    vals = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    A = W._cabi
+    mine = [C.sizeof(A.NefDesc), A.NefDesc.begin_idxes.offset, A.NefDesc.table.offset, A.NefDesc.dens_dims.offset, A.NefDesc.col_params.offset,
+            C.sizeof(A.RaysDesc), A.RaysDesc.near_v.offset, C.sizeof(A.OctreeDesc), A.OctreeDesc.bits_level.offset]
+    assert mine == vals
+
+
+def test_no_cpu_fallback():
+    o = W.OctreeAS.make_dense(2, device="cpu")
+    with pytest.raises(W._cabi.WispB200Error):
+        o.query(torch.zeros(3, 3))
+    g = W.HashGrid.from_geometric(o, 2, 4, 'cat', 0.1, 0.0, 10, 4, 32)
+    with pytest.raises(W._cabi.WispB200Error):
+        g.interpolate(torch.zeros(3, 3), 3)
+    with pytest.raises(W._cabi.WispB200Error):
+        o.raymarch(W.Rays(torch.zeros(2, 3), torch.ones(2, 3), 0.0, 1.0), 'ray', 8)
+
+
+def test_host_spc_builder_matches_oracle():
+    pts = O.lego_like_points(5)
+    oct_t = W.spc.points_to_octree(torch.from_numpy(pts), 5)
+    assert np.array_equal(oct_t.numpy(), O.points_to_octree(pts, 5))
+    ref = O.octree_to_spc(oct_t.numpy())
+    points, pyramid, prefix = W.spc.octree_to_spc(oct_t)
+    assert np.array_equal(points.numpy(), ref.points) and np.array_equal(pyramid.numpy(), ref.pyramid) and np.array_equal(prefix.numpy(), ref.prefix)
+    assert np.array_equal(W.spc.create_dense_octree(3).numpy(), O.dense_octree(3))
+
+
+def test_nef_mirror_matches_reference_names_and_shapes():
+    o = W.OctreeAS.make_dense(2, device="cpu")
+    g = W.HashGrid.from_geometric(o, feature_dim=2, num_lods=16, multiscale_type='cat', feature_std=1e-9, codebook_bitwidth=19,
+                                  min_grid_res=16, max_grid_res=512)
+    assert g.resolutions == [16, 20, 25, 32, 40, 50, 64, 80, 101, 128, 161, 203, 256, 322, 406, 512]
+    assert g.codebook.feats.shape == (5217937, 2)
+    nef = W.NeuralRadianceField(g, view_embedder='positional', view_multires=4, hidden_dim=64, num_layers=1, bias=True)
+    names = dict(nef.named_parameters())
+    assert names["decoder_density.layers.0.weight"].shape == (64, 32) and names["decoder_density.lout.weight"].shape == (16, 64)
+    assert names["decoder_color.layers.0.weight"].shape == (64, 42) and names["decoder_color.lout.weight"].shape == (3, 64)
+    assert "grid.codebook.feats" in names
+    assert sum(p.numel() for n, p in names.items() if n.startswith("decoder_density")) == 3152
+    assert sum(p.numel() for n, p in names.items() if n.startswith("decoder_color")) == 7107
+    assert float(nef.decoder_density.lout.bias[0]) == 1.0
+    spec = nef.fused_spec()
+    assert spec.view_mode == 3 and spec.dens_dims == [32, 64, 16] and spec.col_dims == [42, 64, 64, 3]
+    # view_embedder='none' still feeds ray_d (include_input=True), nerf.py:105-106,116-119
+    nef2 = W.NeuralRadianceField(g, view_embedder='none', hidden_dim=16)
+    assert nef2.view_embed_dim == 3 and nef2.fused_spec().view_mode == 1
+
+
+def test_tracer_channel_negotiation_errors():
+    o = W.OctreeAS.make_dense(2, device="cpu")
+    g = W.HashGrid.from_geometric(o, 2, 4, 'cat', 0.1, 0.0, 10, 4, 32)
+    nef = W.NeuralRadianceField(g, hidden_dim=16)
+    tr = W.PackedRFTracer()
+    assert tr.get_supported_channels() == {"depth", "hit", "rgb", "alpha"} and tr.get_required_nef_channels() == {"rgb", "density"}
+    with pytest.raises(Exception, match="not supported"):
+        tr(nef, rays=W.Rays(torch.zeros(1, 3), torch.ones(1, 3)), channels=["rgb", "normals"])
+    assert tr.get_prev_num_samples() is None
