@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--res", type=int, default=1024)
     ap.add_argument("--num-steps", type=int, default=2048)
     ap.add_argument("--scene", default="lego", choices=["lego", "dense"])
-    ap.add_argument("--precision", type=int, default=0)
+    ap.add_argument("--precision", type=int, default=1, help="0: fp32 decoders, 1: fp16 tensor-core decoders (reference enable_amp)")
     ap.add_argument("--cpu-sample-rays", type=int, default=0, help="rays in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()

@@ -164,10 +164,19 @@ int64_t wb_rf_param_blob_floats(const wb_nef_desc* nef, int32_t precision);
 int wb_rf_pack_params(const wb_nef_desc* nef, int32_t precision, float* blob, wb_stream s);
 int wb_rf_shade_fwd(const wb_nef_desc* nef, const float* blob, int32_t precision, const wb_rays* rays,
                     const float* rec_t, const int32_t* rec_ray, int64_t S, float* shaded, wb_stream s);
-/* grad_table [rows,F], grad_dens / grad_col (packed like the params) are ACCUMULATED into (caller zeroes). */
+/* grad_table [rows,F], grad_dens / grad_col (packed like the params) are ACCUMULATED into (caller zeroes).
+ * loss_scale: device pointer to ONE float, a power of two by which precision 1 scales the incoming gradients while
+ * they are carried in fp16 (unscaled again in fp32 before they leave the kernel); ignored (may be NULL) for precision 0. */
 int wb_rf_shade_bwd(const wb_nef_desc* nef, const float* blob, int32_t precision, const wb_rays* rays,
-                    const float* rec_t, const int32_t* rec_ray, int64_t S, const float* g_shaded,
+                    const float* rec_t, const int32_t* rec_ray, int64_t S, const float* g_shaded, const float* loss_scale,
                     float* grad_table, float* grad_dens, float* grad_col, wb_stream s);
+
+/* ------------------------------------------------------------------------------------------------
+ * Diagnostics: one-tile tcgen05 GEMM that pins the shared-memory operand layouts of the tensor-core decoder
+ * kernels (csrc/wb_tc.cuh).  a_img / b_img are byte images of the operand tiles; D is [128, N] fp32.
+ * mode 0: D = A[128xK] . W[NxK]^T   mode 1: D = A[128xK] . W[KxN]   mode 2: D = A[128x128]^T . B[128xN]
+ * ---------------------------------------------------------------------------------------------- */
+int wb_tc_selftest(const void* a_img, int a_bytes, const void* b_img, int b_bytes, float* D, int N, int K, int mode, wb_stream s);
 
 #ifdef __cplusplus
 }

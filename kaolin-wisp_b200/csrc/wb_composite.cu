@@ -46,8 +46,8 @@ wb_composite_fwd_kernel(const float4* __restrict__ shaded, const float* __restri
 extern "C" int wb_composite_fwd(const float* shaded, const float* depth, const float* deltas, const int64_t* offsets, int64_t R,
                                 const float* bg, float* rgb, float* depth_out, float* alpha, uint8_t* hit, wb_stream s)
 {
-    WB_CHECK_ARG(offsets && bg && rgb && alpha && hit, "null pointer");
     if (R == 0) return WB_OK;
+    WB_CHECK_ARG(offsets && bg && rgb && alpha && hit, "null pointer");
     const float b3[3] = { bg[0], bg[1], bg[2] };   // host pointer (launch parameter)
     int64_t ctas = (R + 7) / 8; const int64_t cap = (int64_t)wb_num_sms() * 32; if (ctas > cap) ctas = cap;
     wb_composite_fwd_kernel<<<(unsigned)ctas, WB_COMP_THREADS, 0, (cudaStream_t)s>>>(
@@ -110,8 +110,8 @@ extern "C" int wb_composite_bwd(const float* shaded, const float* depth, const f
                                 const float* bg, const float* g_rgb, const float* g_depth, const float* g_alpha,
                                 float* g_shaded, wb_stream s)
 {
-    WB_CHECK_ARG(offsets && bg && g_rgb && g_shaded, "null pointer");
     if (R == 0) return WB_OK;
+    WB_CHECK_ARG(offsets && bg && g_rgb, "null pointer");
     const float b3[3] = { bg[0], bg[1], bg[2] };   // host pointer (launch parameter)
     int64_t ctas = (R + 7) / 8; const int64_t cap = (int64_t)wb_num_sms() * 32; if (ctas > cap) ctas = cap;
     wb_composite_bwd_kernel<<<(unsigned)ctas, WB_COMP_THREADS, 0, (cudaStream_t)s>>>(

@@ -60,7 +60,7 @@ int wb_make_grid(const wb_nef_desc* d, WbGrid* g) {
 }
 
 int wb_make_march(const wb_rays* rays, int n, const float* jitter, uint32_t seed, WbMarch* m) {
-    WB_CHECK_ARG(rays != nullptr && rays->origins && rays->dirs, "null rays");
+    WB_CHECK_ARG(rays != nullptr && (rays->num_rays == 0 || (rays->origins && rays->dirs)), "null rays");
     WB_CHECK_ARG(rays->num_rays >= 0 && rays->num_rays < ((int64_t)1 << 31), "num_rays out of range");
     WB_CHECK_ARG(n >= 1 && n <= (1 << 20), "num_samples out of range");
     WB_CHECK_ARG((rays->near_v == nullptr) == (rays->far_v == nullptr), "near_v and far_v must both be given or both be NULL");

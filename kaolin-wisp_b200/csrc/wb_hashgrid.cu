@@ -38,8 +38,8 @@ wb_hashgrid_fwd_kernel(WbGrid g, const float* __restrict__ coords, int64_t N, fl
 extern "C" int wb_hashgrid_fwd(const float* coords, int64_t N, const wb_nef_desc* grid, float* feats, wb_stream s)
 {
     WbGrid g; int rc = wb_make_grid(grid, &g); if (rc) return rc;
-    WB_CHECK_ARG(coords && feats, "null pointer");
     if (N == 0) return WB_OK;
+    WB_CHECK_ARG(coords && feats, "null pointer");
     const int64_t threads = N * g.L;
     const unsigned blocks = (unsigned)((threads + 255) / 256);
     if (g.F == 2) wb_hashgrid_fwd_kernel<2><<<blocks, 256, 0, (cudaStream_t)s>>>(g, coords, N, feats);
@@ -86,8 +86,8 @@ extern "C" int wb_hashgrid_bwd(const float* coords, int64_t N, const wb_nef_desc
                                float* grad_table, wb_stream s)
 {
     WbGrid g; int rc = wb_make_grid(grid, &g); if (rc) return rc;
-    WB_CHECK_ARG(coords && grad_feats && grad_table, "null pointer");
     if (N == 0) return WB_OK;
+    WB_CHECK_ARG(coords && grad_feats && grad_table, "null pointer");
     const int64_t threads = N * g.L;
     const unsigned blocks = (unsigned)((threads + 255) / 256);
     if (g.F == 2) wb_hashgrid_bwd_kernel<2><<<blocks, 256, 0, (cudaStream_t)s>>>(g, coords, N, grad_feats, grad_table);

@@ -48,8 +48,8 @@ extern "C" int wb_raymarch_ray_count(const wb_octree* oct, int32_t level, const 
 {
     WbOct o; int rc = wb_make_oct(oct, level, &o); if (rc) return rc;
     WbMarch m; rc = wb_make_march(rays, num_samples, jitter, seed, &m); if (rc) return rc;
-    WB_CHECK_ARG(hitmask && counts, "null output");
     if (m.R == 0) return WB_OK;
+    WB_CHECK_ARG(hitmask && counts, "null output");
     const int warps_per_cta = WB_MARCH_THREADS / 32;
     int64_t ctas = (m.R + warps_per_cta - 1) / warps_per_cta;
     const int64_t cap = (int64_t)wb_num_sms() * 8 * 4;          // persistent-ish: a few waves of 8 CTAs/SM
@@ -128,7 +128,7 @@ extern "C" int64_t wb_scan_workspace_bytes(int64_t R)
 }
 extern "C" int wb_scan_counts(const int32_t* counts, int64_t R, int64_t* offsets, void* workspace, int64_t workspace_bytes, wb_stream s)
 {
-    WB_CHECK_ARG(counts && offsets && workspace, "null pointer");
+    WB_CHECK_ARG(offsets && workspace && (counts || R == 0), "null pointer");
     WB_CHECK_ARG(R >= 0 && R < ((int64_t)1 << 31), "R out of range");
     WB_CHECK_ARG(workspace_bytes >= wb_scan_workspace_bytes(R), "workspace too small");
     cudaStream_t st = (cudaStream_t)s;
@@ -196,8 +196,8 @@ static int wb_fill_launch(bool fused, const wb_rays* rays, int32_t n, const floa
                           float* deltas, uint8_t* boundary, int32_t* rec_ray, wb_stream s)
 {
     WbMarch m; int rc = wb_make_march(rays, n, jitter, seed, &m); if (rc) return rc;
-    WB_CHECK_ARG(hitmask && offsets, "null pointer");
     if (m.R == 0) return WB_OK;
+    WB_CHECK_ARG(hitmask && offsets, "null pointer");
     const int warps_per_cta = WB_MARCH_THREADS / 32;
     int64_t ctas = (m.R + warps_per_cta - 1) / warps_per_cta;
     const int64_t cap = (int64_t)wb_num_sms() * 8 * 4;
@@ -219,6 +219,5 @@ extern "C" int wb_rf_march_fill(const wb_rays* rays, int32_t num_samples, const 
                                 const uint32_t* hitmask, const int64_t* offsets,
                                 float* rec_t, float* rec_delta, int32_t* rec_ray, wb_stream s)
 {
-    WB_CHECK_ARG(rec_t && rec_delta && rec_ray, "null record buffer");
     return wb_fill_launch(true, rays, num_samples, jitter, seed, hitmask, offsets, nullptr, nullptr, rec_t, rec_delta, nullptr, rec_ray, s);
 }

@@ -19,6 +19,14 @@
 
 #define WB_ML 16          // max linear layers over both decoders
 
+// tensor-core variant (wb_shade_tc.cu)
+int wb_tc_blob_floats(const wb_nef_desc* nef);
+int wb_tc_pack(const wb_nef_desc* nef, float* blob, cudaStream_t st);
+int wb_tc_shade_fwd(const wb_nef_desc* nef, const float* blob, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray,
+                    int64_t S, float* shaded, cudaStream_t st);
+int wb_tc_shade_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray,
+                    int64_t S, const float* g_shaded, const float* scale, float* grad_table, float* grad_dens, float* grad_col, cudaStream_t st);
+
 struct WbMlp {
     int nl_d, nl_c;                      // linear layers: density, colour
     int I[WB_ML], O[WB_ML], Opad[WB_ML], Ipad[WB_ML];
@@ -93,8 +101,8 @@ static int wb_make_mlp(const wb_nef_desc* d, bool retain, WbMlp* m)
 
 extern "C" int64_t wb_rf_param_blob_floats(const wb_nef_desc* nef, int32_t precision)
 {
+    if (precision == 1) return wb_tc_blob_floats(nef);
     WbMlp m; if (wb_make_mlp(nef, false, &m)) return -1;
-    (void)precision;
     return m.total_floats;
 }
 
@@ -123,9 +131,10 @@ __global__ void wb_pack_params_kernel(WbMlp m, const float* __restrict__ dens, c
 
 extern "C" int wb_rf_pack_params(const wb_nef_desc* nef, int32_t precision, float* blob, wb_stream s)
 {
-    WbMlp m; int rc = wb_make_mlp(nef, false, &m); if (rc) return rc;
-    WB_CHECK_ARG(precision == 0, "only precision 0 (fp32) is packed by this entry point");
     WB_CHECK_ARG(blob != nullptr, "null blob");
+    WB_CHECK_ARG(precision == 0 || precision == 1, "precision must be 0 (fp32) or 1 (fp16 tensor cores)");
+    if (precision == 1) return wb_tc_pack(nef, blob, (cudaStream_t)s);
+    WbMlp m; int rc = wb_make_mlp(nef, false, &m); if (rc) return rc;
     wb_pack_params_kernel<<<(m.total_floats + 255) / 256, 256, 0, (cudaStream_t)s>>>(m, nef->dens_params, nef->col_params, blob);
     WB_LAUNCH_CHECK();
     return WB_OK;
@@ -315,11 +324,12 @@ static int wb_shade_fwd_launch(const WbGrid& g, const WbMlp& m, const float* blo
 extern "C" int wb_rf_shade_fwd(const wb_nef_desc* nef, const float* blob, int32_t precision, const wb_rays* rays,
                                const float* rec_t, const int32_t* rec_ray, int64_t S, float* shaded, wb_stream s)
 {
-    WB_CHECK_ARG(precision == 0, "precision 1 (tensor-core decoders) is not in this build");
+    WB_CHECK_ARG(precision == 0 || precision == 1, "precision must be 0 (fp32) or 1 (fp16 tensor cores)");
+    if (S == 0) return WB_OK;
+    WB_CHECK_ARG(blob && rays && rays->origins && rays->dirs && rec_t && rec_ray && shaded, "null pointer");
+    if (precision == 1) return wb_tc_shade_fwd(nef, blob, rays, rec_t, rec_ray, S, shaded, (cudaStream_t)s);
     WbGrid g; int rc = wb_make_grid(nef, &g); if (rc) return rc;
     WbMlp m; rc = wb_make_mlp(nef, false, &m); if (rc) return rc;
-    WB_CHECK_ARG(blob && rays && rays->origins && rays->dirs && rec_t && rec_ray && shaded, "null pointer");
-    if (S == 0) return WB_OK;
     WbShadeIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S };
     rc = wb_shade_fwd_launch<128>(g, m, blob, in, shaded, (cudaStream_t)s);
     if (rc == 1) rc = wb_shade_fwd_launch<64>(g, m, blob, in, shaded, (cudaStream_t)s);
@@ -512,14 +522,15 @@ static int wb_shade_bwd_launch(const WbGrid& g, const WbMlp& m, const float* blo
 
 extern "C" int wb_rf_shade_bwd(const wb_nef_desc* nef, const float* blob, int32_t precision, const wb_rays* rays,
                                const float* rec_t, const int32_t* rec_ray, int64_t S, const float* g_shaded,
-                               float* grad_table, float* grad_dens, float* grad_col, wb_stream s)
+                               const float* loss_scale, float* grad_table, float* grad_dens, float* grad_col, wb_stream s)
 {
-    WB_CHECK_ARG(precision == 0, "precision 1 (tensor-core decoders) is not in this build");
-    WbGrid g; int rc = wb_make_grid(nef, &g); if (rc) return rc;
-    WbMlp m; rc = wb_make_mlp(nef, true, &m); if (rc) return rc;
+    WB_CHECK_ARG(precision == 0 || precision == 1, "precision must be 0 (fp32) or 1 (fp16 tensor cores)");
+    if (S == 0) return WB_OK;
     WB_CHECK_ARG(blob && rays && rays->origins && rays->dirs && rec_t && rec_ray && g_shaded, "null pointer");
     WB_CHECK_ARG(grad_table && grad_dens && grad_col, "null gradient buffer");
-    if (S == 0) return WB_OK;
+    if (precision == 1) return wb_tc_shade_bwd(nef, blob, rays, rec_t, rec_ray, S, g_shaded, loss_scale, grad_table, grad_dens, grad_col, (cudaStream_t)s);
+    WbGrid g; int rc = wb_make_grid(nef, &g); if (rc) return rc;
+    WbMlp m; rc = wb_make_mlp(nef, true, &m); if (rc) return rc;
     WbShadeIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S };
     WbShadeGrads G = { grad_table, grad_dens, grad_col };
     rc = wb_shade_bwd_launch<128>(g, m, blob, in, g_shaded, G, (cudaStream_t)s);

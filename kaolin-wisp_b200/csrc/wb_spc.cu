@@ -89,8 +89,8 @@ extern "C" int wb_query(const wb_octree* oct, const float* coords, int64_t N, in
                         int32_t* out, wb_stream s)
 {
     WbOct o; int rc = wb_make_oct(oct, level, &o); if (rc) return rc;
-    WB_CHECK_ARG(coords && out, "null pointer");
     if (N == 0) return WB_OK;
+    WB_CHECK_ARG(coords && out, "null pointer");
     wb_query_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)s>>>(o, coords, N, with_parents, out);
     WB_LAUNCH_CHECK();
     return WB_OK;

@@ -1,0 +1,110 @@
+// wb_tc.cuh -- tcgen05 / TMEM / mbarrier / bulk-copy primitives for the tensor-core decoder kernels (sm_100a).
+//
+// Operand layouts (no swizzle, "interleaved" canonical form of the UMMA shared-memory descriptor):
+//   core matrix = 8 rows x 16 bytes (8 fp16), stored contiguously (128 B).
+//   SAMPLE TILE  [128 samples x C features], C multiple of 8, "slab" layout:
+//        element (s, f) at byte (f/8)*2048 + s*16 + (f%8)*2            (one slab = 8 features of all 128 samples)
+//     as K-major  A (M = sample,  K = feature): LBO = 2048 (next 8 features), SBO = 128  (next 8 samples)
+//     as MN-major A/B (MN = feature, K = sample): SBO = 2048 (next 8 features), LBO = 128 (next 8 samples)
+//   WEIGHT PACK  W[N x K] (nn.Linear weight, N = out, K = in), N multiple of 8, K multiple of 8:
+//        element (n, k) at byte (k/8)*(N*16) + n*16 + (k%8)*2
+//     as K-major  B (N = out, K = in):  LBO = N*16, SBO = 128
+//     as MN-major B (N' = in, K' = out) for data-grad:  SBO = N*16, LBO = 128
+// Accumulators: D[128 x N] fp32 in TMEM, row r <-> TMEM lane r, column n <-> TMEM column (base + n).
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout) --------------------------------
+__device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);            // start address  [0,14)
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;       // leading byte offset [16,30)
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;       // stride byte offset  [32,46)
+    d |= (uint64_t)1 << 46;                                  // descriptor version 1 (Blackwell) [46,48)
+    return d;                                                // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE
+}
+// ---- instruction descriptor for kind::f16, fp16 x fp16 -> fp32 (cute::UMMA::InstrDescriptor) -----------------
+__host__ __device__ __forceinline__ uint32_t tc_idesc(int M, int N, int a_mn_major, int b_mn_major)
+{
+    return (1u << 4)                       // c_format = F32
+         | (0u << 7) | (0u << 10)          // a_format = b_format = F16
+         | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16)
+         | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread on behalf of the CTA
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// make all previously issued MMAs of this thread arrive on an mbarrier when they complete
+__device__ __forceinline__ void tc_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (tensor core operand fetch)
+__device__ __forceinline__ void tc_fence_smem_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- TMEM allocation (one warp, power-of-two columns >= 32) --------------------------------------------------
+__device__ __forceinline__ void tc_tmem_alloc(uint32_t* dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tc_smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+// 16 consecutive fp32 columns of this thread's TMEM lane (warp w of a warpgroup reads lanes 32*(w%4) .. +31)
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float v[16])
+{
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- mbarrier ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(tc_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(tc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(tc_smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+// TMA bulk copy global -> shared (bytes multiple of 16, both addresses 16-byte aligned); SASS: UBLKCP
+__device__ __forceinline__ void tc_bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(tc_smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(tc_smem_u32(bar)) : "memory");
+}
+
+// ---- fp16 packing ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tc_pack2(float a, float b)
+{
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+// byte offset of (sample s, feature f) in a slab tile
+__device__ __forceinline__ uint32_t tc_slab_off(int s, int f) { return (uint32_t)((f >> 3) * 2048 + s * 16 + (f & 7) * 2); }
