@@ -285,7 +285,7 @@ def test_no_rays_and_no_hits(W):
     o = np.tile(np.array([[5.0, 5.0, 5.0]], np.float32), (5, 1)); d = np.tile(np.array([[1.0, 0, 0]], np.float32), (5, 1))
     rb = tracer(nef, rays=W.Rays(dev(o), dev(d), 0.0, 1.0))
     assert tracer.get_prev_num_samples() == 0
-    np.testing.assert_allclose(rb.rgb.cpu().numpy(), np.tile(np.array([[0.1, 0.2, 0.3]], np.float32), (5, 1)))
+    np.testing.assert_allclose(rb.rgb.detach().cpu().numpy(), np.tile(np.array([[0.1, 0.2, 0.3]], np.float32), (5, 1)))
     assert not rb.hit.any() and float(rb.alpha.abs().sum()) == 0.0
     rb0 = tracer(nef, rays=W.Rays(dev(o[:0]), dev(d[:0]), 0.0, 1.0))
     assert rb0.rgb.shape == (0, 3)
