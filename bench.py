@@ -177,6 +177,7 @@ def run_ours(args):
     pipe = W.Pipeline(nef, tracer)
     params = [p for p in nef.parameters() if p.requires_grad]
     opt = torch.optim.Adam(params, lr=1e-3, eps=1e-15, fused=True)
+    reducer = W.parallel.GradientReducer(params)
 
     R = args.res * args.res
     nsteps_total = args.warmup + args.steps
@@ -196,10 +197,7 @@ def run_ours(args):
         rb = pipe(rays=W.Rays(origins, dirs, dist_min=NEAR, dist_max=FAR), lod_idx=None, channels=["rgb"])
         loss = torch.nn.functional.smooth_l1_loss(rb.rgb, target, reduction='none').mean()       # multiview_trainer.py:144-154
         loss.backward()
-        if world > 1:
-            for p in params:
-                dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
-                p.grad.div_(world)
+        reducer.reduce()                      # N>1: NCCL all-reduce(mean) of table + decoder gradients; no-op at N=1
         opt.step()
         return loss
 

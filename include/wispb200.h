@@ -87,7 +87,9 @@ typedef struct wb_octree {
     int32_t max_level;
     const uint32_t* bits;                   /* optional dense bitmask of `bits_level` built by       */
     int32_t bits_level;                     /*   wb_octree_build_bits; NULL -> descend the bytes     */
-} wb_octree;
+    int32_t has_bbox;                       /* optional: bounding box (normalised [-1,1] coords) of  */
+    float bbox_lo[3], bbox_hi[3];           /*   the occupied cells of the marched level; lets the   */
+} wb_octree;                                /*   marcher skip candidates that cannot be occupied     */
 
 /* ------------------------------------------------------------------------------------------------
  * SPC helpers  -- replace kaolin.ops.spc.{scan_octrees, generate_points, unbatched_query}

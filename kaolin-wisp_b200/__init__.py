@@ -4,7 +4,7 @@ Import as `wisp_b200` (the directory is named kaolin-wisp_b200 per the repo layo
 package aliases it).  Host-side classes mirror the reference's names and arguments; all compute goes through
 libwispb200.so (hand-written CUDA behind a C ABI, include/wispb200.h).  There is no CPU fallback.
 """
-from . import _cabi, ops, spc                                                   # noqa: F401
+from . import _cabi, ops, spc, parallel                                                   # noqa: F401
 from .core import Rays, RenderBuffer                                            # noqa: F401
 from .accelstructs import OctreeAS, ASQueryResults, ASRaymarchResults, ASRaytraceResults   # noqa: F401
 from .grids import HashGrid, MultiTable                                         # noqa: F401

@@ -44,7 +44,8 @@ class RaysDesc(C.Structure):
 class OctreeDesc(C.Structure):
     """struct wb_octree."""
     _fields_ = [("octree", C.c_void_p), ("prefix", C.c_void_p), ("nbytes", C.c_int64), ("max_level", C.c_int32),
-                ("bits", C.c_void_p), ("bits_level", C.c_int32)]
+                ("bits", C.c_void_p), ("bits_level", C.c_int32), ("has_bbox", C.c_int32),
+                ("bbox_lo", C.c_float * 3), ("bbox_hi", C.c_float * 3)]
 
 
 EXPORTS = [

@@ -89,6 +89,7 @@ struct WbOct {
     const uint8_t* octree; const int32_t* prefix; const uint32_t* bits;
     int level; int use_bits;
     float h, inv_h, maxq;        // 2^(L-1), 2^-(L-1), 2^L - 1
+    int has_bbox; float blo[3], bhi[3];   // occupied extent, already widened by the safety margin
 };
 __device__ __forceinline__ bool wb_quantize(float x, float h, float inv_h, float maxq, int& q) {
     float yf = __fmaf_rn(x, h, h);

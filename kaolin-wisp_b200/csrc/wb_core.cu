@@ -79,5 +79,9 @@ int wb_make_oct(const wb_octree* o, int level, WbOct* out) {
     out->octree = o->octree; out->prefix = o->prefix; out->bits = o->bits; out->level = level;
     out->use_bits = (o->bits != nullptr && o->bits_level == level && level <= 10) ? 1 : 0;
     out->h = ldexpf(1.0f, level - 1); out->inv_h = ldexpf(1.0f, -(level - 1)); out->maxq = (float)((1 << level) - 1);
+    out->has_bbox = (o->has_bbox && o->bits_level == level) ? 1 : 0;
+    for (int a = 0; a < 3; ++a) {   // widen by 1e-4: far above the fp32 error of p = fma(d,t,o) near the unit cube
+        out->blo[a] = fmaxf(o->bbox_lo[a], -1.0f) - 1e-4f; out->bhi[a] = fminf(o->bbox_hi[a], 1.0f) + 1e-4f;
+    }
     return WB_OK;
 }

@@ -23,15 +23,43 @@ wb_march_count_kernel(WbOct o, WbMarch m, uint32_t* __restrict__ hitmask, int32_
         const uint32_t key = wb_ray_key(m.seed, (uint32_t)r);
         const float ox = __ldg(m.origins + 3 * r), oy = __ldg(m.origins + 3 * r + 1), oz = __ldg(m.origins + 3 * r + 2);
         const float dx = __ldg(m.dirs + 3 * r), dy = __ldg(m.dirs + 3 * r + 1), dz = __ldg(m.dirs + 3 * r + 2);
+        // Candidates whose depth lies outside the ray's intersection with the (widened) box of occupied cells cannot be
+        // occupied: restrict the exact per-candidate test to the iterations [w0, w1] that can overlap it.  The candidate
+        // index bounds are conservative by one candidate on each side (jitter < one spacing, float slack << spacing).
+        int w0 = 0, w1 = nw - 1;
+        if (o.has_bbox) {
+            float t0 = -3.0e38f, t1 = 3.0e38f; bool miss = false;
+            const float oo[3] = { ox, oy, oz }, dd[3] = { dx, dy, dz };
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                if (fabsf(dd[a]) > 1e-12f) {
+                    const float inv = 1.0f / dd[a];
+                    const float ta = (o.blo[a] - oo[a]) * inv, tb = (o.bhi[a] - oo[a]) * inv;
+                    t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
+                } else if (oo[a] < o.blo[a] || oo[a] > o.bhi[a]) miss = true;
+            }
+            t0 -= 1e-4f * (1.0f + fabsf(t0)); t1 += 1e-4f * (1.0f + fabsf(t1));
+            if (miss || t1 < t0 || !(range > 0.0f)) { if (miss || t1 < t0) { w0 = 1; w1 = 0; } }
+            else {
+                // depth(i) in [lin_i*range + near, (lin_i + 1/n)*range + near], lin_i ~ i/(n-1)
+                const float nm1 = (float)max(m.n - 1, 1);
+                const float f0 = ((t0 - nearv) / range - m.inv_n) * nm1 - 2.0f;
+                const float f1 = ((t1 - nearv) / range) * nm1 + 2.0f;
+                const int i0 = f0 <= 0.0f ? 0 : (f0 >= (float)m.n ? m.n : (int)f0);
+                const int i1 = f1 < 0.0f ? -1 : (f1 >= (float)(m.n - 1) ? m.n - 1 : (int)f1 + 1);
+                w0 = i0 >> 5; w1 = i1 < 0 ? -1 : (i1 >> 5);
+                if (w1 > nw - 1) w1 = nw - 1;
+            }
+        }
         int cnt = 0; uint32_t keep = 0;
         for (int w = 0; w < nw; ++w) {
             const int i = (w << 5) + lane;
             bool hit = false;
-            if (i < m.n) {
+            if (w >= w0 && w <= w1 && i < m.n) {
                 const float d = wb_depth(m, r, key, i, nearv, range);
                 hit = wb_occupied(o, wb_addcmul(ox, dx, d), wb_addcmul(oy, dy, d), wb_addcmul(oz, dz, d));
             }
-            const uint32_t word = __ballot_sync(0xffffffffu, hit);
+            const uint32_t word = (w >= w0 && w <= w1) ? __ballot_sync(0xffffffffu, hit) : 0u;
             cnt += __popc(word);
             if ((w & 31) == lane) keep = word;                   // lane j keeps word j of the current group of 32
             if ((w & 31) == 31 || w == nw - 1) {                  // coalesced 128-byte store of up to 32 words

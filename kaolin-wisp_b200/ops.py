@@ -45,12 +45,18 @@ class OctreeTensors:
     max_level: int
     bits: Optional[torch.Tensor] = None
     bits_level: int = -1
+    bbox: Optional[tuple] = None          # (lo[3], hi[3]) of the occupied cells of `bits_level`, normalised coords
 
     def desc(self) -> A.OctreeDesc:
         d = A.OctreeDesc()
         d.octree, d.prefix, d.nbytes, d.max_level = self.octree.data_ptr(), self.prefix.data_ptr(), self.octree.shape[0], self.max_level
         d.bits = self.bits.data_ptr() if self.bits is not None else None
         d.bits_level = self.bits_level
+        d.has_bbox = 0
+        if self.bbox is not None:
+            d.has_bbox = 1
+            for a in range(3):
+                d.bbox_lo[a], d.bbox_hi[a] = self.bbox[0][a], self.bbox[1][a]
         return d
 
     def ensure_bits(self, level: int) -> None:
@@ -64,6 +70,10 @@ class OctreeTensors:
         lvl = self.points[start:start + cnt].contiguous()
         A.check(A.lib().wb_octree_build_bits(A.ptr(lvl), C.c_int64(cnt), C.c_int32(level), A.ptr(bits), A.stream()))
         self.bits, self.bits_level = bits, level
+        if cnt > 0:     # one-off (per octree) host read of the occupied extent; exact dyadic cell faces
+            mn, mx = lvl.min(0).values.cpu().tolist(), lvl.max(0).values.cpu().tolist()
+            res = float(2 ** level)
+            self.bbox = ([2.0 * m / res - 1.0 for m in mn], [2.0 * (m + 1) / res - 1.0 for m in mx])
 
 
 def query(oct: OctreeTensors, coords: torch.Tensor, level: int, with_parents: bool = False) -> torch.Tensor:
