@@ -164,13 +164,20 @@ int wb_rf_march_fill(const wb_rays* rays, int32_t num_samples, const float* jitt
  * blob: float [wb_rf_param_blob_floats(nef)]. */
 int64_t wb_rf_param_blob_floats(const wb_nef_desc* nef, int32_t precision);
 int wb_rf_pack_params(const wb_nef_desc* nef, int32_t precision, float* blob, wb_stream s);
+/* precision 1 scratch: workspace = per-ray view-embedding rows (+ dL/dfeat planes when backward != 0);
+ * feat = the gathered grid features the forward saves for the backward (2*Kp0 bytes per sample).  Both 0 for precision 0. */
+int64_t wb_rf_workspace_bytes(const wb_nef_desc* nef, int32_t precision, int64_t R, int64_t S, int32_t backward);
+int64_t wb_rf_feat_bytes(const wb_nef_desc* nef, int32_t precision, int64_t S);
+/* feat_save: optional (NULL = inference, nothing saved); workspace: wb_rf_workspace_bytes(.., backward=0) bytes. */
 int wb_rf_shade_fwd(const wb_nef_desc* nef, const float* blob, int32_t precision, const wb_rays* rays,
-                    const float* rec_t, const int32_t* rec_ray, int64_t S, float* shaded, wb_stream s);
+                    const float* rec_t, const int32_t* rec_ray, int64_t S, float* shaded, void* feat_save, void* workspace, wb_stream s);
 /* grad_table [rows,F], grad_dens / grad_col (packed like the params) are ACCUMULATED into (caller zeroes).
  * loss_scale: device pointer to ONE float, a power of two by which precision 1 scales the incoming gradients while
- * they are carried in fp16 (unscaled again in fp32 before they leave the kernel); ignored (may be NULL) for precision 0. */
+ * they are carried in fp16 (unscaled again in fp32 before they leave the kernels); ignored (may be NULL) for precision 0.
+ * feat_saved: what the forward wrote to feat_save; workspace: wb_rf_workspace_bytes(.., backward=1) bytes. */
 int wb_rf_shade_bwd(const wb_nef_desc* nef, const float* blob, int32_t precision, const wb_rays* rays,
                     const float* rec_t, const int32_t* rec_ray, int64_t S, const float* g_shaded, const float* loss_scale,
+                    const void* feat_saved, void* workspace,
                     float* grad_table, float* grad_dens, float* grad_col, wb_stream s);
 
 /* ------------------------------------------------------------------------------------------------

@@ -54,7 +54,7 @@ EXPORTS = [
     "wb_raymarch_ray_count", "wb_scan_workspace_bytes", "wb_scan_counts", "wb_raymarch_ray_fill",
     "wb_hashgrid_fwd", "wb_hashgrid_bwd", "wb_composite_fwd", "wb_composite_bwd",
     "wb_rf_march_fill", "wb_rf_param_blob_floats", "wb_rf_pack_params", "wb_rf_shade_fwd", "wb_rf_shade_bwd",
-    "wb_tc_selftest",
+    "wb_rf_workspace_bytes", "wb_rf_feat_bytes", "wb_tc_selftest",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -79,6 +79,8 @@ def lib() -> C.CDLL:
         L.wb_scan_workspace_bytes.restype = C.c_int64
         L.wb_scan_workspace_bytes.argtypes = [C.c_int64]
         L.wb_rf_param_blob_floats.restype = C.c_int64
+        L.wb_rf_workspace_bytes.restype = C.c_int64
+        L.wb_rf_feat_bytes.restype = C.c_int64
         _lib = L
     return _lib
 

@@ -23,9 +23,23 @@
 int wb_tc_blob_floats(const wb_nef_desc* nef);
 int wb_tc_pack(const wb_nef_desc* nef, float* blob, cudaStream_t st);
 int wb_tc_shade_fwd(const wb_nef_desc* nef, const float* blob, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray,
-                    int64_t S, float* shaded, cudaStream_t st);
+                    int64_t S, float* shaded, void* feat_save, void* workspace, cudaStream_t st);
 int wb_tc_shade_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray,
-                    int64_t S, const float* g_shaded, const float* scale, float* grad_table, float* grad_dens, float* grad_col, cudaStream_t st);
+                    int64_t S, const float* g_shaded, const float* scale, const void* feat_saved, void* workspace,
+                    float* grad_table, float* grad_dens, float* grad_col, cudaStream_t st);
+int64_t wb_tc_workspace_bytes(const wb_nef_desc* nef, int64_t R, int64_t S, int backward);
+int64_t wb_tc_feat_bytes(const wb_nef_desc* nef, int64_t S);
+
+extern "C" int64_t wb_rf_workspace_bytes(const wb_nef_desc* nef, int32_t precision, int64_t R, int64_t S, int32_t backward)
+{
+    if (precision != 1) return 0;
+    return wb_tc_workspace_bytes(nef, R, S, backward);
+}
+extern "C" int64_t wb_rf_feat_bytes(const wb_nef_desc* nef, int32_t precision, int64_t S)
+{
+    if (precision != 1) return 0;
+    return wb_tc_feat_bytes(nef, S);
+}
 
 struct WbMlp {
     int nl_d, nl_c;                      // linear layers: density, colour
@@ -322,12 +336,12 @@ static int wb_shade_fwd_launch(const WbGrid& g, const WbMlp& m, const float* blo
 }
 
 extern "C" int wb_rf_shade_fwd(const wb_nef_desc* nef, const float* blob, int32_t precision, const wb_rays* rays,
-                               const float* rec_t, const int32_t* rec_ray, int64_t S, float* shaded, wb_stream s)
+                               const float* rec_t, const int32_t* rec_ray, int64_t S, float* shaded, void* feat_save, void* workspace, wb_stream s)
 {
     WB_CHECK_ARG(precision == 0 || precision == 1, "precision must be 0 (fp32) or 1 (fp16 tensor cores)");
     if (S == 0) return WB_OK;
     WB_CHECK_ARG(blob && rays && rays->origins && rays->dirs && rec_t && rec_ray && shaded, "null pointer");
-    if (precision == 1) return wb_tc_shade_fwd(nef, blob, rays, rec_t, rec_ray, S, shaded, (cudaStream_t)s);
+    if (precision == 1) return wb_tc_shade_fwd(nef, blob, rays, rec_t, rec_ray, S, shaded, feat_save, workspace, (cudaStream_t)s);
     WbGrid g; int rc = wb_make_grid(nef, &g); if (rc) return rc;
     WbMlp m; rc = wb_make_mlp(nef, false, &m); if (rc) return rc;
     WbShadeIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S };
@@ -522,13 +536,14 @@ static int wb_shade_bwd_launch(const WbGrid& g, const WbMlp& m, const float* blo
 
 extern "C" int wb_rf_shade_bwd(const wb_nef_desc* nef, const float* blob, int32_t precision, const wb_rays* rays,
                                const float* rec_t, const int32_t* rec_ray, int64_t S, const float* g_shaded,
-                               const float* loss_scale, float* grad_table, float* grad_dens, float* grad_col, wb_stream s)
+                               const float* loss_scale, const void* feat_saved, void* workspace,
+                               float* grad_table, float* grad_dens, float* grad_col, wb_stream s)
 {
     WB_CHECK_ARG(precision == 0 || precision == 1, "precision must be 0 (fp32) or 1 (fp16 tensor cores)");
     if (S == 0) return WB_OK;
     WB_CHECK_ARG(blob && rays && rays->origins && rays->dirs && rec_t && rec_ray && g_shaded, "null pointer");
     WB_CHECK_ARG(grad_table && grad_dens && grad_col, "null gradient buffer");
-    if (precision == 1) return wb_tc_shade_bwd(nef, blob, rays, rec_t, rec_ray, S, g_shaded, loss_scale, grad_table, grad_dens, grad_col, (cudaStream_t)s);
+    if (precision == 1) return wb_tc_shade_bwd(nef, blob, rays, rec_t, rec_ray, S, g_shaded, loss_scale, feat_saved, workspace, grad_table, grad_dens, grad_col, (cudaStream_t)s);
     WbGrid g; int rc = wb_make_grid(nef, &g); if (rc) return rc;
     WbMlp m; rc = wb_make_mlp(nef, true, &m); if (rc) return rc;
     WbShadeIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S };

@@ -8,13 +8,22 @@
 // Per layer:  every thread writes its row of the fp16 operand tile (slab layout, wb_tc.cuh) -> fence -> CTA barrier ->
 // ONE thread issues the UMMAs of both sub-tiles (A = sample tile, B = TMA-staged weight pack, D in TMEM) and commits
 // to an mbarrier -> all threads wait, tcgen05.ld their accumulator row, apply bias/relu in fp32, write the next tile.
-// Backward recomputes the forward (tiles stay in shared memory), then per layer issues
-//     weight grad   acc_l[in, out] += X_l^T . dY_l   (both operands MN-major straight from the sample tiles; the
-//                                                     accumulators live in TMEM for the whole kernel; a constant-one
-//                                                     slab behind every X_l tile makes row `Kp_l` the bias gradient)
+//
+// Forward  (wb_shade_fwd_tc_kernel): gather 15 LODs x 8 corners (fp32 blend) -> decoders -> (r,g,b,sigma).  It also saves
+//   the gathered feature rows (fp16, chunk-major [Kp0/8][S] x 16 B: coalesced both ways) for the backward.
+// Backward (wb_mlp_bwd_tc_kernel): reloads those rows -- it touches neither the hash table nor the octree -- recomputes the
+//   decoders (tiles stay in shared memory) and per layer issues
+//     weight grad   acc_l[in, out] += X_l^T . dY_l   (both operands MN-major straight from the sample tiles; accumulators
+//                                                     stay in TMEM for the whole kernel; a constant-one slab behind every
+//                                                     X_l tile makes row `Kp_l` the bias gradient)
 //     data grad     dX_l = dY_l . W_l                (weight pack read MN-major: no transposed copy)
-// and finally scatters dL/dfeat to the hash table (red.global.add.v2.f32).  Gradients are carried in fp16 with a
-// power-of-two loss scale supplied on the device (no host sync), and unscaled in fp32 at the two exits.
+//   and writes dL/dfeat as fp16 level-major planes [L][S][F].
+// Scatter  (wb_table_scatter_kernel, SIMT): lanes = consecutive samples of ONE level; runs of lanes that fall into the same
+//   cell are summed with a segmented warp scan and only the last lane of a run issues the 8 red.global.add.v2.f32.  The
+//   per-SM atomic issue rate bounds the backward, and neighbouring samples of a ray share cells on all but the finest LODs.
+// The per-ray view embedding (positional_embedder.py:51-66) is evaluated once per ray (wb_ray_embed_kernel), not per sample.
+// Gradients are carried in fp16 under a power-of-two loss scale supplied on the device (no host sync) and unscaled in fp32
+// at the two exits (table scatter, weight-gradient flush).
 #include "wb_common.cuh"
 #include "wb_tc.cuh"
 #include <math.h>
@@ -100,6 +109,30 @@ int wb_tc_make(const wb_nef_desc* d, bool backward, WbTc* m)
     return WB_OK;
 }
 
+// number of dL/dfeat planes and halfs per (plane, sample): 'cat' -> one plane per live LOD, 'sum' -> a single plane
+static void tc_dfeat_shape(const wb_nef_desc* d, int* planes, int* width)
+{
+    *width = d->feature_dim;
+    *planes = d->multiscale == 0 ? (d->lod_idx < d->num_lods ? d->lod_idx : d->num_lods) : 1;
+    if (*planes < 0) *planes = 0;
+}
+static int64_t tc_align256(int64_t b) { return (b + 255) / 256 * 256; }
+
+// workspace layout (bytes): [ray_embed: R * Kc * 2][dfeat: planes * S * F * 2 (backward only)]
+int64_t wb_tc_workspace_bytes(const wb_nef_desc* nef, int64_t R, int64_t S, int backward)
+{
+    WbTc m; if (wb_tc_make(nef, false, &m)) return -1;
+    int planes, width; tc_dfeat_shape(nef, &planes, &width);
+    int64_t b = tc_align256(R * m.Kp[m.nl_d] * 2);
+    if (backward) b += tc_align256((int64_t)planes * S * width * 2);
+    return b + 256;
+}
+int64_t wb_tc_feat_bytes(const wb_nef_desc* nef, int64_t S)
+{
+    WbTc m; if (wb_tc_make(nef, false, &m)) return -1;
+    return (int64_t)m.Kp[0] * 2 * S + 256;
+}
+
 // ---- parameter blob: fp16 weight packs (wb_tc.cuh layout) + fp32 biases -------------------------------------------
 __global__ void wb_tc_pack_kernel(WbTc m, const float* __restrict__ dens, const float* __restrict__ col, uint8_t* __restrict__ blob)
 {
@@ -128,10 +161,42 @@ int wb_tc_pack(const wb_nef_desc* nef, float* blob, cudaStream_t st)
     return WB_OK;
 }
 
+// ---- per-ray colour-input rows: zeros with the view embedding at features [dout-1, dout-1+view_dim) -----------------
+__global__ void __launch_bounds__(128)
+wb_ray_embed_kernel(WbTc m, const float* __restrict__ dirs, int64_t R, uint4* __restrict__ out)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const int Kc = m.Kp[m.nl_d], f0 = m.O[m.nl_d - 1] - 1;
+    __align__(16) __half row[128];
+    for (int i = 0; i < Kc; ++i) row[i] = __float2half_rn(0.0f);
+    const float x = dirs[3 * r], y = dirs[3 * r + 1], z = dirs[3 * r + 2];
+    int o = f0;
+    if (m.view_mode == 1 || m.view_mode == 3) { row[o] = __float2half_rn(x); row[o + 1] = __float2half_rn(y); row[o + 2] = __float2half_rn(z); o += 3; }
+    if (m.view_mode >= 2) {
+        float band = 1.0f;
+        for (int f = 0; f < m.view_freq; ++f) {
+            const float w3[3] = { x * band, y * band, z * band };
+            for (int c = 0; c < 3; ++c) {
+                row[o + f * 3 + c] = __float2half_rn(sinf(w3[c]));
+                row[o + 3 * m.view_freq + f * 3 + c] = __float2half_rn(cosf(w3[c]));
+            }
+            band *= 2.0f;
+        }
+    }
+    const uint4* rv = reinterpret_cast<const uint4*>(row);
+    for (int c = 0; c < Kc / 8; ++c) out[r * (Kc / 8) + c] = rv[c];
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------------------------
-struct TcIn { const float* origins; const float* dirs; const float* rec_t; const int32_t* rec_ray; int64_t S; };
+struct TcIn {
+    const float* origins; const float* dirs; const float* rec_t; const int32_t* rec_ray; int64_t S;
+    const uint4* ray_embed;      // [R][Kc/8] rows prepared by wb_ray_embed_kernel
+    uint4* x0_save;              // forward: optional [Kp0/8][S] copy of the density-decoder input rows
+    const uint4* x0_saved;       // backward: the same buffer
+};
 
 __device__ __forceinline__ void tile_store1(uint8_t* tile, int r, int f, float v)
 {
@@ -264,34 +329,13 @@ __device__ __forceinline__ void tc_issue_bwd(const WbTc& m, const TcCtx& c, int 
     }
 }
 
-struct TcSample { float px, py, pz, dx, dy, dz; };
-
-__device__ __forceinline__ TcSample tc_load_sample(const TcIn& in, int64_t s)
-{
-    const int64_t ray = __ldg(in.rec_ray + s);
-    const float t = __ldg(in.rec_t + s);
-    TcSample q;
-    q.dx = __ldg(in.dirs + 3 * ray); q.dy = __ldg(in.dirs + 3 * ray + 1); q.dz = __ldg(in.dirs + 3 * ray + 2);
-    q.px = wb_addcmul(__ldg(in.origins + 3 * ray), q.dx, t);
-    q.py = wb_addcmul(__ldg(in.origins + 3 * ray + 1), q.dy, t);
-    q.pz = wb_addcmul(__ldg(in.origins + 3 * ray + 2), q.dz, t);
-    return q;
-}
-
-// Forward of one 256-sample tile through both decoders.  Returns (in registers) the density-decoder output df[16]
-// and the colour pre-activations c3[3].  Tiles stay in shared memory when the layout is the retained (backward) one.
-__device__ __forceinline__ void tc_forward_tile(const WbGrid& g, const WbTc& m, TcCtx& c, const TcSample& q, float df[16], float c3[3])
+// Decoders of one 256-sample tile, starting from an X0 tile that the caller has already written.
+// Returns (in registers) the density-decoder output df[16] and the colour pre-activations c3[3].
+__device__ __forceinline__ void tc_decoders(const WbTc& m, TcCtx& c, const TcIn& in, int64_t ray, float df[16], float c3[3])
 {
     uint8_t* sub = c.smem + m.sub_off[c.sub];
     const float* P = reinterpret_cast<const float*>(c.smem + m.w_smem_off);
     const int nl = m.nl_d + m.nl_c;
-    // ---- density decoder input: grid features (+ position embedding), zero padded to Kp ----
-    {
-        uint8_t* t0 = sub + m.tile_off[0];
-        tile_gather(g, t0, c.r, q.px, q.py, q.pz);
-        tile_embed(t0, c.r, m.feat_dim, m.pos_mode, m.pos_freq, q.px, q.py, q.pz);
-        tile_zero(t0, c.r, m.I[0], m.Kp[0]);
-    }
     for (int l = 0; l < nl; ++l) {
         tc_round(c, [&]() { tc_issue_fwd(m, c, l); });
         const float* bias = P + m.b_off[l] / 4;
@@ -301,13 +345,22 @@ __device__ __forceinline__ void tc_forward_tile(const WbGrid& g, const WbTc& m, 
             float v[16]; tc_ld16(trow, v);
 #pragma unroll
             for (int j = 0; j < 16; ++j) df[j] = v[j] + bias[j];
-            // colour input = [df[1:], embed(ray_d)], zero padded (nerf.py:248-259)
-            uint8_t* tc = sub + m.tile_off[l + 1];
-            const int dout = m.O[l];
+            // colour input = [df[1:], embed(ray_d)], zero padded (nerf.py:248-259): the per-ray row already holds the
+            // embedding and the zero padding, only the first dout-1 (<= 15) features are per-sample
+            uint8_t* tcol = sub + m.tile_off[l + 1];
+            const int nd = m.O[l] - 1, nch = m.Kp[l + 1] / 8;
+            const uint4* re = in.ray_embed + ray * nch;
+            uint4 q0 = __ldg(re), q1 = __ldg(re + 1);
+            {
+                __half* h0 = reinterpret_cast<__half*>(&q0); __half* h1 = reinterpret_cast<__half*>(&q1);
 #pragma unroll
-            for (int j = 1; j < 16; ++j) if (j < dout) tile_store1(tc, c.r, j - 1, df[j]);
-            tile_embed(tc, c.r, dout - 1, m.view_mode, m.view_freq, q.dx, q.dy, q.dz);
-            tile_zero(tc, c.r, m.I[l + 1], m.Kp[l + 1]);
+                for (int j = 0; j < 8; ++j) { if (j < nd) h0[j] = __float2half_rn(df[j + 1]); }
+#pragma unroll
+                for (int j = 0; j < 7; ++j) { if (8 + j < nd) h1[j] = __float2half_rn(df[9 + j]); }
+            }
+            *reinterpret_cast<uint4*>(tcol + c.r * 16) = q0;
+            *reinterpret_cast<uint4*>(tcol + 2048 + c.r * 16) = q1;
+            for (int ch = 2; ch < nch; ++ch) *reinterpret_cast<uint4*>(tcol + ch * 2048 + c.r * 16) = __ldg(re + ch);
         } else if (last_c) {
             float v[16]; tc_ld16(trow, v);
             c3[0] = v[0] + bias[0]; c3[1] = v[1] + bias[1]; c3[2] = v[2] + bias[2];
@@ -346,14 +399,26 @@ wb_shade_fwd_tc_kernel(WbGrid g, WbTc m, const uint8_t* __restrict__ blob, TcIn 
     tc_mbar_wait(&bars[1], 0);
     TcCtx c; c.smem = smem; c.bar = &bars[0]; c.tmem = tmem_s; c.phase = 0;
     c.sub = threadIdx.x >> 7; c.r = threadIdx.x & 127; c.laneq = ((threadIdx.x >> 5) & 3) * 32;
+    uint8_t* t0 = smem + m.sub_off[c.sub] + m.tile_off[0];
+    const int nch0 = m.Kp[0] / 8;
     const int64_t ntiles = (in.S + TC_THREADS - 1) / TC_THREADS;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         int64_t s = tile * TC_THREADS + threadIdx.x;
         const bool valid = s < in.S;
         if (!valid) s = in.S - 1;
-        const TcSample q = tc_load_sample(in, s);
+        const int64_t ray = __ldg(in.rec_ray + s);
+        const float t = __ldg(in.rec_t + s);
+        const float px = wb_addcmul(__ldg(in.origins + 3 * ray), __ldg(in.dirs + 3 * ray), t);
+        const float py = wb_addcmul(__ldg(in.origins + 3 * ray + 1), __ldg(in.dirs + 3 * ray + 1), t);
+        const float pz = wb_addcmul(__ldg(in.origins + 3 * ray + 2), __ldg(in.dirs + 3 * ray + 2), t);
+        // density-decoder input row: grid features (+ position embedding), zero padded to Kp
+        tile_gather(g, t0, c.r, px, py, pz);
+        tile_embed(t0, c.r, m.feat_dim, m.pos_mode, m.pos_freq, px, py, pz);
+        tile_zero(t0, c.r, m.I[0], m.Kp[0]);
+        if (in.x0_save && valid)
+            for (int ch = 0; ch < nch0; ++ch) in.x0_save[(int64_t)ch * in.S + s] = *reinterpret_cast<const uint4*>(t0 + ch * 2048 + c.r * 16);
         float df[16], c3[3];
-        tc_forward_tile(g, m, c, q, df, c3);
+        tc_decoders(m, c, in, ray, df, c3);
         if (valid) {
             const float r = 1.0f / (1.0f + expf(-c3[0])), gg = 1.0f / (1.0f + expf(-c3[1])), b = 1.0f / (1.0f + expf(-c3[2]));
             shaded[s] = make_float4(r, gg, b, fmaxf(df[0], 0.0f));
@@ -364,12 +429,23 @@ wb_shade_fwd_tc_kernel(WbGrid g, WbTc m, const uint8_t* __restrict__ blob, TcIn 
     if (threadIdx.x < 32) tc_tmem_dealloc(c.tmem, (uint32_t)m.tmem_cols);
 }
 
+static int tc_launch_ray_embed(const WbTc& m, const wb_rays* rays, void* workspace, cudaStream_t st)
+{
+    const int64_t R = rays->num_rays;
+    if (R == 0) return WB_OK;
+    wb_ray_embed_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(m, rays->dirs, R, reinterpret_cast<uint4*>(workspace));
+    WB_LAUNCH_CHECK();
+    return WB_OK;
+}
+
 int wb_tc_shade_fwd(const wb_nef_desc* nef, const float* blob, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray,
-                    int64_t S, float* shaded, cudaStream_t st)
+                    int64_t S, float* shaded, void* feat_save, void* workspace, cudaStream_t st)
 {
     WbGrid g; int rc = wb_make_grid(nef, &g); if (rc) return rc;
     WbTc m; rc = wb_tc_make(nef, false, &m); if (rc) return rc;
-    TcIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S };
+    WB_CHECK_ARG(workspace != nullptr, "precision 1 needs the workspace (wb_rf_workspace_bytes)");
+    rc = tc_launch_ray_embed(m, rays, workspace, st); if (rc) return rc;
+    TcIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S, reinterpret_cast<const uint4*>(workspace), reinterpret_cast<uint4*>(feat_save), nullptr };
     WB_CUDA(cudaFuncSetAttribute(wb_shade_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, m.smem_bytes));
     const int64_t ntiles = (S + TC_THREADS - 1) / TC_THREADS;
     int per_sm = (227 * 1024) / (m.smem_bytes + 2048); per_sm = max(1, min(per_sm, 512 / m.tmem_cols)); per_sm = min(per_sm, 4);
@@ -380,12 +456,12 @@ int wb_tc_shade_fwd(const wb_nef_desc* nef, const float* blob, const wb_rays* ra
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// backward kernel
+// decoder backward kernel
 // ---------------------------------------------------------------------------------------------------------------
-struct TcGrads { float* gtable; float* gdens; float* gcol; const float* scale; };
+struct TcGrads { float* gdens; float* gcol; const float* scale; __half* dfeat; int planes, width; };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-wb_shade_bwd_tc_kernel(WbGrid g, WbTc m, const uint8_t* __restrict__ blob, TcIn in, const float4* __restrict__ g_shaded, TcGrads G)
+wb_mlp_bwd_tc_kernel(WbTc m, const uint8_t* __restrict__ blob, TcIn in, const float4* __restrict__ g_shaded, TcGrads G)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[2];
@@ -412,15 +488,19 @@ wb_shade_bwd_tc_kernel(WbGrid g, WbTc m, const uint8_t* __restrict__ blob, TcIn 
     tc_mbar_wait(&bars[1], 0);
     const float scale = __ldg(G.scale), inv_scale = 1.0f / scale;
     uint8_t* dyt = smem + m.dy_off[c.sub];
+    uint8_t* t0 = sub + m.tile_off[0];
+    const int nch0 = m.Kp[0] / 8;
     const int64_t ntiles = (in.S + TC_THREADS - 1) / TC_THREADS;
     bool first = true;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         int64_t s = tile * TC_THREADS + threadIdx.x;
         const bool valid = s < in.S;
         if (!valid) s = in.S - 1;
-        const TcSample q = tc_load_sample(in, s);
+        const int64_t ray = __ldg(in.rec_ray + s);
+        for (int ch = 0; ch < nch0; ++ch)                          // saved density-decoder input row (coalesced 16 B per lane)
+            *reinterpret_cast<uint4*>(t0 + ch * 2048 + c.r * 16) = __ldg(in.x0_saved + (int64_t)ch * in.S + s);
         float df[16], c3[3];
-        tc_forward_tile(g, m, c, q, df, c3);
+        tc_decoders(m, c, in, ray, df, c3);
         float4 go = valid ? __ldg(g_shaded + s) : make_float4(0, 0, 0, 0);
         // ---- colour decoder, last layer: dY = dL/d(pre-sigmoid), zero padded ----
         {
@@ -430,9 +510,6 @@ wb_shade_bwd_tc_kernel(WbGrid g, WbTc m, const uint8_t* __restrict__ blob, TcIn 
             tile_store8(dyt, c.r, 0, v);
             for (int sl = 1; sl < m.Np[nl - 1] / 8; ++sl) tile_store8(dyt, c.r, sl, z);
         }
-        float gdf[16];                                           // dL/d(density feats), filled at the colour/density hand-over
-#pragma unroll
-        for (int j = 0; j < 16; ++j) gdf[j] = 0.0f;
         const uint32_t trow = c.tmem + ((uint32_t)c.laneq << 16) + m.work_col[c.sub];
         for (int l = nl - 1; l >= 0; --l) {
             tc_round(c, [&]() { tc_issue_bwd(m, c, l, first); });
@@ -441,49 +518,30 @@ wb_shade_bwd_tc_kernel(WbGrid g, WbTc m, const uint8_t* __restrict__ blob, TcIn 
                 // first colour layer: inputs [df[1:dout], embed(ray_d)]; only the first dout-1 carry gradient (nerf.py:259)
                 float v[16]; tc_ld16(trow, v);
                 const int dout = m.O[m.nl_d - 1];
-#pragma unroll
-                for (int j = 1; j < 16; ++j) if (j < dout) gdf[j] = v[j - 1];
+                float gdf[16];
                 gdf[0] = (df[0] > 0.0f) ? go.w * scale : 0.0f;   // relu' of density (nerf.py:263)
+#pragma unroll
+                for (int j = 1; j < 16; ++j) gdf[j] = (j < dout) ? v[j - 1] : 0.0f;
                 tile_store8(dyt, c.r, 0, gdf); tile_store8(dyt, c.r, 1, gdf + 8);
                 float z[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
                 for (int sl = 2; sl < m.Np[l - 1] / 8; ++sl) tile_store8(dyt, c.r, sl, z);
             } else if (l == 0) {
-                // dL/d(grid features): scatter to the hash table (hashgrid_interpolate_cuda.cu:151-160), unscaled in fp32.
-                // tcgen05.ld is warp-collective: every lane loads, only valid samples scatter.
-                const int L = g.L, F = g.F;
-                const int lmax = g.multiscale == 0 ? min(L, g.lod_idx) : L;
-                if (g.multiscale == 0 && F == 2) {
-                    for (int l0 = 0; l0 < lmax; l0 += 8) {
-                        float v[16]; tc_ld16(trow + 2 * l0, v);
+                // dL/d(grid features) -> fp16 planes [plane][S][width] (still loss-scaled); tcgen05.ld is warp-collective
+                const int W = G.width, nfe = G.planes * W;
+                for (int f0 = 0; f0 < nfe; f0 += 16) {
+                    float v[16]; tc_ld16(trow + f0, v);
+                    if (!valid) continue;
+                    if (W == 2) {
 #pragma unroll
                         for (int qq = 0; qq < 8; ++qq) {
-                            const int lv = l0 + qq;
-                            const float g0 = v[2 * qq] * inv_scale, g1 = v[2 * qq + 1] * inv_scale;
-                            if (!valid || lv >= lmax || (g0 == 0.0f && g1 == 0.0f)) continue;
-                            uint32_t idx[8]; float cf[8];
-                            wb_corner_setup(g, lv, q.px, q.py, q.pz, idx, cf);
-                            float2* tb = reinterpret_cast<float2*>(G.gtable + g.begin[lv] * 2);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) atomicAdd(tb + idx[j], make_float2(g0 * cf[j], g1 * cf[j]));
+                            const int pl = (f0 >> 1) + qq;
+                            if (pl < G.planes) reinterpret_cast<__half2*>(G.dfeat)[(int64_t)pl * in.S + s] = __floats2half2_rn(v[2 * qq], v[2 * qq + 1]);
                         }
-                    }
-                } else {
-                    const int nfe = g.multiscale == 0 ? lmax * F : F;
-                    for (int f0 = 0; f0 < nfe; f0 += 16) {
-                        float v[16]; tc_ld16(trow + f0, v);
+                    } else {
 #pragma unroll
                         for (int jj = 0; jj < 16; ++jj) {
                             const int fe = f0 + jj;
-                            const float gv = v[jj] * inv_scale;
-                            if (!valid || fe >= nfe || gv == 0.0f) continue;
-                            const int lv0 = g.multiscale == 0 ? fe / F : 0, lv1 = g.multiscale == 0 ? lv0 + 1 : L, f = g.multiscale == 0 ? fe % F : fe;
-                            for (int lv = lv0; lv < lv1; ++lv) {
-                                uint32_t idx[8]; float cf[8];
-                                wb_corner_setup(g, lv, q.px, q.py, q.pz, idx, cf);
-                                float* tb = G.gtable + g.begin[lv] * F;
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) atomicAdd(tb + (int64_t)idx[j] * F + f, gv * cf[j]);
-                            }
+                            if (fe < nfe) G.dfeat[((int64_t)(fe / W) * in.S + s) * W + (fe % W)] = __float2half_rn(v[jj]);
                         }
                     }
                 }
@@ -541,19 +599,121 @@ wb_shade_bwd_tc_kernel(WbGrid g, WbTc m, const uint8_t* __restrict__ blob, TcIn 
     if (threadIdx.x < 32) tc_tmem_dealloc(c.tmem, (uint32_t)m.tmem_cols);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// table scatter: dL/dfeat planes -> hash table (hashgrid_interpolate_cuda.cu:151-160), with warp-level run merging
+// ---------------------------------------------------------------------------------------------------------------
+template <int F>
+__global__ void __launch_bounds__(256)
+wb_table_scatter_kernel(WbGrid g, TcIn in, const __half* __restrict__ dfeat, int planes, const float* __restrict__ scale_p, float* __restrict__ gtable)
+{
+    const int l = blockIdx.y;                                   // level
+    const int lane = threadIdx.x & 31;
+    const float inv_scale = 1.0f / __ldg(scale_p);
+    const int Fr = F > 0 ? F : g.F;
+    const int pl = g.multiscale == 0 ? l : 0;
+    float* tb = gtable + g.begin[l] * Fr;
+    const int64_t nwork = (in.S + 31) & ~(int64_t)31;            // whole warps
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nwork; s += (int64_t)gridDim.x * blockDim.x) {
+        const bool valid = s < in.S;
+        uint32_t idx[8]; float cf[8]; uint64_t key = ~0ull - (uint64_t)lane;    // invalid lanes never merge
+        float gv[F > 0 ? F : 8];
+#pragma unroll
+        for (int f = 0; f < (F > 0 ? F : 8); ++f) gv[f] = 0.0f;
+        if (valid) {
+            const int64_t ray = __ldg(in.rec_ray + s);
+            const float t = __ldg(in.rec_t + s);
+            const float px = wb_addcmul(__ldg(in.origins + 3 * ray), __ldg(in.dirs + 3 * ray), t);
+            const float py = wb_addcmul(__ldg(in.origins + 3 * ray + 1), __ldg(in.dirs + 3 * ray + 1), t);
+            const float pz = wb_addcmul(__ldg(in.origins + 3 * ray + 2), __ldg(in.dirs + 3 * ray + 2), t);
+            int ix, iy, iz; float wx, wy, wz, jx, jy, jz;
+            wb_cell(px, g.hres[l], g.hi[l], ix, wx, jx); wb_cell(py, g.hres[l], g.hi[l], iy, wy, jy); wb_cell(pz, g.hres[l], g.hi[l], iz, wz, jz);
+            key = (uint64_t)ix | ((uint64_t)iy << 20) | ((uint64_t)iz << 40);
+            const float xy00 = jx * jy, xy01 = jx * wy, xy10 = wx * jy, xy11 = wx * wy;
+            cf[0] = xy00 * jz; cf[1] = xy00 * wz; cf[2] = xy01 * jz; cf[3] = xy01 * wz;
+            cf[4] = xy10 * jz; cf[5] = xy10 * wz; cf[6] = xy11 * jz; cf[7] = xy11 * wz;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) idx[j] = wb_hash_idx(ix + ((j & 4) >> 2), iy + ((j & 2) >> 1), iz + (j & 1), g.res[l], g.Tmask, g.dense[l]);
+            if (F == 2) {
+                const float2 gg = __half22float2(reinterpret_cast<const __half2*>(dfeat)[(int64_t)pl * in.S + s]);
+                gv[0] = gg.x * inv_scale; gv[1] = gg.y * inv_scale;
+            } else {
+                for (int f = 0; f < Fr; ++f) gv[f] = __half2float(dfeat[((int64_t)pl * in.S + s) * Fr + f]) * inv_scale;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { idx[j] = 0; cf[j] = 0.0f; }
+        }
+        // runs of consecutive lanes with the same cell
+        const uint64_t kprev = __shfl_up_sync(0xffffffffu, key, 1);
+        const bool head = (lane == 0) || (kprev != key);
+        const uint32_t heads = __ballot_sync(0xffffffffu, head);
+        const int run_head = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+        const int dist = lane - run_head;
+        const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
+        int maxd = dist;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
+        if (F == 2) {
+            float v0[8], v1[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v0[j] = gv[0] * cf[j]; v1[j] = gv[1] * cf[j]; }
+            for (int o = 1; o <= maxd; o <<= 1) {               // segmented inclusive scan (warp-uniform trip count)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float a = __shfl_up_sync(0xffffffffu, v0[j], o), b = __shfl_up_sync(0xffffffffu, v1[j], o);
+                    if (dist >= o) { v0[j] += a; v1[j] += b; }
+                }
+            }
+            if (tail && valid) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (v0[j] != 0.0f || v1[j] != 0.0f) atomicAdd(reinterpret_cast<float2*>(tb) + idx[j], make_float2(v0[j], v1[j]));
+            }
+        } else {
+            for (int f = 0; f < Fr; ++f) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = gv[f] * cf[j];
+                for (int o = 1; o <= maxd; o <<= 1) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { const float a = __shfl_up_sync(0xffffffffu, v[j], o); if (dist >= o) v[j] += a; }
+                }
+                if (tail && valid) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) if (v[j] != 0.0f) atomicAdd(tb + (int64_t)idx[j] * Fr + f, v[j]);
+                }
+            }
+        }
+    }
+}
+
 int wb_tc_shade_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray,
-                    int64_t S, const float* g_shaded, const float* scale, float* grad_table, float* grad_dens, float* grad_col, cudaStream_t st)
+                    int64_t S, const float* g_shaded, const float* scale, const void* feat_saved, void* workspace,
+                    float* grad_table, float* grad_dens, float* grad_col, cudaStream_t st)
 {
     WbGrid g; int rc = wb_make_grid(nef, &g); if (rc) return rc;
     WbTc m; rc = wb_tc_make(nef, true, &m); if (rc) return rc;
     WB_CHECK_ARG(scale != nullptr, "precision 1 needs the device loss-scale pointer");
-    TcIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S };
-    TcGrads G = { grad_table, grad_dens, grad_col, scale };
-    WB_CUDA(cudaFuncSetAttribute(wb_shade_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, m.smem_bytes));
+    WB_CHECK_ARG(feat_saved != nullptr && workspace != nullptr, "precision 1 backward needs the saved features and the workspace");
+    rc = tc_launch_ray_embed(m, rays, workspace, st); if (rc) return rc;
+    int planes, width; tc_dfeat_shape(nef, &planes, &width);
+    const int64_t R = rays->num_rays;
+    __half* dfeat = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(workspace) + tc_align256(R * m.Kp[m.nl_d] * 2));
+    TcIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S, reinterpret_cast<const uint4*>(workspace), nullptr, reinterpret_cast<const uint4*>(feat_saved) };
+    TcGrads G = { grad_dens, grad_col, scale, dfeat, planes, width };
+    WB_CUDA(cudaFuncSetAttribute(wb_mlp_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, m.smem_bytes));
     const int64_t ntiles = (S + TC_THREADS - 1) / TC_THREADS;
     int64_t grid = (int64_t)wb_num_sms(); if (grid > ntiles) grid = ntiles;       // 1 CTA / SM: TMEM holds the weight-grad accumulators
-    wb_shade_bwd_tc_kernel<<<(unsigned)grid, TC_THREADS, m.smem_bytes, st>>>(g, m, reinterpret_cast<const uint8_t*>(blob), in,
-                                                                             reinterpret_cast<const float4*>(g_shaded), G);
+    wb_mlp_bwd_tc_kernel<<<(unsigned)grid, TC_THREADS, m.smem_bytes, st>>>(m, reinterpret_cast<const uint8_t*>(blob), in,
+                                                                           reinterpret_cast<const float4*>(g_shaded), G);
     WB_LAUNCH_CHECK();
+    const int levels = g.multiscale == 0 ? planes : g.L;
+    if (levels > 0) {
+        int64_t bx = (S + 255) / 256; const int64_t cap = (int64_t)wb_num_sms() * 8; if (bx > cap) bx = cap;
+        dim3 grid2((unsigned)bx, (unsigned)levels);
+        if (g.F == 2) wb_table_scatter_kernel<2><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, scale, grad_table);
+        else wb_table_scatter_kernel<0><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, scale, grad_table);
+        WB_LAUNCH_CHECK();
+    }
     return WB_OK;
 }

@@ -308,9 +308,14 @@ class RFTraceFn(torch.autograd.Function):
         rec_t, rec_delta, rec_ray = march_fill_records(ms, dev)
         S, R = ms.total, ms.rays.num_rays
         shaded = torch.empty((S, 4), dtype=torch.float32, device=dev)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in (table, *params))
+        wsb = int(L.wb_rf_workspace_bytes(C.byref(desc), C.c_int32(precision), C.c_int64(R), C.c_int64(S), C.c_int32(0)))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if wsb > 0 else None
+        fb = int(L.wb_rf_feat_bytes(C.byref(desc), C.c_int32(precision), C.c_int64(S))) if need_grad else 0
+        feat = torch.empty(fb, dtype=torch.uint8, device=dev) if fb > 0 else None
         with _stage("shade_fwd"):
             A.check(L.wb_rf_shade_fwd(C.byref(desc), A.ptr(blob), C.c_int32(precision), C.byref(ms.rays), A.ptr(rec_t), A.ptr(rec_ray),
-                                      C.c_int64(S), A.ptr(shaded), A.stream()))
+                                      C.c_int64(S), A.ptr(shaded), A.ptr(feat), A.ptr(ws), A.stream()))
         rgb = torch.empty((R, 3), dtype=torch.float32, device=dev)
         depth = torch.empty((R, 1), dtype=torch.float32, device=dev)
         alpha = torch.empty((R, 1), dtype=torch.float32, device=dev)
@@ -321,6 +326,7 @@ class RFTraceFn(torch.autograd.Function):
                                        A.ptr(rgb), A.ptr(depth), A.ptr(alpha), A.ptr(hit), A.stream()))
         ctx.ms, ctx.spec, ctx.n_dens, ctx.bg, ctx.precision = ms, spec, n_dens, bgv, precision
         ctx.param_shapes = [p.shape for p in params]
+        ctx.feat = feat
         ctx.save_for_backward(tb, dens_flat, col_flat, blob, rec_t, rec_delta, rec_ray, shaded)
         ctx.mark_non_differentiable(hit)
         return rgb, depth, alpha, hit
@@ -347,9 +353,11 @@ class RFTraceFn(torch.autograd.Function):
             # power-of-two loss scale computed on the device (no host sync): largest |gradient| -> ~64 in fp16
             amax = g_sh.abs().amax().clamp_min(1e-30)
             scale = torch.exp2(torch.floor(torch.log2(64.0 / amax))).clamp(2.0 ** -20, 2.0 ** 60).reshape(1).contiguous()
+        wsb = int(L.wb_rf_workspace_bytes(C.byref(desc), C.c_int32(ctx.precision), C.c_int64(R), C.c_int64(S), C.c_int32(1)))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=tb.device) if wsb > 0 else None
         with _stage("shade_bwd"):
             A.check(L.wb_rf_shade_bwd(C.byref(desc), A.ptr(blob), C.c_int32(ctx.precision), C.byref(ms.rays), A.ptr(rec_t), A.ptr(rec_ray),
-                                      C.c_int64(S), A.ptr(g_sh), A.ptr(scale), A.ptr(g_table), A.ptr(g_dens), A.ptr(g_col), A.stream()))
+                                      C.c_int64(S), A.ptr(g_sh), A.ptr(scale), A.ptr(ctx.feat), A.ptr(ws), A.ptr(g_table), A.ptr(g_dens), A.ptr(g_col), A.stream()))
         grads = []
         for flat, shapes in ((g_dens, ctx.param_shapes[:ctx.n_dens]), (g_col, ctx.param_shapes[ctx.n_dens:])):
             o = 0
