@@ -308,7 +308,7 @@ class RFTraceFn(torch.autograd.Function):
         rec_t, rec_delta, rec_ray = march_fill_records(ms, dev)
         S, R = ms.total, ms.rays.num_rays
         shaded = torch.empty((S, 4), dtype=torch.float32, device=dev)
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in (table, *params))
+        need_grad = any(ctx.needs_input_grad[6:])          # grad mode is off inside Function.forward; ask autograd instead
         wsb = int(L.wb_rf_workspace_bytes(C.byref(desc), C.c_int32(precision), C.c_int64(R), C.c_int64(S), C.c_int32(0)))
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if wsb > 0 else None
         fb = int(L.wb_rf_feat_bytes(C.byref(desc), C.c_int32(precision), C.c_int64(S))) if need_grad else 0
