@@ -123,6 +123,27 @@ int wb_raymarch_ray_fill(const wb_rays* rays, int32_t num_samples, const float* 
                          int64_t* ridx, float* samples, float* depth, float* deltas, uint8_t* boundary, wb_stream s);
 
 /* ------------------------------------------------------------------------------------------------
+ * OctreeAS.raytrace (octree_as.py:165-186 -> kaolin unbatched_raytrace, with_exit=True) and the samplers built on it:
+ * _raymarch_voxel (octree_as.py:188-245) and _raymarch_uniform (octree_as.py:311-374 + wisp._C.ops.uniform_sample_cuda,
+ * wisp/csrc/ops/uniform_sample.cpp:28-42).  count -> wb_scan_counts -> fill.  Nuggets: ridx/pidx int32 [Ng], depth f32 [Ng,2]
+ * (entry, exit), ordered by ray then front to back.  Sample outputs use the ASRaymarchResults layout; any output pointer may
+ * be NULL; rec_ray (int32 ray index per sample) is the extra record the fused path needs.
+ * ---------------------------------------------------------------------------------------------- */
+int wb_raytrace_count(const wb_octree* oct, int32_t level, const wb_rays* rays, int32_t* counts, wb_stream s);
+int wb_raytrace_fill(const wb_octree* oct, int32_t level, const wb_rays* rays, const int64_t* offsets,
+                     int32_t* ridx, int32_t* pidx, float* depth, wb_stream s);
+/* num_samples per nugget; jitter: explicit [Ng, num_samples] or NULL for the counter stream keyed by (seed, nugget, k). */
+int wb_raymarch_voxel_fill(const wb_rays* rays, const int32_t* nug_ridx, const float* nug_depth, int64_t Ng, int32_t num_samples,
+                           const float* jitter, uint32_t seed, int64_t* ridx, float* samples, float* depth, float* deltas,
+                           uint8_t* boundary, int32_t* rec_ray, wb_stream s);
+/* scale = ceil(1 / (2*sqrt(3)/num_samples)) (octree_as.py:336-338), computed by the caller. */
+int wb_raymarch_uniform_count(const float* nug_depth, int64_t Ng, int32_t scale, int32_t* cnt, wb_stream s);
+/* sample_offsets int64 [Ng+1] = scan of cnt; ray_nugget_offsets int64 [R+1] = scan of the raytrace counts. */
+int wb_raymarch_uniform_fill(const wb_rays* rays, const int32_t* nug_ridx, const float* nug_depth, int64_t Ng, int32_t scale,
+                             const int64_t* sample_offsets, const int64_t* ray_nugget_offsets,
+                             int64_t* ridx, float* samples, float* depth, float* deltas, uint8_t* boundary, int32_t* rec_ray, wb_stream s);
+
+/* ------------------------------------------------------------------------------------------------
  * HashGrid.interpolate kernels -- replace wisp._C.ops.hashgrid_interpolate_cuda / _backward_cuda
  *   (wisp/csrc/ops/hashgrid_interpolate.h:18-33, hashgrid_interpolate.cpp:46-105): all LODs in ONE launch.
  *   feats/grad_feats: [N, L*F] raw kernel output (the 'cat' zeroing / 'sum' reduction of hash_grid.py:224-233

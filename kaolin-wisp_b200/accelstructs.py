@@ -75,7 +75,24 @@ class OctreeAS:
         return ASQueryResults(pidx=ops.query(self.tensors(), coords, level, with_parents))
 
     def raytrace(self, rays, level=None, with_exit=False) -> ASRaytraceResults:
-        raise NotImplementedError("OctreeAS.raytrace ('voxel'/'uniform' marching) is the next row of the scope table (DESIGN.md)")
+        """octree_as.py:165-186: all ray / cell intersections ("nuggets") of `level`, by ray then front to back."""
+        if level is None:
+            level = self.max_level
+        ridx, pidx, depth, _ = ops.raytrace(self.tensors(), rays.origins, rays.dirs, level)
+        return ASRaytraceResults(ridx=ridx, pidx=pidx, depth=depth if with_exit else depth[:, 0:1].contiguous())
+
+    def _raymarch_nuggets(self, rays, num_samples, level, kind, jitter=None, seed=0) -> ASRaymarchResults:
+        _, ref = ops.march_nuggets(self.tensors(), rays.origins, rays.dirs, self.max_level if level is None else level, num_samples, kind,
+                                   reference_layout=True, jitter=jitter, seed=seed)
+        return ASRaymarchResults(pack_info=None, **ref)
+
+    def _raymarch_voxel(self, rays, num_samples, level=None, jitter=None, seed=0) -> ASRaymarchResults:
+        """octree_as.py:188-245."""
+        return self._raymarch_nuggets(rays, num_samples, level, 'voxel', jitter, seed)
+
+    def _raymarch_uniform(self, rays, num_samples, level=None) -> ASRaymarchResults:
+        """octree_as.py:311-374."""
+        return self._raymarch_nuggets(rays, num_samples, level, 'uniform')
 
     # --- raymarch (octree_as.py:380-429) ------------------------------------------------------------------------
     def _raymarch_ray(self, rays, num_samples, level=None, jitter=None, seed=0) -> ASRaymarchResults:
@@ -87,10 +104,12 @@ class OctreeAS:
     def raymarch(self, rays, raymarch_type, num_samples, level=None, jitter=None, seed=0) -> ASRaymarchResults:
         if level is None:
             level = self.max_level
-        if raymarch_type == 'ray':
+        if raymarch_type == 'voxel':
+            return self._raymarch_voxel(rays=rays, num_samples=num_samples, level=level, jitter=jitter, seed=seed)
+        elif raymarch_type == 'ray':
             return self._raymarch_ray(rays=rays, num_samples=num_samples, level=level, jitter=jitter, seed=seed)
-        elif raymarch_type in ('voxel', 'uniform'):
-            raise NotImplementedError(f"raymarch_type '{raymarch_type}' needs OctreeAS.raytrace: next scope row (DESIGN.md)")
+        elif raymarch_type == 'uniform':
+            return self._raymarch_uniform(rays=rays, num_samples=num_samples, level=level)
         else:
             raise TypeError(f"Raymarch sampler type: {raymarch_type} is not supported by OctreeAS.")
 

@@ -98,10 +98,11 @@ class MarchState:
     n: int
     jitter: Optional[torch.Tensor]
     seed: int
-    hitmask: torch.Tensor
-    counts: torch.Tensor
-    offsets: torch.Tensor
+    hitmask: Optional[torch.Tensor]
+    counts: Optional[torch.Tensor]
+    offsets: torch.Tensor            # int64 [R+1]: sample range of every ray
     total: int
+    records: Optional[tuple] = None  # (t, delta, ray) already produced by the 'voxel' / 'uniform' samplers
 
 
 def march_count(oct: OctreeTensors, origins, dirs, dist_min, dist_max, num_samples: int, level: int,
@@ -148,6 +149,8 @@ def march_fill_reference_layout(ms: MarchState, device):
 
 def march_fill_records(ms: MarchState, device):
     """Fused-path sample records: depth t, delta, ray index (12 B/sample)."""
+    if ms.records is not None:
+        return ms.records
     S = ms.total
     rec_t = torch.empty(S, dtype=torch.float32, device=device)
     rec_delta = torch.empty(S, dtype=torch.float32, device=device)
@@ -157,6 +160,84 @@ def march_fill_records(ms: MarchState, device):
             A.check(A.lib().wb_rf_march_fill(C.byref(ms.rays), C.c_int32(ms.n), A.ptr(ms.jitter), C.c_uint32(ms.seed), A.ptr(ms.hitmask),
                                              A.ptr(ms.offsets), A.ptr(rec_t), A.ptr(rec_delta), A.ptr(rec_ray), A.stream()))
     return rec_t, rec_delta, rec_ray
+
+
+# --------------------------------------------------------------------------------------------------------------
+# raytrace + 'voxel' / 'uniform' samplers
+# --------------------------------------------------------------------------------------------------------------
+def _scan(counts: torch.Tensor) -> torch.Tensor:
+    n = counts.shape[0]
+    offsets = torch.empty(n + 1, dtype=torch.int64, device=counts.device)
+    L = A.lib()
+    wsb = int(L.wb_scan_workspace_bytes(C.c_int64(n)))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=counts.device)
+    A.check(L.wb_scan_counts(A.ptr(counts), C.c_int64(n), A.ptr(offsets), A.ptr(ws), C.c_int64(wsb), A.stream()))
+    return offsets
+
+
+def raytrace(oct: OctreeTensors, origins, dirs, level: int):
+    """spc_render.unbatched_raytrace(..., return_depth=True, with_exit=True) (octree_as.py:183-185)
+    -> ridx int32 [Ng], pidx int32 [Ng], depth f32 [Ng,2], ray_offsets int64 [R+1]."""
+    A.require_device(origins)
+    rays, keep = A.make_rays(origins, dirs, 0.0, 0.0)
+    R, dev, L = rays.num_rays, origins.device, A.lib()
+    od = oct.desc()
+    counts = torch.empty(R, dtype=torch.int32, device=dev)
+    with _stage("raytrace_count"):
+        A.check(L.wb_raytrace_count(C.byref(od), C.c_int32(level), C.byref(rays), A.ptr(counts), A.stream()))
+    offsets = _scan(counts)
+    Ng = int(offsets[-1].item())
+    ridx = torch.empty(Ng, dtype=torch.int32, device=dev); pidx = torch.empty(Ng, dtype=torch.int32, device=dev)
+    depth = torch.empty((Ng, 2), dtype=torch.float32, device=dev)
+    if Ng > 0:
+        with _stage("raytrace_fill"):
+            A.check(L.wb_raytrace_fill(C.byref(od), C.c_int32(level), C.byref(rays), A.ptr(offsets), A.ptr(ridx), A.ptr(pidx), A.ptr(depth), A.stream()))
+    return ridx, pidx, depth, offsets
+
+
+def uniform_scale(num_samples: int) -> int:
+    """octree_as.py:336-338."""
+    import math
+    return int(math.ceil(1.0 / (2.0 * math.sqrt(3.0) / num_samples)))
+
+
+def march_nuggets(oct: OctreeTensors, origins, dirs, level: int, num_samples: int, kind: str, reference_layout: bool,
+                  jitter: Optional[torch.Tensor] = None, seed: int = 0):
+    """'voxel' / 'uniform' sampling on top of raytrace.  Returns (MarchState with records, reference-layout dict or None)."""
+    ridx_n, pidx_n, depth_n, ray_off = raytrace(oct, origins, dirs, level)
+    rays, keep = A.make_rays(origins, dirs, 0.0, 0.0)
+    R, dev, L = rays.num_rays, origins.device, A.lib()
+    Ng = ridx_n.shape[0]
+    if kind == 'voxel':
+        S = Ng * num_samples
+        sample_off = None
+    else:
+        scale = uniform_scale(num_samples)
+        cnt = torch.empty(Ng, dtype=torch.int32, device=dev)
+        A.check(L.wb_raymarch_uniform_count(A.ptr(depth_n), C.c_int64(Ng), C.c_int32(scale), A.ptr(cnt), A.stream()))
+        sample_off = _scan(cnt)
+        S = int(sample_off[-1].item())
+    t = torch.empty(S, dtype=torch.float32, device=dev); dl = torch.empty(S, dtype=torch.float32, device=dev)
+    rr = torch.empty(S, dtype=torch.int32, device=dev)
+    ref = None
+    ridx = samples = boundary = None
+    if reference_layout:
+        ridx = torch.empty(S, dtype=torch.int64, device=dev); samples = torch.empty((S, 3), dtype=torch.float32, device=dev)
+        boundary = torch.empty(S, dtype=torch.bool, device=dev)
+    jit = None if jitter is None else A.f32c(jitter)
+    with _stage("march_" + kind):
+        if kind == 'voxel':
+            A.check(L.wb_raymarch_voxel_fill(C.byref(rays), A.ptr(ridx_n), A.ptr(depth_n), C.c_int64(Ng), C.c_int32(num_samples), A.ptr(jit),
+                                             C.c_uint32(seed & 0xFFFFFFFF), A.ptr(ridx), A.ptr(samples), A.ptr(t), A.ptr(dl), A.ptr(boundary), A.ptr(rr), A.stream()))
+            offsets = ray_off * num_samples
+        else:
+            A.check(L.wb_raymarch_uniform_fill(C.byref(rays), A.ptr(ridx_n), A.ptr(depth_n), C.c_int64(Ng), C.c_int32(scale), A.ptr(sample_off), A.ptr(ray_off),
+                                               A.ptr(ridx), A.ptr(samples), A.ptr(t), A.ptr(dl), A.ptr(boundary), A.ptr(rr), A.stream()))
+            offsets = sample_off[ray_off]
+    ms = MarchState(rays, keep, num_samples, None, seed & 0xFFFFFFFF, None, None, offsets.contiguous(), S, records=(t, dl, rr))
+    if reference_layout:
+        ref = dict(ridx=ridx, samples=samples, depth_samples=t[:, None], deltas=dl[:, None], boundary=boundary)
+    return ms, ref
 
 
 # --------------------------------------------------------------------------------------------------------------

@@ -64,10 +64,16 @@ class PackedRFTracer(nn.Module):
         jitter, seed = self.jitter, self.seed
         self.seed = (self.seed + 1) & 0x7FFFFFFF
         spec = nef.fused_spec(lod_idx) if hasattr(nef, "fused_spec") else None
-        if spec is not None and raymarch_type == 'ray' and not extra_channels:
+        if raymarch_type not in ('ray', 'voxel', 'uniform'):
+            raise TypeError(f"Raymarch sampler type: {raymarch_type} is not supported by OctreeAS.")       # octree_as.py:427
+        if spec is not None and not extra_channels:
             blas = nef.grid.blas
-            ms = ops.march_count(blas.tensors(), rays.origins, rays.dirs, rays.dist_min, rays.dist_max, num_steps, blas.max_level,
-                                 jitter=jitter, seed=seed)
+            if raymarch_type == 'ray':
+                ms = ops.march_count(blas.tensors(), rays.origins, rays.dirs, rays.dist_min, rays.dist_max, num_steps, blas.max_level,
+                                     jitter=jitter, seed=seed)
+            else:
+                ms, _ = ops.march_nuggets(blas.tensors(), rays.origins, rays.dirs, blas.max_level, num_steps, raymarch_type,
+                                          reference_layout=False, jitter=jitter, seed=seed)
             self.prev_num_samples = ms.total
             rgb, depth, alpha, hit = ops.rf_trace(ms, spec, nef.grid.codebook.feats, nef.decoder_density.packed_params(),
                                                   nef.decoder_color.packed_params(), self.bg_color, precision=self.precision)

@@ -113,11 +113,41 @@ def gen_rf_trace(name, *, level, res, hw, n_steps, num_lods, bw, min_res, max_re
     print(name, "R", R, "S", tracer.get_prev_num_samples(), "hit", int(rb.hit.sum()), "loss", float(lossv))
 
 
+def gen_raymarch_nuggets():
+    """OctreeAS._raymarch_voxel / _raymarch_uniform executed by the reference Python (octree_as.py:188-245, 311-374):
+    pins sample_from_depth_intervals, expand_pack_boundary, the lattice scale, zero-count filtering and the deltas."""
+    from wisp.accelstructs import OctreeAS
+    from wisp.core import Rays
+    level, n_v, n_u = 5, 6, 96
+    oct_np = O.points_to_octree(O.lego_like_points(level), level)
+    blas = OctreeAS(torch.from_numpy(oct_np))
+    o, d = O.look_at_rays([-3.0, 0.65, -3.0], [0, 0, 0], 20, 20, 30.0)
+    rays = Rays(torch.from_numpy(o), torch.from_numpy(d), dist_min=0.0, dist_max=10.0)
+    rt = blas.raytrace(rays, level, with_exit=True)
+    Ng = rt.ridx.shape[0]
+    jit = np.random.default_rng(11).random((Ng, n_v), dtype=np.float32)
+    orig = torch.rand_like
+    torch.rand_like = lambda t, **k: torch.from_numpy(jit)
+    try:
+        mv = blas.raymarch(rays, 'voxel', n_v, level)
+    finally:
+        torch.rand_like = orig
+    mu = blas.raymarch(rays, 'uniform', n_u, level)
+    np.savez_compressed(os.path.join(OUT, "raymarch_nuggets.npz"), octree=oct_np, level=level, origins=o, dirs=d, n_voxel=n_v, n_uniform=n_u,
+                        jitter=jit, nug_ridx=rt.ridx.numpy(), nug_pidx=rt.pidx.numpy(), nug_depth=rt.depth.numpy(),
+                        v_ridx=mv.ridx.numpy(), v_samples=mv.samples.numpy(), v_depth=mv.depth_samples.numpy(), v_deltas=mv.deltas.numpy(),
+                        v_boundary=mv.boundary.numpy(),
+                        u_ridx=mu.ridx.numpy(), u_samples=mu.samples.numpy(), u_depth=mu.depth_samples.numpy(), u_deltas=mu.deltas.numpy(),
+                        u_boundary=mu.boundary.numpy())
+    print("raymarch_nuggets", Ng, mv.ridx.shape, mu.ridx.shape)
+
+
 def main():
     warnings.filterwarnings("ignore")
     ref_import.install()
     os.makedirs(OUT, exist_ok=True)
     gen_hashgrid_naive()
+    gen_raymarch_nuggets()
     # A: miniature of BASELINE config 2 (cat, bias, positional view embedding, sparse lego-like octree)
     gen_rf_trace("rf_trace_cat", level=5, res=None, hw=24, n_steps=96, num_lods=6, bw=11, min_res=4, max_res=48, hidden=32,
                  num_layers=1, bias=True, multiscale="cat", view_embedder="positional", near=0.0, far=10.0, bg=(1.0, 1.0, 1.0))

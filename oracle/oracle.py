@@ -429,3 +429,54 @@ def rf_step(spc, nef: Nef, origins, dirs, near, far, num_steps, target, loss="hu
     lt = {"l2": 0, "l1": 1, "huber": 2}[loss]
     val = lib().wo_rf_step(*args, _p(target), C.c_int(lt), _p(rgb), _p(gt), _p(gdens), _p(gcol), C.byref(total))
     return dict(loss=float(val), rgb=rgb, table=gt, dens=gdens, col=gcol, num_samples=int(total.value))
+
+
+# ----------------------------------------------------------------------------------------------
+# raytrace + 'voxel' / 'uniform' marching
+# ----------------------------------------------------------------------------------------------
+def raytrace(spc: SPC, origins, dirs, level: Optional[int] = None):
+    """OctreeAS.raytrace(with_exit=True) (octree_as.py:165-186) -> ridx i32[Ng], pidx i32[Ng], depth f32[Ng,2], counts i32[R]."""
+    level = spc.max_level if level is None else level
+    o, d = _f32(origins), _f32(dirs)
+    R = o.shape[0]
+    lib().wo_raytrace_count.restype = C.c_int64
+    counts = np.zeros(R, dtype=np.int32)
+    total = int(lib().wo_raytrace_count(_p(spc.octree), _p(spc.prefix), C.c_int(level), _p(o), _p(d), C.c_int64(R), _p(counts)))
+    offsets = np.zeros(R, dtype=np.int64)
+    np.cumsum(counts[:-1], out=offsets[1:])
+    ridx = np.zeros(total, np.int32); pidx = np.zeros(total, np.int32); depth = np.zeros((total, 2), np.float32)
+    lib().wo_raytrace_fill(_p(spc.octree), _p(spc.prefix), C.c_int(level), _p(o), _p(d), C.c_int64(R), _p(offsets), _p(ridx), _p(pidx), _p(depth))
+    return dict(ridx=ridx, pidx=pidx, depth=depth, counts=counts)
+
+
+def raymarch_voxel(spc: SPC, origins, dirs, num_samples: int, level: Optional[int] = None, jitter_arr=None, seed: int = 0):
+    """OctreeAS._raymarch_voxel (octree_as.py:188-245)."""
+    o, d = _f32(origins), _f32(dirs)
+    rt = raytrace(spc, o, d, level)
+    Ng = rt["ridx"].shape[0]
+    S = Ng * num_samples
+    jit = None if jitter_arr is None else _f32(jitter_arr)
+    ridx = np.zeros(S, np.int64); samples = np.zeros((S, 3), np.float32); depth = np.zeros(S, np.float32)
+    deltas = np.zeros(S, np.float32); boundary = np.zeros(S, np.uint8)
+    lib().wo_raymarch_voxel(_p(o), _p(d), _p(rt["ridx"]), _p(rt["depth"]), C.c_int64(Ng), C.c_int(num_samples), _p(jit), C.c_uint32(seed),
+                            _p(ridx), _p(samples), _p(depth), _p(deltas), _p(boundary))
+    return dict(ridx=ridx, samples=samples, depth_samples=depth[:, None], deltas=deltas[:, None], boundary=boundary.astype(bool), nuggets=rt)
+
+
+def raymarch_uniform(spc: SPC, origins, dirs, num_samples: int, level: Optional[int] = None):
+    """OctreeAS._raymarch_uniform (octree_as.py:311-374)."""
+    o, d = _f32(origins), _f32(dirs)
+    rt = raytrace(spc, o, d, level)
+    Ng = rt["ridx"].shape[0]
+    scale = int(lib().wo_uniform_scale(C.c_int(num_samples)))
+    lib().wo_raymarch_uniform_count.restype = C.c_int64
+    cnt = np.zeros(Ng, np.int32)
+    S = int(lib().wo_raymarch_uniform_count(_p(rt["depth"]), C.c_int64(Ng), C.c_int(scale), _p(cnt)))
+    offsets = np.zeros(max(Ng, 1), np.int64)
+    if Ng > 1:
+        np.cumsum(cnt[:-1], out=offsets[1:Ng])
+    ridx = np.zeros(S, np.int64); samples = np.zeros((S, 3), np.float32); depth = np.zeros(S, np.float32)
+    deltas = np.zeros(S, np.float32); boundary = np.zeros(S, np.uint8)
+    lib().wo_raymarch_uniform_fill(_p(o), _p(d), _p(rt["ridx"]), _p(rt["depth"]), C.c_int64(Ng), C.c_int(scale), _p(cnt), _p(offsets),
+                                   _p(ridx), _p(samples), _p(depth), _p(deltas), _p(boundary))
+    return dict(ridx=ridx, samples=samples, depth_samples=depth[:, None], deltas=deltas[:, None], boundary=boundary.astype(bool), nuggets=rt, scale=scale)

@@ -194,6 +194,31 @@ def _hashgrid_interpolate_backward_cuda(coords, grad_output, codebook, codebook_
     return [torch.empty(0), torch.from_numpy(g)]
 
 
+def _unbatched_raytrace(octree, points, pyramid, prefix, origins, dirs, level, return_depth=True, with_exit=False):
+    rt = O.raytrace(_spc_from(octree), _np(origins), _np(dirs), level)
+    depth = rt["depth"] if with_exit else rt["depth"][:, :1]
+    return torch.from_numpy(rt["ridx"]), torch.from_numpy(rt["pidx"]), torch.from_numpy(np.ascontiguousarray(depth))
+
+
+def _uniform_sample_cuda(scale, ridx, depth, insum):
+    """wisp/csrc/ops/uniform_sample_cuda.cu:18-59 restated with numpy (one 'thread' per nugget)."""
+    ridx_n, depth_n, insum_n = _np(ridx), _np(depth), _np(insum)
+    V = ridx_n.shape[0]
+    total = int(insum_n[-1]) if V > 0 else 0
+    new_ridx = np.zeros(total, np.int64); ds = np.zeros((total, 1), np.float32); boundary = np.zeros(total, bool)
+    inv_scale = np.float32(1.0) / np.float32(scale)
+    for t in range(V):
+        base = int(insum_n[t - 1]) if t > 0 else 0
+        n = int(insum_n[t]) - base
+        first = np.ceil(np.float32(scale) * depth_n[t, 0]).astype(np.float32)
+        bval = True if t == 0 else bool(ridx_n[t] != ridx_n[t - 1])
+        f = np.float32(0.0)
+        for i in range(n):
+            ds[base + i, 0] = inv_scale * (first + f); f += np.float32(1.0)
+            new_ridx[base + i] = ridx_n[t]; boundary[base + i] = bval; bval = False
+    return [torch.from_numpy(new_ridx), torch.from_numpy(ds), torch.from_numpy(boundary)]
+
+
 _installed = False
 
 
@@ -213,6 +238,7 @@ def install():
     sys.modules["wisp"] = pkg
     import kaolin.ops.spc as spc_ops          # noqa: stubs
     import kaolin.render.spc as spc_render
+    import kaolin._C.render.spc as kaolin_C_render_spc
     import wisp._C as wisp_C
     import wisp._C.ops as wisp_C_ops
     spc_ops.unbatched_query = _unbatched_query
@@ -223,6 +249,9 @@ def install():
     spc_ops.points_to_corners = _points_to_corners
     spc_render.mark_pack_boundaries = _mark_pack_boundaries
     spc_render.mark_first_hit = _mark_pack_boundaries
+    spc_render.unbatched_raytrace = _unbatched_raytrace
+    kaolin_C_render_spc.inclusive_sum_cuda = lambda t: torch.cumsum(t, 0).int()
+    wisp_C_ops.uniform_sample_cuda = _uniform_sample_cuda
     spc_render.sum_reduce = _sum_reduce
     spc_render.cumsum = _cumsum
     spc_render.exponential_integration = _exponential_integration

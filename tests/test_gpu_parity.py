@@ -327,3 +327,75 @@ def test_tcgen05_operand_layouts(W, mode, N, K):
     A.check(A.lib().wb_tc_selftest(A.ptr(ta), C.c_int(a.size), A.ptr(tb), C.c_int(b.size), A.ptr(D), C.c_int(N), C.c_int(K), C.c_int(mode), A.stream()))
     torch.cuda.synchronize()
     np.testing.assert_allclose(D.cpu().numpy(), ref, atol=2e-3, rtol=1e-3)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# raytrace + 'voxel' / 'uniform' samplers
+# ---------------------------------------------------------------------------------------------------------------
+def test_raytrace_voxel_uniform_golden(W, golden_dir):
+    """Kernels vs what the reference's own _raymarch_voxel / _raymarch_uniform produced (bit-exact)."""
+    g = np.load(os.path.join(golden_dir, "raymarch_nuggets.npz"))
+    blas = W.OctreeAS(dev(g["octree"]))
+    rays = W.Rays(dev(g["origins"]), dev(g["dirs"]), 0.0, 10.0)
+    level = int(g["level"])
+    rt = blas.raytrace(rays, level, with_exit=True)
+    assert rt.ridx.dtype == torch.int32 and rt.depth.shape[1] == 2
+    assert np.array_equal(rt.ridx.cpu().numpy(), g["nug_ridx"]) and np.array_equal(rt.pidx.cpu().numpy(), g["nug_pidx"])
+    assert np.array_equal(rt.depth.cpu().numpy(), g["nug_depth"])
+    assert blas.raytrace(rays, level, with_exit=False).depth.shape[1] == 1
+    mv = blas.raymarch(rays, 'voxel', int(g["n_voxel"]), level, jitter=dev(g["jitter"]))
+    mu = blas.raymarch(rays, 'uniform', int(g["n_uniform"]), level)
+    for m, pre in ((mv, "v_"), (mu, "u_")):
+        assert np.array_equal(m.ridx.cpu().numpy(), g[pre + "ridx"])
+        assert np.array_equal(m.samples.cpu().numpy(), g[pre + "samples"])
+        assert np.array_equal(m.depth_samples.cpu().numpy(), g[pre + "depth"])
+        assert np.array_equal(m.deltas.cpu().numpy(), g[pre + "deltas"])
+        assert np.array_equal(m.boundary.cpu().numpy(), g[pre + "boundary"])
+        assert m.ridx.dtype == torch.int64 and m.boundary.dtype == torch.bool
+
+
+@pytest.mark.parametrize("level,lvl_trace", [(7, 7), (7, 4), (5, 0)])
+def test_raytrace_seeded_vs_oracle(W, level, lvl_trace):
+    spc = O.octree_to_spc(O.points_to_octree(O.lego_like_points(level), level))
+    o, d = O.look_at_rays([-3.0, 0.65, -3.0], [0, 0, 0], 64, 64, 30.0)
+    o = np.concatenate([o, np.array([[0.05, 0.02, -0.03]], np.float32)]); d = np.concatenate([d, np.array([[0.0, 0.0, 1.0]], np.float32)])
+    blas = W.OctreeAS(dev(spc.octree))
+    rt = blas.raytrace(W.Rays(dev(o), dev(d)), lvl_trace, with_exit=True)
+    ref = O.raytrace(spc, o, d, lvl_trace)
+    assert np.array_equal(rt.ridx.cpu().numpy(), ref["ridx"]) and np.array_equal(rt.pidx.cpu().numpy(), ref["pidx"])
+    assert np.array_equal(rt.depth.cpu().numpy(), ref["depth"])
+    mv = blas.raymarch(W.Rays(dev(o), dev(d)), 'voxel', 5, lvl_trace, seed=9)
+    rv = O.raymarch_voxel(spc, o, d, 5, lvl_trace, seed=9)
+    assert np.array_equal(mv.depth_samples.cpu().numpy(), rv["depth_samples"]) and np.array_equal(mv.deltas.cpu().numpy(), rv["deltas"])
+    assert np.array_equal(mv.boundary.cpu().numpy(), rv["boundary"]) and np.array_equal(mv.samples.cpu().numpy(), rv["samples"])
+
+
+@pytest.mark.parametrize("kind,n", [("voxel", 3), ("uniform", 160)])
+def test_fused_trace_with_nugget_samplers(W, kind, n):
+    """PackedRFTracer(raymarch_type='voxel'|'uniform'): fused route == unfused route == oracle nef + compositing."""
+    from gpu_util import nef_from_oracle
+    onef = O.make_nef(num_lods=6, codebook_bitwidth=12, min_res=4, max_res=64, hidden_dim=32, feature_std=0.5, seed=4)
+    spc = O.octree_to_spc(O.points_to_octree(O.lego_like_points(5), 5))
+    o, d = O.look_at_rays([-3.0, 0.65, -3.0], [0, 0, 0], 24, 24, 30.0)
+    outs = []
+    for fused in (True, False):
+        nef, blas = nef_from_oracle(onef, spc)
+        if not fused:
+            nef.fused_spec = lambda lod_idx=None: None
+        tr = W.PackedRFTracer(kind, n, bg_color=(1.0, 1.0, 1.0)); tr.seed = 21
+        rb = tr(nef, rays=W.Rays(dev(o), dev(d), 0.0, 10.0), channels=["rgb", "depth", "alpha", "hit"])
+        outs.append((rb, tr.get_prev_num_samples()))
+    (a, sa), (b, sb) = outs
+    assert sa == sb > 0
+    np.testing.assert_allclose(a.rgb.detach().cpu().numpy(), b.rgb.detach().cpu().numpy(), atol=2e-5)
+    np.testing.assert_allclose(a.depth.detach().cpu().numpy(), b.depth.detach().cpu().numpy(), atol=2e-4)
+    # oracle: samples from the oracle marcher, field + compositing from the oracle
+    mr = O.raymarch_voxel(spc, o, d, n, seed=21) if kind == "voxel" else O.raymarch_uniform(spc, o, d, n)
+    assert mr["ridx"].shape[0] == sa
+    rgb_s, dens_s = O.nef_rgba(onef, mr["samples"], d[mr["ridx"]])
+    cols, w = O.exponential_integration(rgb_s, dens_s[:, 0] * mr["deltas"][:, 0], mr["boundary"])
+    alpha = O.sum_reduce(w, mr["boundary"])
+    exp_rgb = np.ones((o.shape[0], 3), np.float32)
+    hit_rays = mr["ridx"][mr["boundary"]]
+    exp_rgb[hit_rays] = (1.0 - alpha) + cols
+    np.testing.assert_allclose(a.rgb.detach().cpu().numpy(), exp_rgb, atol=1e-4)

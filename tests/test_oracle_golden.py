@@ -96,3 +96,42 @@ def test_jitter_stream_properties():
     assert v.min() >= 0.0 and v.max() < 1.0
     assert abs(v.mean() - 0.5) < 0.06
     assert len(np.unique(v)) > 500
+
+
+def test_raymarch_voxel_uniform_golden(golden_dir):
+    """OctreeAS._raymarch_voxel / _raymarch_uniform run by the reference Python vs the oracle restatement: bit-exact."""
+    g = np.load(os.path.join(golden_dir, "raymarch_nuggets.npz"))
+    spc = O.octree_to_spc(g["octree"])
+    rt = O.raytrace(spc, g["origins"], g["dirs"], int(g["level"]))
+    assert np.array_equal(rt["ridx"], g["nug_ridx"]) and np.array_equal(rt["pidx"], g["nug_pidx"]) and np.array_equal(rt["depth"], g["nug_depth"])
+    mv = O.raymarch_voxel(spc, g["origins"], g["dirs"], int(g["n_voxel"]), int(g["level"]), jitter_arr=g["jitter"])
+    for k, ref in (("ridx", "v_ridx"), ("samples", "v_samples"), ("depth_samples", "v_depth"), ("deltas", "v_deltas"), ("boundary", "v_boundary")):
+        assert np.array_equal(mv[k], g[ref]), k
+    mu = O.raymarch_uniform(spc, g["origins"], g["dirs"], int(g["n_uniform"]), int(g["level"]))
+    for k, ref in (("ridx", "u_ridx"), ("samples", "u_samples"), ("depth_samples", "u_depth"), ("deltas", "u_deltas"), ("boundary", "u_boundary")):
+        assert np.array_equal(mu[k], g[ref]), k
+
+
+def test_raytrace_against_brute_force():
+    """Nugget set == all occupied level cells whose slab intersection is positive and in front of the origin; entry depths
+    non-decreasing along each ray; the root level (AABB tracing, triplanar_grid.py:145-150) gives at most one nugget per ray."""
+    spc = O.octree_to_spc(O.points_to_octree(O.lego_like_points(4), 4))
+    o, d = O.look_at_rays([-3.0, 0.65, -3.0], [0, 0, 0], 24, 24, 30.0)
+    o = np.concatenate([o, np.array([[0.05, 0.02, -0.03], [0.3, 0.3, 0.3]], np.float32)])       # origins inside the volume
+    d = np.concatenate([d, np.array([[0.0, 0.0, 1.0], [-0.57735, -0.57735, -0.57735]], np.float32)])
+    rt = O.raytrace(spc, o, d)
+    lvl = spc.points[spc.pyramid[1, 4]: spc.pyramid[1, 4] + spc.pyramid[0, 4]].astype(np.int64)
+    size = np.float32(2.0 / 16)
+    for r in list(range(0, o.shape[0], 11)) + [o.shape[0] - 2, o.shape[0] - 1]:
+        lo = (lvl.astype(np.float32) * size - np.float32(1.0)); hi = lo + size
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ta, tb = (lo - o[r]) / d[r], (hi - o[r]) / d[r]
+            te = np.where(d[r] != 0, np.minimum(ta, tb), -np.inf).max(1); tx = np.where(d[r] != 0, np.maximum(ta, tb), np.inf).min(1)
+        inside_zero = np.all((d[r] != 0) | ((o[r] >= lo) & (o[r] <= hi)), axis=1)
+        hit = (tx > np.maximum(te, 0)) & inside_zero
+        mine = rt["pidx"][rt["ridx"] == r] - spc.pyramid[1, 4]
+        assert set(mine.tolist()) == set(np.nonzero(hit)[0].tolist()), r
+        dd = rt["depth"][rt["ridx"] == r]
+        assert (np.diff(dd[:, 0]) >= 0).all() and (dd[:, 1] > dd[:, 0]).all() and (dd[:, 0] >= 0).all()
+    root = O.raytrace(spc, o, d, 0)
+    assert root["counts"].max() == 1 and (root["pidx"] == 0).all()
