@@ -154,6 +154,18 @@ int wb_hashgrid_bwd(const float* coords, int64_t N, const wb_nef_desc* grid, con
                     float* grad_table, wb_stream s);
 
 /* ------------------------------------------------------------------------------------------------
+ * TriplanarGrid.interpolate (wisp/models/grids/triplanar_grid.py:98-143, 205-223): replaces 3 F.grid_sample launches per LOD
+ * (align_corners=True, padding_mode='reflection') plus the stack/permute/cat copies.  res[l] = 2^(log_base_resolution + l);
+ * planes: HOST array of 3*num_lods device pointers (fmx, fmy, fmz of LOD 0, then LOD 1, ...), each [1, fdim, res+1, res+1];
+ * feats / grad_feats: [N, num_lods, 3, fdim] (the reference's cat layout; 'sum' is applied by the caller);
+ * grad_planes: same shapes as planes, accumulated into (caller zeroes).
+ * ---------------------------------------------------------------------------------------------- */
+int wb_triplane_fwd(const float* coords, int64_t N, int32_t num_lods, int32_t fdim, const int32_t* res,
+                    const float* const* planes, float* feats, wb_stream s);
+int wb_triplane_bwd(const float* coords, int64_t N, int32_t num_lods, int32_t fdim, const int32_t* res,
+                    const float* const* planes, const float* grad_feats, float* const* grad_planes, wb_stream s);
+
+/* ------------------------------------------------------------------------------------------------
  * Packed compositing -- replaces kaolin.render.spc.{exponential_integration, sum_reduce} + the buffer
  *   scatter of PackedRFTracer.trace (wisp/tracers/packed_rf_tracer.py:136-165).
  *   shaded: float4 [S] = (r, g, b, sigma); offsets int64 [R+1]; depth/deltas [S].

@@ -121,3 +121,13 @@ class OctreeAS:
 
     def name(self) -> str:
         return "Octree"
+
+
+class AxisAlignedBBoxAS(OctreeAS):
+    """wisp.accelstructs.AxisAlignedBBoxAS (aabb_as.py:13-27): a one-level dense octree used as a bounding box."""
+
+    def __init__(self, device="cuda"):
+        super().__init__(spc.create_dense_octree(1, device=device))
+
+    def name(self) -> str:
+        return "AABB"

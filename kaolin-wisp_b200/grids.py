@@ -118,3 +118,64 @@ class HashGrid(nn.Module):
 
     def name(self) -> str:
         return "Hash Grid"
+
+
+class TriplanarFeatureVolume(nn.Module):
+    """One LOD of a TriplanarGrid: three [1, fdim, fsize+1, fsize+1] feature planes (triplanar_grid.py:184-203)."""
+
+    def __init__(self, fdim, fsize, std, bias):
+        super().__init__()
+        self.fsize, self.fdim = fsize, fdim
+        self.fmx = nn.Parameter(torch.randn(1, fdim, fsize + 1, fsize + 1) * std + bias)
+        self.fmy = nn.Parameter(torch.randn(1, fdim, fsize + 1, fsize + 1) * std + bias)
+        self.fmz = nn.Parameter(torch.randn(1, fdim, fsize + 1, fsize + 1) * std + bias)
+        self.padding_mode = 'reflection'
+
+
+class TriplanarGrid(nn.Module):
+    """wisp.models.grids.TriplanarGrid (triplanar_grid.py:24-150): parameter names features.N.fmx/fmy/fmz as in the reference."""
+
+    def __init__(self, blas, feature_dim: int, log_base_resolution: int = 4, num_lods: int = 1, interpolation_type: str = 'linear',
+                 multiscale_type: str = 'sum', feature_std: float = 0.0, feature_bias: float = 0.0):
+        super().__init__()
+        if interpolation_type != 'linear':
+            raise ValueError(f"Interpolation mode '{interpolation_type}' is not supported")       # triplanar_grid.py:141
+        self.blas = blas
+        self.feature_dim = feature_dim * 3          # the reference multiplies by 3 planes (:74)
+        self.num_lods, self.log_base_resolution = num_lods, log_base_resolution
+        self.interpolation_type, self.multiscale_type = interpolation_type, multiscale_type
+        self.feature_std, self.feature_bias = feature_std, feature_bias
+        self.active_lods = [log_base_resolution + x for x in range(num_lods)]
+        self.features = nn.ModuleList([TriplanarFeatureVolume(feature_dim, 2 ** i, feature_std, feature_bias) for i in self.active_lods])
+        self.num_feat = sum(((2 ** i + 1) ** 2) * self.feature_dim * 3 for i in self.active_lods)
+
+    def freeze(self):
+        self.features.requires_grad_(False)
+
+    def interpolate(self, coords, lod_idx):
+        """triplanar_grid.py:98-121."""
+        output_shape = coords.shape[:-1]
+        if coords.ndim < 3:
+            coords = coords[:, None]                 # (batch, 3) -> (batch, num_samples, 3), as the reference (:110-111)
+        planes = []
+        for i in range(lod_idx + 1):
+            f = self.features[i]
+            planes += [f.fmx, f.fmy, f.fmz]
+        feats = ops.TriplaneInterpolate.apply(coords.reshape(-1, 3), lod_idx + 1, *planes)
+        feats = feats.reshape(*coords.shape[:-1], feats.shape[-1])      # 'cat' keeps the inflated shape in the reference
+        if self.multiscale_type == 'sum':
+            feats = feats.reshape(*output_shape, lod_idx + 1, feats.shape[-1] // (lod_idx + 1)).sum(-2)
+        return feats
+
+    def raymarch(self, rays, raymarch_type, num_samples, level=None, **kw) -> ASRaymarchResults:
+        """triplanar_grid.py:145-150: the blas is only used as an AABB tracer (level 0)."""
+        return self.blas.raymarch(rays, raymarch_type=raymarch_type, num_samples=num_samples, level=0, **kw)
+
+    def raytrace(self, rays, level=None, with_exit=False):
+        return self.blas.raytrace(rays, level=level, with_exit=with_exit)
+
+    def query(self, coords, level=None, with_parents=False):
+        return self.blas.query(coords, level=level, with_parents=with_parents)
+
+    def name(self) -> str:
+        return "Triplanar Grid"

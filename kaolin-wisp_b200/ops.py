@@ -286,6 +286,40 @@ def hashgrid(coords, codebook_bitwidth, lod_idx, codebook):
 
 
 # --------------------------------------------------------------------------------------------------------------
+# triplanar grid interpolate
+# --------------------------------------------------------------------------------------------------------------
+class TriplaneInterpolate(torch.autograd.Function):
+    """All LODs x 3 planes of TriplanarGrid.interpolate in one launch (triplanar_grid.py:98-143, 205-223).
+    planes: fmx, fmy, fmz of LOD 0, then LOD 1, ... each [1, fdim, res+1, res+1].  Returns [N, num_lods*3*fdim]."""
+
+    @staticmethod
+    def forward(ctx, coords, num_lods, *planes):
+        A.require_device(planes[0])
+        c = A.f32c(coords)
+        N, fdim = c.shape[0], planes[0].shape[1]
+        pl = [A.f32c(p.detach()) for p in planes[:3 * num_lods]]
+        res = (C.c_int32 * num_lods)(*[pl[3 * l].shape[-1] - 1 for l in range(num_lods)])
+        ptrs = (C.c_void_p * (3 * num_lods))(*[p.data_ptr() for p in pl])
+        feats = torch.empty((N, num_lods * 3 * fdim), dtype=torch.float32, device=c.device)
+        A.check(A.lib().wb_triplane_fwd(A.ptr(c), C.c_int64(N), C.c_int32(num_lods), C.c_int32(fdim), res, ptrs, A.ptr(feats), A.stream()))
+        ctx.save_for_backward(c, *pl)
+        ctx.num_lods, ctx.nplanes = num_lods, len(planes)
+        return feats
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        c, *pl = ctx.saved_tensors
+        num_lods, fdim = ctx.num_lods, pl[0].shape[1]
+        g = A.f32c(grad_output)
+        gp = [torch.zeros_like(p) for p in pl]
+        res = (C.c_int32 * num_lods)(*[pl[3 * l].shape[-1] - 1 for l in range(num_lods)])
+        ptrs = (C.c_void_p * (3 * num_lods))(*[p.data_ptr() for p in pl])
+        gptrs = (C.c_void_p * (3 * num_lods))(*[p.data_ptr() for p in gp])
+        A.check(A.lib().wb_triplane_bwd(A.ptr(c), C.c_int64(c.shape[0]), C.c_int32(num_lods), C.c_int32(fdim), res, ptrs, A.ptr(g), gptrs, A.stream()))
+        return (None, None, *gp, *([None] * (ctx.nplanes - len(gp))))
+
+
+# --------------------------------------------------------------------------------------------------------------
 # packed compositing
 # --------------------------------------------------------------------------------------------------------------
 def _bg3(bg) -> "C.Array":

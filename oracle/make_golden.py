@@ -142,12 +142,36 @@ def gen_raymarch_nuggets():
     print("raymarch_nuggets", Ng, mv.ridx.shape, mu.ridx.shape)
 
 
+def gen_triplanar():
+    """TriplanarGrid.interpolate (triplanar_grid.py:98-143, 205-223) forward + gradients, executed by the reference class
+    (three F.grid_sample calls per LOD on CPU).  Coordinates reach outside [-1,1] to exercise the reflection padding."""
+    from wisp.models.grids.triplanar_grid import TriplanarGrid
+    torch.manual_seed(4)
+    out = {}
+    for ms in ("sum", "cat"):
+        grid = TriplanarGrid(None, feature_dim=4, log_base_resolution=2, num_lods=3, multiscale_type=ms, feature_std=1.0)
+        coords = torch.rand(301, 3) * 2.8 - 1.4
+        coords[:8] = torch.tensor([[-1.0, -1.0, -1.0], [1.0, 1.0, 1.0], [0.0, 0.0, 0.0], [1.0, -1.0, 0.5], [0.25, 0.5, -0.75],
+                                   [-1.4, 1.4, 0.0], [2.5, -2.5, 3.1], [0.999999, -0.999999, 1e-7]])
+        feats = grid.interpolate(coords, 2)
+        go = torch.randn_like(feats)
+        feats.backward(go)
+        planes = [getattr(f, n) for f in grid.features for n in ("fmx", "fmy", "fmz")]
+        out[ms] = dict(coords=coords.numpy(), feats=feats.detach().numpy(), go=go.numpy(),
+                       **{f"plane{i}": p.detach().numpy() for i, p in enumerate(planes)}, **{f"gplane{i}": p.grad.numpy() for i, p in enumerate(planes)})
+        # a lower lod_idx uses only the first LODs
+        out[ms]["feats_lod0"] = grid.interpolate(coords, 0).detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "triplanar.npz"), **{f"{ms}_{k}": v for ms, d in out.items() for k, v in d.items()})
+    print("triplanar", out["sum"]["feats"].shape, out["cat"]["feats"].shape)
+
+
 def main():
     warnings.filterwarnings("ignore")
     ref_import.install()
     os.makedirs(OUT, exist_ok=True)
     gen_hashgrid_naive()
     gen_raymarch_nuggets()
+    gen_triplanar()
     # A: miniature of BASELINE config 2 (cat, bias, positional view embedding, sparse lego-like octree)
     gen_rf_trace("rf_trace_cat", level=5, res=None, hw=24, n_steps=96, num_lods=6, bw=11, min_res=4, max_res=48, hidden=32,
                  num_layers=1, bias=True, multiscale="cat", view_embedder="positional", near=0.0, far=10.0, bg=(1.0, 1.0, 1.0))
