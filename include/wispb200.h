@@ -166,6 +166,26 @@ int wb_triplane_bwd(const float* coords, int64_t N, int32_t num_lods, int32_t fd
                     const float* const* planes, const float* grad_feats, float* const* grad_planes, wb_stream s);
 
 /* ------------------------------------------------------------------------------------------------
+ * OctreeGrid.interpolate (wisp/models/grids/octree_grid.py:130-219): replaces blas.query(with_parents=True) + one
+ * kaolin unbatched_interpolate_trilinear launch per LOD + cat/sum.  points int16 [T,3] and trinkets int32 [T,8] are the
+ * tensors the reference keeps (blas.points, grid.trinkets: LEVEL-LOCAL corner-feature indices); feats: HOST array of
+ * num_lods_used device pointers (grid.features[0..lod_idx], each [pyramid_dual[0,l]+1, feature_dim] fp32).
+ * out: [N, num_lods_used*feature_dim] ('cat', multiscale 0) or [N, feature_dim] ('sum', multiscale 1).
+ * half_round != 0 reproduces the call site's feats.half() ... .float() rounding (octree_grid.py:147-149).
+ * Backward accumulates into grad_feats (caller zeroes); no gradient flows to coords (as in Kaolin).
+ * ---------------------------------------------------------------------------------------------- */
+int wb_octree_interp_fwd(const wb_octree* oct, const int16_t* points, const int32_t* trinkets, const float* coords, int64_t N,
+                         int32_t feature_dim, int32_t base_lod, int32_t num_lods_used, int32_t multiscale, int32_t half_round,
+                         const float* const* feats, float* out, wb_stream s);
+int wb_octree_interp_bwd(const wb_octree* oct, const int16_t* points, const int32_t* trinkets, const float* coords, int64_t N,
+                         int32_t feature_dim, int32_t base_lod, int32_t num_lods_used, int32_t multiscale,
+                         const float* const* feats, const float* grad_out, float* const* grad_feats, wb_stream s);
+/* wisp._C.render.find_depth_bound_cuda(query f32[P,1], curr_idxes i32[P], depth f32[Ng,2]) -> i32[P]
+ * (wisp/csrc/render/find_depth_bound.cpp:23-36, kernel find_depth_bound_cuda.cu:16-45), launched on the given stream. */
+int wb_find_depth_bound(const float* query, const int32_t* curr_idxes, const float* depth, int64_t num_packs, int64_t num_nugs,
+                        int32_t* out, wb_stream s);
+
+/* ------------------------------------------------------------------------------------------------
  * Packed compositing -- replaces kaolin.render.spc.{exponential_integration, sum_reduce} + the buffer
  *   scatter of PackedRFTracer.trace (wisp/tracers/packed_rf_tracer.py:136-165).
  *   shaded: float4 [S] = (r, g, b, sigma); offsets int64 [R+1]; depth/deltas [S].

@@ -7,9 +7,9 @@ libwispb200.so (hand-written CUDA behind a C ABI, include/wispb200.h).  There is
 from . import _cabi, ops, spc, parallel                                                   # noqa: F401
 from .core import Rays, RenderBuffer                                            # noqa: F401
 from .accelstructs import OctreeAS, AxisAlignedBBoxAS, ASQueryResults, ASRaymarchResults, ASRaytraceResults   # noqa: F401
-from .grids import HashGrid, MultiTable, TriplanarGrid, TriplanarFeatureVolume                                         # noqa: F401
-from .nefs import NeuralRadianceField, BasicDecoder, PositionalEmbedder, get_positional_embedder   # noqa: F401
-from .tracers import PackedRFTracer                                             # noqa: F401
+from .grids import HashGrid, MultiTable, TriplanarGrid, TriplanarFeatureVolume, OctreeGrid                                         # noqa: F401
+from .nefs import NeuralRadianceField, NeuralSDF, BasicDecoder, PositionalEmbedder, get_positional_embedder   # noqa: F401
+from .tracers import PackedRFTracer, PackedSDFTracer                                             # noqa: F401
 from .pipeline import Pipeline                                                  # noqa: F401
 
 __version__ = "0.1.0"

@@ -53,7 +53,8 @@ EXPORTS = [
     "wb_octree_generate_points", "wb_octree_build_bits", "wb_query",
     "wb_raymarch_ray_count", "wb_scan_workspace_bytes", "wb_scan_counts", "wb_raymarch_ray_fill",
     "wb_raytrace_count", "wb_raytrace_fill", "wb_raymarch_voxel_fill", "wb_raymarch_uniform_count", "wb_raymarch_uniform_fill",
-    "wb_hashgrid_fwd", "wb_hashgrid_bwd", "wb_triplane_fwd", "wb_triplane_bwd", "wb_composite_fwd", "wb_composite_bwd",
+    "wb_hashgrid_fwd", "wb_hashgrid_bwd", "wb_triplane_fwd", "wb_triplane_bwd",
+    "wb_octree_interp_fwd", "wb_octree_interp_bwd", "wb_find_depth_bound", "wb_composite_fwd", "wb_composite_bwd",
     "wb_rf_march_fill", "wb_rf_param_blob_floats", "wb_rf_pack_params", "wb_rf_shade_fwd", "wb_rf_shade_bwd",
     "wb_rf_workspace_bytes", "wb_rf_feat_bytes", "wb_tc_selftest",
 ]

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import ops, spc
 from .accelstructs import ASRaymarchResults, OctreeAS
 
 
@@ -179,3 +179,54 @@ class TriplanarGrid(nn.Module):
 
     def name(self) -> str:
         return "Triplanar Grid"
+
+
+class OctreeGrid(nn.Module):
+    """wisp.models.grids.OctreeGrid (octree_grid.py:24-226), 'linear' interpolation.  Parameters: features.0 ... features.N-1."""
+
+    def __init__(self, blas, feature_dim: int, num_lods: int = 1, interpolation_type: str = 'linear', multiscale_type: str = 'cat',
+                 feature_std: float = 0.0, feature_bias: float = 0.0):
+        super().__init__()
+        if interpolation_type != 'linear':
+            raise Exception(f"Interpolation mode {interpolation_type} is not supported.")          # octree_grid.py:103,161
+        self.blas = blas
+        self.feature_dim, self.max_lod, self.num_lods = feature_dim, blas.max_level, num_lods
+        self.base_lod = self.max_lod - self.num_lods + 1
+        self.interpolation_type, self.multiscale_type = interpolation_type, multiscale_type
+        self.feature_std, self.feature_bias = feature_std, feature_bias
+        self.active_lods = [self.base_lod + x for x in range(self.num_lods)]
+        self.points_dual, self.pyramid_dual, self.trinkets, self.parents = spc.make_trilinear_spc(blas.points, blas.pyramid)
+        self.features = nn.ParameterList([])
+        for al in self.active_lods:                                                                 # octree_grid.py:88-104
+            fts = torch.zeros(int(self.pyramid_dual[0, al]) + 1, feature_dim) + feature_bias
+            fts = fts + torch.randn_like(fts) * feature_std
+            self.features.append(nn.Parameter(fts))
+        self.num_feat = sum(int(self.pyramid_dual[0, al]) + 1 for al in self.active_lods)
+        self.half_features = True        # the reference interpolates `feats.half()` and returns `.float()` (octree_grid.py:147-149)
+
+    def freeze(self):
+        for f in self.features:
+            f.requires_grad_(False)
+
+    def interpolate(self, coords, lod_idx):
+        """octree_grid.py:165-219."""
+        output_shape = coords.shape[:-1]
+        dev = self.features[0].device
+        if self.trinkets.device != dev:
+            self.trinkets = self.trinkets.to(dev)
+        feats = ops.OctreeInterpolate.apply(coords.reshape(-1, 3), self.blas.tensors(), self.trinkets, self.base_lod, self.multiscale_type if lod_idx > 0 else 'cat',
+                                            self.half_features, *[self.features[i] for i in range(lod_idx + 1)])
+        return feats.reshape(*output_shape, feats.shape[-1])
+
+    def raymarch(self, rays, raymarch_type, num_samples, level=None, **kw) -> ASRaymarchResults:
+        """octree_grid.py:221-226: samples over the coarsest LOD that has features."""
+        return self.blas.raymarch(rays, raymarch_type=raymarch_type, num_samples=num_samples, level=self.base_lod, **kw)
+
+    def raytrace(self, rays, level=None, with_exit=False):
+        return self.blas.raytrace(rays, level=level, with_exit=with_exit)
+
+    def query(self, coords, level=None, with_parents=False):
+        return self.blas.query(coords, level=level, with_parents=with_parents)
+
+    def name(self) -> str:
+        return "Octree Grid"

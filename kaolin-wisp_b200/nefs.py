@@ -212,3 +212,59 @@ class NeuralRadianceField(BaseNeuralField):
                            codebook_size=g.codebook_size, feature_dim=g.feature_dim, multiscale=g.multiscale_type, lod_idx=int(lod_idx),
                            pos_mode=pm, pos_freq=pf, view_mode=vm, view_freq=vf, has_bias=bool(self.bias),
                            dens_dims=self.decoder_density.dims(), col_dims=self.decoder_color.dims())
+
+
+class NeuralSDF(BaseNeuralField):
+    """wisp.models.nefs.NeuralSDF (neural_sdf.py:24-180): grid features (+ position) -> BasicDecoder(bias=True, output_dim=1)."""
+
+    def __init__(self, grid, pos_embedder='none', pos_multires=10, position_input=True, activation_type='relu', layer_type='none',
+                 hidden_dim=128, num_layers=1):
+        super().__init__()
+        self.grid = grid
+        if activation_type != 'relu' or layer_type not in ('linear', 'none'):
+            raise NotImplementedError("wisp_b200 covers activation_type='relu', layer_type='linear'/'none'")
+        self.pos_multires, self.position_input = pos_multires, position_input
+        self.pos_embedder, self.pos_embed_dim = self.init_embedder(pos_embedder, pos_multires, position_input)
+        self.activation_type, self.layer_type, self.hidden_dim, self.num_layers = activation_type, layer_type, hidden_dim, num_layers
+        self.decoder = BasicDecoder(self.decoder_input_dim(), 1, torch.relu, True, nn.Linear, num_layers, hidden_dim)
+
+    def init_embedder(self, embedder_type, frequencies=None, position_input=True):
+        """neural_sdf.py:86-99."""
+        if embedder_type == 'none' and not position_input:
+            return None, 0
+        if embedder_type == 'identity' or (embedder_type == 'none' and position_input):
+            return nn.Identity(), 3
+        if embedder_type == 'positional':
+            return get_positional_embedder(frequencies=frequencies, include_input=position_input)
+        raise NotImplementedError(f'Unsupported embedder type for NeuralSDF: {embedder_type}')
+
+    def register_forward_functions(self):
+        self._register_forward_function(self.sdf, ["sdf"])
+
+    def get_forward_function(self, channel):
+        fn = next(f for f, ch in self._forward_functions.items() if channel in ch)
+        return lambda coords, lod_idx=None: fn(coords, lod_idx)[channel]
+
+    def sdf(self, coords, lod_idx=None):
+        """neural_sdf.py:120-155."""
+        shape = coords.shape
+        if shape[0] == 0:
+            return dict(sdf=torch.zeros_like(coords)[..., 0:1])
+        if lod_idx is None:
+            lod_idx = self.grid.num_lods - 1
+        if len(shape) == 2:
+            coords = coords[:, None]
+        num_samples = coords.shape[1]
+        feats = self.grid.interpolate(coords, lod_idx)
+        if self.pos_embedder is not None:
+            feats = torch.cat([self.pos_embedder(coords.reshape(-1, 3)).view(-1, num_samples, self.pos_embed_dim), feats], dim=-1)
+        sdf = self.decoder(feats)
+        if len(shape) == 2:
+            sdf = sdf[:, 0]
+        return dict(sdf=sdf)
+
+    def effective_feature_dim(self):
+        return self.grid.feature_dim * self.grid.num_lods if self.grid.multiscale_type == 'cat' else self.grid.feature_dim
+
+    def decoder_input_dim(self):
+        return self.effective_feature_dim() + self.pos_embed_dim

@@ -320,6 +320,58 @@ class TriplaneInterpolate(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------------------------------------------
+# octree grid interpolate + SDF-tracer helpers
+# --------------------------------------------------------------------------------------------------------------
+class OctreeInterpolate(torch.autograd.Function):
+    """OctreeGrid.interpolate for LODs 0..lod_idx in one launch (octree_grid.py:165-219)."""
+
+    @staticmethod
+    def forward(ctx, coords, oct, trinkets, base_lod, multiscale, half_round, *feats):
+        A.require_device(feats[0])
+        c = A.f32c(coords)
+        N, F, nl = c.shape[0], feats[0].shape[1], len(feats)
+        fl = [A.f32c(f.detach()) for f in feats]
+        ptrs = (C.c_void_p * nl)(*[f.data_ptr() for f in fl])
+        out = torch.empty((N, F if multiscale == 'sum' else nl * F), dtype=torch.float32, device=c.device)
+        od = oct.desc()
+        A.check(A.lib().wb_octree_interp_fwd(C.byref(od), A.ptr(oct.points), A.ptr(trinkets), A.ptr(c), C.c_int64(N), C.c_int32(F), C.c_int32(base_lod),
+                                             C.c_int32(nl), C.c_int32(1 if multiscale == 'sum' else 0), C.c_int32(int(half_round)), ptrs, A.ptr(out), A.stream()))
+        ctx.save_for_backward(c, trinkets, *fl)
+        ctx.meta = (oct, base_lod, multiscale)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        c, trinkets, *fl = ctx.saved_tensors
+        oct, base_lod, multiscale = ctx.meta
+        nl, F = len(fl), fl[0].shape[1]
+        gf = [torch.zeros_like(f) for f in fl]
+        ptrs = (C.c_void_p * nl)(*[f.data_ptr() for f in fl]); gptrs = (C.c_void_p * nl)(*[f.data_ptr() for f in gf])
+        od = oct.desc()
+        A.check(A.lib().wb_octree_interp_bwd(C.byref(od), A.ptr(oct.points), A.ptr(trinkets), A.ptr(c), C.c_int64(c.shape[0]), C.c_int32(F), C.c_int32(base_lod),
+                                             C.c_int32(nl), C.c_int32(1 if multiscale == 'sum' else 0), ptrs, A.ptr(A.f32c(g)), gptrs, A.stream()))
+        return (None, None, None, None, None, None, *gf)
+
+
+def find_depth_bound(query: torch.Tensor, nug_depth: torch.Tensor, info=None, curr_idxes: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """wisp.ops.geometric.find_depth_bound (geometric.py:15-22)."""
+    if curr_idxes is None:
+        curr_idxes = torch.nonzero(info)[..., 0].int()
+    A.require_device(query)
+    q, ci, dp = A.f32c(query).reshape(-1), curr_idxes.int().contiguous(), A.f32c(nug_depth)
+    out = torch.empty(q.shape[0], dtype=torch.int32, device=q.device)
+    A.check(A.lib().wb_find_depth_bound(A.ptr(q), A.ptr(ci), A.ptr(dp), C.c_int64(q.shape[0]), C.c_int64(dp.shape[0]), A.ptr(out), A.stream()))
+    return out
+
+
+def finitediff_gradient(x: torch.Tensor, f, eps: float = 0.005) -> torch.Tensor:
+    """wisp.ops.differential.finitediff_gradient (gradients.py:29-45)."""
+    ex = torch.tensor([eps, 0.0, 0.0], device=x.device); ey = torch.tensor([0.0, eps, 0.0], device=x.device); ez = torch.tensor([0.0, 0.0, eps], device=x.device)
+    grad = torch.cat([f(x + ex) - f(x - ex), f(x + ey) - f(x - ey), f(x + ez) - f(x - ez)], dim=-1)
+    return grad / (eps * 2.0)
+
+
+# --------------------------------------------------------------------------------------------------------------
 # packed compositing
 # --------------------------------------------------------------------------------------------------------------
 def _bg3(bg) -> "C.Array":

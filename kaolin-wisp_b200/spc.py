@@ -102,3 +102,36 @@ def quantize_points(x: torch.Tensor, level: int) -> torch.Tensor:
     """spc_ops.quantize_points: floor(clamp(2^level (x+1)/2, 0, 2^level-1)) -> int16."""
     res = 2 ** level
     return torch.floor(torch.clamp(res * (x + 1.0) / 2.0, 0, res - 1.0)).short()
+
+
+def make_trilinear_spc(points: torch.Tensor, pyramid: torch.Tensor):
+    """wisp.ops.spc.make_trilinear_spc (constructors.py:31-47 -> kaolin unbatched_make_dual / unbatched_make_trinkets).
+    -> points_dual int16 [Td,3] (per level: Morton-sorted unique cell corners), pyramid_dual int32 [2, L+2],
+       trinkets int32 [T,8] (LEVEL-LOCAL dual index of corner j = 4x+2y+z), parents int32 [T] (-1 for the root)."""
+    dev = points.device
+    L = pyramid.shape[-1] - 2
+    ar = torch.arange(8, device=dev)
+    corners = torch.stack([(ar >> 2) & 1, (ar >> 1) & 1, ar & 1], -1).long()
+    pts = points.long()
+    duals = []
+    trinkets = torch.zeros(pts.shape[0], 8, dtype=torch.int32, device=dev)
+    parents = torch.full((pts.shape[0],), -1, dtype=torch.int32, device=dev)
+    pyr = torch.zeros(2, L + 2, dtype=torch.int32)
+    off = 0
+    for l in range(L + 1):
+        s, c = int(pyramid[1, l]), int(pyramid[0, l])
+        cell = pts[s:s + c]
+        cor = (cell[:, None, :] + corners[None]).reshape(-1, 3)
+        key = morton3(cor, l + 1)
+        uk, inv = torch.unique(key, return_inverse=True)           # sorted
+        first = torch.full((uk.shape[0],), cor.shape[0], dtype=torch.int64, device=dev)
+        first.scatter_reduce_(0, inv, torch.arange(cor.shape[0], device=dev), reduce="amin")
+        duals.append(cor[first].to(torch.int16))
+        trinkets[s:s + c] = inv.reshape(c, 8).to(torch.int32)
+        pyr[0, l] = uk.shape[0]; pyr[1, l] = off; off += uk.shape[0]
+        if l > 0:
+            ps, pc = int(pyramid[1, l - 1]), int(pyramid[0, l - 1])
+            pkey = morton3(pts[ps:ps + pc], l)
+            parents[s:s + c] = (ps + torch.searchsorted(pkey, morton3(cell >> 1, l))).to(torch.int32)
+    pyr[1, L + 1] = off
+    return torch.cat(duals), pyr, trinkets, parents

@@ -105,3 +105,104 @@ class PackedRFTracer(nn.Module):
                 outs.append(f3[:, :chunk.shape[1]])
             extra_outputs[channel] = alpha * torch.cat(outs, -1)   # packed_rf_tracer.py:176
         return RenderBuffer(depth=depth if "depth" in channels else None, hit=hit, rgb=rgb, alpha=alpha, **extra_outputs)
+
+
+class PackedSDFTracer(nn.Module):
+    """wisp.tracers.PackedSDFTracer (packed_sdf_tracer.py:20-174): sphere tracing over the nugget list of OctreeAS.raytrace with
+    find_depth_bound jumping between occupied cells; normals by central differences.  Same control flow as the reference; the
+    raytrace, the nugget cursor and the grid interpolation are native kernels."""
+
+    def __init__(self, num_steps=64, step_size=1.0, min_dis=1e-4):
+        super().__init__()
+        self.num_steps, self.step_size, self.min_dis = num_steps, step_size, min_dis
+
+    def get_supported_channels(self):
+        return {"depth", "normal", "xyz", "hit", "rgb", "alpha"}
+
+    def get_required_nef_channels(self):
+        return {"sdf"}
+
+    def forward(self, nef, rays, channels=None, **kwargs):
+        nef_channels = nef.get_supported_channels()
+        unsupported_inputs = self.get_required_nef_channels() - nef_channels
+        if unsupported_inputs:
+            raise Exception(f"The neural field class {type(nef)} does not output the required channels {unsupported_inputs}.")
+        requested = self.get_supported_channels() if channels is None else {channels} if isinstance(channels, str) else set(channels)
+        extra = requested - self.get_supported_channels()
+        if extra - nef_channels:
+            raise Exception(f"Channels {extra - nef_channels} are not supported in the tracer {type(self)} or neural field {type(nef)}.")
+        args = {}
+        for a in ("lod_idx", "num_steps", "step_size", "min_dis"):
+            if a in kwargs:
+                args[a] = kwargs[a]
+            elif getattr(self, a, None) is not None:
+                args[a] = getattr(self, a)
+        return self.trace(nef, rays, requested, extra, **args)
+
+    def trace(self, nef, rays, channels, extra_channels, lod_idx=None, num_steps=64, step_size=1.0, min_dis=1e-4):
+        assert nef.grid is not None and "this tracer requires a grid"
+        if lod_idx is None:
+            lod_idx = nef.grid.num_lods - 1
+        invres = 1.0
+        rt = nef.grid.raytrace(rays, nef.grid.active_lods[lod_idx], with_exit=True)
+        ridx, pidx, depth = rt.ridx, rt.pidx, rt.depth
+        dev = rays.origins.device
+        depth[..., 0:1] += 1e-5                                                 # packed_sdf_tracer.py:91
+        first_hit = torch.ones_like(ridx, dtype=torch.bool)
+        if ridx.shape[0] > 1:
+            first_hit[1:] = ridx[1:] != ridx[:-1]                               # mark_pack_boundaries
+        curr_idxes = torch.nonzero(first_hit)[..., 0].int()
+        first_ridx = ridx[first_hit].long()
+        nug_o, nug_d = rays.origins[first_ridx], rays.dirs[first_ridx]
+        mask = torch.ones([first_ridx.shape[0]], device=dev).bool()
+        hit = torch.zeros_like(mask).bool()
+        t = depth[first_hit][..., 0:1]
+        x = torch.addcmul(nug_o, nug_d, t)
+        dist = torch.zeros_like(t)
+        dist_max = rays.dist_max
+        with torch.no_grad():
+            sdf = nef(coords=x[mask], lod_idx=lod_idx, channels="sdf") * invres * step_size
+            dist[mask] = sdf.to(dist.dtype)
+            dist[~mask] = 20
+            dist_prev = dist.clone()
+            for i in range(num_steps):
+                t += dist
+                x = torch.where(mask.view(mask.shape[0], 1), torch.addcmul(nug_o, nug_d, t), x)
+                hit = torch.where(mask, torch.abs(dist)[..., 0] < min_dis * invres, hit)
+                hit |= torch.where(mask, torch.abs(dist + dist_prev)[..., 0] * 0.5 < (min_dis * 5) * invres, hit)
+                mask = torch.where(mask, (t < dist_max)[..., 0], mask)
+                mask &= ~hit
+                if not mask.any():
+                    break
+                dist_prev = torch.where(mask.view(mask.shape[0], 1), dist, dist_prev)
+                next_idxes = ops.find_depth_bound(t, depth, first_hit, curr_idxes=curr_idxes)
+                mask &= (next_idxes != -1)
+                aabb_mask = (next_idxes != curr_idxes)
+                curr_idxes = torch.where(mask, next_idxes, curr_idxes)
+                t = torch.where((mask & aabb_mask).view(mask.shape[0], 1), depth[curr_idxes.long(), 0:1], t)
+                x = torch.where(mask.view(mask.shape[0], 1), torch.addcmul(nug_o, nug_d, t), x)
+                if not mask.any():
+                    break
+                sdf = nef(coords=x[mask], lod_idx=lod_idx, channels="sdf") * invres * step_size
+                dist[mask] = sdf.to(dist.dtype)
+        x_buffer = torch.zeros_like(rays.origins)
+        depth_buffer = torch.zeros_like(rays.origins[..., 0:1])
+        hit_buffer = torch.zeros_like(rays.origins[..., 0]).bool()
+        normal_buffer = torch.zeros_like(rays.origins)
+        rgb_buffer = torch.zeros(*rays.origins.shape[:-1], 3, device=dev)
+        alpha_buffer = torch.zeros(*rays.origins.shape[:-1], 1, device=dev)
+        hit_buffer[first_ridx] = hit
+        extra_outputs = {}
+        for channel in extra_channels:
+            feats = nef(coords=x[hit], lod_idx=lod_idx, channels=channel)
+            extra_buffer = torch.zeros(*rays.origins.shape[:-1], feats.shape[-1], device=dev)
+            extra_buffer[hit_buffer] = feats.to(extra_buffer.dtype)
+            extra_outputs[channel] = extra_buffer
+        x_buffer[hit_buffer] = x[hit]
+        depth_buffer[hit_buffer] = t[hit]
+        if "rgb" in channels or "normal" in channels:
+            grad = ops.finitediff_gradient(x[hit], nef.get_forward_function("sdf"))
+            normal_buffer[hit_buffer] = torch.nn.functional.normalize(grad, p=2, dim=-1, eps=1e-5)
+            rgb_buffer[..., :3] = (normal_buffer + 1.0) / 2.0
+        alpha_buffer[hit_buffer] = 1.0
+        return RenderBuffer(xyz=x_buffer, depth=depth_buffer, hit=hit_buffer, normal=normal_buffer, rgb=rgb_buffer, alpha=alpha_buffer, **extra_outputs)

@@ -165,6 +165,62 @@ def gen_triplanar():
     print("triplanar", out["sum"]["feats"].shape, out["cat"]["feats"].shape)
 
 
+def octahedron_points(level: int, radius: float = 0.52, n: int = 400000, seed: int = 0) -> np.ndarray:
+    """Quantised points on the surface |x|+|y|+|z| = radius (the zero set of the synthetic SDF below)."""
+    rng = np.random.default_rng(seed)
+    p = rng.standard_normal((n, 3))
+    p = p / np.abs(p).sum(-1, keepdims=True) * radius
+    q = np.floor(np.clip((2 ** level) * (p + 1.0) / 2.0, 0, 2 ** level - 1)).astype(np.int16)
+    return np.unique(q, axis=0)
+
+
+def gen_sdf():
+    """app/nglod path in miniature (BASELINE config 3): OctreeGrid.interpolate (octree_grid.py:165-219), NeuralSDF.sdf
+    (neural_sdf.py:120-155) and PackedSDFTracer.trace (packed_sdf_tracer.py:57-174) run by the reference classes."""
+    from wisp.accelstructs import OctreeAS
+    from wisp.models.grids import OctreeGrid
+    from wisp.models.nefs import NeuralSDF
+    from wisp.tracers import PackedSDFTracer
+    from wisp.core import Rays
+    torch.manual_seed(7)
+    level = 5
+    oct_np = O.points_to_octree(octahedron_points(level), level)
+    blas = OctreeAS(torch.from_numpy(oct_np))
+    out = dict(octree=oct_np, level=level)
+    for ms in ("sum", "cat"):
+        grid = OctreeGrid(blas, feature_dim=8, num_lods=3, interpolation_type='linear', multiscale_type=ms, feature_std=0.05)
+        nef = NeuralSDF(grid, pos_embedder='none', position_input=True, hidden_dim=16, num_layers=1)
+        with torch.no_grad():       # sdf ~ (|x|+|y|+|z|)/sqrt(3) - 0.3 + small learned perturbation
+            W0 = nef.decoder.layers[0].weight; W0.mul_(0.05)
+            W0[:6, :3] = torch.tensor([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1.0]])
+            nef.decoder.layers[0].bias.zero_()
+            nef.decoder.lout.weight.mul_(0.05); nef.decoder.lout.weight[0, :6] = 1.0 / np.sqrt(3.0)
+            nef.decoder.lout.bias.fill_(-0.3)
+        coords = torch.rand(500, 3) * 1.4 - 0.7
+        feats = grid.interpolate(coords, 2)
+        feats0 = grid.interpolate(coords, 0)
+        sdf = nef(coords=coords, lod_idx=2, channels="sdf")
+        (sdf.abs().sum()).backward()
+        d = {f"{ms}_coords": coords.numpy(), f"{ms}_feats": feats.detach().numpy(), f"{ms}_feats_lod0": feats0.detach().numpy(), f"{ms}_sdf": sdf.detach().numpy()}
+        for i, f in enumerate(grid.features):
+            d[f"{ms}_feat{i}"] = f.detach().numpy(); d[f"{ms}_gfeat{i}"] = f.grad.numpy()
+        d[f"{ms}_W0"] = nef.decoder.layers[0].weight.detach().numpy(); d[f"{ms}_b0"] = nef.decoder.layers[0].bias.detach().numpy()
+        d[f"{ms}_W1"] = nef.decoder.lout.weight.detach().numpy(); d[f"{ms}_b1"] = nef.decoder.lout.bias.detach().numpy()
+        d[f"{ms}_gW0"] = nef.decoder.layers[0].weight.grad.numpy()
+        if ms == "sum":
+            o, dd = O.look_at_rays([-2.0, 0.9, -1.6], [0, 0, 0], 20, 20, 40.0)
+            tracer = PackedSDFTracer(num_steps=24, step_size=0.8, min_dis=1e-3)
+            rb = tracer(nef, rays=Rays(torch.from_numpy(o), torch.from_numpy(dd), dist_min=0.0, dist_max=6.0), lod_idx=2,
+                        channels=["rgb", "depth", "hit", "normal", "alpha", "xyz"])
+            d.update(origins=o, dirs=dd, t_xyz=rb.xyz.detach().numpy(), t_depth=rb.depth.detach().numpy(), t_hit=rb.hit.numpy(),
+                     t_normal=rb.normal.detach().numpy(), t_rgb=rb.rgb.detach().numpy(), t_alpha=rb.alpha.detach().numpy())
+            print("sdf trace hits", int(rb.hit.sum()), "of", o.shape[0])
+        out.update(d)
+        out[f"{ms}_trinkets"] = grid.trinkets.numpy(); out[f"{ms}_pyramid_dual"] = grid.pyramid_dual.numpy()
+    np.savez_compressed(os.path.join(OUT, "sdf_octree.npz"), **out)
+    print("sdf_octree", out["sum_feats"].shape, out["cat_feats"].shape)
+
+
 def main():
     warnings.filterwarnings("ignore")
     ref_import.install()
@@ -172,6 +228,7 @@ def main():
     gen_hashgrid_naive()
     gen_raymarch_nuggets()
     gen_triplanar()
+    gen_sdf()
     # A: miniature of BASELINE config 2 (cat, bias, positional view embedding, sparse lego-like octree)
     gen_rf_trace("rf_trace_cat", level=5, res=None, hw=24, n_steps=96, num_lods=6, bw=11, min_res=4, max_res=48, hidden=32,
                  num_layers=1, bias=True, multiscale="cat", view_embedder="positional", near=0.0, far=10.0, bg=(1.0, 1.0, 1.0))

@@ -219,6 +219,60 @@ def _uniform_sample_cuda(scale, ridx, depth, insum):
     return [torch.from_numpy(new_ridx), torch.from_numpy(ds), torch.from_numpy(boundary)]
 
 
+class _SpcView:
+    def __init__(self, points, pyramid):
+        self.points = _np(points); self.pyramid = _np(pyramid).astype(np.int64); self.max_level = self.pyramid.shape[-1] - 2
+
+
+def _unbatched_make_dual(points, pyramid):
+    from . import octree_grid as OG
+    pd, pyr, _, _ = OG.make_trilinear_spc(_SpcView(points, pyramid))
+    return torch.from_numpy(pd), torch.from_numpy(pyr.astype(np.int32))
+
+
+def _unbatched_make_trinkets(points, pyramid, points_dual, pyramid_dual):
+    from . import octree_grid as OG
+    _, _, tr, par = OG.make_trilinear_spc(_SpcView(points, pyramid))
+    return torch.from_numpy(tr), torch.from_numpy(par)
+
+
+class _InterpTrilinear(torch.autograd.Function):
+    """kaolin.ops.spc.unbatched_interpolate_trilinear: fwd via the oracle, bwd = index_add of coef*grad."""
+
+    @staticmethod
+    def forward(ctx, coords, pidx, points, trinkets, feats, level):
+        from . import octree_grid as OG
+        N, Ns = coords.shape[:2]
+        c = _np(coords).reshape(-1, 3).astype(np.float32)
+        p = np.repeat(_np(pidx).astype(np.int64), Ns)
+        half = feats.dtype == torch.float16
+        out = OG.interpolate_trilinear(c, p, _np(points), _np(trinkets), _np(feats).astype(np.float32), level, half=half)
+        ctx.meta = (c, p, _np(points), _np(trinkets), level, feats.shape, feats.dtype)
+        return torch.from_numpy(out).reshape(N, Ns, -1).to(feats.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import octree_grid as OG
+        c, p, points, trinkets, level, shape, dtype = ctx.meta
+        gf = np.zeros(shape, np.float32)
+        ok = p >= 0
+        gn = _np(g).reshape(-1, shape[1]).astype(np.float32)
+        if ok.any():
+            cf = OG.trilinear_coeffs(c[ok], points[p[ok]], level)
+            for j in range(8):
+                np.add.at(gf, trinkets[p[ok], j].astype(np.int64), gn[ok] * cf[:, j:j + 1])
+        return None, None, None, None, torch.from_numpy(gf).to(dtype), None
+
+
+def _unbatched_interpolate_trilinear(coords, pidx, points, trinkets, feats, level):
+    return _InterpTrilinear.apply(coords, pidx, points, trinkets, feats, level)
+
+
+def _find_depth_bound_cuda(query, curr_idxes, depth):
+    from . import octree_grid as OG
+    return torch.from_numpy(OG.find_depth_bound(_np(query), _np(curr_idxes), _np(depth)))
+
+
 _installed = False
 
 
@@ -241,6 +295,7 @@ def install():
     import kaolin._C.render.spc as kaolin_C_render_spc
     import wisp._C as wisp_C
     import wisp._C.ops as wisp_C_ops
+    import wisp._C.render as wisp_C_render
     spc_ops.unbatched_query = _unbatched_query
     spc_ops.scan_octrees = _scan_octrees
     spc_ops.generate_points = _generate_points
@@ -252,6 +307,11 @@ def install():
     spc_render.unbatched_raytrace = _unbatched_raytrace
     kaolin_C_render_spc.inclusive_sum_cuda = lambda t: torch.cumsum(t, 0).int()
     wisp_C_ops.uniform_sample_cuda = _uniform_sample_cuda
+    spc_ops.unbatched_make_dual = _unbatched_make_dual
+    spc_ops.unbatched_make_trinkets = _unbatched_make_trinkets
+    spc_ops.unbatched_interpolate_trilinear = _unbatched_interpolate_trilinear
+    wisp_C_render.find_depth_bound_cuda = _find_depth_bound_cuda
+    wisp_C.render = wisp_C_render
     spc_render.sum_reduce = _sum_reduce
     spc_render.cumsum = _cumsum
     spc_render.exponential_integration = _exponential_integration

@@ -481,3 +481,86 @@ def test_triplanar_nerf_voxel_trace(W):
     cols, w = O.exponential_integration(rgb_s, sig * mr["deltas"][:, 0], mr["boundary"])
     exp = np.zeros((o.shape[0], 3), np.float32); exp[mr["ridx"][mr["boundary"]]] = cols
     np.testing.assert_allclose(rb.rgb.detach().cpu().numpy(), exp, atol=2e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# OctreeGrid / NeuralSDF / PackedSDFTracer (BASELINE config 3 path)
+# ---------------------------------------------------------------------------------------------------------------
+def _sdf_from_golden(W, g, ms):
+    blas = W.OctreeAS(dev(g["octree"]))
+    grid = W.OctreeGrid(blas, feature_dim=8, num_lods=3, multiscale_type=ms, feature_std=0.0)
+    nef = W.NeuralSDF(grid, pos_embedder='none', position_input=True, hidden_dim=16, num_layers=1).cuda()
+    assert np.array_equal(grid.trinkets.cpu().numpy(), g[f"{ms}_trinkets"]) and np.array_equal(grid.pyramid_dual.numpy(), g[f"{ms}_pyramid_dual"])
+    with torch.no_grad():
+        for i, f in enumerate(grid.features):
+            f.copy_(dev(g[f"{ms}_feat{i}"]))
+        nef.decoder.layers[0].weight.copy_(dev(g[f"{ms}_W0"])); nef.decoder.layers[0].bias.copy_(dev(g[f"{ms}_b0"]))
+        nef.decoder.lout.weight.copy_(dev(g[f"{ms}_W1"])); nef.decoder.lout.bias.copy_(dev(g[f"{ms}_b1"]))
+    return nef, grid, blas
+
+
+@pytest.mark.parametrize("ms", ["sum", "cat"])
+def test_octree_grid_golden(W, golden_dir, ms):
+    """OctreeGrid.interpolate + NeuralSDF.sdf forward/backward vs the reference classes (fp16-feature semantics of the call site;
+    tolerance = the reference's fp16 interpolation tolerance 1e-2, tests/core/test_grid_interpolation.py:56-59, tightened to 2e-3)."""
+    g = np.load(os.path.join(golden_dir, "sdf_octree.npz"))
+    nef, grid, blas = _sdf_from_golden(W, g, ms)
+    coords = dev(g[f"{ms}_coords"])
+    np.testing.assert_allclose(grid.interpolate(coords, 2).detach().cpu().numpy(), g[f"{ms}_feats"], atol=2e-3)
+    np.testing.assert_allclose(grid.interpolate(coords, 0).detach().cpu().numpy(), g[f"{ms}_feats_lod0"], atol=2e-3)
+    sdf = nef(coords=coords, lod_idx=2, channels="sdf")
+    np.testing.assert_allclose(sdf.detach().cpu().numpy(), g[f"{ms}_sdf"], atol=2e-3)
+    sdf.abs().sum().backward()
+    for i, f in enumerate(grid.features):
+        ref = g[f"{ms}_gfeat{i}"]
+        assert np.abs(f.grad.cpu().numpy() - ref).max() <= 2e-2 * max(np.abs(ref).max(), 1e-6), i
+    refw = g[f"{ms}_gW0"]
+    assert np.abs(nef.decoder.layers[0].weight.grad.cpu().numpy() - refw).max() <= 2e-2 * np.abs(refw).max()
+
+
+def test_octree_grid_fp32_vs_oracle(W):
+    """Same kernel without the fp16 rounding (half_features=False) against the numpy oracle at fp32 tolerance, larger tree."""
+    from oracle import octree_grid as OG
+    rng = np.random.default_rng(2)
+    spc = O.octree_to_spc(O.points_to_octree(O.lego_like_points(6), 6))
+    _, pyr, tr, _ = OG.make_trilinear_spc(spc)
+    blas = W.OctreeAS(dev(spc.octree))
+    grid = W.OctreeGrid(blas, feature_dim=16, num_lods=4, multiscale_type='sum', feature_std=1.0).cuda()
+    grid.half_features = False
+    coords = rng.uniform(-0.9, 0.9, (20000, 3)).astype(np.float32)
+    out = grid.interpolate(dev(coords), 3).detach().cpu().numpy()
+    ref = OG.octree_grid_interpolate(spc, tr, [f.detach().cpu().numpy() for f in grid.features], grid.active_lods, coords, 3, "sum", half=False)
+    np.testing.assert_allclose(out, ref, atol=2e-5, rtol=1e-5)
+    assert np.abs(ref).max() > 0.1
+
+
+def test_find_depth_bound_vs_oracle(W):
+    from oracle import octree_grid as OG
+    rng = np.random.default_rng(3)
+    P = 300
+    counts = rng.integers(1, 6, P); offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    Ng = int(offs[-1])
+    en = np.sort(rng.random(Ng) * 5).astype(np.float32); depth = np.stack([en, en + 0.01 + rng.random(Ng).astype(np.float32) * 0.05], -1).astype(np.float32)
+    curr = offs[:-1].copy(); curr[::13] = -1
+    q = (rng.random(P) * 5).astype(np.float32)
+    got = W.ops.find_depth_bound(dev(q)[:, None], dev(depth), curr_idxes=dev(curr)).cpu().numpy()
+    assert np.array_equal(got, OG.find_depth_bound(q, curr, depth))
+
+
+def test_sdf_tracer_golden(W, golden_dir):
+    """PackedSDFTracer.trace (sphere tracing + find_depth_bound + finite-difference normals) vs the reference tracer."""
+    g = np.load(os.path.join(golden_dir, "sdf_octree.npz"))
+    nef, grid, blas = _sdf_from_golden(W, g, "sum")
+    tracer = W.PackedSDFTracer(num_steps=24, step_size=0.8, min_dis=1e-3)
+    rb = tracer(nef, rays=W.Rays(dev(g["origins"]), dev(g["dirs"]), dist_min=0.0, dist_max=6.0), lod_idx=2,
+                channels=["rgb", "depth", "hit", "normal", "alpha", "xyz"])
+    hit, ref_hit = rb.hit.cpu().numpy(), g["t_hit"]
+    # fp16 feature rounding can flip a ray that ends within min_dis of the threshold: allow 2 % disagreement, compare the rest
+    agree = hit == ref_hit
+    assert agree.mean() >= 0.98 and ref_hit.sum() > 20
+    both = hit & ref_hit
+    np.testing.assert_allclose(rb.depth.cpu().numpy()[both], g["t_depth"][both], atol=5e-3)
+    np.testing.assert_allclose(rb.xyz.cpu().numpy()[both], g["t_xyz"][both], atol=5e-3)
+    np.testing.assert_allclose(rb.alpha.cpu().numpy()[both], g["t_alpha"][both])
+    dotn = (rb.normal.cpu().numpy()[both] * g["t_normal"][both]).sum(-1)
+    assert np.median(dotn) > 0.99
