@@ -562,5 +562,5 @@ def test_sdf_tracer_golden(W, golden_dir):
     np.testing.assert_allclose(rb.depth.cpu().numpy()[both], g["t_depth"][both], atol=5e-3)
     np.testing.assert_allclose(rb.xyz.cpu().numpy()[both], g["t_xyz"][both], atol=5e-3)
     np.testing.assert_allclose(rb.alpha.cpu().numpy()[both], g["t_alpha"][both])
-    dotn = (rb.normal.cpu().numpy()[both] * g["t_normal"][both]).sum(-1)
+    dotn = (rb.normal.detach().cpu().numpy()[both] * g["t_normal"][both]).sum(-1)
     assert np.median(dotn) > 0.99
