@@ -233,6 +233,15 @@ int wb_rf_shade_bwd(const wb_nef_desc* nef, const float* blob, int32_t precision
                     const void* feat_saved, void* workspace,
                     float* grad_table, float* grad_dens, float* grad_col, wb_stream s);
 
+/* The two stages of the precision-1 backward, callable separately (wb_rf_shade_bwd runs them back to back):
+ * wb_rf_decoder_bwd writes the weight gradients and leaves dL/dfeat (fp16 planes) in the workspace; wb_rf_table_scatter
+ * turns those planes into hash-table updates with warp-level merging of samples that share a cell. */
+int wb_rf_decoder_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray,
+                      int64_t S, const float* g_shaded, const float* loss_scale, const void* feat_saved, void* workspace,
+                      float* grad_dens, float* grad_col, wb_stream s);
+int wb_rf_table_scatter(const wb_nef_desc* nef, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray, int64_t S,
+                        const float* loss_scale, void* workspace, float* grad_table, wb_stream s);
+
 /* ------------------------------------------------------------------------------------------------
  * Diagnostics: one-tile tcgen05 GEMM that pins the shared-memory operand layouts of the tensor-core decoder
  * kernels (csrc/wb_tc.cuh).  a_img / b_img are byte images of the operand tiles; D is [128, N] fp32.

@@ -27,6 +27,11 @@ int wb_tc_shade_fwd(const wb_nef_desc* nef, const float* blob, const wb_rays* ra
 int wb_tc_shade_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray,
                     int64_t S, const float* g_shaded, const float* scale, const void* feat_saved, void* workspace,
                     float* grad_table, float* grad_dens, float* grad_col, cudaStream_t st);
+int wb_tc_decoder_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray,
+                      int64_t S, const float* g_shaded, const float* scale, const void* feat_saved, void* workspace,
+                      float* grad_dens, float* grad_col, cudaStream_t st);
+int wb_tc_table_scatter(const wb_nef_desc* nef, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray, int64_t S,
+                        const float* scale, void* workspace, float* grad_table, cudaStream_t st);
 int64_t wb_tc_workspace_bytes(const wb_nef_desc* nef, int64_t R, int64_t S, int backward);
 int64_t wb_tc_feat_bytes(const wb_nef_desc* nef, int64_t S);
 
@@ -34,6 +39,22 @@ extern "C" int64_t wb_rf_workspace_bytes(const wb_nef_desc* nef, int32_t precisi
 {
     if (precision != 1) return 0;
     return wb_tc_workspace_bytes(nef, R, S, backward);
+}
+// precision-1 backward in its two stages (wb_rf_shade_bwd == decoder_bwd followed by table_scatter)
+extern "C" int wb_rf_decoder_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray,
+                                 int64_t S, const float* g_shaded, const float* loss_scale, const void* feat_saved, void* workspace,
+                                 float* grad_dens, float* grad_col, wb_stream s)
+{
+    if (S == 0) return WB_OK;
+    WB_CHECK_ARG(nef && blob && rays && rays->origins && rays->dirs && rec_t && rec_ray && g_shaded && grad_dens && grad_col, "null pointer");
+    return wb_tc_decoder_bwd(nef, blob, rays, rec_t, rec_ray, S, g_shaded, loss_scale, feat_saved, workspace, grad_dens, grad_col, (cudaStream_t)s);
+}
+extern "C" int wb_rf_table_scatter(const wb_nef_desc* nef, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray, int64_t S,
+                                   const float* loss_scale, void* workspace, float* grad_table, wb_stream s)
+{
+    if (S == 0) return WB_OK;
+    WB_CHECK_ARG(nef && rays && rays->origins && rays->dirs && rec_t && rec_ray, "null pointer");
+    return wb_tc_table_scatter(nef, rays, rec_t, rec_ray, S, loss_scale, workspace, grad_table, (cudaStream_t)s);
 }
 extern "C" int64_t wb_rf_feat_bytes(const wb_nef_desc* nef, int32_t precision, int64_t S)
 {

@@ -687,12 +687,12 @@ wb_table_scatter_kernel(WbGrid g, TcIn in, const __half* __restrict__ dfeat, int
     }
 }
 
-int wb_tc_shade_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray,
-                    int64_t S, const float* g_shaded, const float* scale, const void* feat_saved, void* workspace,
-                    float* grad_table, float* grad_dens, float* grad_col, cudaStream_t st)
+// decoder backward only: dL/d(shaded) -> weight gradients + dL/dfeat planes in the workspace
+int wb_tc_decoder_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray,
+                      int64_t S, const float* g_shaded, const float* scale, const void* feat_saved, void* workspace,
+                      float* grad_dens, float* grad_col, cudaStream_t st)
 {
-    WbGrid g; int rc = wb_make_grid(nef, &g); if (rc) return rc;
-    WbTc m; rc = wb_tc_make(nef, true, &m); if (rc) return rc;
+    WbTc m; int rc = wb_tc_make(nef, true, &m); if (rc) return rc;
     WB_CHECK_ARG(scale != nullptr, "precision 1 needs the device loss-scale pointer");
     WB_CHECK_ARG(feat_saved != nullptr && workspace != nullptr, "precision 1 backward needs the saved features and the workspace");
     rc = tc_launch_ray_embed(m, rays, workspace, st); if (rc) return rc;
@@ -707,6 +707,19 @@ int wb_tc_shade_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* ra
     wb_mlp_bwd_tc_kernel<<<(unsigned)grid, TC_THREADS, m.smem_bytes, st>>>(m, reinterpret_cast<const uint8_t*>(blob), in,
                                                                            reinterpret_cast<const float4*>(g_shaded), G);
     WB_LAUNCH_CHECK();
+    return WB_OK;
+}
+// table scatter only: dL/dfeat planes (written by wb_tc_decoder_bwd into the same workspace) -> grad_table
+int wb_tc_table_scatter(const wb_nef_desc* nef, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray, int64_t S,
+                        const float* scale, void* workspace, float* grad_table, cudaStream_t st)
+{
+    WbGrid g; int rc = wb_make_grid(nef, &g); if (rc) return rc;
+    WbTc m; rc = wb_tc_make(nef, true, &m); if (rc) return rc;
+    WB_CHECK_ARG(scale != nullptr && workspace != nullptr && grad_table != nullptr, "null pointer");
+    int planes, width; tc_dfeat_shape(nef, &planes, &width);
+    const int64_t R = rays->num_rays;
+    const __half* dfeat = reinterpret_cast<const __half*>(reinterpret_cast<const uint8_t*>(workspace) + tc_align256(R * m.Kp[m.nl_d] * 2));
+    TcIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S, nullptr, nullptr, nullptr };
     const int levels = g.multiscale == 0 ? planes : g.L;
     if (levels > 0) {
         int64_t bx = (S + 255) / 256; const int64_t cap = (int64_t)wb_num_sms() * 8; if (bx > cap) bx = cap;
@@ -716,4 +729,13 @@ int wb_tc_shade_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* ra
         WB_LAUNCH_CHECK();
     }
     return WB_OK;
+}
+
+int wb_tc_shade_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray,
+                    int64_t S, const float* g_shaded, const float* scale, const void* feat_saved, void* workspace,
+                    float* grad_table, float* grad_dens, float* grad_col, cudaStream_t st)
+{
+    int rc = wb_tc_decoder_bwd(nef, blob, rays, rec_t, rec_ray, S, g_shaded, scale, feat_saved, workspace, grad_dens, grad_col, st);
+    if (rc) return rc;
+    return wb_tc_table_scatter(nef, rays, rec_t, rec_ray, S, scale, workspace, grad_table, st);
 }

@@ -564,3 +564,66 @@ def test_sdf_tracer_golden(W, golden_dir):
     np.testing.assert_allclose(rb.alpha.cpu().numpy()[both], g["t_alpha"][both])
     dotn = (rb.normal.detach().cpu().numpy()[both] * g["t_normal"][both]).sum(-1)
     assert np.median(dotn) > 0.99
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# full BASELINE config-2 size: size-independent properties (the oracle cannot finish 2.1e9 candidates in seconds)
+# ---------------------------------------------------------------------------------------------------------------
+def test_full_frame_properties(W):
+    """1024^2 rays x 2048 steps, lego-like level-7 octree, L=16/F=2/T=2^19, 64-wide decoders, tensor-core precision.
+    Checks: packed sample list is consistent (offsets == scan of counts == popcount of the hit masks, ray-sorted records);
+    a strided subset of rays reproduces the oracle's per-ray sample counts bit-exactly; outputs are in range and idempotent;
+    the backward is linear in the upstream gradient; rays that miss the occupied box get the background."""
+    torch.manual_seed(0)
+    pts = torch.from_numpy(O.lego_like_points(7)).cuda()
+    blas = W.OctreeAS.from_quantized_points(pts, 7)
+    grid = W.HashGrid.from_geometric(blas, feature_dim=2, num_lods=16, multiscale_type='cat', feature_std=0.05, codebook_bitwidth=19,
+                                     min_grid_res=16, max_grid_res=512)
+    nef = W.NeuralRadianceField(grid, view_embedder='positional', view_multires=4, hidden_dim=64, num_layers=1, bias=True).cuda()
+    o, d = O.look_at_rays([-3.0, 0.65, -3.0], [0, 0, 0], 1024, 1024, 30.0)
+    R = o.shape[0]
+    od, dd = dev(o), dev(d)
+    ms = W.ops.march_count(blas.tensors(), od, dd, 0.0, 10.0, 2048, 7, seed=5)
+    counts = ms.counts.long()
+    assert int(counts.sum()) == ms.total and int(ms.offsets[-1]) == ms.total
+    assert torch.equal(ms.offsets[1:] - ms.offsets[:-1], counts)
+    pop = torch.zeros(R, dtype=torch.int64, device="cuda")
+    hm = ms.hitmask.view(torch.int32)
+    for b in range(32):
+        pop += ((hm >> b) & 1).long().sum(1)
+    assert torch.equal(pop, counts)
+    rec_t, rec_delta, rec_ray = W.ops.march_fill_records(ms, od.device)
+    assert bool((rec_ray[1:] >= rec_ray[:-1]).all())                                # ray-sorted
+    same = rec_ray[1:] == rec_ray[:-1]
+    assert bool((rec_t[1:][same] > rec_t[:-1][same]).all())                         # front to back inside a ray
+    assert bool((rec_delta > 0).all()) and float(rec_t.min()) >= 0.0 and float(rec_t.max()) <= 10.0
+    sel = np.arange(0, R, 2731)
+    spc = O.octree_to_spc(O.points_to_octree(O.lego_like_points(7), 7))
+    # oracle on a strided subset: the counter-based jitter is keyed by the GLOBAL ray index, so re-march those rays on the GPU as their own batch
+    sub = W.ops.march_count(blas.tensors(), od[sel], dd[sel], 0.0, 10.0, 2048, 7, seed=5)
+    ref = O.raymarch_ray(spc, o[sel], d[sel], 0.0, 10.0, 2048, seed=5)
+    assert np.array_equal(sub.counts.cpu().numpy(), ref["counts"])
+    tracer = W.PackedRFTracer('ray', 2048, bg_color=(0.25, 0.5, 0.75)); tracer.precision = 1; tracer.seed = 5
+    rays = W.Rays(od, dd, 0.0, 10.0)
+    rb = tracer(nef, rays=rays, channels=["rgb", "alpha", "depth", "hit"])
+    assert tracer.get_prev_num_samples() == ms.total
+    rgb = rb.rgb.detach(); alpha = rb.alpha.detach()
+    assert float(rgb.min()) >= 0.0 and float(rgb.max()) <= 1.0 + 1e-5 and float(alpha.max()) <= 1.0 + 1e-5 and float(alpha.min()) >= 0.0
+    miss = counts == 0
+    assert bool(miss.any()) and torch.allclose(rgb[miss], torch.tensor([0.25, 0.5, 0.75], device="cuda").expand(int(miss.sum()), 3))
+    assert float(alpha[miss].abs().sum()) == 0.0 and not bool(rb.hit[miss].any())
+    tracer.seed = 5
+    rb2 = tracer(nef, rays=rays, channels=["rgb"])
+    assert torch.equal(rb2.rgb.detach(), rgb)                                       # idempotent / deterministic forward
+    # backward linearity: grad(2*g) == 2*grad(g) up to atomic-order noise
+    g1 = torch.randn(R, 3, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1)) / R
+    grads = []
+    for k in (1.0, 2.0):
+        nef.zero_grad(set_to_none=True)
+        tracer.seed = 5
+        out = tracer(nef, rays=rays, channels=["rgb"]).rgb
+        out.backward(g1 * k)
+        grads.append((grid.codebook.feats.grad.clone(), nef.decoder_color.layers[0].weight.grad.clone()))
+    for a, b in zip(grads[0], grads[1]):
+        assert float((2 * a - b).abs().max()) <= 2e-2 * float(b.abs().max()) + 1e-12
+    assert float(grads[0][0][int(grid.codebook.begin_idxes[15]):].abs().sum()) == 0.0      # the zeroed last LOD receives no gradient
