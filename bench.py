@@ -219,15 +219,21 @@ def run_ours(args):
     launches0 = W._cabi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    dev_allocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     e0.record()
+    step_ev[0].record()
     total_samples = 0
     for k in range(args.steps):
         i = args.warmup + k
         step(i, *dev_rays[i], dev_tgt[i])
         total_samples += tracer.get_prev_num_samples()
+        step_ev[k + 1].record()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    step_ms = [step_ev[k].elapsed_time(step_ev[k + 1]) for k in range(args.steps)]
+    dev_allocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - dev_allocs0
     launches = W._cabi.launch_count() - launches0
     prof = W.ops.PROFILE
     W.ops.PROFILE = None
@@ -312,7 +318,8 @@ def run_ours(args):
                     "last_loss": loss_host},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "rooflines": rooflines,
             "march": {"candidates_per_step": R * args.num_steps, "candidates_per_sec": R * args.num_steps / (mean_ms.get("march_count", float("nan")) * 1e-3)},
-            "samples_per_step_per_gpu": S_step, "samples_per_sec": total_samples / (ms * 1e-3), "stage_ms": mean_ms}
+            "samples_per_step_per_gpu": S_step, "samples_per_sec": total_samples / (ms * 1e-3), "stage_ms": mean_ms,
+            "step_ms": step_ms, "cudaMalloc_calls_in_timed_region": int(dev_allocs)}
 
     if not args.no_cpu_baseline:
         Oc, onef, spc = cpu_scene(args)

@@ -71,6 +71,8 @@ def lib() -> C.CDLL:
     """Load libwispb200.so; raise loudly if it was not built (no fallback path exists)."""
     global _lib
     if _lib is None:
+        global LIB_PATH
+        LIB_PATH = os.environ.get("WISPB200_LIB", LIB_PATH)          # debug builds (tools/tc_timing.py) live beside the product library
         if not os.path.exists(LIB_PATH):
             raise WispB200Error(
                 f"{LIB_PATH} not found: build it with `python kaolin-wisp_b200/build.py` (or __graft_entry__.build()). "

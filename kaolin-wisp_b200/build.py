@@ -15,10 +15,11 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "libwispb200.so")
+LIB = os.path.join(LIBDIR, os.environ.get("WB_LIB_NAME", "libwispb200.so"))      # WB_LIB_NAME + WB_EXTRA_NVCC_FLAGS: debug variants
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+FLAGS += os.environ.get("WB_EXTRA_NVCC_FLAGS", "").split()          # debug builds only (e.g. -DWB_TC_TIMING)
 
 
 def sources():
@@ -33,7 +34,7 @@ def _deps_mtime():
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(LIBDIR, "obj")
+    objdir = os.path.join(LIBDIR, "obj" + ("_" + os.path.splitext(os.path.basename(LIB))[0] if "WB_LIB_NAME" in os.environ else ""))
     os.makedirs(objdir, exist_ok=True)
     hdr_m = _deps_mtime()
     jobs = []

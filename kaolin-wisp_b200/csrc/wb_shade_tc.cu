@@ -29,12 +29,17 @@
 #include <math.h>
 
 #define TC_ML 16
-constexpr int TC_THREADS = 256;
+constexpr int TC_ROWS = 128;          // samples per sub-tile (UMMA M)
+constexpr int TC_GROUP = 256;         // threads per sub-tile group: 128 rows x 2 column halves
+constexpr int TC_BWD_GROUPS = 2;      // sub-tile groups per CTA in the decoder backward
+constexpr int TC_ISSUERS = 2;         // issuer warps per group (backward: weight grad | data grad)
 
 struct WbTc {
     int nl_d, nl_c;
     int I[TC_ML], O[TC_ML], Kp[TC_ML], Np[TC_ML];
-    int w_off[TC_ML], b_off[TC_ML];            // byte offsets in the parameter blob
+    int w_off[TC_ML], b_off[TC_ML];            // byte offsets in the parameter blob: weight pack, bias pack [Np x 16] (bias at k = 0)
+    int has_bias;
+    int ones_off;                              // byte offset (from smem base) of the constant [128 x 16] tile (feature 0 = 1) of the bias UMMA
     int src_w[TC_ML], src_b[TC_ML];
     int blob_bytes;
     int tile_off[TC_ML];                       // byte offset of layer l's INPUT tile inside a sub-tile region
@@ -46,6 +51,7 @@ struct WbTc {
     int work_col[2];                           // TMEM working accumulator of sub-tile 0/1
     int tmem_cols;
     int feat_dim, pos_dim, view_dim, pos_mode, pos_freq, view_mode, view_freq;
+    int skew;                                  // backward: group 1 starts half a tile behind group 0
 };
 
 static int tc_round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -75,33 +81,38 @@ int wb_tc_make(const wb_nef_desc* d, bool backward, WbTc* m)
         WB_CHECK_ARG(I >= 1 && I <= 128 && O >= 1 && O <= 128, "tensor-core path: layer widths must be <= 128");
         m->I[l] = I; m->O[l] = O; m->Kp[l] = tc_round_up(I, 16); m->Np[l] = tc_round_up(O, 16);
         m->w_off[l] = off; off += m->Kp[l] * m->Np[l] * 2;
-        m->b_off[l] = off; off += m->Np[l] * 4;
+        m->b_off[l] = off; off += m->Np[l] * 32;
         int& src = dens ? srcd : srcc;
         m->src_w[l] = src; src += I * O;
         if (d->has_bias) { m->src_b[l] = src; src += O; } else m->src_b[l] = -1;
         maxw = max(maxw, max(m->Kp[l], m->Np[l]));
     }
     m->blob_bytes = tc_round_up(off, 16);
+    m->has_bias = d->has_bias ? 1 : 0;
     // shared memory map: [sub0 tiles][sub1 tiles][dY0][dY1][params][pad]
     int sub_bytes = 0;
     if (backward) {
         for (int l = 0; l < nl; ++l) { m->tile_off[l] = sub_bytes; sub_bytes += (m->Kp[l] / 8 + 1) * 2048; }   // + constant-one slab
     } else {
-        for (int l = 0; l < nl; ++l) m->tile_off[l] = (l & 1) * (maxw / 8) * 2048;                              // ping-pong
-        sub_bytes = 2 * (maxw / 8) * 2048;
+        // forward: every layer's input tile is overwritten in place by its output (the layer's UMMAs have completed before the
+        // epilogue writes, and each thread only touches its own row) -> 16 KB per sub-tile, 4 CTAs per SM for the gather
+        for (int l = 0; l < nl; ++l) m->tile_off[l] = 0;
+        sub_bytes = (maxw / 8) * 2048;
     }
+    const int groups = backward ? TC_BWD_GROUPS : 1;             // sub-tile groups per CTA
     m->sub_off[0] = 0; m->sub_off[1] = sub_bytes;
-    int p = 2 * sub_bytes;
+    int p = groups * sub_bytes;
     if (backward) { m->dy_off[0] = p; p += (maxw / 8) * 2048; m->dy_off[1] = p; p += (maxw / 8) * 2048; }
     m->w_smem_off = p; p += m->blob_bytes;
+    m->ones_off = p; p += 2 * 2048;
     if (backward) {   // weight-grad MMAs read 16 slabs (M = 128 feature rows) from every X tile: keep that window inside the allocation
-        const int need = m->sub_off[1] + m->tile_off[nl - 1] + 16 * 2048;
+        const int need = m->sub_off[groups - 1] + m->tile_off[nl - 1] + 16 * 2048;
         if (p < need) p = need;
     }
     m->smem_bytes = p + 64;
     WB_CHECK_ARG(m->smem_bytes <= 227 * 1024, "tensor-core path: decoder does not fit in shared memory (use precision 0)");
     int col = 0;
-    m->work_col[0] = col; col += maxw; m->work_col[1] = col; col += maxw;
+    for (int gi = 0; gi < groups; ++gi) { m->work_col[gi] = col; col += maxw; }
     if (backward) for (int l = 0; l < nl; ++l) { m->acc_col[l] = col; col += m->Np[l]; }
     WB_CHECK_ARG(col <= 512, "tensor-core path: accumulators do not fit in TMEM (use precision 0)");
     int alloc = 32; while (alloc < col) alloc <<= 1;
@@ -145,9 +156,14 @@ __global__ void wb_tc_pack_kernel(WbTc m, const float* __restrict__ dens, const 
             const int kc = e / (Np * 8), n = (e / 8) % Np, k = kc * 8 + (e & 7);      // element (n,k) at (k/8)*(Np*8) + n*8 + k%8 halves
             w[e] = __float2half_rn((n < O && k < I) ? src[m.src_w[l] + n * I + k] : 0.0f);
         }
-        float* b = reinterpret_cast<float*>(blob + m.b_off[l]);
-        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < Np; e += gridDim.x * blockDim.x)
-            b[e] = (e < O && m.src_b[l] >= 0) ? src[m.src_b[l] + e] : 0.0f;
+        // bias pack B[Np x 16] (K-major, same layout as the weights): column k = 0 holds the bias.  An init UMMA
+        // D = Ones[128 x 16] . B^T puts the bias into the accumulator; the layer UMMAs accumulate on top (fp16 bias: what
+        // F.linear under autocast does)
+        __half* b = reinterpret_cast<__half*>(blob + m.b_off[l]);
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < Np * 16; e += gridDim.x * blockDim.x) {
+            const int kc = e / (Np * 8), n = (e / 8) % Np, k = kc * 8 + (e & 7);
+            b[e] = __float2half_rn((k == 0 && n < O && m.src_b[l] >= 0) ? src[m.src_b[l] + n] : 0.0f);
+        }
     }
 }
 
@@ -223,11 +239,13 @@ __device__ __forceinline__ void tile_embed(uint8_t* tile, int r, int f0, int mod
     }
 }
 // hash-grid gather of one sample -> features [0, feat_dim) of the X0 tile (fp32 blend, fp16 store)
-__device__ __forceinline__ void tile_gather(const WbGrid& g, uint8_t* tile, int r, float px, float py, float pz)
+// `half` (0/1): the two threads of a row split the work -- slab (4 LODs) k goes to half k & 1 on the F == 2 'cat' path, the
+// generic paths are done by half 0 alone
+__device__ __forceinline__ void tile_gather(const WbGrid& g, uint8_t* tile, int r, int half, float px, float py, float pz)
 {
     const int L = g.L, F = g.F;
     if (g.multiscale == 0 && F == 2) {
-        for (int l0 = 0; l0 < L; l0 += 4) {                     // 4 levels = 8 features = one slab row (16 B store)
+        for (int l0 = 4 * half; l0 < L; l0 += 8) {              // 4 levels = 8 features = one slab row (16 B store)
             float v[8];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -246,6 +264,8 @@ __device__ __forceinline__ void tile_gather(const WbGrid& g, uint8_t* tile, int 
             }
             tile_store8(tile, r, l0 >> 2, v);
         }
+    } else if (half != 0) {
+        return;
     } else if (g.multiscale == 0) {
         for (int l = 0; l < L; ++l) {
             if (l >= g.lod_idx) { for (int f = 0; f < F; ++f) tile_store1(tile, r, l * F + f, 0.0f); continue; }
@@ -282,96 +302,185 @@ __device__ __forceinline__ void tile_gather(const WbGrid& g, uint8_t* tile, int 
 // zero features [f0, f1) of this thread's row
 __device__ __forceinline__ void tile_zero(uint8_t* tile, int r, int f0, int f1) { for (int f = f0; f < f1; ++f) tile_store1(tile, r, f, 0.0f); }
 
+// ---- optional phase timestamps (debug builds only: WB_EXTRA_NVCC_FLAGS=-DWB_TC_TIMING, read by tools/tc_timing.py) ----
+#ifdef WB_TC_TIMING
+#define TC_TS_N 1024
+__device__ long long g_tc_ts[2][2][TC_TS_N];      // [kernel: 0 fwd, 1 bwd][thread 0 / (fwd: last thread, bwd: first thread of group 1)][event]
+#define TC_TS(c) do { if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == ((c).tsk ? TC_GROUP : TC_GROUP - 1)) && (c).tsn < TC_TS_N) \
+        g_tc_ts[(c).tsk][threadIdx.x ? 1 : 0][(c).tsn++] = clock64(); } while (0)
+__device__ long long g_tc_ts2[2][TC_TS_N];        // thread 0 only: inside the issue branch (after elect+fence, after the UMMAs, after commit)
+#define TC_TS2(c, n2) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (n2) < TC_TS_N) g_tc_ts2[(c).tsk][(n2)++] = clock64(); } while (0)
+extern "C" int wb_tc_timing_dump2(long long* out)
+{ return (int)cudaMemcpyFromSymbol(out, g_tc_ts2, sizeof(long long) * 2 * TC_TS_N); }
+extern "C" int wb_tc_timing_dump(long long* out)
+{ return (int)cudaMemcpyFromSymbol(out, g_tc_ts, sizeof(long long) * 2 * 2 * TC_TS_N); }
+#else
+#define TC_TS(c) do { } while (0)
+#define TC_TS2(c, n2) do { } while (0)
+#endif
+
+// Issue table (shared memory, built once per CTA): everything the issuer needs for one UMMA chain, so that the critical path
+// after the group barrier is two LDS.128 (issued BEFORE the barrier) + the UTCHMMAs.  Deriving the descriptors from the
+// kernel parameters instead costs ~400 cycles of dependent constant loads / uniform ALU per round (measured).
+struct __align__(16) TcRec {
+    uint32_t a_lo, a_hi, b_lo, b_hi;          // shared-memory descriptors of the first UMMA
+    uint32_t idesc, tmem_d, nk_acc, adv;      // nk | (accumulate-from-start << 8); a advance | b advance << 16 (16-byte units)
+};
+enum { TC_K_FWD = 0, TC_K_BIAS = 1, TC_K_WGRAD = 2, TC_K_DGRAD = 3, TC_KINDS = 4 };
+
 struct TcCtx {
     uint8_t* smem; uint64_t* bar; uint32_t tmem; uint32_t phase;
-    int sub, r, laneq;          // sub-tile, row in sub-tile, 32*(warp%4)
+    const TcRec* tab;           // this group's records: tab[kind * TC_ML + layer]
+    int g;                      // sub-tile group of this thread inside the CTA
+    int r, h;                   // row of the sub-tile (== TMEM lane), column half
+    int laneq;                  // 32*(warp%4): the TMEM lane quarter this warp may access
+    int wig;                    // warp index inside the group (warp-uniform)
+#ifdef WB_TC_TIMING
+    int tsn, tsk, tsn2;
+#endif
 };
-
-// CTA-wide: operand tiles written -> one thread issues `issue()` -> everybody waits for completion
-template <class IssueFn>
-__device__ __forceinline__ void tc_round(TcCtx& c, IssueFn issue)
+__device__ __forceinline__ void tc_ctx_init(TcCtx& c, uint8_t* smem, uint64_t* bars, const TcRec* tab, uint32_t tmem, int kernel_id)
 {
+    const int tig = threadIdx.x & (TC_GROUP - 1);
+    c.smem = smem; c.g = threadIdx.x / TC_GROUP; c.bar = bars + c.g; c.tmem = tmem; c.phase = 0;
+    c.tab = tab + c.g * (TC_KINDS * TC_ML);
+    c.r = tig & (TC_ROWS - 1); c.h = tig / TC_ROWS; c.laneq = ((tig >> 5) & 3) * 32;
+    c.wig = __shfl_sync(0xffffffffu, tig >> 5, 0);
+#ifdef WB_TC_TIMING
+    c.tsn = 0; c.tsk = kernel_id; c.tsn2 = 0;
+#endif
+}
+
+// one record per (group, kind, layer) + the constant tile of the bias UMMA; called by all threads before the first round
+__device__ __forceinline__ void tc_build_table(const WbTc& m, TcRec* tab, uint8_t* smem, uint32_t tmem, int groups, bool backward)
+{
+    const int nl = m.nl_d + m.nl_c;
+    const int e = threadIdx.x;
+    if (e < TC_ROWS) {                                           // Ones[128 x 16]: feature 0 = 1, features 1..15 = 0
+        uint4 one; one.x = 0x00003C00u; one.y = 0; one.z = 0; one.w = 0;
+        *reinterpret_cast<uint4*>(smem + m.ones_off + e * 16) = one;
+        *reinterpret_cast<uint4*>(smem + m.ones_off + 2048 + e * 16) = make_uint4(0, 0, 0, 0);
+    }
+    if (e >= groups * TC_KINDS * nl) return;
+    const int l = e % nl, kind = (e / nl) % TC_KINDS, g = e / (nl * TC_KINDS);
+    const uint32_t base = tc_smem_u32(smem);
+    const int Np = m.Np[l], Kp = m.Kp[l];
+    uint64_t da = 0, db = 0; uint32_t id = 0, d = 0, nk = 0, acc = 0, aadv = 0, badv = 0;
+    if (kind == TC_K_FWD) {            // D_work[g] (+)= X_l . W_l^T
+        da = tc_desc(base + m.sub_off[g] + m.tile_off[l], 2048, 128); db = tc_desc(base + m.w_smem_off + m.w_off[l], Np * 16, 128);
+        id = tc_idesc(128, Np, 0, 0); d = tmem + m.work_col[g]; nk = Kp / 16; acc = m.has_bias; aadv = 4096 >> 4; badv = (2 * Np * 16) >> 4;
+    } else if (kind == TC_K_BIAS) {    // D_work[g] = Ones . Bias_l^T
+        da = tc_desc(base + m.ones_off, 2048, 128); db = tc_desc(base + m.w_smem_off + m.b_off[l], Np * 16, 128);
+        id = tc_idesc(128, Np, 0, 0); d = tmem + m.work_col[g]; nk = m.has_bias ? 1 : 0;
+    } else if (!backward) {
+        nk = 0;
+    } else if (kind == TC_K_WGRAD) {   // acc_l[in, out] += X_l^T . dY_l   (K = 128 samples)
+        da = tc_desc(base + m.sub_off[g] + m.tile_off[l], 128, 2048); db = tc_desc(base + m.dy_off[g], 128, 2048);
+        id = tc_idesc(128, Np, 1, 1); d = tmem + m.acc_col[l]; nk = 8; acc = 1; aadv = 256 >> 4; badv = 256 >> 4;
+    } else {                           // D_work[g] = dY_l . W_l         (K = out features)
+        da = tc_desc(base + m.dy_off[g], 2048, 128); db = tc_desc(base + m.w_smem_off + m.w_off[l], 128, Np * 16);
+        id = tc_idesc(128, Kp, 0, 1); d = tmem + m.work_col[g]; nk = Np / 16; aadv = 4096 >> 4; badv = 256 >> 4;
+    }
+    TcRec r = { (uint32_t)da, (uint32_t)(da >> 32), (uint32_t)db, (uint32_t)(db >> 32), id, d, nk | (acc << 8), aadv | (badv << 16) };
+    tab[(g * TC_KINDS + kind) * TC_ML + l] = r;
+}
+__device__ __forceinline__ void tc_issue_rec(const uint4 q0, const uint4 q1)
+{
+    uint64_t da = ((uint64_t)q0.y << 32) | q0.x, db = ((uint64_t)q0.w << 32) | q0.z;
+    const int nk = (int)(q1.z & 0xffu);
+    const uint32_t acc = q1.z >> 8, aadv = q1.w & 0xffffu, badv = q1.w >> 16;
+    for (int kb = 0; kb < nk; ++kb) { tc_mma(q1.y, da, db, q1.x, acc | (uint32_t)(kb > 0)); da += aadv; db += badv; }
+}
+
+// One round of a sub-tile group: operand tiles written -> group barrier -> the group's two issuer warps launch their UMMA
+// chains (warp 0: kind k0a then k0b; warp 1: k1; a negative kind = nothing) and commit to the group's mbarrier -> the group
+// waits for all of them.
+// Measured on B200 (tools/tc_timing.py), first version of this file: a round cost ~600-1200 cycles from barrier to completion and
+// the epilogue of a 64-wide layer another ~1200; the tensor pipe was ~10 % busy.  What this version does about it:
+//  (a) issue table + elect.sync in a warp-uniform branch (descriptors in uniform registers, UTCHMMAs back to back; the first
+//      version's per-thread branch ran a one-lane waterfall loop of ~200 cycles per UMMA),
+//  (b) weight-grad and data-grad chains issued by two different warps,
+//  (c) bias added by an init UMMA (Ones x Bias^T) and relu fused into the fp32->fp16x2 conversion: the hidden-layer epilogue is
+//      tcgen05.ld + 16 F2FP.RELU + 4 STS.128 instead of ~130 instructions,
+//  (d) a row is shared by two threads (column halves),
+//  (e) the groups of a CTA (backward) / the CTAs of an SM (forward) have independent barriers and overlap each other.
+__device__ __forceinline__ void tc_round(TcCtx& c, int l, int k0a, int k0b, int k1)
+{
+    TC_TS(c);
+    uint4 qa0 = make_uint4(0, 0, 0, 0), qa1 = qa0, qb0 = qa0, qb1 = qa0;
+    if (c.wig < TC_ISSUERS) {                     // table reads do not depend on the barrier
+        const int ka = c.wig == 0 ? k0a : k1, kb = c.wig == 0 ? k0b : -1;
+        if (ka >= 0) { const uint4* p = reinterpret_cast<const uint4*>(c.tab + ka * TC_ML + l); qa0 = p[0]; qa1 = p[1]; }
+        if (kb >= 0) { const uint4* p = reinterpret_cast<const uint4*>(c.tab + kb * TC_ML + l); qb0 = p[0]; qb1 = p[1]; }
+    }
     tc_fence_smem_async();
     tc_fence_before();
-    __syncthreads();
-    if (threadIdx.x == 0) { tc_fence_after(); issue(); tc_commit(c.bar); }
+    tc_group_sync(c.g + 1, TC_GROUP);
+    TC_TS(c);
+    if (c.wig < TC_ISSUERS) {
+        if (tc_elect_one()) {
+            tc_fence_after();
+            TC_TS2(c, c.tsn2);
+            if (((qa1.z | qb1.z) & 0xffu) != 0) { tc_issue_rec(qa0, qa1); tc_issue_rec(qb0, qb1); TC_TS2(c, c.tsn2); tc_commit(c.bar); }
+            else tc_mbar_arrive(c.bar);
+            TC_TS2(c, c.tsn2);
+        }
+        __syncwarp();
+    }
+    TC_TS(c);
     tc_mbar_wait(c.bar, c.phase);
     c.phase ^= 1u;
     tc_fence_after();
+    TC_TS(c);
 }
 
-// forward UMMAs of layer l for both sub-tiles: D_work[sub] = X_l . W_l^T
-__device__ __forceinline__ void tc_issue_fwd(const WbTc& m, const TcCtx& c, int l)
-{
-    const uint32_t base = tc_smem_u32(c.smem);
-    const uint32_t id = tc_idesc(128, m.Np[l], 0, 0);
-    const uint32_t b0 = base + m.w_smem_off + m.w_off[l];
-    for (int sub = 0; sub < 2; ++sub) {
-        const uint32_t a0 = base + m.sub_off[sub] + m.tile_off[l];
-        for (int kb = 0; kb < m.Kp[l] / 16; ++kb)
-            tc_mma(c.tmem + m.work_col[sub], tc_desc(a0 + kb * 4096, 2048, 128), tc_desc(b0 + kb * 2 * m.Np[l] * 16, m.Np[l] * 16, 128), id, kb > 0);
-    }
-}
-// backward UMMAs of layer l: weight grad into acc_l (persistent), data grad into D_work[sub] (N = Kp_l)
-__device__ __forceinline__ void tc_issue_bwd(const WbTc& m, const TcCtx& c, int l, bool first_tile)
-{
-    const uint32_t base = tc_smem_u32(c.smem);
-    const uint32_t idw = tc_idesc(128, m.Np[l], 1, 1);
-    const uint32_t idd = tc_idesc(128, m.Kp[l], 0, 1);
-    const uint32_t w0 = base + m.w_smem_off + m.w_off[l];
-    for (int sub = 0; sub < 2; ++sub) {
-        const uint32_t x0 = base + m.sub_off[sub] + m.tile_off[l];
-        const uint32_t y0 = base + m.dy_off[sub];
-        for (int kb = 0; kb < 8; ++kb)            // K = 128 samples
-            tc_mma(c.tmem + m.acc_col[l], tc_desc(x0 + kb * 256, 128, 2048), tc_desc(y0 + kb * 256, 128, 2048), idw, !(first_tile && sub == 0 && kb == 0));
-        for (int kb = 0; kb < m.Np[l] / 16; ++kb) // K = out features
-            tc_mma(c.tmem + m.work_col[sub], tc_desc(y0 + kb * 4096, 2048, 128), tc_desc(w0 + kb * 256, 128, m.Np[l] * 16), idd, kb > 0);
-    }
-}
-
-// Decoders of one 256-sample tile, starting from an X0 tile that the caller has already written.
-// Returns (in registers) the density-decoder output df[16] and the colour pre-activations c3[3].
+// Decoders of one 128-sample sub-tile, starting from an X0 tile that the group has already written.
+// Returns (in registers, both column halves) the density-decoder output df[16] and the colour pre-activations c3[3].
 __device__ __forceinline__ void tc_decoders(const WbTc& m, TcCtx& c, const TcIn& in, int64_t ray, float df[16], float c3[3])
 {
-    uint8_t* sub = c.smem + m.sub_off[c.sub];
-    const float* P = reinterpret_cast<const float*>(c.smem + m.w_smem_off);
+    uint8_t* sub = c.smem + m.sub_off[c.g];
     const int nl = m.nl_d + m.nl_c;
     for (int l = 0; l < nl; ++l) {
-        tc_round(c, [&]() { tc_issue_fwd(m, c, l); });
-        const float* bias = P + m.b_off[l] / 4;
-        const uint32_t trow = c.tmem + ((uint32_t)c.laneq << 16) + m.work_col[c.sub];
+        tc_round(c, l, TC_K_BIAS, TC_K_FWD, -1);                 // accumulator = bias + X_l . W_l^T
+        const uint32_t trow = c.tmem + ((uint32_t)c.laneq << 16) + m.work_col[c.g];
         const bool last_d = (l == m.nl_d - 1), last_c = (l == nl - 1);
         if (last_d) {
-            float v[16]; tc_ld16(trow, v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) df[j] = v[j] + bias[j];
+            tc_ld16(trow, df);
             // colour input = [df[1:], embed(ray_d)], zero padded (nerf.py:248-259): the per-ray row already holds the
-            // embedding and the zero padding, only the first dout-1 (<= 15) features are per-sample
+            // embedding and the zero padding, only the first dout-1 (<= 15) features are per-sample.  16-byte chunk ch of the
+            // row is written by column half ch & 1.
             uint8_t* tcol = sub + m.tile_off[l + 1];
             const int nd = m.O[l] - 1, nch = m.Kp[l + 1] / 8;
             const uint4* re = in.ray_embed + ray * nch;
-            uint4 q0 = __ldg(re), q1 = __ldg(re + 1);
-            {
-                __half* h0 = reinterpret_cast<__half*>(&q0); __half* h1 = reinterpret_cast<__half*>(&q1);
+            uint4 q = __ldg(re + c.h);
+            __half* hq = reinterpret_cast<__half*>(&q);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { if (j < nd) h0[j] = __float2half_rn(df[j + 1]); }
-#pragma unroll
-                for (int j = 0; j < 7; ++j) { if (8 + j < nd) h1[j] = __float2half_rn(df[9 + j]); }
+            for (int j = 0; j < 8; ++j) {
+                // feature 8*h + j <- df[8*h + j + 1]; select without dynamic register indexing
+                const float dv = c.h == 0 ? df[(j + 1) & 15] : df[(j + 9) & 15];
+                if (8 * c.h + j < nd) hq[j] = __float2half_rn(dv);
             }
-            *reinterpret_cast<uint4*>(tcol + c.r * 16) = q0;
-            *reinterpret_cast<uint4*>(tcol + 2048 + c.r * 16) = q1;
-            for (int ch = 2; ch < nch; ++ch) *reinterpret_cast<uint4*>(tcol + ch * 2048 + c.r * 16) = __ldg(re + ch);
+            *reinterpret_cast<uint4*>(tcol + c.h * 2048 + c.r * 16) = q;
+            for (int ch = 2 + c.h; ch < nch; ch += 2) *reinterpret_cast<uint4*>(tcol + ch * 2048 + c.r * 16) = __ldg(re + ch);
         } else if (last_c) {
             float v[16]; tc_ld16(trow, v);
-            c3[0] = v[0] + bias[0]; c3[1] = v[1] + bias[1]; c3[2] = v[2] + bias[2];
+            c3[0] = v[0]; c3[1] = v[1]; c3[2] = v[2];
         } else {
+            // hidden layer: relu(acc) -> next input tile (F2FP.RELU); column half h owns columns [64k + 32h, 64k + 32h + 32)
             uint8_t* tn = sub + m.tile_off[l + 1];
-            for (int cc = 0; cc < m.Np[l]; cc += 16) {
-                float v[16]; tc_ld16(trow + cc, v);
-                float h[16];
+            const int Np = m.Np[l];
+            for (int cc = c.h * 32; cc < Np; cc += 64) {
+                float v[32];
+                const int nq = (Np - cc >= 32) ? 4 : 2;
+                if (nq == 4) tc_ld32(trow + cc, v); else tc_ld16(trow + cc, v);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) h[j] = fmaxf(v[j] + bias[cc + j], 0.0f);          // relu
-                tile_store8(tn, c.r, (cc >> 3), h); tile_store8(tn, c.r, (cc >> 3) + 1, h + 8);
+                for (int q = 0; q < 4; ++q) {
+                    if (q >= nq) break;
+                    uint4 o;
+                    o.x = tc_pack2_relu(v[q * 8], v[q * 8 + 1]); o.y = tc_pack2_relu(v[q * 8 + 2], v[q * 8 + 3]);
+                    o.z = tc_pack2_relu(v[q * 8 + 4], v[q * 8 + 5]); o.w = tc_pack2_relu(v[q * 8 + 6], v[q * 8 + 7]);
+                    *reinterpret_cast<uint4*>(tn + ((cc >> 3) + q) * 2048 + c.r * 16) = o;
+                }
             }
             // Np[l] == Kp[l+1] (both round_up(hidden,16)); padded outputs are relu(0 + 0) = 0
         }
@@ -379,16 +488,18 @@ __device__ __forceinline__ void tc_decoders(const WbTc& m, TcCtx& c, const TcIn&
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// forward kernel
+// forward kernel: CTA = one group = one 128-sample sub-tile at a time; several CTAs per SM overlap gather / UMMA / epilogue
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS)
+template <int MINB>                  // resident CTAs per SM the register allocation is bounded for
+__global__ void __launch_bounds__(TC_GROUP, MINB)
 wb_shade_fwd_tc_kernel(WbGrid g, WbTc m, const uint8_t* __restrict__ blob, TcIn in, float4* __restrict__ shaded)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ uint32_t tmem_s;
+    __shared__ TcRec itab[TC_KINDS * TC_ML];
     if (threadIdx.x == 0) {
-        tc_mbar_init(&bars[0], 1); tc_mbar_init(&bars[1], 1); tc_mbar_init_fence();
+        tc_mbar_init(&bars[0], TC_ISSUERS); tc_mbar_init(&bars[1], 1); tc_mbar_init_fence();
         tc_mbar_expect_tx(&bars[1], (uint32_t)m.blob_bytes);
         tc_bulk_g2s(smem + m.w_smem_off, blob, (uint32_t)m.blob_bytes, &bars[1]);      // TMA: parameters -> shared memory
     }
@@ -396,14 +507,15 @@ wb_shade_fwd_tc_kernel(WbGrid g, WbTc m, const uint8_t* __restrict__ blob, TcIn 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    tc_build_table(m, itab, smem, tmem_s, 1, false);
+    __syncthreads();
     tc_mbar_wait(&bars[1], 0);
-    TcCtx c; c.smem = smem; c.bar = &bars[0]; c.tmem = tmem_s; c.phase = 0;
-    c.sub = threadIdx.x >> 7; c.r = threadIdx.x & 127; c.laneq = ((threadIdx.x >> 5) & 3) * 32;
-    uint8_t* t0 = smem + m.sub_off[c.sub] + m.tile_off[0];
+    TcCtx c; tc_ctx_init(c, smem, bars, itab, tmem_s, 0);
+    uint8_t* t0 = smem + m.sub_off[0] + m.tile_off[0];
     const int nch0 = m.Kp[0] / 8;
-    const int64_t ntiles = (in.S + TC_THREADS - 1) / TC_THREADS;
+    const int64_t ntiles = (in.S + TC_ROWS - 1) / TC_ROWS;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        int64_t s = tile * TC_THREADS + threadIdx.x;
+        int64_t s = tile * TC_ROWS + c.r;
         const bool valid = s < in.S;
         if (!valid) s = in.S - 1;
         const int64_t ray = __ldg(in.rec_ray + s);
@@ -411,15 +523,20 @@ wb_shade_fwd_tc_kernel(WbGrid g, WbTc m, const uint8_t* __restrict__ blob, TcIn 
         const float px = wb_addcmul(__ldg(in.origins + 3 * ray), __ldg(in.dirs + 3 * ray), t);
         const float py = wb_addcmul(__ldg(in.origins + 3 * ray + 1), __ldg(in.dirs + 3 * ray + 1), t);
         const float pz = wb_addcmul(__ldg(in.origins + 3 * ray + 2), __ldg(in.dirs + 3 * ray + 2), t);
-        // density-decoder input row: grid features (+ position embedding), zero padded to Kp
-        tile_gather(g, t0, c.r, px, py, pz);
-        tile_embed(t0, c.r, m.feat_dim, m.pos_mode, m.pos_freq, px, py, pz);
-        tile_zero(t0, c.r, m.I[0], m.Kp[0]);
-        if (in.x0_save && valid)
-            for (int ch = 0; ch < nch0; ++ch) in.x0_save[(int64_t)ch * in.S + s] = *reinterpret_cast<const uint4*>(t0 + ch * 2048 + c.r * 16);
+        // density-decoder input row: grid features (+ position embedding), zero padded to Kp; the two threads of a row split the LODs
+        tile_gather(g, t0, c.r, c.h, px, py, pz);
+        if (c.h == 0) {
+            tile_embed(t0, c.r, m.feat_dim, m.pos_mode, m.pos_freq, px, py, pz);
+            tile_zero(t0, c.r, m.I[0], m.Kp[0]);
+        }
+        if (in.x0_save) {
+            tc_group_sync(1, TC_GROUP);
+            if (valid)
+                for (int ch = c.h; ch < nch0; ch += 2) in.x0_save[(int64_t)ch * in.S + s] = *reinterpret_cast<const uint4*>(t0 + ch * 2048 + c.r * 16);
+        }
         float df[16], c3[3];
         tc_decoders(m, c, in, ray, df, c3);
-        if (valid) {
+        if (valid && c.h == 0) {
             const float r = 1.0f / (1.0f + expf(-c3[0])), gg = 1.0f / (1.0f + expf(-c3[1])), b = 1.0f / (1.0f + expf(-c3[2]));
             shaded[s] = make_float4(r, gg, b, fmaxf(df[0], 0.0f));
         }
@@ -438,6 +555,8 @@ static int tc_launch_ray_embed(const WbTc& m, const wb_rays* rays, void* workspa
     return WB_OK;
 }
 
+static int tc_env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
+
 int wb_tc_shade_fwd(const wb_nef_desc* nef, const float* blob, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray,
                     int64_t S, float* shaded, void* feat_save, void* workspace, cudaStream_t st)
 {
@@ -446,73 +565,94 @@ int wb_tc_shade_fwd(const wb_nef_desc* nef, const float* blob, const wb_rays* ra
     WB_CHECK_ARG(workspace != nullptr, "precision 1 needs the workspace (wb_rf_workspace_bytes)");
     rc = tc_launch_ray_embed(m, rays, workspace, st); if (rc) return rc;
     TcIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S, reinterpret_cast<const uint4*>(workspace), reinterpret_cast<uint4*>(feat_save), nullptr };
-    WB_CUDA(cudaFuncSetAttribute(wb_shade_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, m.smem_bytes));
-    const int64_t ntiles = (S + TC_THREADS - 1) / TC_THREADS;
-    int per_sm = (227 * 1024) / (m.smem_bytes + 2048); per_sm = max(1, min(per_sm, 512 / m.tmem_cols)); per_sm = min(per_sm, 4);
+    // CTAs per SM: each is one sub-tile group; more groups in flight hide the gather and round latencies (measured sweep in
+    // profiles/README.md).  The register bound of the instantiation must match, or the hardware silently runs fewer.
+    int per_sm = (227 * 1024) / (m.smem_bytes + 4096); per_sm = max(1, min(per_sm, 512 / m.tmem_cols));
+    per_sm = max(2, min(min(per_sm, 4), tc_env_int("WB_TC_FWD_CTAS", 3)));
+    auto kern = per_sm == 2 ? wb_shade_fwd_tc_kernel<2> : per_sm == 3 ? wb_shade_fwd_tc_kernel<3> : wb_shade_fwd_tc_kernel<4>;
+    WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, m.smem_bytes));
+    WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 min(100, tc_env_int("WB_TC_FWD_CARVE", (per_sm * (m.smem_bytes + 4096) * 100) / (228 * 1024) + 1))));
+    const int64_t ntiles = (S + TC_ROWS - 1) / TC_ROWS;
     int64_t grid = (int64_t)wb_num_sms() * per_sm; if (grid > ntiles) grid = ntiles;
-    wb_shade_fwd_tc_kernel<<<(unsigned)grid, TC_THREADS, m.smem_bytes, st>>>(g, m, reinterpret_cast<const uint8_t*>(blob), in, reinterpret_cast<float4*>(shaded));
+    kern<<<(unsigned)grid, TC_GROUP, m.smem_bytes, st>>>(g, m, reinterpret_cast<const uint8_t*>(blob), in, reinterpret_cast<float4*>(shaded));
     WB_LAUNCH_CHECK();
     return WB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// decoder backward kernel
+// decoder backward kernel: CTA = TC_BWD_GROUPS groups (one per SM: TMEM holds the weight-grad accumulators), each group walks
+// its own sequence of 128-sample sub-tiles with its own barriers, so the groups drift out of phase and overlap
 // ---------------------------------------------------------------------------------------------------------------
 struct TcGrads { float* gdens; float* gcol; const float* scale; __half* dfeat; int planes, width; };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_BWD_GROUPS * TC_GROUP, 1)
 wb_mlp_bwd_tc_kernel(WbTc m, const uint8_t* __restrict__ blob, TcIn in, const float4* __restrict__ g_shaded, TcGrads G)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ __align__(8) uint64_t bars[TC_BWD_GROUPS + 2];
     __shared__ uint32_t tmem_s;
+    __shared__ TcRec itab[TC_BWD_GROUPS * TC_KINDS * TC_ML];
     const int nl = m.nl_d + m.nl_c;
     if (threadIdx.x == 0) {
-        tc_mbar_init(&bars[0], 1); tc_mbar_init(&bars[1], 1); tc_mbar_init_fence();
-        tc_mbar_expect_tx(&bars[1], (uint32_t)m.blob_bytes);
-        tc_bulk_g2s(smem + m.w_smem_off, blob, (uint32_t)m.blob_bytes, &bars[1]);
+        for (int i = 0; i < TC_BWD_GROUPS; ++i) tc_mbar_init(&bars[i], TC_ISSUERS);
+        tc_mbar_init(&bars[TC_BWD_GROUPS], 1); tc_mbar_init(&bars[TC_BWD_GROUPS + 1], 1); tc_mbar_init_fence();
+        tc_mbar_expect_tx(&bars[TC_BWD_GROUPS], (uint32_t)m.blob_bytes);
+        tc_bulk_g2s(smem + m.w_smem_off, blob, (uint32_t)m.blob_bytes, &bars[TC_BWD_GROUPS]);
     }
     if (threadIdx.x < 32) tc_tmem_alloc(&tmem_s, (uint32_t)m.tmem_cols);
-    TcCtx c; c.smem = smem; c.bar = &bars[0]; c.phase = 0;
-    c.sub = threadIdx.x >> 7; c.r = threadIdx.x & 127; c.laneq = ((threadIdx.x >> 5) & 3) * 32;
-    uint8_t* sub = smem + m.sub_off[c.sub];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    tc_build_table(m, itab, smem, tmem_s, TC_BWD_GROUPS, true);
+    TcCtx c; tc_ctx_init(c, smem, bars, itab, tmem_s, 1);
+    uint8_t* sub = smem + m.sub_off[c.g];
     // constant-one slab behind every input tile: feature 0 = 1, features 1..7 = 0  (bias gradient row of the weight grad)
-    for (int l = 0; l < nl; ++l) {
+    for (int l = c.h; l < nl; l += 2) {
         uint4 one; one.x = 0x00003C00u; one.y = 0; one.z = 0; one.w = 0;           // fp16 1.0 in the low half
         *reinterpret_cast<uint4*>(sub + m.tile_off[l] + (m.Kp[l] / 8) * 2048 + c.r * 16) = one;
+    }
+    if (threadIdx.x < 128) {                                       // zero the resident weight-grad accumulators (all 128 lanes)
+        const uint32_t tr = c.tmem + ((uint32_t)c.laneq << 16);
+        for (int l = 0; l < nl; ++l)
+            for (int cc = 0; cc < m.Np[l]; cc += 16) tc_st16_zero(tr + m.acc_col[l] + cc);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    c.tmem = tmem_s;
-    tc_mbar_wait(&bars[1], 0);
+    tc_mbar_wait(&bars[TC_BWD_GROUPS], 0);
     const float scale = __ldg(G.scale), inv_scale = 1.0f / scale;
-    uint8_t* dyt = smem + m.dy_off[c.sub];
+    uint8_t* dyt = smem + m.dy_off[c.g];
     uint8_t* t0 = sub + m.tile_off[0];
     const int nch0 = m.Kp[0] / 8;
-    const int64_t ntiles = (in.S + TC_THREADS - 1) / TC_THREADS;
-    bool first = true;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        int64_t s = tile * TC_THREADS + threadIdx.x;
+    const int64_t ntiles = (in.S + TC_ROWS - 1) / TC_ROWS;
+    const float z8[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    if (m.skew && c.g == 1) tc_mbar_wait(&bars[TC_BWD_GROUPS + 1], 0);     // start half a tile behind group 0 (see tc_round)
+    bool first_tile = true;
+    for (int64_t tile = (int64_t)blockIdx.x * TC_BWD_GROUPS + c.g; tile < ntiles; tile += (int64_t)gridDim.x * TC_BWD_GROUPS) {
+        int64_t s = tile * TC_ROWS + c.r;
         const bool valid = s < in.S;
         if (!valid) s = in.S - 1;
         const int64_t ray = __ldg(in.rec_ray + s);
-        for (int ch = 0; ch < nch0; ++ch)                          // saved density-decoder input row (coalesced 16 B per lane)
+        for (int ch = c.h; ch < nch0; ch += 2)                     // saved density-decoder input row (coalesced 16 B per lane)
             *reinterpret_cast<uint4*>(t0 + ch * 2048 + c.r * 16) = __ldg(in.x0_saved + (int64_t)ch * in.S + s);
         float df[16], c3[3];
         tc_decoders(m, c, in, ray, df, c3);
         float4 go = valid ? __ldg(g_shaded + s) : make_float4(0, 0, 0, 0);
+        if (first_tile && c.g == 0 && threadIdx.x == 0) tc_mbar_arrive(&bars[TC_BWD_GROUPS + 1]);
+        first_tile = false;
         // ---- colour decoder, last layer: dY = dL/d(pre-sigmoid), zero padded ----
         {
-            const float r = 1.0f / (1.0f + expf(-c3[0])), gg = 1.0f / (1.0f + expf(-c3[1])), b = 1.0f / (1.0f + expf(-c3[2]));
-            float v[8] = { go.x * r * (1.0f - r) * scale, go.y * gg * (1.0f - gg) * scale, go.z * b * (1.0f - b) * scale, 0, 0, 0, 0, 0 };
-            float z[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-            tile_store8(dyt, c.r, 0, v);
-            for (int sl = 1; sl < m.Np[nl - 1] / 8; ++sl) tile_store8(dyt, c.r, sl, z);
+            if (c.h == 0) {
+                const float r = 1.0f / (1.0f + expf(-c3[0])), gg = 1.0f / (1.0f + expf(-c3[1])), b = 1.0f / (1.0f + expf(-c3[2]));
+                float v[8] = { go.x * r * (1.0f - r) * scale, go.y * gg * (1.0f - gg) * scale, go.z * b * (1.0f - b) * scale, 0, 0, 0, 0, 0 };
+                tile_store8(dyt, c.r, 0, v);
+            }
+            for (int sl = 1 + c.h; sl < m.Np[nl - 1] / 8; sl += 2) tile_store8(dyt, c.r, sl, z8);
         }
-        const uint32_t trow = c.tmem + ((uint32_t)c.laneq << 16) + m.work_col[c.sub];
+        const uint32_t trow = c.tmem + ((uint32_t)c.laneq << 16) + m.work_col[c.g];
         for (int l = nl - 1; l >= 0; --l) {
-            tc_round(c, [&]() { tc_issue_bwd(m, c, l, first); });
+            tc_round(c, l, TC_K_WGRAD, -1, TC_K_DGRAD);
             // D_work row = dL/d(input of layer l), Kp[l] wide
             if (l == m.nl_d) {
                 // first colour layer: inputs [df[1:dout], embed(ray_d)]; only the first dout-1 carry gradient (nerf.py:259)
@@ -522,13 +662,12 @@ wb_mlp_bwd_tc_kernel(WbTc m, const uint8_t* __restrict__ blob, TcIn in, const fl
                 gdf[0] = (df[0] > 0.0f) ? go.w * scale : 0.0f;   // relu' of density (nerf.py:263)
 #pragma unroll
                 for (int j = 1; j < 16; ++j) gdf[j] = (j < dout) ? v[j - 1] : 0.0f;
-                tile_store8(dyt, c.r, 0, gdf); tile_store8(dyt, c.r, 1, gdf + 8);
-                float z[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-                for (int sl = 2; sl < m.Np[l - 1] / 8; ++sl) tile_store8(dyt, c.r, sl, z);
+                if (c.h == 0) tile_store8(dyt, c.r, 0, gdf); else tile_store8(dyt, c.r, 1, gdf + 8);
+                for (int sl = 2 + c.h; sl < m.Np[l - 1] / 8; sl += 2) tile_store8(dyt, c.r, sl, z8);
             } else if (l == 0) {
                 // dL/d(grid features) -> fp16 planes [plane][S][width] (still loss-scaled); tcgen05.ld is warp-collective
                 const int W = G.width, nfe = G.planes * W;
-                for (int f0 = 0; f0 < nfe; f0 += 16) {
+                for (int f0 = c.h * 16; f0 < nfe; f0 += 32) {
                     float v[16]; tc_ld16(trow + f0, v);
                     if (!valid) continue;
                     if (W == 2) {
@@ -548,25 +687,27 @@ wb_mlp_bwd_tc_kernel(WbTc m, const uint8_t* __restrict__ blob, TcIn in, const fl
             } else {
                 // hidden layer input: apply relu' from the retained activation tile, write the next dY (Np[l-1] == Kp[l])
                 const uint8_t* xt = sub + m.tile_off[l];
-                for (int cc = 0; cc < m.Kp[l]; cc += 16) {
-                    float v[16]; tc_ld16(trow + cc, v);
+                const int Kp = m.Kp[l];
+                for (int cc = c.h * 32; cc < Kp; cc += 64) {
+                    float v[32];
+                    const int nq = (Kp - cc >= 32) ? 4 : 2;
+                    if (nq == 4) tc_ld32(trow + cc, v); else tc_ld16(trow + cc, v);
 #pragma unroll
-                    for (int hsl = 0; hsl < 2; ++hsl) {
-                        const uint4 a = *reinterpret_cast<const uint4*>(xt + ((cc >> 3) + hsl) * 2048 + c.r * 16);
-                        const __half2* ah = reinterpret_cast<const __half2*>(&a);
-                        float o8[8];
-#pragma unroll
-                        for (int p = 0; p < 4; ++p) {
-                            const float2 af = __half22float2(ah[p]);
-                            o8[2 * p] = af.x > 0.0f ? v[hsl * 8 + 2 * p] : 0.0f;
-                            o8[2 * p + 1] = af.y > 0.0f ? v[hsl * 8 + 2 * p + 1] : 0.0f;
-                        }
-                        tile_store8(dyt, c.r, (cc >> 3) + hsl, o8);
+                    for (int q = 0; q < 4; ++q) {
+                        if (q >= nq) break;
+                        // relu'(x) as a 16-bit lane mask of the retained fp16 activation (>= 0 by construction)
+                        const uint4 a = *reinterpret_cast<const uint4*>(xt + ((cc >> 3) + q) * 2048 + c.r * 16);
+                        const __half2 z2 = __float2half2_rn(0.0f);
+                        uint4 o;
+                        o.x = tc_pack2(v[q * 8], v[q * 8 + 1]) & __hgt2_mask(*reinterpret_cast<const __half2*>(&a.x), z2);
+                        o.y = tc_pack2(v[q * 8 + 2], v[q * 8 + 3]) & __hgt2_mask(*reinterpret_cast<const __half2*>(&a.y), z2);
+                        o.z = tc_pack2(v[q * 8 + 4], v[q * 8 + 5]) & __hgt2_mask(*reinterpret_cast<const __half2*>(&a.z), z2);
+                        o.w = tc_pack2(v[q * 8 + 6], v[q * 8 + 7]) & __hgt2_mask(*reinterpret_cast<const __half2*>(&a.w), z2);
+                        *reinterpret_cast<uint4*>(dyt + ((cc >> 3) + q) * 2048 + c.r * 16) = o;
                     }
                 }
             }
         }
-        first = false;
     }
     // ---- flush weight / bias gradient accumulators (TMEM rows = input feature, row Kp = bias) ----
     tc_fence_before();
@@ -693,6 +834,7 @@ int wb_tc_decoder_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* 
                       float* grad_dens, float* grad_col, cudaStream_t st)
 {
     WbTc m; int rc = wb_tc_make(nef, true, &m); if (rc) return rc;
+    m.skew = tc_env_int("WB_TC_BWD_SKEW", 1);
     WB_CHECK_ARG(scale != nullptr, "precision 1 needs the device loss-scale pointer");
     WB_CHECK_ARG(feat_saved != nullptr && workspace != nullptr, "precision 1 backward needs the saved features and the workspace");
     rc = tc_launch_ray_embed(m, rays, workspace, st); if (rc) return rc;
@@ -702,9 +844,9 @@ int wb_tc_decoder_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* 
     TcIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S, reinterpret_cast<const uint4*>(workspace), nullptr, reinterpret_cast<const uint4*>(feat_saved) };
     TcGrads G = { grad_dens, grad_col, scale, dfeat, planes, width };
     WB_CUDA(cudaFuncSetAttribute(wb_mlp_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, m.smem_bytes));
-    const int64_t ntiles = (S + TC_THREADS - 1) / TC_THREADS;
-    int64_t grid = (int64_t)wb_num_sms(); if (grid > ntiles) grid = ntiles;       // 1 CTA / SM: TMEM holds the weight-grad accumulators
-    wb_mlp_bwd_tc_kernel<<<(unsigned)grid, TC_THREADS, m.smem_bytes, st>>>(m, reinterpret_cast<const uint8_t*>(blob), in,
+    const int64_t nctas = ((S + TC_ROWS - 1) / TC_ROWS + TC_BWD_GROUPS - 1) / TC_BWD_GROUPS;
+    int64_t grid = (int64_t)wb_num_sms(); if (grid > nctas) grid = nctas;         // 1 CTA / SM: TMEM holds the weight-grad accumulators
+    wb_mlp_bwd_tc_kernel<<<(unsigned)grid, TC_BWD_GROUPS * TC_GROUP, m.smem_bytes, st>>>(m, reinterpret_cast<const uint8_t*>(blob), in,
                                                                            reinterpret_cast<const float4*>(g_shaded), G);
     WB_LAUNCH_CHECK();
     return WB_OK;

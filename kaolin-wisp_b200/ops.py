@@ -147,14 +147,29 @@ def march_fill_reference_layout(ms: MarchState, device):
     return ridx, samples, depth, deltas, boundary
 
 
+def _bucket(S: int) -> int:
+    """Capacity for a per-sample buffer: S rounded up to 1/8 of its power of two (<= 12.5 % slack, >= 64 Ki samples).
+    The sample count changes with every batch of rays; bucketed sizes let the caching allocator hand the same blocks back
+    instead of going to cudaMalloc / cudaFree (a device sync) whenever S reaches a new maximum."""
+    if S <= 0:
+        return 0
+    gran = max(1 << 16, 1 << max(0, S.bit_length() - 4))
+    return (S + gran - 1) // gran * gran
+
+
+def _empty_s(S: int, tail: tuple, dtype, device):
+    """torch.empty((S, *tail)) carved from a bucketed allocation."""
+    return torch.empty((_bucket(S),) + tuple(tail), dtype=dtype, device=device)[:S]
+
+
 def march_fill_records(ms: MarchState, device):
     """Fused-path sample records: depth t, delta, ray index (12 B/sample)."""
     if ms.records is not None:
         return ms.records
     S = ms.total
-    rec_t = torch.empty(S, dtype=torch.float32, device=device)
-    rec_delta = torch.empty(S, dtype=torch.float32, device=device)
-    rec_ray = torch.empty(S, dtype=torch.int32, device=device)
+    rec_t = _empty_s(S, (), torch.float32, device)
+    rec_delta = _empty_s(S, (), torch.float32, device)
+    rec_ray = _empty_s(S, (), torch.int32, device)
     if S > 0:
         with _stage("march_fill"):
             A.check(A.lib().wb_rf_march_fill(C.byref(ms.rays), C.c_int32(ms.n), A.ptr(ms.jitter), C.c_uint32(ms.seed), A.ptr(ms.hitmask),
@@ -474,11 +489,12 @@ class RFTraceFn(torch.autograd.Function):
         A.check(L.wb_rf_pack_params(C.byref(desc), C.c_int32(precision), A.ptr(blob), A.stream()))
         rec_t, rec_delta, rec_ray = march_fill_records(ms, dev)
         S, R = ms.total, ms.rays.num_rays
-        shaded = torch.empty((S, 4), dtype=torch.float32, device=dev)
+        shaded = _empty_s(S, (4,), torch.float32, dev)
         need_grad = any(ctx.needs_input_grad[6:])          # grad mode is off inside Function.forward; ask autograd instead
-        wsb = int(L.wb_rf_workspace_bytes(C.byref(desc), C.c_int32(precision), C.c_int64(R), C.c_int64(S), C.c_int32(0)))
+        Scap = _bucket(S)                                  # byte sizes for the bucketed capacity (layouts still use S)
+        wsb = int(L.wb_rf_workspace_bytes(C.byref(desc), C.c_int32(precision), C.c_int64(R), C.c_int64(Scap), C.c_int32(0)))
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if wsb > 0 else None
-        fb = int(L.wb_rf_feat_bytes(C.byref(desc), C.c_int32(precision), C.c_int64(S))) if need_grad else 0
+        fb = int(L.wb_rf_feat_bytes(C.byref(desc), C.c_int32(precision), C.c_int64(Scap))) if need_grad else 0
         feat = torch.empty(fb, dtype=torch.uint8, device=dev) if fb > 0 else None
         with _stage("shade_fwd"):
             A.check(L.wb_rf_shade_fwd(C.byref(desc), A.ptr(blob), C.c_int32(precision), C.byref(ms.rays), A.ptr(rec_t), A.ptr(rec_ray),
@@ -505,7 +521,7 @@ class RFTraceFn(torch.autograd.Function):
         L = A.lib()
         S, R = ms.total, ms.rays.num_rays
         desc = spec.desc(tb, dens_flat, col_flat)
-        g_sh = torch.empty_like(shaded)
+        g_sh = _empty_s(S, (4,), torch.float32, shaded.device)
         gd = A.f32c(g_depth).reshape(-1) if g_depth is not None else None
         ga = A.f32c(g_alpha).reshape(-1) if g_alpha is not None else None
         grgb = A.f32c(g_rgb)
@@ -520,7 +536,7 @@ class RFTraceFn(torch.autograd.Function):
             # power-of-two loss scale computed on the device (no host sync): largest |gradient| -> ~64 in fp16
             amax = g_sh.abs().amax().clamp_min(1e-30)
             scale = torch.exp2(torch.floor(torch.log2(64.0 / amax))).clamp(2.0 ** -20, 2.0 ** 60).reshape(1).contiguous()
-        wsb = int(L.wb_rf_workspace_bytes(C.byref(desc), C.c_int32(ctx.precision), C.c_int64(R), C.c_int64(S), C.c_int32(1)))
+        wsb = int(L.wb_rf_workspace_bytes(C.byref(desc), C.c_int32(ctx.precision), C.c_int64(R), C.c_int64(_bucket(S)), C.c_int32(1)))
         ws = torch.empty(wsb, dtype=torch.uint8, device=tb.device) if wsb > 0 else None
         if ctx.precision == 1 and S > 0:
             with _stage("decoder_bwd"):
