@@ -89,7 +89,10 @@ typedef struct wb_octree {
     int32_t bits_level;                     /*   wb_octree_build_bits; NULL -> descend the bytes     */
     int32_t has_bbox;                       /* optional: bounding box (normalised [-1,1] coords) of  */
     float bbox_lo[3], bbox_hi[3];           /*   the occupied cells of the marched level; lets the   */
-} wb_octree;                                /*   marcher skip candidates that cannot be occupied     */
+                                            /*   marcher skip candidates that cannot be occupied     */
+    const uint32_t* coarse_bits;            /* optional: dilated occupancy of `coarse_level` built   */
+    int32_t coarse_level;                   /*   by wb_octree_build_coarse from `bits`; lets the     */
+} wb_octree;                                /*   marcher skip whole 32-candidate words. NULL -> off  */
 
 /* ------------------------------------------------------------------------------------------------
  * SPC helpers  -- replace kaolin.ops.spc.{scan_octrees, generate_points, unbatched_query}
@@ -100,6 +103,11 @@ int wb_octree_generate_points(const uint8_t* octree, const int32_t* prefix, int6
                               int16_t* points, int64_t total, wb_stream s);
 /* bits: zero-initialised uint32 [(8^level + 31)/32]; bit (x<<2L | y<<L | z) set iff the level-L cell is occupied. */
 int wb_octree_build_bits(const int16_t* level_points, int64_t num_points, int32_t level, uint32_t* bits, wb_stream s);
+/* coarse_bits: zero-initialised uint32 [(8^coarse_level + 31)/32]; a bit is set iff the coarse cell or one of its 26
+ * neighbours contains an occupied level-`level` cell (coarse_level < level <= 10).  No reference counterpart: it is an
+ * exact (conservative) accelerator for wb_raymarch_ray_count, results are identical with and without it. */
+int wb_octree_build_coarse(const int16_t* level_points, int64_t num_points, int32_t level, int32_t coarse_level,
+                           uint32_t* coarse_bits, wb_stream s);
 /* OctreeAS.query (octree_as.py:146-163): out int32 [N] or [N, level+1] (with_parents). */
 int wb_query(const wb_octree* oct, const float* coords, int64_t N, int32_t level, int32_t with_parents,
              int32_t* out, wb_stream s);

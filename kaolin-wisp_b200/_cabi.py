@@ -45,12 +45,13 @@ class OctreeDesc(C.Structure):
     """struct wb_octree."""
     _fields_ = [("octree", C.c_void_p), ("prefix", C.c_void_p), ("nbytes", C.c_int64), ("max_level", C.c_int32),
                 ("bits", C.c_void_p), ("bits_level", C.c_int32), ("has_bbox", C.c_int32),
-                ("bbox_lo", C.c_float * 3), ("bbox_hi", C.c_float * 3)]
+                ("bbox_lo", C.c_float * 3), ("bbox_hi", C.c_float * 3),
+                ("coarse_bits", C.c_void_p), ("coarse_level", C.c_int32)]
 
 
 EXPORTS = [
     "wb_last_error", "wb_version", "wb_device_check", "wb_launch_count",
-    "wb_octree_generate_points", "wb_octree_build_bits", "wb_query",
+    "wb_octree_generate_points", "wb_octree_build_bits", "wb_octree_build_coarse", "wb_query",
     "wb_raymarch_ray_count", "wb_scan_workspace_bytes", "wb_scan_counts", "wb_raymarch_ray_fill",
     "wb_raytrace_count", "wb_raytrace_fill", "wb_raymarch_voxel_fill", "wb_raymarch_uniform_count", "wb_raymarch_uniform_fill",
     "wb_hashgrid_fwd", "wb_hashgrid_bwd", "wb_triplane_fwd", "wb_triplane_bwd",

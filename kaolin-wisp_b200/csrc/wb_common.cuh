@@ -90,6 +90,8 @@ struct WbOct {
     int level; int use_bits;
     float h, inv_h, maxq;        // 2^(L-1), 2^-(L-1), 2^L - 1
     int has_bbox; float blo[3], bhi[3];   // occupied extent, already widened by the safety margin
+    const uint32_t* coarse; int clevel;   // dilated coarse occupancy (wb_octree_build_coarse) or nullptr
+    float ch, cmax;                       // 2^(clevel-1), 2^clevel - 1
 };
 __device__ __forceinline__ bool wb_quantize(float x, float h, float inv_h, float maxq, int& q) {
     float yf = __fmaf_rn(x, h, h);

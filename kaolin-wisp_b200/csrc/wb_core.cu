@@ -83,5 +83,8 @@ int wb_make_oct(const wb_octree* o, int level, WbOct* out) {
     for (int a = 0; a < 3; ++a) {   // widen by 1e-4: far above the fp32 error of p = fma(d,t,o) near the unit cube
         out->blo[a] = fmaxf(o->bbox_lo[a], -1.0f) - 1e-4f; out->bhi[a] = fminf(o->bbox_hi[a], 1.0f) + 1e-4f;
     }
+    const bool coarse_ok = out->has_bbox && o->coarse_bits != nullptr && o->coarse_level >= 1 && o->coarse_level < level;
+    out->coarse = coarse_ok ? o->coarse_bits : nullptr; out->clevel = coarse_ok ? o->coarse_level : 0;
+    out->ch = ldexpf(1.0f, out->clevel - 1); out->cmax = (float)((1 << out->clevel) - 1);
     return WB_OK;
 }

@@ -27,6 +27,7 @@ wb_march_count_kernel(WbOct o, WbMarch m, uint32_t* __restrict__ hitmask, int32_
         // occupied: restrict the exact per-candidate test to the iterations [w0, w1] that can overlap it.  The candidate
         // index bounds are conservative by one candidate on each side (jitter < one spacing, float slack << spacing).
         int w0 = 0, w1 = nw - 1;
+        float tc0 = -3.0e38f, tc1 = 3.0e38f;                     // depth range of the ray inside the widened box
         if (o.has_bbox) {
             float t0 = -3.0e38f, t1 = 3.0e38f; bool miss = false;
             const float oo[3] = { ox, oy, oz }, dd[3] = { dx, dy, dz };
@@ -39,6 +40,7 @@ wb_march_count_kernel(WbOct o, WbMarch m, uint32_t* __restrict__ hitmask, int32_
                 } else if (oo[a] < o.blo[a] || oo[a] > o.bhi[a]) miss = true;
             }
             t0 -= 1e-4f * (1.0f + fabsf(t0)); t1 += 1e-4f * (1.0f + fabsf(t1));
+            tc0 = t0; tc1 = t1;
             if (miss || t1 < t0 || !(range > 0.0f)) { if (miss || t1 < t0) { w0 = 1; w1 = 0; } }
             else {
                 // depth(i) in [lin_i*range + near, (lin_i + 1/n)*range + near], lin_i ~ i/(n-1)
@@ -51,21 +53,58 @@ wb_march_count_kernel(WbOct o, WbMarch m, uint32_t* __restrict__ hitmask, int32_
                 if (w1 > nw - 1) w1 = nw - 1;
             }
         }
-        int cnt = 0; uint32_t keep = 0;
-        for (int w = 0; w < nw; ++w) {
-            const int i = (w << 5) + lane;
-            bool hit = false;
-            if (w >= w0 && w <= w1 && i < m.n) {
-                const float d = wb_depth(m, r, key, i, nearv, range);
-                hit = wb_occupied(o, wb_addcmul(ox, dx, d), wb_addcmul(oy, dy, d), wb_addcmul(oz, dz, d));
+        // Word-level rejection with the dilated coarse mask (wb_octree_build_coarse): test points every half coarse cell along the
+        // clipped segment; a word is visited only if one of them falls into a marked coarse cell.  Conservative: an occupied
+        // candidate X at depth d has a test point within a quarter coarse cell, whose (clamped) cell is c(X) or a neighbour, and
+        // the candidate indices whose depth can lie within one spacing of that test point are all flagged (+-2 slack).
+        uint64_t active = ~0ull;
+        if (o.coarse != nullptr && nw <= 64 && w1 >= w0 && range > 0.0f) {
+            const float dlen = sqrtf(dx * dx + dy * dy + dz * dz);
+            const float delta = (0.5f / o.ch) / fmaxf(dlen, 1e-20f);           // half a coarse cell, in depth units
+            const float ta = fmaxf(tc0, nearv), tb = fminf(tc1, nearv + range * (1.0f + m.inv_n));
+            const float fn = (tb - ta) / delta;
+            if (tb >= ta && fn < 1024.0f) {
+                const int npts = (int)fn + 2;
+                const float nm1 = (float)max(m.n - 1, 1);
+                uint32_t lo = 0, hi = 0;
+                for (int k = lane; k < npts; k += 32) {
+                    const float tau = fminf(ta + (float)k * delta, tb);
+                    const float px = __fmaf_rn(dx, tau, ox), py = __fmaf_rn(dy, tau, oy), pz = __fmaf_rn(dz, tau, oz);
+                    const int qx = (int)fminf(fmaxf(floorf(__fmaf_rn(px, o.ch, o.ch)), 0.0f), o.cmax);
+                    const int qy = (int)fminf(fmaxf(floorf(__fmaf_rn(py, o.ch, o.ch)), 0.0f), o.cmax);
+                    const int qz = (int)fminf(fmaxf(floorf(__fmaf_rn(pz, o.ch, o.ch)), 0.0f), o.cmax);
+                    const uint32_t idx = ((uint32_t)qx << (2 * o.clevel)) | ((uint32_t)qy << o.clevel) | (uint32_t)qz;
+                    if ((__ldg(o.coarse + (idx >> 5)) >> (idx & 31)) & 1u) {
+                        const float f0 = ((tau - delta - nearv) / range - m.inv_n) * nm1 - 2.0f;
+                        const float f1 = ((tau + delta - nearv) / range) * nm1 + 2.0f;
+                        const int i0 = f0 <= 0.0f ? 0 : (f0 >= (float)(m.n - 1) ? m.n - 1 : (int)f0);
+                        const int i1 = f1 <= 0.0f ? 0 : (f1 >= (float)(m.n - 1) ? m.n - 1 : (int)f1 + 1);
+                        const int a0 = i0 >> 5, a1 = min(i1 >> 5, 63);
+                        const uint64_t span = (a1 >= 63 ? ~0ull : ((1ull << (a1 + 1)) - 1ull)) & ~((1ull << a0) - 1ull);
+                        lo |= (uint32_t)span; hi |= (uint32_t)(span >> 32);
+                    }
+                }
+                lo = __reduce_or_sync(0xffffffffu, lo); hi = __reduce_or_sync(0xffffffffu, hi);
+                active = ((uint64_t)hi << 32) | lo;
             }
-            const uint32_t word = (w >= w0 && w <= w1) ? __ballot_sync(0xffffffffu, hit) : 0u;
-            cnt += __popc(word);
-            if ((w & 31) == lane) keep = word;                   // lane j keeps word j of the current group of 32
-            if ((w & 31) == 31 || w == nw - 1) {                  // coalesced 128-byte store of up to 32 words
-                const int wbase = w & ~31;
-                if (wbase + lane <= w) hitmask[r * nw + wbase + lane] = keep;
+        }
+        int cnt = 0;
+        for (int wg = 0; wg < nw; wg += 32) {                    // groups of 32 words: lane j keeps word wg + j, one coalesced store
+            uint32_t keep = 0;
+            const int wa = max(wg, w0), wb = min(wg + 31, w1);
+            for (int w = wa; w <= wb; ++w) {
+                if (nw <= 64 && !((active >> w) & 1ull)) continue;
+                const int i = (w << 5) + lane;
+                bool hit = false;
+                if (i < m.n) {
+                    const float d = wb_depth(m, r, key, i, nearv, range);
+                    hit = wb_occupied(o, wb_addcmul(ox, dx, d), wb_addcmul(oy, dy, d), wb_addcmul(oz, dz, d));
+                }
+                const uint32_t word = __ballot_sync(0xffffffffu, hit);
+                cnt += __popc(word);
+                if ((w & 31) == lane) keep = word;
             }
+            if (wg + lane < nw) hitmask[r * nw + wg + lane] = keep;
         }
         if (lane == 0) counts[r] = cnt;
     }

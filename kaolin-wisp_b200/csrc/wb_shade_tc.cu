@@ -743,9 +743,9 @@ wb_mlp_bwd_tc_kernel(WbTc m, const uint8_t* __restrict__ blob, TcIn in, const fl
 // ---------------------------------------------------------------------------------------------------------------
 // table scatter: dL/dfeat planes -> hash table (hashgrid_interpolate_cuda.cu:151-160), with warp-level run merging
 // ---------------------------------------------------------------------------------------------------------------
-template <int F>
-__global__ void __launch_bounds__(256)
-wb_table_scatter_kernel(WbGrid g, TcIn in, const __half* __restrict__ dfeat, int planes, const float* __restrict__ scale_p, float* __restrict__ gtable)
+template <int F, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+wb_table_scatter_kernel(WbGrid g, TcIn in, const __half* __restrict__ dfeat, int planes, const float* __restrict__ scale_p, float* __restrict__ gtable, int pair_v4)
 {
     const int l = blockIdx.y;                                   // level
     const int lane = threadIdx.x & 31;
@@ -753,6 +753,7 @@ wb_table_scatter_kernel(WbGrid g, TcIn in, const __half* __restrict__ dfeat, int
     const int Fr = F > 0 ? F : g.F;
     const int pl = g.multiscale == 0 ? l : 0;
     float* tb = gtable + g.begin[l] * Fr;
+    const bool pair_ok = pair_v4 && ((reinterpret_cast<uintptr_t>(tb) & 15u) == 0);       // level base 16-byte aligned
     const int64_t nwork = (in.S + 31) & ~(int64_t)31;            // whole warps
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nwork; s += (int64_t)gridDim.x * blockDim.x) {
         const bool valid = s < in.S;
@@ -806,9 +807,24 @@ wb_table_scatter_kernel(WbGrid g, TcIn in, const __half* __restrict__ dfeat, int
                 }
             }
             if (tail && valid) {
+                // corners j and j + 4 are x-neighbours at the same (y, z).  When their entries differ only in bit 0 (dense level with
+                // an even index; hashed level with an even x, because (x | 1) ^ A == (x ^ A) ^ 1) the two 8-byte updates are one
+                // aligned 16-byte red.global.add.v4.f32: up to 25 % fewer atomic operations, which is what bounds this kernel.
+                float2* t2 = reinterpret_cast<float2*>(tb);
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (v0[j] != 0.0f || v1[j] != 0.0f) atomicAdd(reinterpret_cast<float2*>(tb) + idx[j], make_float2(v0[j], v1[j]));
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t i0 = idx[j], i1 = idx[j + 4];
+                    const bool nz0 = (v0[j] != 0.0f || v1[j] != 0.0f), nz1 = (v0[j + 4] != 0.0f || v1[j + 4] != 0.0f);
+                    if (pair_ok && ((i0 ^ i1) == 1u)) {
+                        if (nz0 || nz1) {
+                            const float4 val = (i0 & 1u) ? make_float4(v0[j + 4], v1[j + 4], v0[j], v1[j]) : make_float4(v0[j], v1[j], v0[j + 4], v1[j + 4]);
+                            atomicAdd(reinterpret_cast<float4*>(t2 + (i0 & ~1u)), val);
+                        }
+                    } else {
+                        if (nz0) atomicAdd(t2 + i0, make_float2(v0[j], v1[j]));
+                        if (nz1) atomicAdd(t2 + i1, make_float2(v0[j + 4], v1[j + 4]));
+                    }
+                }
             }
         } else {
             for (int f = 0; f < Fr; ++f) {
@@ -866,8 +882,11 @@ int wb_tc_table_scatter(const wb_nef_desc* nef, const wb_rays* rays, const float
     if (levels > 0) {
         int64_t bx = (S + 255) / 256; const int64_t cap = (int64_t)wb_num_sms() * 8; if (bx > cap) bx = cap;
         dim3 grid2((unsigned)bx, (unsigned)levels);
-        if (g.F == 2) wb_table_scatter_kernel<2><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, scale, grad_table);
-        else wb_table_scatter_kernel<0><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, scale, grad_table);
+        const int minb = tc_env_int("WB_TC_SCATTER_MINB", 4), v4 = tc_env_int("WB_TC_SCATTER_V4", 1);
+        if (g.F == 2 && minb == 5) wb_table_scatter_kernel<2, 5><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, scale, grad_table, v4);
+        else if (g.F == 2 && minb == 6) wb_table_scatter_kernel<2, 6><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, scale, grad_table, v4);
+        else if (g.F == 2) wb_table_scatter_kernel<2, 4><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, scale, grad_table, v4);
+        else wb_table_scatter_kernel<0, 4><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, scale, grad_table, 0);
         WB_LAUNCH_CHECK();
     }
     return WB_OK;

@@ -68,6 +68,33 @@ extern "C" int wb_octree_build_bits(const int16_t* level_points, int64_t num_poi
     return WB_OK;
 }
 
+__global__ void wb_build_coarse_kernel(const int16_t* __restrict__ pts, int64_t n, int shift, int cl, uint32_t* __restrict__ cbits)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cx = (int)(uint16_t)pts[i * 3] >> shift, cy = (int)(uint16_t)pts[i * 3 + 1] >> shift, cz = (int)(uint16_t)pts[i * 3 + 2] >> shift;
+    const int cres = 1 << cl;
+    for (int ax = -1; ax <= 1; ++ax) for (int ay = -1; ay <= 1; ++ay) for (int az = -1; az <= 1; ++az) {
+        const int x = cx + ax, y = cy + ay, z = cz + az;
+        if (x < 0 || y < 0 || z < 0 || x >= cres || y >= cres || z >= cres) continue;
+        const uint32_t idx = ((uint32_t)x << (2 * cl)) | ((uint32_t)y << cl) | (uint32_t)z;
+        const uint32_t bit = 1u << (idx & 31);
+        if (!(cbits[idx >> 5] & bit)) atomicOr(cbits + (idx >> 5), bit);
+    }
+}
+
+extern "C" int wb_octree_build_coarse(const int16_t* level_points, int64_t num_points, int32_t level, int32_t coarse_level,
+                                      uint32_t* coarse_bits, wb_stream s)
+{
+    WB_CHECK_ARG(level_points && coarse_bits, "null pointer");
+    WB_CHECK_ARG(level >= 1 && level <= 10 && coarse_level >= 1 && coarse_level < level, "need 1 <= coarse_level < level <= 10");
+    if (num_points == 0) return WB_OK;
+    wb_build_coarse_kernel<<<(unsigned)((num_points + 255) / 256), 256, 0, (cudaStream_t)s>>>(level_points, num_points, level - coarse_level,
+                                                                                            coarse_level, coarse_bits);
+    WB_LAUNCH_CHECK();
+    return WB_OK;
+}
+
 // OctreeAS.query -> unbatched_query(octree, prefix, coords, level, with_parents) (octree_as.py:146-163)
 __global__ void wb_query_kernel(WbOct o, const float* __restrict__ coords, int64_t N, int with_parents, int32_t* __restrict__ out)
 {

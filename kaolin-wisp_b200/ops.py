@@ -36,6 +36,9 @@ class _stage:
 # --------------------------------------------------------------------------------------------------------------
 # octree handle: the SPC tensors the reference's OctreeAS keeps (octree_as.py:58-62) + the optional dense bitmask
 # --------------------------------------------------------------------------------------------------------------
+COARSE_LEVEL = 5      # level of the dilated mask the marcher uses to skip empty 32-candidate words (0 disables it)
+
+
 @dataclass
 class OctreeTensors:
     octree: torch.Tensor          # uint8 [nbytes]
@@ -46,6 +49,8 @@ class OctreeTensors:
     bits: Optional[torch.Tensor] = None
     bits_level: int = -1
     bbox: Optional[tuple] = None          # (lo[3], hi[3]) of the occupied cells of `bits_level`, normalised coords
+    coarse: Optional[torch.Tensor] = None # dilated occupancy of `coarse_level` (word-skipping in the marcher), or None
+    coarse_level: int = 0
 
     def desc(self) -> A.OctreeDesc:
         d = A.OctreeDesc()
@@ -57,6 +62,8 @@ class OctreeTensors:
             d.has_bbox = 1
             for a in range(3):
                 d.bbox_lo[a], d.bbox_hi[a] = self.bbox[0][a], self.bbox[1][a]
+        d.coarse_bits = self.coarse.data_ptr() if self.coarse is not None else None
+        d.coarse_level = self.coarse_level if self.coarse is not None else 0
         return d
 
     def ensure_bits(self, level: int) -> None:
@@ -70,6 +77,12 @@ class OctreeTensors:
         lvl = self.points[start:start + cnt].contiguous()
         A.check(A.lib().wb_octree_build_bits(A.ptr(lvl), C.c_int64(cnt), C.c_int32(level), A.ptr(bits), A.stream()))
         self.bits, self.bits_level = bits, level
+        self.coarse, self.coarse_level = None, 0
+        cl = min(level - 2, COARSE_LEVEL)
+        if cl >= 2 and cnt > 0:
+            coarse = torch.zeros((8 ** cl + 31) // 32, dtype=torch.int32, device=self.octree.device)
+            A.check(A.lib().wb_octree_build_coarse(A.ptr(lvl), C.c_int64(cnt), C.c_int32(level), C.c_int32(cl), A.ptr(coarse), A.stream()))
+            self.coarse, self.coarse_level = coarse, cl
         if cnt > 0:     # one-off (per octree) host read of the occupied extent; exact dyadic cell faces
             mn, mx = lvl.min(0).values.cpu().tolist(), lvl.max(0).values.cpu().tolist()
             res = float(2 ** level)

@@ -119,6 +119,35 @@ def test_raymarch_seeded_vs_oracle(W, n, level, pernear):
     assert np.array_equal(mr.boundary.cpu().numpy(), ref["boundary"])
 
 
+@pytest.mark.parametrize("level,coarse,n", [(7, 5, 2048), (7, 3, 512), (6, 2, 100), (5, 3, 33)])
+def test_raymarch_word_skipping_is_exact(W, level, coarse, n):
+    """The dilated coarse mask only skips 32-candidate words that cannot hold a sample: hit masks are identical with and
+    without it, for camera rays, rays starting inside the volume, axis-aligned / grazing rays and unnormalised directions."""
+    rng = np.random.default_rng(level * 10 + coarse)
+    spc = O.octree_to_spc(O.points_to_octree(O.lego_like_points(level), level))
+    o, d = O.look_at_rays([-3.0, 0.65, -3.0], [0, 0, 0], 40, 40, 30.0)
+    oi = rng.uniform(-1.2, 1.2, (3000, 3)).astype(np.float32); di = rng.standard_normal((3000, 3)).astype(np.float32)
+    di[:500] /= np.linalg.norm(di[:500], axis=1, keepdims=True)
+    di[500:700] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 200)] * rng.choice([-1.0, 1.0], (200, 1)).astype(np.float32)   # axis aligned
+    oi[700:900] = np.round(oi[700:900] * 2 ** (level - 1)) / 2 ** (level - 1)                                             # on cell faces
+    di[900:1000] *= 7.5                                                                                                   # long directions
+    o = np.concatenate([o, oi]); d = np.concatenate([d, di])
+    from wisp_b200 import ops
+    saved = ops.COARSE_LEVEL
+    res = []
+    try:
+        for cl in (0, coarse):
+            ops.COARSE_LEVEL = cl
+            blas = W.OctreeAS(dev(spc.octree))
+            ms = ops.march_count(blas.tensors(), dev(o), dev(d), 0.0, 6.0, n, level, seed=99)
+            assert (blas.tensors().coarse is not None) == (cl > 0)
+            res.append((ms.hitmask.cpu().numpy().copy(), ms.counts.cpu().numpy().copy(), ms.total))
+    finally:
+        ops.COARSE_LEVEL = saved
+    assert res[0][2] == res[1][2] > 0
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+
+
 def test_raymarch_empty_and_errors(W):
     spc = O.octree_to_spc(O.points_to_octree(np.array([[0, 0, 0]], dtype=np.int16), 4))
     blas = W.OctreeAS(dev(spc.octree))
