@@ -312,11 +312,20 @@ __device__ long long g_tc_ts2[2][TC_TS_N];        // thread 0 only: inside the i
 #define TC_TS2(c, n2) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (n2) < TC_TS_N) g_tc_ts2[(c).tsk][(n2)++] = clock64(); } while (0)
 extern "C" int wb_tc_timing_dump2(long long* out)
 { return (int)cudaMemcpyFromSymbol(out, g_tc_ts2, sizeof(long long) * 2 * TC_TS_N); }
+__device__ long long g_tc_ts3[2][TC_TS_N];        // thread 0 only: hidden-layer epilogue (before tcgen05.ld, after its wait, after the stores)
+#define TC_TS3(c) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (c).tsn3 < TC_TS_N) g_tc_ts3[(c).tsk][(c).tsn3++] = clock64(); } while (0)
+extern "C" int wb_tc_timing_dump3(long long* out)
+{ return (int)cudaMemcpyFromSymbol(out, g_tc_ts3, sizeof(long long) * 2 * TC_TS_N); }
+__device__ long long g_tc_ts4[2][64][16];        // thread 0: stamp before the chain and after every UMMA of the first 64 rounds
+__device__ int g_tc_ts4_round[2];
+extern "C" int wb_tc_timing_dump4(long long* out)
+{ return (int)cudaMemcpyFromSymbol(out, g_tc_ts4, sizeof(long long) * 2 * 64 * 16); }
 extern "C" int wb_tc_timing_dump(long long* out)
 { return (int)cudaMemcpyFromSymbol(out, g_tc_ts, sizeof(long long) * 2 * 2 * TC_TS_N); }
 #else
 #define TC_TS(c) do { } while (0)
 #define TC_TS2(c, n2) do { } while (0)
+#define TC_TS3(c) do { } while (0)
 #endif
 
 // Issue table (shared memory, built once per CTA): everything the issuer needs for one UMMA chain, so that the critical path
@@ -336,7 +345,7 @@ struct TcCtx {
     int laneq;                  // 32*(warp%4): the TMEM lane quarter this warp may access
     int wig;                    // warp index inside the group (warp-uniform)
 #ifdef WB_TC_TIMING
-    int tsn, tsk, tsn2;
+    int tsn, tsk, tsn2, tsn3;
 #endif
 };
 __device__ __forceinline__ void tc_ctx_init(TcCtx& c, uint8_t* smem, uint64_t* bars, const TcRec* tab, uint32_t tmem, int kernel_id)
@@ -347,7 +356,7 @@ __device__ __forceinline__ void tc_ctx_init(TcCtx& c, uint8_t* smem, uint64_t* b
     c.r = tig & (TC_ROWS - 1); c.h = tig / TC_ROWS; c.laneq = ((tig >> 5) & 3) * 32;
     c.wig = __shfl_sync(0xffffffffu, tig >> 5, 0);
 #ifdef WB_TC_TIMING
-    c.tsn = 0; c.tsk = kernel_id; c.tsn2 = 0;
+    c.tsn = 0; c.tsk = kernel_id; c.tsn2 = 0; c.tsn3 = 0;
 #endif
 }
 
@@ -384,12 +393,17 @@ __device__ __forceinline__ void tc_build_table(const WbTc& m, TcRec* tab, uint8_
     TcRec r = { (uint32_t)da, (uint32_t)(da >> 32), (uint32_t)db, (uint32_t)(db >> 32), id, d, nk | (acc << 8), aadv | (badv << 16) };
     tab[(g * TC_KINDS + kind) * TC_ML + l] = r;
 }
-__device__ __forceinline__ void tc_issue_rec(const uint4 q0, const uint4 q1)
+__device__ __forceinline__ void tc_issue_rec(const uint4 q0, const uint4 q1, long long* ts = nullptr, int* tn = nullptr)
 {
     uint64_t da = ((uint64_t)q0.y << 32) | q0.x, db = ((uint64_t)q0.w << 32) | q0.z;
     const int nk = (int)(q1.z & 0xffu);
     const uint32_t acc = q1.z >> 8, aadv = q1.w & 0xffffu, badv = q1.w >> 16;
-    for (int kb = 0; kb < nk; ++kb) { tc_mma(q1.y, da, db, q1.x, acc | (uint32_t)(kb > 0)); da += aadv; db += badv; }
+    for (int kb = 0; kb < nk; ++kb) {
+        tc_mma(q1.y, da, db, q1.x, acc | (uint32_t)(kb > 0)); da += aadv; db += badv;
+#ifdef WB_TC_TIMING
+        if (ts && *tn < 16) ts[(*tn)++] = clock64();
+#endif
+    }
 }
 
 // One round of a sub-tile group: operand tiles written -> group barrier -> the group's two issuer warps launch their UMMA
@@ -421,7 +435,13 @@ __device__ __forceinline__ void tc_round(TcCtx& c, int l, int k0a, int k0b, int 
         if (tc_elect_one()) {
             tc_fence_after();
             TC_TS2(c, c.tsn2);
+#ifdef WB_TC_TIMING
+            long long* ts4 = nullptr; int tn4 = 0;
+            if (blockIdx.x == 0 && threadIdx.x == 0 && c.tsn2 / 3 < 64) { ts4 = g_tc_ts4[c.tsk][c.tsn2 / 3]; ts4[tn4++] = clock64(); }
+            if (((qa1.z | qb1.z) & 0xffu) != 0) { tc_issue_rec(qa0, qa1, ts4, &tn4); tc_issue_rec(qb0, qb1, ts4, &tn4); TC_TS2(c, c.tsn2); tc_commit(c.bar); }
+#else
             if (((qa1.z | qb1.z) & 0xffu) != 0) { tc_issue_rec(qa0, qa1); tc_issue_rec(qb0, qb1); TC_TS2(c, c.tsn2); tc_commit(c.bar); }
+#endif
             else tc_mbar_arrive(c.bar);
             TC_TS2(c, c.tsn2);
         }
@@ -472,7 +492,9 @@ __device__ __forceinline__ void tc_decoders(const WbTc& m, TcCtx& c, const TcIn&
             for (int cc = c.h * 32; cc < Np; cc += 64) {
                 float v[32];
                 const int nq = (Np - cc >= 32) ? 4 : 2;
+                TC_TS3(c);
                 if (nq == 4) tc_ld32(trow + cc, v); else tc_ld16(trow + cc, v);
+                TC_TS3(c);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     if (q >= nq) break;
@@ -481,6 +503,7 @@ __device__ __forceinline__ void tc_decoders(const WbTc& m, TcCtx& c, const TcIn&
                     o.z = tc_pack2_relu(v[q * 8 + 4], v[q * 8 + 5]); o.w = tc_pack2_relu(v[q * 8 + 6], v[q * 8 + 7]);
                     *reinterpret_cast<uint4*>(tn + ((cc >> 3) + q) * 2048 + c.r * 16) = o;
                 }
+                TC_TS3(c);
             }
             // Np[l] == Kp[l+1] (both round_up(hidden,16)); padded outputs are relu(0 + 0) = 0
         }
@@ -743,101 +766,111 @@ wb_mlp_bwd_tc_kernel(WbTc m, const uint8_t* __restrict__ blob, TcIn in, const fl
 // ---------------------------------------------------------------------------------------------------------------
 // table scatter: dL/dfeat planes -> hash table (hashgrid_interpolate_cuda.cu:151-160), with warp-level run merging
 // ---------------------------------------------------------------------------------------------------------------
-template <int F, int MINB>
-__global__ void __launch_bounds__(256, MINB)
-wb_table_scatter_kernel(WbGrid g, TcIn in, const __half* __restrict__ dfeat, int planes, const float* __restrict__ scale_p, float* __restrict__ gtable, int pair_v4)
+template <int F>
+__global__ void __launch_bounds__(256)
+wb_table_scatter_kernel(WbGrid g, TcIn in, const __half* __restrict__ dfeat, int planes, int levels, int lpb,
+                        const float* __restrict__ scale_p, float* __restrict__ gtable, int pair_v4)
 {
-    const int l = blockIdx.y;                                   // level
+    const int l_begin = blockIdx.y * lpb, l_end = min(levels, l_begin + lpb);     // this CTA's LODs; the sample position is built once for all of them
     const int lane = threadIdx.x & 31;
     const float inv_scale = 1.0f / __ldg(scale_p);
     const int Fr = F > 0 ? F : g.F;
-    const int pl = g.multiscale == 0 ? l : 0;
-    float* tb = gtable + g.begin[l] * Fr;
-    const bool pair_ok = pair_v4 && ((reinterpret_cast<uintptr_t>(tb) & 15u) == 0);       // level base 16-byte aligned
     const int64_t nwork = (in.S + 31) & ~(int64_t)31;            // whole warps
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nwork; s += (int64_t)gridDim.x * blockDim.x) {
         const bool valid = s < in.S;
-        uint32_t idx[8]; float cf[8]; uint64_t key = ~0ull - (uint64_t)lane;    // invalid lanes never merge
-        float gv[F > 0 ? F : 8];
-#pragma unroll
-        for (int f = 0; f < (F > 0 ? F : 8); ++f) gv[f] = 0.0f;
+        float px = 0.0f, py = 0.0f, pz = 0.0f;
         if (valid) {
             const int64_t ray = __ldg(in.rec_ray + s);
             const float t = __ldg(in.rec_t + s);
-            const float px = wb_addcmul(__ldg(in.origins + 3 * ray), __ldg(in.dirs + 3 * ray), t);
-            const float py = wb_addcmul(__ldg(in.origins + 3 * ray + 1), __ldg(in.dirs + 3 * ray + 1), t);
-            const float pz = wb_addcmul(__ldg(in.origins + 3 * ray + 2), __ldg(in.dirs + 3 * ray + 2), t);
-            int ix, iy, iz; float wx, wy, wz, jx, jy, jz;
-            wb_cell(px, g.hres[l], g.hi[l], ix, wx, jx); wb_cell(py, g.hres[l], g.hi[l], iy, wy, jy); wb_cell(pz, g.hres[l], g.hi[l], iz, wz, jz);
-            key = (uint64_t)ix | ((uint64_t)iy << 20) | ((uint64_t)iz << 40);
-            const float xy00 = jx * jy, xy01 = jx * wy, xy10 = wx * jy, xy11 = wx * wy;
-            cf[0] = xy00 * jz; cf[1] = xy00 * wz; cf[2] = xy01 * jz; cf[3] = xy01 * wz;
-            cf[4] = xy10 * jz; cf[5] = xy10 * wz; cf[6] = xy11 * jz; cf[7] = xy11 * wz;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) idx[j] = wb_hash_idx(ix + ((j & 4) >> 2), iy + ((j & 2) >> 1), iz + (j & 1), g.res[l], g.Tmask, g.dense[l]);
-            if (F == 2) {
-                const float2 gg = __half22float2(reinterpret_cast<const __half2*>(dfeat)[(int64_t)pl * in.S + s]);
-                gv[0] = gg.x * inv_scale; gv[1] = gg.y * inv_scale;
-            } else {
-                for (int f = 0; f < Fr; ++f) gv[f] = __half2float(dfeat[((int64_t)pl * in.S + s) * Fr + f]) * inv_scale;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { idx[j] = 0; cf[j] = 0.0f; }
+            px = wb_addcmul(__ldg(in.origins + 3 * ray), __ldg(in.dirs + 3 * ray), t);
+            py = wb_addcmul(__ldg(in.origins + 3 * ray + 1), __ldg(in.dirs + 3 * ray + 1), t);
+            pz = wb_addcmul(__ldg(in.origins + 3 * ray + 2), __ldg(in.dirs + 3 * ray + 2), t);
         }
-        // runs of consecutive lanes with the same cell
-        const uint64_t kprev = __shfl_up_sync(0xffffffffu, key, 1);
-        const bool head = (lane == 0) || (kprev != key);
-        const uint32_t heads = __ballot_sync(0xffffffffu, head);
-        const int run_head = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-        const int dist = lane - run_head;
-        const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
-        int maxd = dist;
+        __half2 gnext = __float2half2_rn(0.0f);                  // F == 2: the next LOD's gradient is fetched one LOD ahead
+        if (F == 2 && valid && l_begin < l_end)
+            gnext = reinterpret_cast<const __half2*>(dfeat)[(int64_t)(g.multiscale == 0 ? l_begin : 0) * in.S + s];
+        for (int l = l_begin; l < l_end; ++l) {
+            const int pl = g.multiscale == 0 ? l : 0;
+            float* tb = gtable + g.begin[l] * Fr;
+            const bool pair_ok = pair_v4 && ((reinterpret_cast<uintptr_t>(tb) & 15u) == 0);       // level base 16-byte aligned
+            uint32_t idx[8]; float cf[8]; uint64_t key = ~0ull - (uint64_t)lane;    // invalid lanes never merge
+            float gv[F > 0 ? F : 8];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
-        if (F == 2) {
-            float v0[8], v1[8];
+            for (int f = 0; f < (F > 0 ? F : 8); ++f) gv[f] = 0.0f;
+            if (valid) {
+                int ix, iy, iz; float wx, wy, wz, jx, jy, jz;
+                wb_cell(px, g.hres[l], g.hi[l], ix, wx, jx); wb_cell(py, g.hres[l], g.hi[l], iy, wy, jy); wb_cell(pz, g.hres[l], g.hi[l], iz, wz, jz);
+                key = (uint64_t)ix | ((uint64_t)iy << 20) | ((uint64_t)iz << 40);
+                const float xy00 = jx * jy, xy01 = jx * wy, xy10 = wx * jy, xy11 = wx * wy;
+                cf[0] = xy00 * jz; cf[1] = xy00 * wz; cf[2] = xy01 * jz; cf[3] = xy01 * wz;
+                cf[4] = xy10 * jz; cf[5] = xy10 * wz; cf[6] = xy11 * jz; cf[7] = xy11 * wz;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { v0[j] = gv[0] * cf[j]; v1[j] = gv[1] * cf[j]; }
-            for (int o = 1; o <= maxd; o <<= 1) {               // segmented inclusive scan (warp-uniform trip count)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float a = __shfl_up_sync(0xffffffffu, v0[j], o), b = __shfl_up_sync(0xffffffffu, v1[j], o);
-                    if (dist >= o) { v0[j] += a; v1[j] += b; }
+                for (int j = 0; j < 8; ++j) idx[j] = wb_hash_idx(ix + ((j & 4) >> 2), iy + ((j & 2) >> 1), iz + (j & 1), g.res[l], g.Tmask, g.dense[l]);
+                if (F == 2) {
+                    const float2 gg = __half22float2(gnext);
+                    gv[0] = gg.x * inv_scale; gv[1] = gg.y * inv_scale;
+                    if (l + 1 < l_end) gnext = reinterpret_cast<const __half2*>(dfeat)[(int64_t)(g.multiscale == 0 ? l + 1 : 0) * in.S + s];
+                } else {
+                    for (int f = 0; f < Fr; ++f) gv[f] = __half2float(dfeat[((int64_t)pl * in.S + s) * Fr + f]) * inv_scale;
                 }
-            }
-            if (tail && valid) {
-                // corners j and j + 4 are x-neighbours at the same (y, z).  When their entries differ only in bit 0 (dense level with
-                // an even index; hashed level with an even x, because (x | 1) ^ A == (x ^ A) ^ 1) the two 8-byte updates are one
-                // aligned 16-byte red.global.add.v4.f32: up to 25 % fewer atomic operations, which is what bounds this kernel.
-                float2* t2 = reinterpret_cast<float2*>(tb);
+            } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t i0 = idx[j], i1 = idx[j + 4];
-                    const bool nz0 = (v0[j] != 0.0f || v1[j] != 0.0f), nz1 = (v0[j + 4] != 0.0f || v1[j + 4] != 0.0f);
-                    if (pair_ok && ((i0 ^ i1) == 1u)) {
-                        if (nz0 || nz1) {
-                            const float4 val = (i0 & 1u) ? make_float4(v0[j + 4], v1[j + 4], v0[j], v1[j]) : make_float4(v0[j], v1[j], v0[j + 4], v1[j + 4]);
-                            atomicAdd(reinterpret_cast<float4*>(t2 + (i0 & ~1u)), val);
-                        }
-                    } else {
-                        if (nz0) atomicAdd(t2 + i0, make_float2(v0[j], v1[j]));
-                        if (nz1) atomicAdd(t2 + i1, make_float2(v0[j + 4], v1[j + 4]));
+                for (int j = 0; j < 8; ++j) { idx[j] = 0; cf[j] = 0.0f; }
+            }
+            // runs of consecutive lanes with the same cell
+            const uint64_t kprev = __shfl_up_sync(0xffffffffu, key, 1);
+            const bool head = (lane == 0) || (kprev != key);
+            const uint32_t heads = __ballot_sync(0xffffffffu, head);
+            const int run_head = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+            const int dist = lane - run_head;
+            const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
+            int maxd = dist;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
+            if (F == 2) {
+                float v0[8], v1[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { v0[j] = gv[0] * cf[j]; v1[j] = gv[1] * cf[j]; }
+                for (int o = 1; o <= maxd; o <<= 1) {               // segmented inclusive scan (warp-uniform trip count)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float a = __shfl_up_sync(0xffffffffu, v0[j], o), b = __shfl_up_sync(0xffffffffu, v1[j], o);
+                        if (dist >= o) { v0[j] += a; v1[j] += b; }
                     }
                 }
-            }
-        } else {
-            for (int f = 0; f < Fr; ++f) {
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = gv[f] * cf[j];
-                for (int o = 1; o <= maxd; o <<= 1) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { const float a = __shfl_up_sync(0xffffffffu, v[j], o); if (dist >= o) v[j] += a; }
-                }
                 if (tail && valid) {
+                    // corners j and j + 4 are x-neighbours at the same (y, z).  When their entries differ only in bit 0 (dense level with
+                    // an even index; hashed level with an even x, because (x | 1) ^ A == (x ^ A) ^ 1) the two 8-byte updates are one
+                    // aligned 16-byte red.global.add.v4.f32 (measured: -6 % kernel time).
+                    float2* t2 = reinterpret_cast<float2*>(tb);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) if (v[j] != 0.0f) atomicAdd(tb + (int64_t)idx[j] * Fr + f, v[j]);
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t i0 = idx[j], i1 = idx[j + 4];
+                        const bool nz0 = (v0[j] != 0.0f || v1[j] != 0.0f), nz1 = (v0[j + 4] != 0.0f || v1[j + 4] != 0.0f);
+                        if (pair_ok && ((i0 ^ i1) == 1u)) {
+                            if (nz0 || nz1) {
+                                const float4 val = (i0 & 1u) ? make_float4(v0[j + 4], v1[j + 4], v0[j], v1[j]) : make_float4(v0[j], v1[j], v0[j + 4], v1[j + 4]);
+                                atomicAdd(reinterpret_cast<float4*>(t2 + (i0 & ~1u)), val);
+                            }
+                        } else {
+                            if (nz0) atomicAdd(t2 + i0, make_float2(v0[j], v1[j]));
+                            if (nz1) atomicAdd(t2 + i1, make_float2(v0[j + 4], v1[j + 4]));
+                        }
+                    }
+                }
+            } else {
+                for (int f = 0; f < Fr; ++f) {
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = gv[f] * cf[j];
+                    for (int o = 1; o <= maxd; o <<= 1) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { const float a = __shfl_up_sync(0xffffffffu, v[j], o); if (dist >= o) v[j] += a; }
+                    }
+                    if (tail && valid) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) if (v[j] != 0.0f) atomicAdd(tb + (int64_t)idx[j] * Fr + f, v[j]);
+                    }
                 }
             }
         }
@@ -880,13 +913,13 @@ int wb_tc_table_scatter(const wb_nef_desc* nef, const wb_rays* rays, const float
     TcIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S, nullptr, nullptr, nullptr };
     const int levels = g.multiscale == 0 ? planes : g.L;
     if (levels > 0) {
+        // LODs per CTA row: the sample position / record loads are shared by `lpb` LODs (measured sweep in profiles/README.md)
+        const int lpb = max(1, min(levels, tc_env_int("WB_TC_SCATTER_LPB", 16)));
         int64_t bx = (S + 255) / 256; const int64_t cap = (int64_t)wb_num_sms() * 8; if (bx > cap) bx = cap;
-        dim3 grid2((unsigned)bx, (unsigned)levels);
-        const int minb = tc_env_int("WB_TC_SCATTER_MINB", 4), v4 = tc_env_int("WB_TC_SCATTER_V4", 1);
-        if (g.F == 2 && minb == 5) wb_table_scatter_kernel<2, 5><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, scale, grad_table, v4);
-        else if (g.F == 2 && minb == 6) wb_table_scatter_kernel<2, 6><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, scale, grad_table, v4);
-        else if (g.F == 2) wb_table_scatter_kernel<2, 4><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, scale, grad_table, v4);
-        else wb_table_scatter_kernel<0, 4><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, scale, grad_table, 0);
+        dim3 grid2((unsigned)bx, (unsigned)((levels + lpb - 1) / lpb));
+        const int v4 = tc_env_int("WB_TC_SCATTER_V4", 1);
+        if (g.F == 2) wb_table_scatter_kernel<2><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, levels, lpb, scale, grad_table, v4);
+        else wb_table_scatter_kernel<0><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, levels, lpb, scale, grad_table, 0);
         WB_LAUNCH_CHECK();
     }
     return WB_OK;

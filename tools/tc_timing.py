@@ -56,3 +56,20 @@ if hasattr(lib, "wb_tc_timing_dump2") and lib.wb_tc_timing_dump2(buf2.ctypes.dat
         for r in range(rounds):
             print("   round %d: %6.0f %6.0f %6.0f %6.0f" % (r, (b[:, r, 0] - a[:, r, 1]).mean(), (b[:, r, 1] - b[:, r, 0]).mean(),
                                                          (b[:, r, 2] - b[:, r, 1]).mean(), (a[:, r, 2] - b[:, r, 2]).mean()))
+
+buf3 = np.zeros((2, N), np.int64)
+if hasattr(lib, "wb_tc_timing_dump3") and lib.wb_tc_timing_dump3(buf3.ctypes.data_as(ctypes.c_void_p)) == 0:
+    for k, name in ((0, "fwd"), (1, "bwd")):
+        t3 = buf3[k]; n = int((t3 > 0).sum()) // 3 * 3
+        if n < 30:
+            continue
+        a = t3[:n].reshape(-1, 3)[6:]
+        print(f"{name} thread 0, hidden-layer epilogue (32 columns): tcgen05.ld+wait {(a[:, 1] - a[:, 0]).mean():.0f}  convert+store {(a[:, 2] - a[:, 1]).mean():.0f} cycles")
+
+buf4 = np.zeros((2, 64, 16), np.int64)
+if hasattr(lib, "wb_tc_timing_dump4") and lib.wb_tc_timing_dump4(buf4.ctypes.data_as(ctypes.c_void_p)) == 0:
+    for k, name, rounds in ((0, "fwd", 5), (1, "bwd", 10)):
+        print(f"{name} thread 0: cycles from chain start to each UTCHMMA issued (rounds of the 3rd tile)")
+        for r in range(2 * rounds, 3 * rounds):
+            row = buf4[k, r]; n = int((row > 0).sum())
+            print("   round %2d:" % (r - 2 * rounds), [int(row[i] - row[0]) for i in range(1, n)])
