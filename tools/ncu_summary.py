@@ -26,8 +26,13 @@ def raw(rep):
     return rows[0], rows[1], rows[2:]
 
 
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
 def main(tag):
+    import json
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+    traffic = {}
     for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"prof_*_{tag}.ncu-rep"))):
         hdr, units, vals = raw(rep)
         name = os.path.basename(rep)[5:-8][:-(len(tag) + 1)]
@@ -35,6 +40,11 @@ def main(tag):
             f.write(f"# ncu --set full --clock-control none --import-source on (one launch)  source: gpurun_out/{os.path.basename(rep)}\n")
             for v in vals:
                 f.write(f"kernel: {v[hdr.index('Kernel Name')]}\n")
+                try:     # DRAM bytes per launch (read + write) -> profiles/traffic.json, the `traffic` key of bench.py's roofline
+                    ir, iw = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
+                    traffic[name] = float(v[ir].replace(',', '')) * UNIT[units[ir]] + float(v[iw].replace(',', '')) * UNIT[units[iw]]
+                except (ValueError, KeyError):
+                    pass
                 for w in WANT:
                     if w in hdr:
                         f.write(f"  {w:72s} {v[hdr.index(w)]:>18s} {units[hdr.index(w)]}\n")
@@ -47,6 +57,10 @@ def main(tag):
                         except ValueError:
                             pass
         print("wrote", f"profiles/{tag}_{name}.txt")
+    if traffic:
+        with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
+            json.dump({"tag": tag, **traffic}, f, indent=1)
+        print("wrote profiles/traffic.json", traffic)
     for lc in glob.glob(os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")):
         rows = list(csv.reader(open(lc)))
         st = next(i for i, r in enumerate(rows) if r and r[0] == 'ID')
