@@ -56,3 +56,40 @@ def sync_sample_counts(num_samples: int, num_rays: int, device, group=None) -> T
     t = torch.tensor([num_samples, num_rays], dtype=torch.int64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return int(t[0]), int(t[1])
+
+
+class HostPrefetcher:
+    """Pinned host batches -> device, one batch ahead, on a side stream (the trainer-side analogue of the reference's
+    DataLoader(pin_memory=True) + `.to(device)` in the step, multiview_trainer.py:73-82): the host->device copy of batch
+    i+1 overlaps the render step of batch i.  Iterating yields tuples of device tensors that are safe to use on the
+    current stream."""
+
+    def __init__(self, batches: Iterable, device):
+        self.batches, self.device = batches, torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+
+    def _stage(self, batch):
+        if self.stream is None:
+            return tuple(t.to(self.device) for t in batch), None
+        with torch.cuda.stream(self.stream):
+            out = tuple(t.to(self.device, non_blocking=True) for t in batch)
+            ev = torch.cuda.Event(); ev.record(self.stream)
+        return out, ev
+
+    def __iter__(self):
+        it = iter(self.batches)
+        try:
+            nxt = self._stage(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur, ev = nxt
+            try:
+                nxt = self._stage(next(it))         # enqueue the next copy before handing out the current batch
+            except StopIteration:
+                nxt = None
+            if ev is not None:
+                torch.cuda.current_stream(self.device).wait_event(ev)
+                for t in cur:
+                    t.record_stream(torch.cuda.current_stream(self.device))
+            yield cur

@@ -19,7 +19,9 @@ class PackedRFTracer(nn.Module):
         self.raymarch_type, self.num_steps, self.step_size = raymarch_type, num_steps, step_size
         self.bg_color = torch.tensor(bg_color, dtype=torch.float32)
         self.prev_num_samples = None
-        self.precision = 0          # 0: fp32 decoders (autocast off), 1: fp16 tensor-core decoders (autocast on)
+        # decoder arithmetic of the fused path: 0 = fp32 (autocast off), 1 = fp16 tensor cores with fp32 accumulation (what the
+        # reference runs under `enable_amp: True`, base_trainer.py autocast); None = follow torch.is_autocast_enabled()
+        self.precision = None
         self.seed = 0               # base of the counter-based jitter stream; advanced once per trace() call
         self.jitter = None          # optional explicit [R, num_steps] jitter (parity tests)
 
@@ -76,7 +78,8 @@ class PackedRFTracer(nn.Module):
                                           reference_layout=False, jitter=jitter, seed=seed)
             self.prev_num_samples = ms.total
             rgb, depth, alpha, hit = ops.rf_trace(ms, spec, nef.grid.codebook.feats, nef.decoder_density.packed_params(),
-                                                  nef.decoder_color.packed_params(), self.bg_color, precision=self.precision)
+                                                  nef.decoder_color.packed_params(), self.bg_color,
+                                                  precision=(int(torch.is_autocast_enabled()) if self.precision is None else int(self.precision)))
             return RenderBuffer(depth=depth if "depth" in channels else None, hit=hit, rgb=rgb, alpha=alpha)
 
         # ---- unfused route: same operators, nef evaluated through its own forward() ----

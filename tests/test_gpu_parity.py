@@ -273,6 +273,19 @@ def test_trace_golden(W, golden_dir, name, fused, precision):
         assert np.abs(got - ref).max() <= tol["grad"] * scale, (nm, np.abs(got - ref).max(), scale)
 
 
+def test_trace_follows_autocast(W, golden_dir):
+    """tracer.precision = None: the fused path runs the tensor-core decoders exactly when torch autocast is on
+    (the reference's `enable_amp`), the fp32 decoders otherwise."""
+    g, onef, spc = load_case(os.path.join(golden_dir, CASES[0] + ".npz"))
+    out = {}
+    for key, prec, amp in (("p0", 0, False), ("p1", 1, False), ("auto_off", None, False), ("auto_on", None, True)):
+        with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
+            _, _, rb = _run_fused(W, g, onef, spc, True, prec)
+        out[key] = rb.rgb.detach().cpu().numpy()
+    assert np.array_equal(out["auto_off"], out["p0"]) and np.array_equal(out["auto_on"], out["p1"])
+    assert not np.array_equal(out["p0"], out["p1"])
+
+
 @pytest.mark.parametrize("precision", [0, 1])
 def test_trace_config2_slice_vs_oracle(W, precision):
     """BASELINE config 2 shapes (L=16, F=2, T=2^19, 64-wide decoders, n=2048, level-7 lego-like octree) on a

@@ -99,3 +99,15 @@ def test_tracer_channel_negotiation_errors():
     with pytest.raises(Exception, match="not supported"):
         tr(nef, rays=W.Rays(torch.zeros(1, 3), torch.ones(1, 3)), channels=["rgb", "normals"])
     assert tr.get_prev_num_samples() is None
+
+
+def test_host_prefetcher_cpu_passthrough():
+    """HostPrefetcher keeps order and arity; on a CPU 'device' it degenerates to plain .to() (no stream)."""
+    import torch
+    from wisp_b200.parallel import HostPrefetcher
+    batches = [(torch.full((3,), float(i)), torch.full((2, 2), float(-i))) for i in range(4)]
+    got = list(HostPrefetcher(batches, "cpu"))
+    assert len(got) == 4
+    for i, (a, b) in enumerate(got):
+        assert float(a[0]) == i and float(b[0, 0]) == -i
+    assert list(HostPrefetcher([], "cpu")) == []
