@@ -232,10 +232,10 @@ wb_march_fill_kernel(WbMarch m, const uint32_t* __restrict__ hitmask, const int6
         int64_t run = base;
         for (int wb = 0; wb < nw; wb += 32) {
             const uint32_t mine = (wb + lane < nw) ? __ldg(hitmask + r * nw + wb + lane) : 0u;
-            const int wend = min(32, nw - wb);
-            for (int j = 0; j < wend; ++j) {
+            uint32_t nz = __ballot_sync(0xffffffffu, mine != 0u);     // visit only the words that hold samples
+            while (nz) {
+                const int j = __ffs(nz) - 1; nz &= nz - 1u;
                 const uint32_t word = __shfl_sync(0xffffffffu, mine, j);
-                if (word == 0u) continue;
                 if (word & (1u << lane)) {
                     const int i = ((wb + j) << 5) + lane;
                     const int64_t dst = run + __popc(word & ((1u << lane) - 1u));
