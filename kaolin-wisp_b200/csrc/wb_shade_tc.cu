@@ -4,10 +4,13 @@
 // fp16, fp32 accumulation; unlike the reference the hash table is read as fp32 master (no per-call .half() copy,
 // ops/grid.py:88-89), features are blended in fp32 and table gradients accumulate in fp32.
 //
-// CTA = 256 threads = two 128-sample sub-tiles; thread r of a sub-tile owns sample row r == TMEM lane r.
-// Per layer:  every thread writes its row of the fp16 operand tile (slab layout, wb_tc.cuh) -> fence -> CTA barrier ->
-// ONE thread issues the UMMAs of both sub-tiles (A = sample tile, B = TMA-staged weight pack, D in TMEM) and commits
-// to an mbarrier -> all threads wait, tcgen05.ld their accumulator row, apply bias/relu in fp32, write the next tile.
+// Unit of work = a 128-sample sub-tile handled by a GROUP of 256 threads: row r of the tile == TMEM lane r is shared by two
+// threads (column halves).  Per layer ("round", tc_round):  every thread writes its part of the fp16 operand tile (slab layout,
+// wb_tc.cuh) -> fence -> group barrier -> two elected issuer threads launch the round's UMMA chains from a shared-memory issue
+// table (A = sample tile, B = TMA-staged weight pack, D in TMEM; the bias is an init UMMA Ones x Bias^T) and commit to the
+// group's mbarrier -> the group waits, tcgen05.ld's its accumulator columns, applies the activation, writes the next tile.
+// Groups are independent (own named barrier, own mbarrier, own TMEM columns): the forward runs 3 one-group CTAs per SM, the
+// backward one two-group CTA per SM.
 //
 // Forward  (wb_shade_fwd_tc_kernel): gather 15 LODs x 8 corners (fp32 blend) -> decoders -> (r,g,b,sigma).  It also saves
 //   the gathered feature rows (fp16, chunk-major [Kp0/8][S] x 16 B: coalesced both ways) for the backward.
@@ -18,9 +21,10 @@
 //                                                     X_l tile makes row `Kp_l` the bias gradient)
 //     data grad     dX_l = dY_l . W_l                (weight pack read MN-major: no transposed copy)
 //   and writes dL/dfeat as fp16 level-major planes [L][S][F].
-// Scatter  (wb_table_scatter_kernel, SIMT): lanes = consecutive samples of ONE level; runs of lanes that fall into the same
-//   cell are summed with a segmented warp scan and only the last lane of a run issues the 8 red.global.add.v2.f32.  The
-//   per-SM atomic issue rate bounds the backward, and neighbouring samples of a ray share cells on all but the finest LODs.
+// Scatter  (wb_table_scatter_kernel, SIMT): lanes = consecutive samples; a thread builds its sample position once and walks all
+//   LODs; per LOD, runs of lanes that fall into the same cell are summed with a segmented warp scan and only the last lane of a
+//   run issues the reductions (x-neighbour entries that differ only in bit 0 as one 16-byte red.global.add.v4.f32).
+//   Neighbouring samples of a ray share cells on all but the finest LODs.
 // The per-ray view embedding (positional_embedder.py:51-66) is evaluated once per ray (wb_ray_embed_kernel), not per sample.
 // Gradients are carried in fp16 under a power-of-two loss scale supplied on the device (no host sync) and unscaled in fp32
 // at the two exits (table scatter, weight-gradient flush).
@@ -51,7 +55,6 @@ struct WbTc {
     int work_col[2];                           // TMEM working accumulator of sub-tile 0/1
     int tmem_cols;
     int feat_dim, pos_dim, view_dim, pos_mode, pos_freq, view_mode, view_freq;
-    int skew;                                  // backward: group 1 starts half a tile behind group 0
 };
 
 static int tc_round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -578,7 +581,12 @@ static int tc_launch_ray_embed(const WbTc& m, const wb_rays* rays, void* workspa
     return WB_OK;
 }
 
+// Tuning knobs (defaults = the measured optimum on B200 for the app/nerf configuration, profiles/README.md); the environment
+// overrides exist for the sweeps and are read once per process.
 static int tc_env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
+static int tc_knob_fwd_ctas() { static const int v = tc_env_int("WB_TC_FWD_CTAS", 3); return v; }
+static int tc_knob_scatter_lpb() { static const int v = tc_env_int("WB_TC_SCATTER_LPB", 16); return v; }
+static int tc_knob_scatter_v4() { static const int v = tc_env_int("WB_TC_SCATTER_V4", 1); return v; }
 
 int wb_tc_shade_fwd(const wb_nef_desc* nef, const float* blob, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray,
                     int64_t S, float* shaded, void* feat_save, void* workspace, cudaStream_t st)
@@ -591,11 +599,11 @@ int wb_tc_shade_fwd(const wb_nef_desc* nef, const float* blob, const wb_rays* ra
     // CTAs per SM: each is one sub-tile group; more groups in flight hide the gather and round latencies (measured sweep in
     // profiles/README.md).  The register bound of the instantiation must match, or the hardware silently runs fewer.
     int per_sm = (227 * 1024) / (m.smem_bytes + 4096); per_sm = max(1, min(per_sm, 512 / m.tmem_cols));
-    per_sm = max(2, min(min(per_sm, 4), tc_env_int("WB_TC_FWD_CTAS", 3)));
+    per_sm = max(2, min(min(per_sm, 4), tc_knob_fwd_ctas()));
     auto kern = per_sm == 2 ? wb_shade_fwd_tc_kernel<2> : per_sm == 3 ? wb_shade_fwd_tc_kernel<3> : wb_shade_fwd_tc_kernel<4>;
     WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, m.smem_bytes));
     WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 min(100, tc_env_int("WB_TC_FWD_CARVE", (per_sm * (m.smem_bytes + 4096) * 100) / (228 * 1024) + 1))));
+                                 min(100, (per_sm * (m.smem_bytes + 4096) * 100) / (228 * 1024) + 1)));
     const int64_t ntiles = (S + TC_ROWS - 1) / TC_ROWS;
     int64_t grid = (int64_t)wb_num_sms() * per_sm; if (grid > ntiles) grid = ntiles;
     kern<<<(unsigned)grid, TC_GROUP, m.smem_bytes, st>>>(g, m, reinterpret_cast<const uint8_t*>(blob), in, reinterpret_cast<float4*>(shaded));
@@ -613,13 +621,13 @@ __global__ void __launch_bounds__(TC_BWD_GROUPS * TC_GROUP, 1)
 wb_mlp_bwd_tc_kernel(WbTc m, const uint8_t* __restrict__ blob, TcIn in, const float4* __restrict__ g_shaded, TcGrads G)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[TC_BWD_GROUPS + 2];
+    __shared__ __align__(8) uint64_t bars[TC_BWD_GROUPS + 1];
     __shared__ uint32_t tmem_s;
     __shared__ TcRec itab[TC_BWD_GROUPS * TC_KINDS * TC_ML];
     const int nl = m.nl_d + m.nl_c;
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_BWD_GROUPS; ++i) tc_mbar_init(&bars[i], TC_ISSUERS);
-        tc_mbar_init(&bars[TC_BWD_GROUPS], 1); tc_mbar_init(&bars[TC_BWD_GROUPS + 1], 1); tc_mbar_init_fence();
+        tc_mbar_init(&bars[TC_BWD_GROUPS], 1); tc_mbar_init_fence();
         tc_mbar_expect_tx(&bars[TC_BWD_GROUPS], (uint32_t)m.blob_bytes);
         tc_bulk_g2s(smem + m.w_smem_off, blob, (uint32_t)m.blob_bytes, &bars[TC_BWD_GROUPS]);
     }
@@ -650,8 +658,6 @@ wb_mlp_bwd_tc_kernel(WbTc m, const uint8_t* __restrict__ blob, TcIn in, const fl
     const int nch0 = m.Kp[0] / 8;
     const int64_t ntiles = (in.S + TC_ROWS - 1) / TC_ROWS;
     const float z8[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-    if (m.skew && c.g == 1) tc_mbar_wait(&bars[TC_BWD_GROUPS + 1], 0);     // start half a tile behind group 0 (see tc_round)
-    bool first_tile = true;
     for (int64_t tile = (int64_t)blockIdx.x * TC_BWD_GROUPS + c.g; tile < ntiles; tile += (int64_t)gridDim.x * TC_BWD_GROUPS) {
         int64_t s = tile * TC_ROWS + c.r;
         const bool valid = s < in.S;
@@ -662,8 +668,6 @@ wb_mlp_bwd_tc_kernel(WbTc m, const uint8_t* __restrict__ blob, TcIn in, const fl
         float df[16], c3[3];
         tc_decoders(m, c, in, ray, df, c3);
         float4 go = valid ? __ldg(g_shaded + s) : make_float4(0, 0, 0, 0);
-        if (first_tile && c.g == 0 && threadIdx.x == 0) tc_mbar_arrive(&bars[TC_BWD_GROUPS + 1]);
-        first_tile = false;
         // ---- colour decoder, last layer: dY = dL/d(pre-sigmoid), zero padded ----
         {
             if (c.h == 0) {
@@ -883,7 +887,6 @@ int wb_tc_decoder_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* 
                       float* grad_dens, float* grad_col, cudaStream_t st)
 {
     WbTc m; int rc = wb_tc_make(nef, true, &m); if (rc) return rc;
-    m.skew = tc_env_int("WB_TC_BWD_SKEW", 1);
     WB_CHECK_ARG(scale != nullptr, "precision 1 needs the device loss-scale pointer");
     WB_CHECK_ARG(feat_saved != nullptr && workspace != nullptr, "precision 1 backward needs the saved features and the workspace");
     rc = tc_launch_ray_embed(m, rays, workspace, st); if (rc) return rc;
@@ -914,10 +917,10 @@ int wb_tc_table_scatter(const wb_nef_desc* nef, const wb_rays* rays, const float
     const int levels = g.multiscale == 0 ? planes : g.L;
     if (levels > 0) {
         // LODs per CTA row: the sample position / record loads are shared by `lpb` LODs (measured sweep in profiles/README.md)
-        const int lpb = max(1, min(levels, tc_env_int("WB_TC_SCATTER_LPB", 16)));
+        const int lpb = max(1, min(levels, tc_knob_scatter_lpb()));
         int64_t bx = (S + 255) / 256; const int64_t cap = (int64_t)wb_num_sms() * 8; if (bx > cap) bx = cap;
         dim3 grid2((unsigned)bx, (unsigned)((levels + lpb - 1) / lpb));
-        const int v4 = tc_env_int("WB_TC_SCATTER_V4", 1);
+        const int v4 = tc_knob_scatter_v4();
         if (g.F == 2) wb_table_scatter_kernel<2><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, levels, lpb, scale, grad_table, v4);
         else wb_table_scatter_kernel<0><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, levels, lpb, scale, grad_table, 0);
         WB_LAUNCH_CHECK();
