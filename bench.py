@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--res", type=int, default=1024)
     ap.add_argument("--num-steps", type=int, default=2048)
     ap.add_argument("--scene", default="lego", choices=["lego", "dense"])
+    ap.add_argument("--premarch", type=int, default=1, help="1: march batch i+1 on a side stream while batch i renders (PackedRFTracer.premarch)")
     ap.add_argument("--precision", type=int, default=1, help="0: fp32 decoders, 1: fp16 tensor-core decoders (reference enable_amp)")
     ap.add_argument("--cpu-sample-rays", type=int, default=0, help="rays in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -52,6 +53,8 @@ def workload_config(args):
             "rays_per_step_per_gpu": args.res * args.res, "num_steps": args.num_steps, "scene": args.scene,
             "camera": {"origin": CAM_ORIGIN, "lookat": CAM_LOOKAT, "fov": CAM_FOV, "near": NEAR, "far": FAR},
             "loss": "huber/rays", "optimizer": "Adam(fused, torch) on table + decoders",
+            "pipeline": ("march of batch i+1 enqueued on a side stream while batch i renders (one march per timed step, none carried "
+                         "in from the warm-up)") if args.premarch else "none",
             "l2": "per-step working set (hit masks + sample records, >1 GB) exceeds the 126 MB L2; a different camera every step",
             "parallelism": f"dp{args.gpus} (one view per GPU per step, NCCL all-reduce of gradients)" if args.gpus > 1 else "single GPU"}
 
@@ -191,9 +194,16 @@ def run_ours(args):
     dev_rays = [(o.to(dev), d.to(dev)) for o, d in host_rays]
     dev_tgt = [t.to(dev) for t in host_tgt]
 
-    def step(i, origins, dirs, target):
+    def seed_of(i):
+        return 1000 + i * world + rank
+
+    def step(i, origins, dirs, target, nxt=None, nxt_ready=None):
+        # software pipeline of the training loop: the sample selection of batch i+1 (it depends on rays + occupancy, not on the
+        # weights) is enqueued on a side stream before batch i is rendered.  Every timed step enqueues exactly one march.
+        if nxt is not None and args.premarch:
+            tracer.premarch(nef, W.Rays(nxt[0], nxt[1], dist_min=NEAR, dist_max=FAR), seed_of(i + 1), ready=nxt_ready)
         opt.zero_grad(set_to_none=False)
-        tracer.seed = 1000 + i * world + rank
+        tracer.seed = seed_of(i)
         rb = pipe(rays=W.Rays(origins, dirs, dist_min=NEAR, dist_max=FAR), lod_idx=None, channels=["rgb"])
         loss = torch.nn.functional.smooth_l1_loss(rb.rgb, target, reduction='none').mean()       # multiview_trainer.py:144-154
         loss.backward()
@@ -207,8 +217,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- warm-up ----
-    for i in range(args.warmup):
-        step(i, *dev_rays[i], dev_tgt[i])
+    for i in range(args.warmup):      # the warm-up exercises the same pipeline, but nothing is carried over into the timed region
+        step(i, *dev_rays[i], dev_tgt[i], nxt=dev_rays[i + 1] if i + 1 < args.warmup else None)
     barrier()
 
     # ---- timed: device-resident inputs ----
@@ -226,7 +236,7 @@ def run_ours(args):
     total_samples = 0
     for k in range(args.steps):
         i = args.warmup + k
-        step(i, *dev_rays[i], dev_tgt[i])
+        step(i, *dev_rays[i], dev_tgt[i], nxt=dev_rays[i + 1] if k + 1 < args.steps else None)
         total_samples += tracer.get_prev_num_samples()
         step_ev[k + 1].record()
     e1.record()
@@ -246,8 +256,9 @@ def run_ours(args):
     barrier()
     e2.record()
     host_batches = [(host_rays[args.warmup + k][0], host_rays[args.warmup + k][1], host_tgt[args.warmup + k]) for k in range(args.steps)]
-    for k, (o, d, t) in enumerate(W.parallel.HostPrefetcher(host_batches, dev)):     # every step's H2D copy is inside the timed region
-        loss = step(args.warmup + k, o, d, t)
+    pre = W.parallel.HostPrefetcher(host_batches, dev)
+    for k, (o, d, t) in enumerate(pre):                        # every step's H2D copy and march are inside the timed region
+        loss = step(args.warmup + k, o, d, t, nxt=pre.staged, nxt_ready=pre.staged_event)
         loss_host = float(loss.item())
     e3.record()
     barrier()

@@ -224,6 +224,10 @@ int wb_rf_march_fill(const wb_rays* rays, int32_t num_samples, const float* jitt
 /* Packs decoder parameters into the shared-memory image the shade kernels stage with one bulk (TMA) copy.
  * blob: float [wb_rf_param_blob_floats(nef)]. */
 int64_t wb_rf_param_blob_floats(const wb_nef_desc* nef, int32_t precision);
+/* 1 if the decoder configuration can run at `precision` (forward only, or forward + backward), else 0 with the reason in
+ * wb_last_error().  precision 0 always can; precision 1 is limited by shared memory / TMEM (e.g. 64-wide decoders with
+ * backward, 128-wide forward only).  Host-side query, no device work. */
+int wb_rf_precision_supported(const wb_nef_desc* nef, int32_t precision, int32_t backward);
 int wb_rf_pack_params(const wb_nef_desc* nef, int32_t precision, float* blob, wb_stream s);
 /* precision 1 scratch: workspace = per-ray view-embedding rows (+ dL/dfeat planes when backward != 0);
  * feat = the gathered grid features the forward saves for the backward (2*Kp0 bytes per sample).  Both 0 for precision 0. */

@@ -5,6 +5,7 @@ package aliases it).  Host-side classes mirror the reference's names and argumen
 libwispb200.so (hand-written CUDA behind a C ABI, include/wispb200.h).  There is no CPU fallback.
 """
 from . import _cabi, ops, spc, parallel                                                   # noqa: F401
+from ._cabi import WispB200Error                                                # noqa: F401
 from .core import Rays, RenderBuffer                                            # noqa: F401
 from .accelstructs import OctreeAS, AxisAlignedBBoxAS, ASQueryResults, ASRaymarchResults, ASRaytraceResults   # noqa: F401
 from .grids import HashGrid, MultiTable, TriplanarGrid, TriplanarFeatureVolume, OctreeGrid                                         # noqa: F401

@@ -56,7 +56,7 @@ EXPORTS = [
     "wb_raytrace_count", "wb_raytrace_fill", "wb_raymarch_voxel_fill", "wb_raymarch_uniform_count", "wb_raymarch_uniform_fill",
     "wb_hashgrid_fwd", "wb_hashgrid_bwd", "wb_triplane_fwd", "wb_triplane_bwd",
     "wb_octree_interp_fwd", "wb_octree_interp_bwd", "wb_find_depth_bound", "wb_composite_fwd", "wb_composite_bwd",
-    "wb_rf_march_fill", "wb_rf_param_blob_floats", "wb_rf_pack_params", "wb_rf_shade_fwd", "wb_rf_shade_bwd",
+    "wb_rf_march_fill", "wb_rf_param_blob_floats", "wb_rf_precision_supported", "wb_rf_pack_params", "wb_rf_shade_fwd", "wb_rf_shade_bwd",
     "wb_rf_workspace_bytes", "wb_rf_feat_bytes", "wb_rf_decoder_bwd", "wb_rf_table_scatter", "wb_tc_selftest",
 ]
 

@@ -61,6 +61,13 @@ extern "C" int64_t wb_rf_feat_bytes(const wb_nef_desc* nef, int32_t precision, i
     if (precision != 1) return 0;
     return wb_tc_feat_bytes(nef, S);
 }
+int wb_tc_supported(const wb_nef_desc* nef, int backward);
+extern "C" int wb_rf_precision_supported(const wb_nef_desc* nef, int32_t precision, int32_t backward)
+{
+    if (precision == 0) return 1;
+    if (precision != 1 || nef == nullptr) return 0;
+    return wb_tc_supported(nef, backward);
+}
 
 struct WbMlp {
     int nl_d, nl_c;                      // linear layers: density, colour

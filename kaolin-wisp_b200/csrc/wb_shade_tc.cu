@@ -113,7 +113,10 @@ int wb_tc_make(const wb_nef_desc* d, bool backward, WbTc* m)
         if (p < need) p = need;
     }
     m->smem_bytes = p + 64;
-    WB_CHECK_ARG(m->smem_bytes <= 227 * 1024, "tensor-core path: decoder does not fit in shared memory (use precision 0)");
+    // static shared memory of the kernels (issue table, barriers): 3 KB forward, 5 KB backward
+    WB_CHECK_ARG(m->smem_bytes + (backward ? 5632 : 3584) <= 227 * 1024,
+                 backward ? "tensor-core path: decoder backward does not fit in shared memory (use precision 0)"
+                          : "tensor-core path: decoder does not fit in shared memory (use precision 0)");
     int col = 0;
     for (int gi = 0; gi < groups; ++gi) { m->work_col[gi] = col; col += maxw; }
     if (backward) for (int l = 0; l < nl; ++l) { m->acc_col[l] = col; col += m->Np[l]; }
@@ -141,9 +144,16 @@ int64_t wb_tc_workspace_bytes(const wb_nef_desc* nef, int64_t R, int64_t S, int 
     if (backward) b += tc_align256((int64_t)planes * S * width * 2);
     return b + 256;
 }
+int wb_tc_supported(const wb_nef_desc* nef, int backward)
+{
+    WbTc m; if (wb_tc_make(nef, false, &m)) return 0;
+    if (backward && wb_tc_make(nef, true, &m)) return 0;
+    return 1;
+}
+// the features are only saved for a backward pass: refuse here (at forward time) if that pass cannot run
 int64_t wb_tc_feat_bytes(const wb_nef_desc* nef, int64_t S)
 {
-    WbTc m; if (wb_tc_make(nef, false, &m)) return -1;
+    WbTc m; if (wb_tc_make(nef, true, &m) || wb_tc_make(nef, false, &m)) return -1;
     return (int64_t)m.Kp[0] * 2 * S + 256;
 }
 

@@ -132,6 +132,15 @@ class BaseNeuralField(nn.Module):
         return ret
 
 
+def sample_unif_sphere(n):
+    """Uniformly random points on the unit sphere, np.array [n, 3] (wisp/ops/geometric.py:25-39)."""
+    u = np.random.rand(2, n)
+    z = 1 - 2 * u[0, :]
+    r = np.sqrt(1. - z * z)
+    phi = 2 * np.pi * u[1, :]
+    return np.array([r * np.cos(phi), r * np.sin(phi), z]).transpose()
+
+
 class NeuralRadianceField(BaseNeuralField):
     def __init__(self, grid, pos_embedder='none', view_embedder='none', pos_multires=10, view_multires=4, position_input=False,
                  activation_type='relu', layer_type='linear', hidden_dim=128, num_layers=1, bias=False,
@@ -160,6 +169,34 @@ class NeuralRadianceField(BaseNeuralField):
         if embedder_type == 'positional':
             return get_positional_embedder(frequencies=frequencies, include_input=include_input)
         raise NotImplementedError(f'Unsupported embedder type for NeuralRadianceField: {embedder_type}')
+
+    def prune(self):
+        """Prunes the blas based on the current state (nerf.py:175-212): decay the running occupancy, query the density at one
+        random point per finest-level cell (native hash-grid kernel + decoder_density), keep the cells above `prune_min_density`
+        and rebuild the occupancy structure from them.  The next raymarch rebuilds the native bit masks (OctreeAS.tensors())."""
+        if self.prune_density_decay is None or self.prune_min_density is None:
+            return
+        if self.grid is None:
+            return
+        if not hasattr(self.grid, "occupancy") or not hasattr(self.grid, "dense_points"):
+            raise NotImplementedError(f'Pruning not implemented for grid type {self.grid.__class__.__name__}')
+        dev = self.grid.codebook.feats.device if hasattr(self.grid, "codebook") else next(self.parameters()).device
+        self.grid.occupancy = self.grid.occupancy.to(dev) * self.prune_density_decay
+        points = self.grid.dense_points.to(dev)
+        res = 2.0 ** self.grid.blas.max_level
+        samples = torch.rand(points.shape[0], 3, device=points.device)
+        samples = (points.float() + samples) / res * 2.0 - 1.0
+        sample_views = torch.from_numpy(sample_unif_sphere(samples.shape[0])).float().to(points.device)
+        with torch.no_grad():
+            density = self.forward(coords=samples, ray_d=sample_views, channels="density")
+        self.grid.occupancy = torch.stack([density[:, 0], self.grid.occupancy], -1).max(dim=-1)[0]
+        _points = points[self.grid.occupancy > self.prune_min_density]
+        if _points.shape[0] == 0:
+            return
+        if not hasattr(self.grid.blas.__class__, "from_quantized_points"):
+            raise Exception(f"The BLAS {self.grid.blas.__class__.__name__} does not support initialization "
+                            "from_quantized_points, which is required for pruning.")
+        self.grid.blas = self.grid.blas.__class__.from_quantized_points(_points, self.grid.blas.max_level)
 
     def register_forward_functions(self):
         self._register_forward_function(self.rgba, ["density", "rgb"])

@@ -119,7 +119,7 @@ class MarchState:
 
 
 def march_count(oct: OctreeTensors, origins, dirs, dist_min, dist_max, num_samples: int, level: int,
-                jitter: Optional[torch.Tensor] = None, seed: int = 0) -> MarchState:
+                jitter: Optional[torch.Tensor] = None, seed: int = 0, defer_total: bool = False):
     """Sample culling of OctreeAS._raymarch_ray (octree_as.py:272-288) without materialising candidates."""
     A.require_device(origins)
     oct.ensure_bits(level)
@@ -142,8 +142,33 @@ def march_count(oct: OctreeTensors, origins, dirs, dist_min, dist_max, num_sampl
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     with _stage("scan"):
         A.check(L.wb_scan_counts(A.ptr(counts), C.c_int64(R), A.ptr(offsets), A.ptr(ws), C.c_int64(wsb), A.stream()))
-    total = int(offsets[-1].item())       # the one host sync of the path (the reference syncs in torch.nonzero, octree_as.py:288)
-    return MarchState(rays, keep + [jit], num_samples, jit, seed & 0xFFFFFFFF, hitmask, counts, offsets, total)
+    ms = MarchState(rays, keep + [jit], num_samples, jit, seed & 0xFFFFFFFF, hitmask, counts, offsets, -1)
+    if defer_total:                        # pre-march on a side stream: the total travels to pinned memory, no host sync here
+        host = torch.empty(1, dtype=torch.int64, pin_memory=True)
+        host.copy_(offsets[-1:], non_blocking=True)
+        ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream(dev))
+        return PendingMarch(ms, host, ev, torch.cuda.current_stream(dev))
+    ms.total = int(offsets[-1].item())     # the one host sync of the path (the reference syncs in torch.nonzero, octree_as.py:288)
+    return ms
+
+
+@dataclass
+class PendingMarch:
+    """A raymarch whose kernels were enqueued on a side stream (PackedRFTracer.premarch): finalize() makes the consumer stream
+    wait for them and reads the sample total (normally long since on the host by the time the batch is rendered)."""
+    ms: MarchState
+    host_total: torch.Tensor
+    event: "torch.cuda.Event"
+    stream: "torch.cuda.Stream"
+
+    def finalize(self) -> MarchState:
+        cur = torch.cuda.current_stream(self.ms.offsets.device)
+        cur.wait_event(self.event)
+        for t in (self.ms.hitmask, self.ms.counts, self.ms.offsets):
+            t.record_stream(cur)
+        self.event.synchronize()
+        self.ms.total = int(self.host_total[0])
+        return self.ms
 
 
 def march_fill_reference_layout(ms: MarchState, device):
@@ -488,7 +513,7 @@ class RFTraceFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, ms: MarchState, spec: NefSpec, n_dens: int, bg, precision: int, want_depth: bool, table, *params):
+    def forward(ctx, ms: MarchState, spec: NefSpec, n_dens: int, bg, precision: int, want_grad: bool, table, *params):
         A.require_device(table)
         L = A.lib()
         dev = table.device
@@ -503,11 +528,15 @@ class RFTraceFn(torch.autograd.Function):
         rec_t, rec_delta, rec_ray = march_fill_records(ms, dev)
         S, R = ms.total, ms.rays.num_rays
         shaded = _empty_s(S, (4,), torch.float32, dev)
-        need_grad = any(ctx.needs_input_grad[6:])          # grad mode is off inside Function.forward; ask autograd instead
+        # grad mode is always off inside Function.forward and needs_input_grad ignores torch.no_grad(): the caller (rf_trace)
+        # tells us whether a backward pass can follow, so that inference neither saves features nor needs the backward tiles
+        need_grad = bool(want_grad) and any(ctx.needs_input_grad[6:])
         Scap = _bucket(S)                                  # byte sizes for the bucketed capacity (layouts still use S)
         wsb = int(L.wb_rf_workspace_bytes(C.byref(desc), C.c_int32(precision), C.c_int64(R), C.c_int64(Scap), C.c_int32(0)))
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if wsb > 0 else None
         fb = int(L.wb_rf_feat_bytes(C.byref(desc), C.c_int32(precision), C.c_int64(Scap))) if need_grad else 0
+        if fb < 0 or wsb < 0:        # e.g. the tensor-core backward of this decoder does not fit: fail at the forward, not mid-backward
+            raise A.WispB200Error(L.wb_last_error().decode())
         feat = torch.empty(fb, dtype=torch.uint8, device=dev) if fb > 0 else None
         with _stage("shade_fwd"):
             A.check(L.wb_rf_shade_fwd(C.byref(desc), A.ptr(blob), C.c_int32(precision), C.byref(ms.rays), A.ptr(rec_t), A.ptr(rec_ray),
@@ -571,7 +600,15 @@ class RFTraceFn(torch.autograd.Function):
         return (None, None, None, None, None, None, g_table, *grads)
 
 
+def precision_supported(spec, nef, precision: int, backward: bool) -> bool:
+    """Host-side query (wb_rf_precision_supported): can this decoder configuration run at `precision`?"""
+    tb = A.f32c(nef.grid.codebook.feats.detach())
+    dens, col = _flatten(nef.decoder_density.packed_params()), _flatten(nef.decoder_color.packed_params())
+    desc = spec.desc(tb, dens, col)
+    return bool(A.lib().wb_rf_precision_supported(C.byref(desc), C.c_int32(precision), C.c_int32(1 if backward else 0)))
+
+
 def rf_trace(ms: MarchState, spec: NefSpec, table: torch.Tensor, dens_params: Sequence[torch.Tensor],
              col_params: Sequence[torch.Tensor], bg, precision: int = 0):
     """-> rgb [R,3], depth [R,1], alpha [R,1], hit [R]."""
-    return RFTraceFn.apply(ms, spec, len(dens_params), bg, precision, True, table, *dens_params, *col_params)
+    return RFTraceFn.apply(ms, spec, len(dens_params), bg, precision, torch.is_grad_enabled(), table, *dens_params, *col_params)

@@ -67,6 +67,7 @@ class HostPrefetcher:
     def __init__(self, batches: Iterable, device):
         self.batches, self.device = batches, torch.device(device)
         self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self.staged, self.staged_event = None, None       # the batch after the one being consumed (device tensors, copy event)
 
     def _stage(self, batch):
         if self.stream is None:
@@ -88,6 +89,7 @@ class HostPrefetcher:
                 nxt = self._stage(next(it))         # enqueue the next copy before handing out the current batch
             except StopIteration:
                 nxt = None
+            self.staged, self.staged_event = nxt if nxt is not None else (None, None)
             if ev is not None:
                 torch.cuda.current_stream(self.device).wait_event(ev)
                 for t in cur:

@@ -5,6 +5,7 @@ the neural field is a NeuralRadianceField(HashGrid) with the 'ray' sampler, and 
 from __future__ import annotations
 
 import inspect
+from typing import Optional
 
 import torch
 import torch.nn as nn
@@ -24,6 +25,47 @@ class PackedRFTracer(nn.Module):
         self.precision = None
         self.seed = 0               # base of the counter-based jitter stream; advanced once per trace() call
         self.jitter = None          # optional explicit [R, num_steps] jitter (parity tests)
+        self._pending = {}          # pre-marched batches (premarch), keyed by (origins ptr, dirs ptr, num rays, seed, num_steps)
+        self._march_stream = None
+
+    def _resolve_precision(self, spec, nef) -> int:
+        """Explicit precision is taken literally (an unsupported configuration raises); `None` follows autocast and quietly
+        stays on the fp32 kernels when the decoders do not fit the tensor-core path (both are native CUDA)."""
+        if self.precision is not None:
+            return int(self.precision)
+        if not torch.is_autocast_enabled():
+            return 0
+        need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in nef.parameters())
+        return 1 if ops.precision_supported(spec, nef, 1, need_bwd) else 0
+
+    def __getstate__(self):                                  # deepcopy / pickle: streams and in-flight marches are not state
+        d = self.__dict__.copy()
+        d["_pending"], d["_march_stream"] = {}, None
+        return d
+
+    def premarch(self, nef, rays, seed: int, num_steps: Optional[int] = None, ready=None):
+        """Enqueue the ray march of a FUTURE batch on a side stream.  Sample selection depends only on the rays, the occupancy
+        structure and the jitter seed -- not on the weights -- so the march (and its sample-count read-back, the one host sync
+        of the path) of batch i+1 can overlap the shading / backward / optimiser step of batch i.  The matching trace() call
+        (same ray tensors, same seed, 'ray' marching) picks the result up; anything else ignores it.  Do not prune() in between."""
+        blas = nef.grid.blas
+        n = self.num_steps if num_steps is None else num_steps
+        dev = rays.origins.device
+        if self._march_stream is None:
+            self._march_stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        self._march_stream.wait_stream(cur)                 # the rays (and octree masks) are ready on the caller's stream ...
+        if ready is not None:
+            self._march_stream.wait_event(ready)            # ... or when `ready` fires (e.g. HostPrefetcher.staged_event)
+        blas.tensors().ensure_bits(blas.max_level)
+        with torch.cuda.stream(self._march_stream):
+            pm = ops.march_count(blas.tensors(), rays.origins, rays.dirs, rays.dist_min, rays.dist_max, n, blas.max_level,
+                                 seed=seed, defer_total=True)
+        for t in (rays.origins, rays.dirs):
+            t.record_stream(self._march_stream)
+        if len(self._pending) >= 4:
+            self._pending.clear()
+        self._pending[(rays.origins.data_ptr(), rays.dirs.data_ptr(), rays.origins.shape[0], seed & 0xFFFFFFFF, n, id(blas))] = pm
 
     def get_prev_num_samples(self):
         return self.prev_num_samples
@@ -71,15 +113,18 @@ class PackedRFTracer(nn.Module):
         if spec is not None and not extra_channels:
             blas = nef.grid.blas
             if raymarch_type == 'ray':
-                ms = ops.march_count(blas.tensors(), rays.origins, rays.dirs, rays.dist_min, rays.dist_max, num_steps, blas.max_level,
-                                     jitter=jitter, seed=seed)
+                pm = self._pending.pop((rays.origins.data_ptr(), rays.dirs.data_ptr(), N, seed & 0xFFFFFFFF, num_steps, id(blas)), None) \
+                    if (self._pending and jitter is None) else None
+                ms = pm.finalize() if pm is not None else \
+                    ops.march_count(blas.tensors(), rays.origins, rays.dirs, rays.dist_min, rays.dist_max, num_steps, blas.max_level,
+                                    jitter=jitter, seed=seed)
             else:
                 ms, _ = ops.march_nuggets(blas.tensors(), rays.origins, rays.dirs, blas.max_level, num_steps, raymarch_type,
                                           reference_layout=False, jitter=jitter, seed=seed)
             self.prev_num_samples = ms.total
             rgb, depth, alpha, hit = ops.rf_trace(ms, spec, nef.grid.codebook.feats, nef.decoder_density.packed_params(),
                                                   nef.decoder_color.packed_params(), self.bg_color,
-                                                  precision=(int(torch.is_autocast_enabled()) if self.precision is None else int(self.precision)))
+                                                  precision=self._resolve_precision(spec, nef))
             return RenderBuffer(depth=depth if "depth" in channels else None, hit=hit, rgb=rgb, alpha=alpha)
 
         # ---- unfused route: same operators, nef evaluated through its own forward() ----

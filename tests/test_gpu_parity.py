@@ -286,6 +286,97 @@ def test_trace_follows_autocast(W, golden_dir):
     assert not np.array_equal(out["p0"], out["p1"])
 
 
+def test_premarch_is_the_same_march(W, golden_dir):
+    """PackedRFTracer.premarch (side stream, deferred sample count) + trace() == trace() alone, bit for bit; a premarch for other
+    rays / another seed is ignored."""
+    import copy
+    g, onef, spc = load_case(os.path.join(golden_dir, CASES[0] + ".npz"))
+    from gpu_util import nef_from_oracle
+    nef, blas = nef_from_oracle(onef, spc)
+    rays = W.Rays(dev(g["origins"]), dev(g["dirs"]), dist_min=float(g["near"]), dist_max=float(g["far"]))
+    other = W.Rays(dev(g["origins"]).clone(), dev(g["dirs"]).clone(), dist_min=float(g["near"]), dist_max=float(g["far"]))
+    outs = []
+    for mode in ("direct", "premarch", "stale"):
+        tracer = W.PackedRFTracer('ray', int(g["n_steps"]), bg_color=(1.0, 1.0, 1.0)); tracer.seed = 77
+        if mode == "premarch":
+            tracer.premarch(nef, rays, 77)
+        if mode == "stale":
+            tracer.premarch(nef, other, 77); tracer.premarch(nef, rays, 78)
+        rb = W.Pipeline(nef, tracer)(rays=rays, channels=["rgb", "depth"])
+        assert (len(tracer._pending) == 0) == (mode != "stale")
+        copy.deepcopy(tracer)                                   # streams / pending marches are not part of the state
+        outs.append((rb.rgb.detach().cpu().numpy(), rb.depth.detach().cpu().numpy(), tracer.get_prev_num_samples()))
+    for o in outs[1:]:
+        assert o[2] == outs[0][2] and np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])
+
+
+def test_nef_prune_rebuilds_occupancy(W):
+    """NeuralRadianceField.prune() (nerf.py:175-212): occupancy decay, one random density probe per cell, threshold, new OctreeAS.
+    Checked against a line-by-line restatement run with the same RNG state; the marcher then only samples kept cells."""
+    level = 5
+    blas = W.OctreeAS.make_dense(level, device="cuda")
+    torch.manual_seed(1)
+    grid = W.HashGrid.from_geometric(blas, feature_dim=2, num_lods=8, multiscale_type='cat', feature_std=0.5, codebook_bitwidth=12,
+                                     min_grid_res=8, max_grid_res=64)
+    nef = W.NeuralRadianceField(grid, view_embedder='positional', view_multires=2, hidden_dim=32, num_layers=1, bias=True,
+                                prune_density_decay=0.5, prune_min_density=1.02).cuda()
+    with torch.no_grad():
+        nef.decoder_density.lout.weight.mul_(8.0)             # spread the densities around the threshold
+    nef.grid.occupancy = torch.rand(nef.grid.num_cells)
+    occ0 = nef.grid.occupancy.clone()
+    # --- restatement (same RNG draws as prune(): torch.rand on the device, then np.random.rand) ---
+    torch.manual_seed(7); np.random.seed(7)
+    pts = nef.grid.dense_points.cuda()
+    smp = (pts.float() + torch.rand(pts.shape[0], 3, device="cuda")) / 2.0 ** level * 2.0 - 1.0
+    u = np.random.rand(2, pts.shape[0]); z = 1 - 2 * u[0]; r = np.sqrt(1.0 - z * z); phi = 2 * np.pi * u[1]
+    views = torch.from_numpy(np.array([r * np.cos(phi), r * np.sin(phi), z]).transpose()).float().cuda()
+    with torch.no_grad():
+        dens = nef(coords=smp, ray_d=views, channels="density")
+    occ_exp = torch.maximum(dens[:, 0], occ0.cuda() * 0.5)
+    keep = occ_exp > 1.02
+    assert 0 < int(keep.sum()) < pts.shape[0]                 # a non-trivial prune
+    # --- the method ---
+    torch.manual_seed(7); np.random.seed(7)
+    nef.prune()
+    assert torch.allclose(nef.grid.occupancy, occ_exp)
+    new = nef.grid.blas
+    s0, c0 = int(new.pyramid[1, level]), int(new.pyramid[0, level])
+    got = set(map(tuple, new.points[s0:s0 + c0].cpu().numpy().tolist()))
+    assert got == set(map(tuple, pts[keep].cpu().numpy().tolist()))
+    o, d = O.look_at_rays([-3.0, 0.65, -3.0], [0, 0, 0], 24, 24, 30.0)
+    mr = new.raymarch(W.Rays(dev(o), dev(d), dist_min=0.0, dist_max=8.0), 'ray', 128, seed=3)
+    cells = torch.floor((mr.samples + 1.0) * 0.5 * 2 ** level).clamp(0, 2 ** level - 1).to(torch.int16).cpu().numpy()
+    assert mr.samples.shape[0] > 0 and set(map(tuple, cells.tolist())) <= got
+
+
+def test_wide_decoders_under_autocast_stay_native(W):
+    """128-wide decoders: the tensor-core backward does not fit in shared memory.  precision=None under autocast trains on the
+    fp32 kernels (same results as precision 0); an explicit precision=1 with gradients raises at the forward."""
+    torch.manual_seed(0)
+    blas = W.OctreeAS.make_dense(4, device="cuda")
+    grid = W.HashGrid.from_geometric(blas, feature_dim=2, num_lods=8, multiscale_type='cat', feature_std=0.1, codebook_bitwidth=12,
+                                     min_grid_res=8, max_grid_res=64)
+    nef = W.NeuralRadianceField(grid, view_embedder='positional', view_multires=2, hidden_dim=128, num_layers=1, bias=True).cuda()
+    o, d = O.look_at_rays([-3.0, 0.65, -3.0], [0, 0, 0], 16, 16, 30.0)
+    rays = W.Rays(dev(o), dev(d), dist_min=0.0, dist_max=8.0)
+    outs = []
+    for prec, amp in ((0, False), (None, True)):
+        tracer = W.PackedRFTracer('ray', 64); tracer.seed = 3; tracer.precision = prec
+        nef.zero_grad()
+        with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
+            rb = W.Pipeline(nef, tracer)(rays=rays, channels=["rgb"])
+        rb.rgb.sum().backward()
+        outs.append((rb.rgb.detach().clone(), nef.grid.codebook.feats.grad.detach().clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.allclose(outs[0][1], outs[1][1], atol=1e-6, rtol=1e-4)
+    tracer = W.PackedRFTracer('ray', 64); tracer.precision = 1
+    with pytest.raises(W.WispB200Error):
+        W.Pipeline(nef, tracer)(rays=rays, channels=["rgb"])
+    tracer.seed = 3
+    with torch.no_grad():                                   # inference at precision 1 is fine (forward-only tiles fit)
+        rb = W.Pipeline(nef, tracer)(rays=rays, channels=["rgb"])
+    assert torch.isfinite(rb.rgb).all() and float((rb.rgb - outs[0][0]).abs().max()) < 2e-2
+
+
 @pytest.mark.parametrize("precision", [0, 1])
 def test_trace_config2_slice_vs_oracle(W, precision):
     """BASELINE config 2 shapes (L=16, F=2, T=2^19, 64-wide decoders, n=2048, level-7 lego-like octree) on a

@@ -111,3 +111,21 @@ def test_host_prefetcher_cpu_passthrough():
     for i, (a, b) in enumerate(got):
         assert float(a[0]) == i and float(b[0, 0]) == -i
     assert list(HostPrefetcher([], "cpu")) == []
+
+
+def test_precision_support_query_is_host_side():
+    """wb_rf_precision_supported answers without a device: the 64-wide app/nerf decoders fit the tensor-core path forward
+    and backward; wider / deeper decoders fit forward only (their backward stays on the fp32 kernels)."""
+    import wisp_b200 as W
+    from wisp_b200 import ops
+    ans = {}
+    for hidden, layers in ((64, 1), (128, 1), (64, 2)):
+        blas = W.OctreeAS.make_dense(3, device='cpu')
+        grid = W.HashGrid.from_geometric(blas, feature_dim=2, num_lods=16, multiscale_type='cat', feature_std=1e-4, codebook_bitwidth=19,
+                                         min_grid_res=16, max_grid_res=512)
+        nef = W.NeuralRadianceField(grid, view_embedder='positional', view_multires=4, hidden_dim=hidden, num_layers=layers, bias=True)
+        spec = nef.fused_spec()
+        ans[(hidden, layers)] = (ops.precision_supported(spec, nef, 1, False), ops.precision_supported(spec, nef, 1, True),
+                                 ops.precision_supported(spec, nef, 0, True))
+    assert ans[(64, 1)] == (True, True, True)
+    assert ans[(128, 1)] == (True, False, True) and ans[(64, 2)] == (True, False, True)
