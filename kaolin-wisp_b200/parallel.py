@@ -64,9 +64,9 @@ class HostPrefetcher:
     i+1 overlaps the render step of batch i.  Iterating yields tuples of device tensors that are safe to use on the
     current stream."""
 
-    def __init__(self, batches: Iterable, device):
+    def __init__(self, batches: Iterable, device, stream=None):
         self.batches, self.device = batches, torch.device(device)
-        self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self.stream = stream if stream is not None else (torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None)
         self.staged, self.staged_event = None, None       # the batch after the one being consumed (device tensors, copy event)
 
     def _stage(self, batch):
