@@ -145,6 +145,25 @@ __device__ __forceinline__ uint32_t wb_hash_idx(int x, int y, int z, int res, ui
     uint32_t h = ((uint32_t)x) ^ ((uint32_t)y * 2654435761u) ^ ((uint32_t)z * 805459861u);
     return h & Tmask;
 }
+// The 8 corner entries of cell (px,py,pz), corner j = (x + (j>>2&1), y + (j>>1&1), z + (j&1)): the same values as 8 calls of
+// wb_hash_idx, evaluated with one multiply per axis.  The level kind is warp-uniform, so this is a branch, not a select: the
+// straightforward form made ptxas compute BOTH index kinds for all 8 corners with the products and the constant loads repeated
+// (~100 instructions per level in the gather and the scatter).
+__device__ __forceinline__ void wb_corner_indices(const WbGrid& g, int l, int px, int py, int pz, uint32_t idx[8]) {
+    if (g.dense[l]) {
+        const uint32_t r1 = (uint32_t)g.res[l], r2 = r1 * r1;
+        const uint32_t b = (uint32_t)px + (uint32_t)py * r1 + (uint32_t)pz * r2;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) idx[j] = b + ((j & 4) ? 1u : 0u) + ((j & 2) ? r1 : 0u) + ((j & 1) ? r2 : 0u);
+    } else {
+        const uint32_t m = g.Tmask;
+        const uint32_t x0 = (uint32_t)px, x1 = x0 + 1u;
+        const uint32_t y0 = (uint32_t)py * 2654435761u, y1 = y0 + 2654435761u;
+        const uint32_t z0 = (uint32_t)pz * 805459861u, z1 = z0 + 805459861u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) idx[j] = (((j & 4) ? x1 : x0) ^ ((j & 2) ? y1 : y0) ^ ((j & 1) ? z1 : z0)) & m;
+    }
+}
 // position math: the reference evaluates res*(c*0.5+0.5) in double and rounds to float
 // (hashgrid_interpolate_cuda.cu:40-42); fmaf(c, res/2, res/2) rounds the same exact value once.
 __device__ __forceinline__ void wb_cell(float c, float hres, float hi, int& pos, float& w, float& iw) {
@@ -163,10 +182,7 @@ __device__ __forceinline__ void wb_corner_setup(const WbGrid& g, int l, float cx
     float xy00 = ix * iy, xy01 = ix * wy, xy10 = wx * iy, xy11 = wx * wy;
     coef[0] = xy00 * iz; coef[1] = xy00 * wz; coef[2] = xy01 * iz; coef[3] = xy01 * wz;
     coef[4] = xy10 * iz; coef[5] = xy10 * wz; coef[6] = xy11 * iz; coef[7] = xy11 * wz;
-    const int res = g.res[l]; const int dn = g.dense[l];
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-        idx[j] = wb_hash_idx(px + ((j & 4) >> 2), py + ((j & 2) >> 1), pz + (j & 1), res, g.Tmask, dn);
+    wb_corner_indices(g, l, px, py, pz, idx);
 }
 
 int wb_make_grid(const wb_nef_desc* d, WbGrid* g);     // host: validate + derive per-level constants
