@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--res", type=int, default=1024)
     ap.add_argument("--num-steps", type=int, default=2048)
     ap.add_argument("--scene", default="lego", choices=["lego", "dense"])
+    ap.add_argument("--trace-host", action="store_true", help="print host-side phase times of every step to stderr (diagnostics)")
     ap.add_argument("--premarch", type=int, default=1, help="1: march batch i+1 on a side stream while batch i renders (PackedRFTracer.premarch)")
     ap.add_argument("--precision", type=int, default=1, help="0: fp32 decoders, 1: fp16 tensor-core decoders (reference enable_amp)")
     ap.add_argument("--cpu-sample-rays", type=int, default=0, help="rays in the CPU-baseline sample (0 = auto)")
@@ -119,7 +120,7 @@ def run_reference(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 50 ms while the timed regions run."""
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms (the interval of the profiling recipe) while the timed regions run."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -128,7 +129,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "50"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -197,18 +198,30 @@ def run_ours(args):
     def seed_of(i):
         return 1000 + i * world + rank
 
+    host_trace = []                        # --trace-host: wall-clock of the host-side phases of every step (diagnostics only)
+
     def step(i, origins, dirs, target, nxt=None, nxt_ready=None):
+        import time
+        t0 = time.perf_counter()
         # software pipeline of the training loop: the sample selection of batch i+1 (it depends on rays + occupancy, not on the
         # weights) is enqueued on a side stream before batch i is rendered.  Every timed step enqueues exactly one march.
         if nxt is not None and args.premarch:
             tracer.premarch(nef, W.Rays(nxt[0], nxt[1], dist_min=NEAR, dist_max=FAR), seed_of(i + 1), ready=nxt_ready)
+        t1 = time.perf_counter()
         opt.zero_grad(set_to_none=True)      # autograd then adopts the returned gradient buffers: no zero-fill + accumulate pass over the 42 MB table
         tracer.seed = seed_of(i)
         rb = pipe(rays=W.Rays(origins, dirs, dist_min=NEAR, dist_max=FAR), lod_idx=None, channels=["rgb"])
+        t2 = time.perf_counter()
         loss = torch.nn.functional.smooth_l1_loss(rb.rgb, target, reduction='none').mean()       # multiview_trainer.py:144-154
+        t3 = time.perf_counter()
         loss.backward()
+        t4 = time.perf_counter()
         reducer.reduce()                      # N>1: NCCL all-reduce(mean) of table + decoder gradients; no-op at N=1
         opt.step()
+        if args.trace_host:
+            t5 = time.perf_counter()
+            host_trace.append((i, round((t1 - t0) * 1e3, 2), round((t2 - t1) * 1e3, 2), round((t3 - t2) * 1e3, 2), round((t4 - t3) * 1e3, 2),
+                               round((t5 - t4) * 1e3, 2), torch.cuda.memory_stats(dev).get("num_device_alloc", 0)))
         return loss
 
     def barrier():
@@ -216,15 +229,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)          # started before the warm-up so that samples exist for short timed regions; it keeps
+    if rank == 0:                          # running (one nvidia-smi process, 200 ms period) through both timed loops
+        sampler.start()
     # ---- warm-up ----
     for i in range(args.warmup):      # the warm-up exercises the same pipeline, but nothing is carried over into the timed region
         step(i, *dev_rays[i], dev_tgt[i], nxt=dev_rays[i + 1] if i + 1 < args.warmup else None)
     barrier()
 
     # ---- timed: device-resident inputs ----
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     W.ops.PROFILE = []
     launches0 = W._cabi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -349,6 +362,10 @@ def run_ours(args):
         dt, ns = cpu_time_step(Oc, onef, spc, args, nr, args.warmup, 1000 + args.warmup)
         line["cpu_baseline"] = {"value": nr / dt, "unit": "rays/s", "cores": Oc.num_threads(), "kind": "port",
                                 "sample": f"{nr} rays strided over the {args.res}^2 frame, full config, {ns} hit samples, {dt:.1f} s"}
+    if args.trace_host:
+        print("step, premarch ms, zero_grad+forward ms, loss ms, backward ms, reduce+opt ms, cudaMallocs so far", file=sys.stderr)
+        for row in host_trace:
+            print(row, file=sys.stderr)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

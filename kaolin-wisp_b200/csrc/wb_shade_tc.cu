@@ -596,6 +596,7 @@ static int tc_launch_ray_embed(const WbTc& m, const wb_rays* rays, void* workspa
 static int tc_env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
 static int tc_knob_fwd_ctas() { static const int v = tc_env_int("WB_TC_FWD_CTAS", 3); return v; }
 static int tc_knob_scatter_lpb() { static const int v = tc_env_int("WB_TC_SCATTER_LPB", 16); return v; }
+static int tc_knob_scatter_h2() { static const int v = tc_env_int("WB_TC_SCATTER_H2", 1); return v; }
 static int tc_knob_scatter_v4() { static const int v = tc_env_int("WB_TC_SCATTER_V4", 1); return v; }
 
 int wb_tc_shade_fwd(const wb_nef_desc* nef, const float* blob, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray,
@@ -611,9 +612,15 @@ int wb_tc_shade_fwd(const wb_nef_desc* nef, const float* blob, const wb_rays* ra
     int per_sm = (227 * 1024) / (m.smem_bytes + 4096); per_sm = max(1, min(per_sm, 512 / m.tmem_cols));
     per_sm = max(2, min(min(per_sm, 4), tc_knob_fwd_ctas()));
     auto kern = per_sm == 2 ? wb_shade_fwd_tc_kernel<2> : per_sm == 3 ? wb_shade_fwd_tc_kernel<3> : wb_shade_fwd_tc_kernel<4>;
-    WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, m.smem_bytes));
-    WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 min(100, (per_sm * (m.smem_bytes + 4096) * 100) / (228 * 1024) + 1)));
+    {   // function attributes are driver calls that can wait behind other driver work (e.g. an NVML poll): set them once, not per launch
+        static int done_for[5] = { -1, -1, -1, -1, -1 };
+        if (done_for[per_sm] != m.smem_bytes) {
+            WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, m.smem_bytes));
+            WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         min(100, (per_sm * (m.smem_bytes + 4096) * 100) / (228 * 1024) + 1)));
+            done_for[per_sm] = m.smem_bytes;
+        }
+    }
     const int64_t ntiles = (S + TC_ROWS - 1) / TC_ROWS;
     int64_t grid = (int64_t)wb_num_sms() * per_sm; if (grid > ntiles) grid = ntiles;
     kern<<<(unsigned)grid, TC_GROUP, m.smem_bytes, st>>>(g, m, reinterpret_cast<const uint8_t*>(blob), in, reinterpret_cast<float4*>(shaded));
@@ -780,14 +787,14 @@ wb_mlp_bwd_tc_kernel(WbTc m, const uint8_t* __restrict__ blob, TcIn in, const fl
 // ---------------------------------------------------------------------------------------------------------------
 // table scatter: dL/dfeat planes -> hash table (hashgrid_interpolate_cuda.cu:151-160), with warp-level run merging
 // ---------------------------------------------------------------------------------------------------------------
-template <int F>
+template <int F, bool H2>              // H2: the run sums travel through the warp scan as loss-scaled fp16 pairs (one shuffle per corner)
 __global__ void __launch_bounds__(256)
 wb_table_scatter_kernel(WbGrid g, TcIn in, const __half* __restrict__ dfeat, int planes, int levels, int lpb,
                         const float* __restrict__ scale_p, float* __restrict__ gtable, int pair_v4)
 {
     const int l_begin = blockIdx.y * lpb, l_end = min(levels, l_begin + lpb);     // this CTA's LODs; the sample position is built once for all of them
     const int lane = threadIdx.x & 31;
-    const float inv_scale = 1.0f / __ldg(scale_p);
+    const float scale = __ldg(scale_p), inv_scale = 1.0f / scale;
     const int Fr = F > 0 ? F : g.F;
     const int64_t nwork = (in.S + 31) & ~(int64_t)31;            // whole warps
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nwork; s += (int64_t)gridDim.x * blockDim.x) {
@@ -843,13 +850,30 @@ wb_table_scatter_kernel(WbGrid g, TcIn in, const __half* __restrict__ dfeat, int
             for (int o = 16; o > 0; o >>= 1) maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
             if (F == 2) {
                 float v0[8], v1[8];
+                if (H2 && maxd > 0) {
+                    // gradients arrive as fp16 anyway: scan the (still loss-scaled) products as half2, unscale after the scan
+                    const float s0 = gv[0] * scale, s1 = gv[1] * scale;
+                    __half2 h[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { v0[j] = gv[0] * cf[j]; v1[j] = gv[1] * cf[j]; }
-                for (int o = 1; o <= maxd; o <<= 1) {               // segmented inclusive scan (warp-uniform trip count)
+                    for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(s0 * cf[j], s1 * cf[j]);
+                    for (int o = 1; o <= maxd; o <<= 1) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float a = __shfl_up_sync(0xffffffffu, v0[j], o), b = __shfl_up_sync(0xffffffffu, v1[j], o);
-                        if (dist >= o) { v0[j] += a; v1[j] += b; }
+                        for (int j = 0; j < 8; ++j) {
+                            const __half2 a = __shfl_up_sync(0xffffffffu, h[j], o);
+                            if (dist >= o) h[j] = __hadd2(h[j], a);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { const float2 f = __half22float2(h[j]); v0[j] = f.x * inv_scale; v1[j] = f.y * inv_scale; }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { v0[j] = gv[0] * cf[j]; v1[j] = gv[1] * cf[j]; }
+                    for (int o = 1; o <= maxd; o <<= 1) {               // segmented inclusive scan (warp-uniform trip count)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float a = __shfl_up_sync(0xffffffffu, v0[j], o), b = __shfl_up_sync(0xffffffffu, v1[j], o);
+                            if (dist >= o) { v0[j] += a; v1[j] += b; }
+                        }
                     }
                 }
                 if (tail && valid) {
@@ -905,7 +929,13 @@ int wb_tc_decoder_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* 
     __half* dfeat = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(workspace) + tc_align256(R * m.Kp[m.nl_d] * 2));
     TcIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S, reinterpret_cast<const uint4*>(workspace), nullptr, reinterpret_cast<const uint4*>(feat_saved) };
     TcGrads G = { grad_dens, grad_col, scale, dfeat, planes, width };
-    WB_CUDA(cudaFuncSetAttribute(wb_mlp_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, m.smem_bytes));
+    {
+        static int done_for = -1;
+        if (done_for != m.smem_bytes) {
+            WB_CUDA(cudaFuncSetAttribute(wb_mlp_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, m.smem_bytes));
+            done_for = m.smem_bytes;
+        }
+    }
     const int64_t nctas = ((S + TC_ROWS - 1) / TC_ROWS + TC_BWD_GROUPS - 1) / TC_BWD_GROUPS;
     int64_t grid = (int64_t)wb_num_sms(); if (grid > nctas) grid = nctas;         // 1 CTA / SM: TMEM holds the weight-grad accumulators
     wb_mlp_bwd_tc_kernel<<<(unsigned)grid, TC_BWD_GROUPS * TC_GROUP, m.smem_bytes, st>>>(m, reinterpret_cast<const uint8_t*>(blob), in,
@@ -931,8 +961,9 @@ int wb_tc_table_scatter(const wb_nef_desc* nef, const wb_rays* rays, const float
         int64_t bx = (S + 255) / 256; const int64_t cap = (int64_t)wb_num_sms() * 8; if (bx > cap) bx = cap;
         dim3 grid2((unsigned)bx, (unsigned)((levels + lpb - 1) / lpb));
         const int v4 = tc_knob_scatter_v4();
-        if (g.F == 2) wb_table_scatter_kernel<2><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, levels, lpb, scale, grad_table, v4);
-        else wb_table_scatter_kernel<0><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, levels, lpb, scale, grad_table, 0);
+        if (g.F == 2 && tc_knob_scatter_h2()) wb_table_scatter_kernel<2, true><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, levels, lpb, scale, grad_table, v4);
+        else if (g.F == 2) wb_table_scatter_kernel<2, false><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, levels, lpb, scale, grad_table, v4);
+        else wb_table_scatter_kernel<0, false><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, levels, lpb, scale, grad_table, 0);
         WB_LAUNCH_CHECK();
     }
     return WB_OK;

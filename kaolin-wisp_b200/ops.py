@@ -144,12 +144,27 @@ def march_count(oct: OctreeTensors, origins, dirs, dist_min, dist_max, num_sampl
         A.check(L.wb_scan_counts(A.ptr(counts), C.c_int64(R), A.ptr(offsets), A.ptr(ws), C.c_int64(wsb), A.stream()))
     ms = MarchState(rays, keep + [jit], num_samples, jit, seed & 0xFFFFFFFF, hitmask, counts, offsets, -1)
     if defer_total:                        # pre-march on a side stream: the total travels to pinned memory, no host sync here
-        host = torch.empty(1, dtype=torch.int64, pin_memory=True)
+        host = _pinned_slot()
         host.copy_(offsets[-1:], non_blocking=True)
         ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream(dev))
         return PendingMarch(ms, host, ev, torch.cuda.current_stream(dev))
     ms.total = int(offsets[-1].item())     # the one host sync of the path (the reference syncs in torch.nonzero, octree_as.py:288)
     return ms
+
+
+_PINNED_RING: list = []
+_PINNED_NEXT = 0
+
+
+def _pinned_slot() -> torch.Tensor:
+    """One of 8 page-locked int64 slots allocated once per process (cudaHostAlloc in the training loop costs milliseconds and
+    synchronises); a slot is reused only 8 pre-marches later, long after its copy has been consumed."""
+    global _PINNED_NEXT
+    if not _PINNED_RING:
+        buf = torch.empty(8, dtype=torch.int64, pin_memory=True)
+        _PINNED_RING.extend(buf[i:i + 1] for i in range(8))
+    _PINNED_NEXT = (_PINNED_NEXT + 1) % 8
+    return _PINNED_RING[_PINNED_NEXT]
 
 
 @dataclass

@@ -59,6 +59,15 @@ class PackedRFTracer(nn.Module):
             self._march_stream.wait_event(ready)            # ... or when `ready` fires (e.g. HostPrefetcher.staged_event)
         blas.tensors().ensure_bits(blas.max_level)
         with torch.cuda.stream(self._march_stream):
+            key = (rays.origins.shape[0], n)
+            if getattr(self, "_primed", None) != key:
+                # first pre-march of this shape: reserve three sets of march buffers in the side stream's allocator pool, so that
+                # the steady state (one set being filled, one consumed, one waiting for its cross-stream events) never calls cudaMalloc
+                R, nw = key[0], (n + 31) // 32
+                spare = [(torch.empty((R, nw), dtype=torch.int32, device=dev), torch.empty(R, dtype=torch.int32, device=dev),
+                          torch.empty(R + 1, dtype=torch.int64, device=dev)) for _ in range(3)]
+                del spare
+                self._primed = key
             pm = ops.march_count(blas.tensors(), rays.origins, rays.dirs, rays.dist_min, rays.dist_max, n, blas.max_level,
                                  seed=seed, defer_total=True)
         for t in (rays.origins, rays.dirs):
