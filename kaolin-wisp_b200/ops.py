@@ -592,7 +592,9 @@ class RFTraceFn(torch.autograd.Function):
         if ctx.precision == 1 and S > 0:
             # power-of-two loss scale computed on the device (no host sync): largest |gradient| -> ~64 in fp16
             amax = g_sh.abs().amax().clamp_min(1e-30)
-            scale = torch.exp2(torch.floor(torch.log2(64.0 / amax))).clamp(2.0 ** -20, 2.0 ** 60).reshape(1).contiguous()
+            # 2^k assembled from the exponent bits (torch.exp2 is a jiterator op: NVRTC compile at first use)
+            k = torch.floor(torch.log2(64.0 / amax)).clamp(-20.0, 60.0).to(torch.int32)
+            scale = ((k + 127) << 23).view(torch.float32).reshape(1).contiguous()
         wsb = int(L.wb_rf_workspace_bytes(C.byref(desc), C.c_int32(ctx.precision), C.c_int64(R), C.c_int64(_bucket(S)), C.c_int32(1)))
         ws = torch.empty(wsb, dtype=torch.uint8, device=tb.device) if wsb > 0 else None
         if ctx.precision == 1 and S > 0:
