@@ -409,6 +409,39 @@ def test_trace_config2_slice_vs_oracle(W, precision):
         assert np.abs(got - ref).max() <= max(2e-3, tol["grad"]) * scale, (nm, np.abs(got - ref).max(), scale)
 
 
+SHAPES = [dict(num_lods=8, feature_dim=4, codebook_bitwidth=14, min_res=8, max_res=128, hidden_dim=32, multiscale="cat", view_freq=4, bias=True),
+          dict(num_lods=6, feature_dim=8, codebook_bitwidth=12, min_res=8, max_res=96, hidden_dim=64, multiscale="sum", view_freq=2, bias=False),
+          dict(num_lods=12, feature_dim=2, codebook_bitwidth=15, min_res=16, max_res=256, hidden_dim=48, multiscale="cat", view_freq=3, bias=True),
+          dict(num_lods=4, feature_dim=2, codebook_bitwidth=10, min_res=4, max_res=32, hidden_dim=16, multiscale="sum", view_freq=1, bias=True)]
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda c: f"F{c['feature_dim']}{c['multiscale']}L{c['num_lods']}h{c['hidden_dim']}")
+def test_trace_other_shapes_vs_oracle(W, shape, precision):
+    """Feature widths 2/4/8, 'cat' and 'sum', decoder widths that are not powers of two, no bias: the generic gather / scatter paths
+    of the fused kernels (the app/nerf shape takes the specialised F == 2 'cat' path), forward + backward vs the oracle."""
+    from gpu_util import nef_from_oracle, packed_grads
+    tol = TOL[precision]
+    onef = O.make_nef(feature_std=0.3, seed=11, **shape)
+    spc = O.octree_to_spc(O.points_to_octree(O.lego_like_points(5), 5))
+    o, d = O.look_at_rays([-3.0, 0.65, -3.0], [0, 0, 0], 24, 24, 30.0)
+    nef, blas = nef_from_oracle(onef, spc)
+    tracer = W.PackedRFTracer('ray', 256, bg_color=(1.0, 1.0, 1.0)); tracer.seed = 5
+    tracer.precision = precision
+    rb = W.Pipeline(nef, tracer)(rays=W.Rays(dev(o), dev(d), 0.0, 8.0), channels=["rgb", "depth", "alpha", "hit"])
+    f = O.rf_trace_fwd(spc, onef, o, d, 0.0, 8.0, 256, bg=(1, 1, 1), seed=5)
+    assert tracer.get_prev_num_samples() == f["num_samples"] > 1000
+    np.testing.assert_allclose(rb.rgb.detach().cpu().numpy(), f["rgb"], atol=tol["rgb"])
+    np.testing.assert_allclose(rb.alpha.detach().cpu().numpy(), f["alpha"], atol=tol["rgb"])
+    tgt = torch.sigmoid(torch.randn(o.shape[0], 3, generator=torch.Generator().manual_seed(4)))
+    torch.nn.functional.smooth_l1_loss(rb.rgb, tgt.cuda()).backward()
+    st = O.rf_step(spc, onef, o, d, 0.0, 8.0, 256, tgt.numpy(), bg=(1, 1, 1), seed=5)
+    gt, gd, gc = packed_grads(nef)
+    for got, ref, nm in ((gt, st["table"], "table"), (gd, st["dens"], "dens"), (gc, st["col"], "col")):
+        scale = np.abs(ref).max()
+        assert np.abs(got - ref).max() <= max(2e-3, tol["grad"]) * scale, (nm, np.abs(got - ref).max(), scale)
+
+
 def test_no_rays_and_no_hits(W):
     from gpu_util import nef_from_oracle
     onef = O.make_nef(num_lods=4, codebook_bitwidth=10, min_res=4, max_res=32, hidden_dim=16, feature_std=0.5, seed=1)
@@ -419,7 +452,7 @@ def test_no_rays_and_no_hits(W):
     rb = tracer(nef, rays=W.Rays(dev(o), dev(d), 0.0, 1.0))
     assert tracer.get_prev_num_samples() == 0
     np.testing.assert_allclose(rb.rgb.detach().cpu().numpy(), np.tile(np.array([[0.1, 0.2, 0.3]], np.float32), (5, 1)))
-    assert not rb.hit.any() and float(rb.alpha.abs().sum()) == 0.0
+    assert not rb.hit.any() and float(rb.alpha.detach().abs().sum()) == 0.0
     rb0 = tracer(nef, rays=W.Rays(dev(o[:0]), dev(d[:0]), 0.0, 1.0))
     assert rb0.rgb.shape == (0, 3)
 
