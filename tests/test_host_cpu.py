@@ -129,3 +129,14 @@ def test_precision_support_query_is_host_side():
                                  ops.precision_supported(spec, nef, 0, True))
     assert ans[(64, 1)] == (True, True, True)
     assert ans[(128, 1)] == (True, False, True) and ans[(64, 2)] == (True, False, True)
+
+
+def test_bucketed_capacities():
+    """Per-sample buffers are carved from capacities with at most 1/8 slack that repeat across nearby sample counts."""
+    from wisp_b200.ops import _bucket
+    assert _bucket(0) == 0 and _bucket(1) == 1 << 16 and _bucket((1 << 16) + 1) == 2 << 16
+    for S in (15_592_267, 15_667_821, 12_191_426, 333_000_000, 70_001):
+        c = _bucket(S)
+        assert S <= c <= S * 1.125 + (1 << 16)
+    assert _bucket(15_592_267) == _bucket(15_667_821)            # neighbouring frames of the orbit share their blocks
+    assert len({_bucket(s) for s in range(15_000_000, 16_000_000, 10_007)}) <= 2
