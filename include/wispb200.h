@@ -202,10 +202,12 @@ int wb_find_depth_bound(const float* query, const int32_t* curr_idxes, const flo
  * ---------------------------------------------------------------------------------------------- */
 int wb_composite_fwd(const float* shaded, const float* depth, const float* deltas, const int64_t* offsets, int64_t R,
                      const float* bg, float* rgb, float* depth_out, float* alpha, uint8_t* hit, wb_stream s);
-/* g_shaded float4 [S] = dL/d(r,g,b,sigma).  g_depth / g_alpha may be NULL. */
+/* g_shaded float4 [S] = dL/d(r,g,b,sigma).  g_depth / g_alpha may be NULL.
+ * absmax (may be NULL): device float, zero-initialised by the caller; receives max |g_shaded| (atomic max), from which the
+ * caller derives the power-of-two loss scale of the fp16 decoder backward without another pass over g_shaded. */
 int wb_composite_bwd(const float* shaded, const float* depth, const float* deltas, const int64_t* offsets, int64_t R,
                      const float* bg, const float* g_rgb, const float* g_depth, const float* g_alpha,
-                     float* g_shaded, wb_stream s);
+                     float* g_shaded, float* absmax, wb_stream s);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused render path -- replaces PackedRFTracer.trace + NeuralRadianceField.rgba + HashGrid.interpolate

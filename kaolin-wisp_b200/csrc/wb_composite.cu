@@ -63,8 +63,9 @@ __global__ void __launch_bounds__(WB_COMP_THREADS)
 wb_composite_bwd_kernel(const float4* __restrict__ shaded, const float* __restrict__ depth, const float* __restrict__ deltas,
                         const int64_t* __restrict__ offsets, int64_t R, float bgr, float bgg, float bgb,
                         const float* __restrict__ g_rgb, const float* __restrict__ g_depth, const float* __restrict__ g_alpha,
-                        float4* __restrict__ g_shaded)
+                        float4* __restrict__ g_shaded, float* __restrict__ absmax)
 {
+    float amax = 0.0f;
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -99,16 +100,25 @@ wb_composite_bwd_kernel(const float4* __restrict__ shaded, const float* __restri
             const float gw_incl = wb_warp_incl_scan(gw, lane);
             const float suffix = G - (gw_carry + gw_incl);          // sum_{j>k} g_j w_j
             const float gtau = gk * Tn - suffix;
-            if (k < e) g_shaded[k] = make_float4(gr * w, gg * w, gb * w, gtau * dl);
+            if (k < e) {
+                const float4 gs = make_float4(gr * w, gg * w, gb * w, gtau * dl);
+                g_shaded[k] = gs;
+                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(gs.x), fabsf(gs.y)), fmaxf(fabsf(gs.z), fabsf(gs.w))));
+            }
             carry += __shfl_sync(0xffffffffu, incl, 31);
             gw_carry += __shfl_sync(0xffffffffu, gw_incl, 31);
         }
+    }
+    if (absmax != nullptr) {      // non-negative floats order like their bit patterns: one atomicMax per warp (NaN/Inf sort above finite values)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        if (lane == 0 && amax > 0.0f) atomicMax(reinterpret_cast<unsigned int*>(absmax), __float_as_uint(amax));
     }
 }
 
 extern "C" int wb_composite_bwd(const float* shaded, const float* depth, const float* deltas, const int64_t* offsets, int64_t R,
                                 const float* bg, const float* g_rgb, const float* g_depth, const float* g_alpha,
-                                float* g_shaded, wb_stream s)
+                                float* g_shaded, float* absmax, wb_stream s)
 {
     if (R == 0) return WB_OK;
     WB_CHECK_ARG(offsets && bg && g_rgb, "null pointer");
@@ -116,7 +126,7 @@ extern "C" int wb_composite_bwd(const float* shaded, const float* depth, const f
     int64_t ctas = (R + 7) / 8; const int64_t cap = (int64_t)wb_num_sms() * 32; if (ctas > cap) ctas = cap;
     wb_composite_bwd_kernel<<<(unsigned)ctas, WB_COMP_THREADS, 0, (cudaStream_t)s>>>(
         reinterpret_cast<const float4*>(shaded), depth, deltas, offsets, R, b3[0], b3[1], b3[2], g_rgb, g_depth, g_alpha,
-        reinterpret_cast<float4*>(g_shaded));
+        reinterpret_cast<float4*>(g_shaded), absmax);
     WB_LAUNCH_CHECK();
     return WB_OK;
 }

@@ -476,7 +476,7 @@ class CompositeFn(torch.autograd.Function):
         g_sh = torch.zeros_like(sh)
         A.check(A.lib().wb_composite_bwd(A.ptr(sh), A.ptr(dp), A.ptr(dl), A.ptr(offsets), C.c_int64(R), ctx.bg,
                                          A.ptr(A.f32c(g_rgb)), A.ptr(A.f32c(g_depth).reshape(-1)) if g_depth is not None else None,
-                                         A.ptr(A.f32c(g_alpha).reshape(-1)) if g_alpha is not None else None, A.ptr(g_sh), A.stream()))
+                                         A.ptr(A.f32c(g_alpha).reshape(-1)) if g_alpha is not None else None, A.ptr(g_sh), None, A.stream()))
         return g_sh, None, None, None, None
 
 
@@ -582,16 +582,17 @@ class RFTraceFn(torch.autograd.Function):
         gd = A.f32c(g_depth).reshape(-1) if g_depth is not None else None
         ga = A.f32c(g_alpha).reshape(-1) if g_alpha is not None else None
         grgb = A.f32c(g_rgb)
+        absmax = torch.zeros(1, dtype=torch.float32, device=shaded.device) if ctx.precision == 1 else None
         with _stage("composite_bwd"):
             A.check(L.wb_composite_bwd(A.ptr(shaded), A.ptr(rec_t), A.ptr(rec_delta), A.ptr(ms.offsets), C.c_int64(R), ctx.bg,
-                                       A.ptr(grgb), A.ptr(gd), A.ptr(ga), A.ptr(g_sh), A.stream()))
+                                       A.ptr(grgb), A.ptr(gd), A.ptr(ga), A.ptr(g_sh), A.ptr(absmax), A.stream()))
         g_table = torch.zeros_like(tb)
         g_dens = torch.zeros_like(dens_flat)
         g_col = torch.zeros_like(col_flat)
         scale = None
         if ctx.precision == 1 and S > 0:
             # power-of-two loss scale computed on the device (no host sync): largest |gradient| -> ~64 in fp16
-            amax = g_sh.abs().amax().clamp_min(1e-30)
+            amax = absmax[0].clamp_min(1e-30)              # max |g_shaded|, gathered by the compositing backward itself
             # 2^k assembled from the exponent bits (torch.exp2 is a jiterator op: NVRTC compile at first use)
             k = torch.floor(torch.log2(64.0 / amax)).clamp(-20.0, 60.0).to(torch.int32)
             scale = ((k + 127) << 23).view(torch.float32).reshape(1).contiguous()
