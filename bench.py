@@ -288,6 +288,25 @@ def run_ours(args):
     barrier()
     e2e_step_ms = [e2e_ev[k].elapsed_time(e2e_ev[k + 1]) for k in range(args.steps)]
     ms_e2e = e2.elapsed_time(e3)
+
+    # ---- extra (SURVEY.md 8(d) "also forward-only rays/s"): inference render of the same frames, no gradients ----
+    render = None
+    try:
+        with torch.no_grad():
+            n_r = min(3, args.steps)
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            pipe(rays=W.Rays(*dev_rays[0], dist_min=NEAR, dist_max=FAR), lod_idx=None, channels=["rgb"])      # untimed
+            torch.cuda.synchronize()
+            r0.record()
+            for k in range(n_r):
+                tracer.seed = seed_of(args.warmup + k)
+                pipe(rays=W.Rays(*dev_rays[args.warmup + k], dist_min=NEAR, dist_max=FAR), lod_idx=None, channels=["rgb"])
+            r1.record()
+            torch.cuda.synchronize()
+            render = {"value": R * n_r / (r0.elapsed_time(r1) * 1e-3), "unit": "rays/s", "ms_per_frame": r0.elapsed_time(r1) / n_r,
+                      "what": "forward only (march + shade + composite), device-resident rays, per GPU"}
+    except Exception as ex:                                    # never let the extra figure break the contract line
+        render = {"error": repr(ex)[:200]}
     clocks = sampler.stop() if rank == 0 else None
 
     tms = torch.tensor([ms, ms_e2e, float(total_samples)], dtype=torch.float64, device=dev)
@@ -355,7 +374,7 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "rooflines": rooflines,
             "march": {"candidates_per_step": R * args.num_steps, "candidates_per_sec": R * args.num_steps / (mean_ms.get("march_count", float("nan")) * 1e-3)},
             "samples_per_step_per_gpu": S_step, "samples_per_sec": total_samples / (ms * 1e-3), "stage_ms": mean_ms,
-            "step_ms": step_ms, "cudaMalloc_calls_in_timed_region": int(dev_allocs)}
+            "step_ms": step_ms, "cudaMalloc_calls_in_timed_region": int(dev_allocs), "render_only": render}
 
     if not args.no_cpu_baseline:
         Oc, onef, spc = cpu_scene(args)
