@@ -135,3 +135,36 @@ def test_raytrace_against_brute_force():
         assert (np.diff(dd[:, 0]) >= 0).all() and (dd[:, 1] > dd[:, 0]).all() and (dd[:, 0] >= 0).all()
     root = O.raytrace(spc, o, d, 0)
     assert root["counts"].max() == 1 and (root["pidx"] == 0).all()
+
+
+SHAPES = [dict(num_lods=8, feature_dim=4, codebook_bitwidth=14, min_res=8, max_res=128, hidden_dim=32, multiscale="cat", view_freq=4, bias=True),
+          dict(num_lods=6, feature_dim=8, codebook_bitwidth=12, min_res=8, max_res=96, hidden_dim=64, multiscale="sum", view_freq=2, bias=False),
+          dict(num_lods=12, feature_dim=2, codebook_bitwidth=15, min_res=16, max_res=256, hidden_dim=48, multiscale="cat", view_freq=3, bias=True),
+          dict(num_lods=4, feature_dim=2, codebook_bitwidth=10, min_res=4, max_res=32, hidden_dim=16, multiscale="sum", view_freq=1, bias=True)]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda c: f"F{c['feature_dim']}{c['multiscale']}L{c['num_lods']}h{c['hidden_dim']}")
+def test_oracle_step_vs_torch_twin_other_shapes(shape):
+    """The shapes the GPU suite uses beyond the golden fixtures (feature widths 4 / 8, 'sum', 48-wide decoders, no bias):
+    the C oracle's hand-written forward + backward against the op-for-op torch twin differentiated by autograd."""
+    import torch
+    from oracle import torch_twin as T
+    rng = np.random.default_rng(2)
+    nef = O.make_nef(feature_std=0.3, seed=11, **shape)
+    spc = O.octree_to_spc(O.points_to_octree(O.lego_like_points(4), 4))
+    o, d = O.look_at_rays([-3.0, 0.65, -3.0], [0, 0, 0], 12, 12, 30.0)
+    n = 48
+    jit = rng.random((o.shape[0], n), dtype=np.float32)
+    tgt = rng.random((o.shape[0], 3), dtype=np.float32)
+    st = O.rf_step(spc, nef, o, d, 0.0, 8.0, n, tgt, loss="huber", bg=(1, 1, 1), jitter_arr=jit)
+    p = T.TwinParams(nef)
+    rgb, _, _, _, mr = T.trace(p, spc, o, d, 0.0, 8.0, n, jit, (1.0, 1.0, 1.0))
+    loss = torch.nn.functional.smooth_l1_loss(rgb, torch.from_numpy(tgt), reduction='none').mean()
+    loss.backward()
+    assert st["num_samples"] == int(mr["ridx"].shape[0]) > 100
+    np.testing.assert_allclose(st["rgb"], rgb.detach().numpy(), atol=2e-6)
+    assert abs(st["loss"] - float(loss.detach())) < 1e-6
+    gt, gd, gc = p.packed_grads()
+    for got, ref, nm in ((st["table"], gt, "table"), (st["dens"], gd, "dens"), (st["col"], gc, "col")):
+        scale = max(np.abs(ref).max(), 1e-12)
+        assert np.abs(got - ref).max() <= 2e-4 * scale + 1e-9, (nm, np.abs(got - ref).max(), scale)
