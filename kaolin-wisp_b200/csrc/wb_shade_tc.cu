@@ -596,6 +596,8 @@ static int tc_launch_ray_embed(const WbTc& m, const wb_rays* rays, void* workspa
 static int tc_env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
 static int tc_knob_fwd_ctas() { static const int v = tc_env_int("WB_TC_FWD_CTAS", 3); return v; }
 static int tc_knob_scatter_lpb() { static const int v = tc_env_int("WB_TC_SCATTER_LPB", 16); return v; }
+static int tc_knob_scatter_idx2() { static const int v = tc_env_int("WB_TC_SCATTER_IDX2", 1); return v; }
+static int tc_knob_scatter_ctas() { static const int v = tc_env_int("WB_TC_SCATTER_CTAS", 16); return v; }
 static int tc_knob_scatter_h2() { static const int v = tc_env_int("WB_TC_SCATTER_H2", 1); return v; }
 static int tc_knob_scatter_v4() { static const int v = tc_env_int("WB_TC_SCATTER_V4", 1); return v; }
 
@@ -787,7 +789,8 @@ wb_mlp_bwd_tc_kernel(WbTc m, const uint8_t* __restrict__ blob, TcIn in, const fl
 // ---------------------------------------------------------------------------------------------------------------
 // table scatter: dL/dfeat planes -> hash table (hashgrid_interpolate_cuda.cu:151-160), with warp-level run merging
 // ---------------------------------------------------------------------------------------------------------------
-template <int F, bool H2>              // H2: the run sums travel through the warp scan as loss-scaled fp16 pairs (one shuffle per corner)
+template <int F, bool H2, bool IDX2>   // H2: the run sums travel through the warp scan as loss-scaled fp16 pairs (one shuffle per corner)
+                                       // IDX2: corner entries through wb_corner_indices (one multiply per axis) instead of 8 x wb_hash_idx
 __global__ void __launch_bounds__(256)
 wb_table_scatter_kernel(WbGrid g, TcIn in, const __half* __restrict__ dfeat, int planes, int levels, int lpb,
                         const float* __restrict__ scale_p, float* __restrict__ gtable, int pair_v4)
@@ -825,8 +828,11 @@ wb_table_scatter_kernel(WbGrid g, TcIn in, const __half* __restrict__ dfeat, int
                 const float xy00 = jx * jy, xy01 = jx * wy, xy10 = wx * jy, xy11 = wx * wy;
                 cf[0] = xy00 * jz; cf[1] = xy00 * wz; cf[2] = xy01 * jz; cf[3] = xy01 * wz;
                 cf[4] = xy10 * jz; cf[5] = xy10 * wz; cf[6] = xy11 * jz; cf[7] = xy11 * wz;
+                if (IDX2) wb_corner_indices(g, l, ix, iy, iz, idx);
+                else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) idx[j] = wb_hash_idx(ix + ((j & 4) >> 2), iy + ((j & 2) >> 1), iz + (j & 1), g.res[l], g.Tmask, g.dense[l]);
+                    for (int j = 0; j < 8; ++j) idx[j] = wb_hash_idx(ix + ((j & 4) >> 2), iy + ((j & 2) >> 1), iz + (j & 1), g.res[l], g.Tmask, g.dense[l]);
+                }
                 if (F == 2) {
                     const float2 gg = __half22float2(gnext);
                     gv[0] = gg.x * inv_scale; gv[1] = gg.y * inv_scale;
@@ -958,12 +964,13 @@ int wb_tc_table_scatter(const wb_nef_desc* nef, const wb_rays* rays, const float
     if (levels > 0) {
         // LODs per CTA row: the sample position / record loads are shared by `lpb` LODs (measured sweep in profiles/README.md)
         const int lpb = max(1, min(levels, tc_knob_scatter_lpb()));
-        int64_t bx = (S + 255) / 256; const int64_t cap = (int64_t)wb_num_sms() * 8; if (bx > cap) bx = cap;
+        int64_t bx = (S + 255) / 256; const int64_t cap = (int64_t)wb_num_sms() * tc_knob_scatter_ctas(); if (bx > cap) bx = cap;
         dim3 grid2((unsigned)bx, (unsigned)((levels + lpb - 1) / lpb));
         const int v4 = tc_knob_scatter_v4();
-        if (g.F == 2 && tc_knob_scatter_h2()) wb_table_scatter_kernel<2, true><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, levels, lpb, scale, grad_table, v4);
-        else if (g.F == 2) wb_table_scatter_kernel<2, false><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, levels, lpb, scale, grad_table, v4);
-        else wb_table_scatter_kernel<0, false><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, levels, lpb, scale, grad_table, 0);
+        if (g.F == 2 && tc_knob_scatter_h2() && tc_knob_scatter_idx2()) wb_table_scatter_kernel<2, true, true><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, levels, lpb, scale, grad_table, v4);
+        else if (g.F == 2 && tc_knob_scatter_h2()) wb_table_scatter_kernel<2, true, false><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, levels, lpb, scale, grad_table, v4);
+        else if (g.F == 2) wb_table_scatter_kernel<2, false, false><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, levels, lpb, scale, grad_table, v4);
+        else wb_table_scatter_kernel<0, false, false><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, levels, lpb, scale, grad_table, 0);
         WB_LAUNCH_CHECK();
     }
     return WB_OK;
