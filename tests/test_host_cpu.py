@@ -140,3 +140,30 @@ def test_bucketed_capacities():
         assert S <= c <= S * 1.125 + (1 << 16)
     assert _bucket(15_592_267) == _bucket(15_667_821)            # neighbouring frames of the orbit share their blocks
     assert len({_bucket(s) for s in range(15_000_000, 16_000_000, 10_007)}) <= 2
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` needs no GPU: it times the CPU oracle on a bounded sample and prints ONE JSON line carrying
+    the contract keys with impl = reference, zero-byte e2e and a cpu_baseline that repeats the line's value."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-sample-rays", "256"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "e2e", "cpu_baseline"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "rays/s" and d["value"] > 0 and d["steps"] == 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert "workload" in d["config"]
+    # ranks other than 0 of a torchrun launch print nothing and exit 0
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                          capture_output=True, text=True, timeout=300, env=env)
+    assert out1.returncode == 0 and out1.stdout.strip() == ""
