@@ -54,7 +54,6 @@ struct WbTc {
     int acc_col[TC_ML];                        // TMEM column of the weight-grad accumulator of layer l
     int work_col[2];                           // TMEM working accumulator of sub-tile 0/1
     int tmem_cols;
-    int a_col;                                 // forward TMEM-A variant: first column of the fp16 activation tile (lane = row), else -1
     int feat_dim, pos_dim, view_dim, pos_mode, pos_freq, view_mode, view_freq;
 };
 
@@ -120,8 +119,8 @@ int wb_tc_make(const wb_nef_desc* d, bool backward, WbTc* m, bool tmem_a = false
                           : "tensor-core path: decoder does not fit in shared memory (use precision 0)");
     int col = 0;
     for (int gi = 0; gi < groups; ++gi) { m->work_col[gi] = col; col += maxw; }
-    m->a_col = -1;
-    if (tmem_a && !backward) { m->a_col = col; col += maxw / 2; }       // two halfs per 32-bit column
+    // forward TMEM-A variant (one group): work_col[1] is otherwise unused and holds the first column of the fp16 activation tile
+    if (tmem_a && !backward) { m->work_col[1] = col; col += maxw / 2; }  // two halfs per 32-bit column
     if (backward) for (int l = 0; l < nl; ++l) { m->acc_col[l] = col; col += m->Np[l]; }
     WB_CHECK_ARG(col <= 512, "tensor-core path: accumulators do not fit in TMEM (use precision 0)");
     int alloc = 32; while (alloc < col) alloc <<= 1;
@@ -378,7 +377,7 @@ __device__ __forceinline__ void tc_ctx_init(TcCtx& c, uint8_t* smem, uint64_t* b
 }
 
 // one record per (group, kind, layer) + the constant tile of the bias UMMA; called by all threads before the first round
-__device__ __forceinline__ void tc_build_table(const WbTc& m, TcRec* tab, uint8_t* smem, uint32_t tmem, int groups, bool backward)
+__device__ __forceinline__ void tc_build_table(const WbTc& m, TcRec* tab, uint8_t* smem, uint32_t tmem, int groups, bool backward, bool ta = false)
 {
     const int nl = m.nl_d + m.nl_c;
     const int e = threadIdx.x;
@@ -398,9 +397,9 @@ __device__ __forceinline__ void tc_build_table(const WbTc& m, TcRec* tab, uint8_
     } else if (kind == TC_K_BIAS) {    // D_work[g] = Ones . Bias_l^T
         da = tc_desc(base + m.ones_off, 2048, 128); db = tc_desc(base + m.w_smem_off + m.b_off[l], Np * 16, 128);
         id = tc_idesc(128, Np, 0, 0); d = tmem + m.work_col[g]; nk = m.has_bias ? 1 : 0;
-    } else if (!backward && kind == TC_K_FWD_TA && m.a_col >= 0) {   // D_work (+)= X_l[TMEM] . W_l^T ; a_lo = TMEM address, 8 columns per K step
-        da = (uint64_t)(tmem + (uint32_t)m.a_col); db = tc_desc(base + m.w_smem_off + m.w_off[l], Np * 16, 128);
-        id = tc_idesc(128, Np, 0, 0); d = tmem + m.work_col[g]; nk = (uint32_t)(Kp / 16) | (1u << 16); acc = m.has_bias; aadv = 8; badv = (2 * Np * 16) >> 4;
+    } else if (!backward && kind == TC_K_FWD_TA && ta) {   // D_work (+)= X_l[TMEM] . W_l^T ; a_lo = TMEM address, 8 columns per K step
+        da = (uint64_t)(tmem + (uint32_t)m.work_col[1]); db = tc_desc(base + m.w_smem_off + m.w_off[l], Np * 16, 128);
+        id = tc_idesc(128, Np, 0, 0); d = tmem + m.work_col[g]; nk = (uint32_t)(Kp / 16); acc = m.has_bias; aadv = 8; badv = (2 * Np * 16) >> 4;
     } else if (!backward) {
         nk = 0;
     } else if (kind == TC_K_WGRAD) {   // acc_l[in, out] += X_l^T . dY_l   (K = 128 samples)
@@ -410,16 +409,17 @@ __device__ __forceinline__ void tc_build_table(const WbTc& m, TcRec* tab, uint8_
         da = tc_desc(base + m.dy_off[g], 2048, 128); db = tc_desc(base + m.w_smem_off + m.w_off[l], 128, Np * 16);
         id = tc_idesc(128, Kp, 0, 1); d = tmem + m.work_col[g]; nk = Np / 16; aadv = 4096 >> 4; badv = 256 >> 4;
     }
-    TcRec r = { (uint32_t)da, (uint32_t)(da >> 32), (uint32_t)db, (uint32_t)(db >> 32), id, d, (nk & 0x100ffu) | (acc << 8), aadv | (badv << 16) };
+    TcRec r = { (uint32_t)da, (uint32_t)(da >> 32), (uint32_t)db, (uint32_t)(db >> 32), id, d, nk | (acc << 8), aadv | (badv << 16) };
     tab[(g * TC_KINDS + kind) * TC_ML + l] = r;
 }
+template <bool A_IN_TMEM = false>
 __device__ __forceinline__ void tc_issue_rec(const uint4 q0, const uint4 q1, long long* ts = nullptr, int* tn = nullptr)
 {
     uint64_t da = ((uint64_t)q0.y << 32) | q0.x, db = ((uint64_t)q0.w << 32) | q0.z;
     const int nk = (int)(q1.z & 0xffu);
-    const uint32_t acc = (q1.z >> 8) & 1u, a_in_tmem = (q1.z >> 16) & 1u, aadv = q1.w & 0xffffu, badv = q1.w >> 16;
+    const uint32_t acc = q1.z >> 8, aadv = q1.w & 0xffffu, badv = q1.w >> 16;
     for (int kb = 0; kb < nk; ++kb) {
-        if (a_in_tmem) tc_mma_ts(q1.y, (uint32_t)da, db, q1.x, acc | (uint32_t)(kb > 0));
+        if (A_IN_TMEM) tc_mma_ts(q1.y, (uint32_t)da, db, q1.x, acc | (uint32_t)(kb > 0));
         else tc_mma(q1.y, da, db, q1.x, acc | (uint32_t)(kb > 0));
         da += aadv; db += badv;
 #ifdef WB_TC_TIMING
@@ -440,6 +440,7 @@ __device__ __forceinline__ void tc_issue_rec(const uint4 q0, const uint4 q1, lon
 //      tcgen05.ld + 16 F2FP.RELU + 4 STS.128 instead of ~130 instructions,
 //  (d) a row is shared by two threads (column halves),
 //  (e) the groups of a CTA (backward) / the CTAs of an SM (forward) have independent barriers and overlap each other.
+template <bool TA = false>          // TA: warp 0's second chain (k0b) reads its A operand from tensor memory
 __device__ __forceinline__ void tc_round(TcCtx& c, int l, int k0a, int k0b, int k1)
 {
     TC_TS(c);
@@ -460,9 +461,9 @@ __device__ __forceinline__ void tc_round(TcCtx& c, int l, int k0a, int k0b, int 
 #ifdef WB_TC_TIMING
             long long* ts4 = nullptr; int tn4 = 0;
             if (blockIdx.x == 0 && threadIdx.x == 0 && c.tsn2 / 3 < 64) { ts4 = g_tc_ts4[c.tsk][c.tsn2 / 3]; ts4[tn4++] = clock64(); }
-            if (((qa1.z | qb1.z) & 0xffu) != 0) { tc_issue_rec(qa0, qa1, ts4, &tn4); tc_issue_rec(qb0, qb1, ts4, &tn4); TC_TS2(c, c.tsn2); tc_commit(c.bar); }
+            if (((qa1.z | qb1.z) & 0xffu) != 0) { tc_issue_rec(qa0, qa1, ts4, &tn4); tc_issue_rec<TA>(qb0, qb1, ts4, &tn4); TC_TS2(c, c.tsn2); tc_commit(c.bar); }
 #else
-            if (((qa1.z | qb1.z) & 0xffu) != 0) { tc_issue_rec(qa0, qa1); tc_issue_rec(qb0, qb1); TC_TS2(c, c.tsn2); tc_commit(c.bar); }
+            if (((qa1.z | qb1.z) & 0xffu) != 0) { tc_issue_rec(qa0, qa1); tc_issue_rec<TA>(qb0, qb1); TC_TS2(c, c.tsn2); tc_commit(c.bar); }
 #endif
             else tc_mbar_arrive(c.bar);
             TC_TS2(c, c.tsn2);
@@ -478,16 +479,16 @@ __device__ __forceinline__ void tc_round(TcCtx& c, int l, int k0a, int k0b, int 
 
 // Decoders of one 128-sample sub-tile, starting from an X0 tile that the group has already written.
 // Returns (in registers, both column halves) the density-decoder output df[16] and the colour pre-activations c3[3].
-// TA (experimental forward variant): the activation tile lives in tensor memory (m.a_col; lane = row, two halfs per column) and
+// TA (experimental forward variant): the activation tile lives in tensor memory (m.work_col[1]; lane = row, two halfs per column) and
 // feeds the UMMAs as the A operand directly; nothing but the weights is in shared memory.
 template <bool TA = false>
 __device__ __forceinline__ void tc_decoders(const WbTc& m, TcCtx& c, const TcIn& in, int64_t ray, float df[16], float c3[3])
 {
     uint8_t* sub = c.smem + m.sub_off[c.g];
     const int nl = m.nl_d + m.nl_c;
-    const uint32_t arow = c.tmem + ((uint32_t)c.laneq << 16) + (uint32_t)(TA ? m.a_col : 0);
+    const uint32_t arow = c.tmem + ((uint32_t)c.laneq << 16) + (uint32_t)(TA ? m.work_col[1] : 0);
     for (int l = 0; l < nl; ++l) {
-        tc_round(c, l, TC_K_BIAS, TA ? TC_K_FWD_TA : TC_K_FWD, -1);   // accumulator = bias + X_l . W_l^T
+        tc_round<TA>(c, l, TC_K_BIAS, TA ? TC_K_FWD_TA : TC_K_FWD, -1);   // accumulator = bias + X_l . W_l^T
         const uint32_t trow = c.tmem + ((uint32_t)c.laneq << 16) + m.work_col[c.g];
         const bool last_d = (l == m.nl_d - 1), last_c = (l == nl - 1);
         if (last_d) {
@@ -593,7 +594,7 @@ wb_shade_fwd_tc_kernel(WbGrid g, WbTc m, const uint8_t* __restrict__ blob, TcIn 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    tc_build_table(m, itab, smem, tmem_s, 1, false);
+    tc_build_table(m, itab, smem, tmem_s, 1, false, TA);
     __syncthreads();
     tc_mbar_wait(&bars[1], 0);
     TcCtx c; tc_ctx_init(c, smem, bars, itab, tmem_s, 0);
@@ -611,7 +612,7 @@ wb_shade_fwd_tc_kernel(WbGrid g, WbTc m, const uint8_t* __restrict__ blob, TcIn 
         const float pz = wb_addcmul(__ldg(in.origins + 3 * ray + 2), __ldg(in.dirs + 3 * ray + 2), t);
         // density-decoder input row: grid features (+ position embedding), zero padded to Kp; the two threads of a row split the LODs
         if (TA) {
-            tile_gather_ta(g, c.tmem + ((uint32_t)c.laneq << 16) + (uint32_t)m.a_col, c.h, px, py, pz, in.x0_save, in.S, s, valid);
+            tile_gather_ta(g, c.tmem + ((uint32_t)c.laneq << 16) + (uint32_t)m.work_col[1], c.h, px, py, pz, in.x0_save, in.S, s, valid);
         } else {
             tile_gather(g, t0, c.r, c.h, px, py, pz);
             if (c.h == 0) {
