@@ -61,7 +61,7 @@ static int tc_round_up(int v, int m) { return (v + m - 1) / m * m; }
 static int tc_embed_dim(int mode, int freq) { return mode == 0 ? 0 : mode == 1 ? 3 : mode == 2 ? 6 * freq : 3 + 6 * freq; }
 
 // returns WB_OK, or WB_ERR_INVALID with a message when the configuration does not fit the tensor-core path
-int wb_tc_make(const wb_nef_desc* d, bool backward, WbTc* m)
+int wb_tc_make(const wb_nef_desc* d, bool backward, WbTc* m, bool tmem_a = false)
 {
     WB_CHECK_ARG(d->dens_layers >= 1 && d->col_layers >= 1 && d->dens_layers + d->col_layers <= TC_ML, "unsupported decoder depth");
     WB_CHECK_ARG(d->dens_params && d->col_params, "null decoder parameters");
@@ -119,6 +119,8 @@ int wb_tc_make(const wb_nef_desc* d, bool backward, WbTc* m)
                           : "tensor-core path: decoder does not fit in shared memory (use precision 0)");
     int col = 0;
     for (int gi = 0; gi < groups; ++gi) { m->work_col[gi] = col; col += maxw; }
+    // forward TMEM-A variant (one group): work_col[1] is otherwise unused and holds the first column of the fp16 activation tile
+    if (tmem_a && !backward) { m->work_col[1] = col; col += maxw / 2; }  // two halfs per 32-bit column
     if (backward) for (int l = 0; l < nl; ++l) { m->acc_col[l] = col; col += m->Np[l]; }
     WB_CHECK_ARG(col <= 512, "tensor-core path: accumulators do not fit in TMEM (use precision 0)");
     int alloc = 32; while (alloc < col) alloc <<= 1;
@@ -348,7 +350,8 @@ struct __align__(16) TcRec {
     uint32_t a_lo, a_hi, b_lo, b_hi;          // shared-memory descriptors of the first UMMA
     uint32_t idesc, tmem_d, nk_acc, adv;      // nk | (accumulate-from-start << 8); a advance | b advance << 16 (16-byte units)
 };
-enum { TC_K_FWD = 0, TC_K_BIAS = 1, TC_K_WGRAD = 2, TC_K_DGRAD = 3, TC_KINDS = 4 };
+enum { TC_K_FWD = 0, TC_K_BIAS = 1, TC_K_WGRAD = 2, TC_K_DGRAD = 3, TC_KINDS = 4,
+       TC_K_FWD_TA = TC_K_WGRAD };           // forward kernels have no weight grad: the slot holds the A-from-TMEM chain of the TMEM-A variant
 
 struct TcCtx {
     uint8_t* smem; uint64_t* bar; uint32_t tmem; uint32_t phase;
@@ -374,7 +377,7 @@ __device__ __forceinline__ void tc_ctx_init(TcCtx& c, uint8_t* smem, uint64_t* b
 }
 
 // one record per (group, kind, layer) + the constant tile of the bias UMMA; called by all threads before the first round
-__device__ __forceinline__ void tc_build_table(const WbTc& m, TcRec* tab, uint8_t* smem, uint32_t tmem, int groups, bool backward)
+__device__ __forceinline__ void tc_build_table(const WbTc& m, TcRec* tab, uint8_t* smem, uint32_t tmem, int groups, bool backward, bool ta = false)
 {
     const int nl = m.nl_d + m.nl_c;
     const int e = threadIdx.x;
@@ -394,6 +397,9 @@ __device__ __forceinline__ void tc_build_table(const WbTc& m, TcRec* tab, uint8_
     } else if (kind == TC_K_BIAS) {    // D_work[g] = Ones . Bias_l^T
         da = tc_desc(base + m.ones_off, 2048, 128); db = tc_desc(base + m.w_smem_off + m.b_off[l], Np * 16, 128);
         id = tc_idesc(128, Np, 0, 0); d = tmem + m.work_col[g]; nk = m.has_bias ? 1 : 0;
+    } else if (!backward && kind == TC_K_FWD_TA && ta) {   // D_work (+)= X_l[TMEM] . W_l^T ; a_lo = TMEM address, 8 columns per K step
+        da = (uint64_t)(tmem + (uint32_t)m.work_col[1]); db = tc_desc(base + m.w_smem_off + m.w_off[l], Np * 16, 128);
+        id = tc_idesc(128, Np, 0, 0); d = tmem + m.work_col[g]; nk = (uint32_t)(Kp / 16); acc = m.has_bias; aadv = 8; badv = (2 * Np * 16) >> 4;
     } else if (!backward) {
         nk = 0;
     } else if (kind == TC_K_WGRAD) {   // acc_l[in, out] += X_l^T . dY_l   (K = 128 samples)
@@ -406,13 +412,16 @@ __device__ __forceinline__ void tc_build_table(const WbTc& m, TcRec* tab, uint8_
     TcRec r = { (uint32_t)da, (uint32_t)(da >> 32), (uint32_t)db, (uint32_t)(db >> 32), id, d, nk | (acc << 8), aadv | (badv << 16) };
     tab[(g * TC_KINDS + kind) * TC_ML + l] = r;
 }
+template <bool A_IN_TMEM = false>
 __device__ __forceinline__ void tc_issue_rec(const uint4 q0, const uint4 q1, long long* ts = nullptr, int* tn = nullptr)
 {
     uint64_t da = ((uint64_t)q0.y << 32) | q0.x, db = ((uint64_t)q0.w << 32) | q0.z;
     const int nk = (int)(q1.z & 0xffu);
     const uint32_t acc = q1.z >> 8, aadv = q1.w & 0xffffu, badv = q1.w >> 16;
     for (int kb = 0; kb < nk; ++kb) {
-        tc_mma(q1.y, da, db, q1.x, acc | (uint32_t)(kb > 0)); da += aadv; db += badv;
+        if (A_IN_TMEM) tc_mma_ts(q1.y, (uint32_t)da, db, q1.x, acc | (uint32_t)(kb > 0));
+        else tc_mma(q1.y, da, db, q1.x, acc | (uint32_t)(kb > 0));
+        da += aadv; db += badv;
 #ifdef WB_TC_TIMING
         if (ts && *tn < 16) ts[(*tn)++] = clock64();
 #endif
@@ -431,6 +440,7 @@ __device__ __forceinline__ void tc_issue_rec(const uint4 q0, const uint4 q1, lon
 //      tcgen05.ld + 16 F2FP.RELU + 4 STS.128 instead of ~130 instructions,
 //  (d) a row is shared by two threads (column halves),
 //  (e) the groups of a CTA (backward) / the CTAs of an SM (forward) have independent barriers and overlap each other.
+template <bool TA = false>          // TA: warp 0's second chain (k0b) reads its A operand from tensor memory
 __device__ __forceinline__ void tc_round(TcCtx& c, int l, int k0a, int k0b, int k1)
 {
     TC_TS(c);
@@ -451,9 +461,9 @@ __device__ __forceinline__ void tc_round(TcCtx& c, int l, int k0a, int k0b, int 
 #ifdef WB_TC_TIMING
             long long* ts4 = nullptr; int tn4 = 0;
             if (blockIdx.x == 0 && threadIdx.x == 0 && c.tsn2 / 3 < 64) { ts4 = g_tc_ts4[c.tsk][c.tsn2 / 3]; ts4[tn4++] = clock64(); }
-            if (((qa1.z | qb1.z) & 0xffu) != 0) { tc_issue_rec(qa0, qa1, ts4, &tn4); tc_issue_rec(qb0, qb1, ts4, &tn4); TC_TS2(c, c.tsn2); tc_commit(c.bar); }
+            if (((qa1.z | qb1.z) & 0xffu) != 0) { tc_issue_rec(qa0, qa1, ts4, &tn4); tc_issue_rec<TA>(qb0, qb1, ts4, &tn4); TC_TS2(c, c.tsn2); tc_commit(c.bar); }
 #else
-            if (((qa1.z | qb1.z) & 0xffu) != 0) { tc_issue_rec(qa0, qa1); tc_issue_rec(qb0, qb1); TC_TS2(c, c.tsn2); tc_commit(c.bar); }
+            if (((qa1.z | qb1.z) & 0xffu) != 0) { tc_issue_rec(qa0, qa1); tc_issue_rec<TA>(qb0, qb1); TC_TS2(c, c.tsn2); tc_commit(c.bar); }
 #endif
             else tc_mbar_arrive(c.bar);
             TC_TS2(c, c.tsn2);
@@ -469,12 +479,16 @@ __device__ __forceinline__ void tc_round(TcCtx& c, int l, int k0a, int k0b, int 
 
 // Decoders of one 128-sample sub-tile, starting from an X0 tile that the group has already written.
 // Returns (in registers, both column halves) the density-decoder output df[16] and the colour pre-activations c3[3].
+// TA (experimental forward variant): the activation tile lives in tensor memory (m.work_col[1]; lane = row, two halfs per column) and
+// feeds the UMMAs as the A operand directly; nothing but the weights is in shared memory.
+template <bool TA = false>
 __device__ __forceinline__ void tc_decoders(const WbTc& m, TcCtx& c, const TcIn& in, int64_t ray, float df[16], float c3[3])
 {
     uint8_t* sub = c.smem + m.sub_off[c.g];
     const int nl = m.nl_d + m.nl_c;
+    const uint32_t arow = c.tmem + ((uint32_t)c.laneq << 16) + (uint32_t)(TA ? m.work_col[1] : 0);
     for (int l = 0; l < nl; ++l) {
-        tc_round(c, l, TC_K_BIAS, TC_K_FWD, -1);                 // accumulator = bias + X_l . W_l^T
+        tc_round<TA>(c, l, TC_K_BIAS, TA ? TC_K_FWD_TA : TC_K_FWD, -1);   // accumulator = bias + X_l . W_l^T
         const uint32_t trow = c.tmem + ((uint32_t)c.laneq << 16) + m.work_col[c.g];
         const bool last_d = (l == m.nl_d - 1), last_c = (l == nl - 1);
         if (last_d) {
@@ -493,8 +507,14 @@ __device__ __forceinline__ void tc_decoders(const WbTc& m, TcCtx& c, const TcIn&
                 const float dv = c.h == 0 ? df[(j + 1) & 15] : df[(j + 9) & 15];
                 if (8 * c.h + j < nd) hq[j] = __float2half_rn(dv);
             }
-            *reinterpret_cast<uint4*>(tcol + c.h * 2048 + c.r * 16) = q;
-            for (int ch = 2 + c.h; ch < nch; ch += 2) *reinterpret_cast<uint4*>(tcol + ch * 2048 + c.r * 16) = __ldg(re + ch);
+            if (TA) {                                            // chunk ch = 8 features = 4 TMEM columns
+                tc_st4(arow + c.h * 4, q);
+                for (int ch = 2 + c.h; ch < nch; ch += 2) tc_st4(arow + ch * 4, __ldg(re + ch));
+                tc_st_wait();
+            } else {
+                *reinterpret_cast<uint4*>(tcol + c.h * 2048 + c.r * 16) = q;
+                for (int ch = 2 + c.h; ch < nch; ch += 2) *reinterpret_cast<uint4*>(tcol + ch * 2048 + c.r * 16) = __ldg(re + ch);
+            }
         } else if (last_c) {
             float v[16]; tc_ld16(trow, v);
             c3[0] = v[0]; c3[1] = v[1]; c3[2] = v[2];
@@ -514,8 +534,10 @@ __device__ __forceinline__ void tc_decoders(const WbTc& m, TcCtx& c, const TcIn&
                     uint4 o;
                     o.x = tc_pack2_relu(v[q * 8], v[q * 8 + 1]); o.y = tc_pack2_relu(v[q * 8 + 2], v[q * 8 + 3]);
                     o.z = tc_pack2_relu(v[q * 8 + 4], v[q * 8 + 5]); o.w = tc_pack2_relu(v[q * 8 + 6], v[q * 8 + 7]);
-                    *reinterpret_cast<uint4*>(tn + ((cc >> 3) + q) * 2048 + c.r * 16) = o;
+                    if (TA) tc_st4(arow + (cc >> 1) + q * 4, o);         // features cc + 8q .. +7 -> columns (cc + 8q) / 2 ..
+                    else *reinterpret_cast<uint4*>(tn + ((cc >> 3) + q) * 2048 + c.r * 16) = o;
                 }
+                if (TA) tc_st_wait();
                 TC_TS3(c);
             }
             // Np[l] == Kp[l+1] (both round_up(hidden,16)); padded outputs are relu(0 + 0) = 0
@@ -526,7 +548,36 @@ __device__ __forceinline__ void tc_decoders(const WbTc& m, TcCtx& c, const TcIn&
 // ---------------------------------------------------------------------------------------------------------------
 // forward kernel: CTA = one group = one 128-sample sub-tile at a time; several CTAs per SM overlap gather / UMMA / epilogue
 // ---------------------------------------------------------------------------------------------------------------
-template <int MINB>                  // resident CTAs per SM the register allocation is bounded for
+// F == 2 'cat' gather straight into the TMEM activation tile (experimental TMEM-A variant): 4 LODs = 8 features = one 16-byte chunk =
+// 4 TMEM columns of this thread's lane; the chunk is also what the backward wants saved.
+__device__ __forceinline__ void tile_gather_ta(const WbGrid& g, uint32_t arow, int half, float px, float py, float pz,
+                                               uint4* __restrict__ save, int64_t S, int64_t s, bool valid)
+{
+    for (int l0 = 4 * half; l0 < g.L; l0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int l = l0 + q;
+            if (l >= g.L || l >= g.lod_idx) { v[2 * q] = 0.0f; v[2 * q + 1] = 0.0f; continue; }       // hash_grid.py:226-229
+            uint32_t idx[8]; float cf[8];
+            wb_corner_setup(g, l, px, py, pz, idx, cf);
+            const float2* tb = reinterpret_cast<const float2*>(g.table + g.begin[l] * 2);
+            float2 c[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) c[j] = __ldg(tb + idx[j]);
+            float a0 = c[0].x * cf[0], a1 = c[0].y * cf[0];
+#pragma unroll
+            for (int j = 1; j < 8; ++j) { a0 = fmaf(c[j].x, cf[j], a0); a1 = fmaf(c[j].y, cf[j], a1); }
+            v[2 * q] = a0; v[2 * q + 1] = a1;
+        }
+        uint4 qv; qv.x = tc_pack2(v[0], v[1]); qv.y = tc_pack2(v[2], v[3]); qv.z = tc_pack2(v[4], v[5]); qv.w = tc_pack2(v[6], v[7]);
+        tc_st4(arow + (uint32_t)(l0 >> 2) * 4u, qv);
+        if (save != nullptr && valid) save[(int64_t)(l0 >> 2) * S + s] = qv;
+    }
+    tc_st_wait();
+}
+
+template <int MINB, bool TA>         // MINB: resident CTAs per SM the register allocation is bounded for; TA: activations in tensor memory
 __global__ void __launch_bounds__(TC_GROUP, MINB)
 wb_shade_fwd_tc_kernel(WbGrid g, WbTc m, const uint8_t* __restrict__ blob, TcIn in, float4* __restrict__ shaded)
 {
@@ -543,7 +594,7 @@ wb_shade_fwd_tc_kernel(WbGrid g, WbTc m, const uint8_t* __restrict__ blob, TcIn 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    tc_build_table(m, itab, smem, tmem_s, 1, false);
+    tc_build_table(m, itab, smem, tmem_s, 1, false, TA);
     __syncthreads();
     tc_mbar_wait(&bars[1], 0);
     TcCtx c; tc_ctx_init(c, smem, bars, itab, tmem_s, 0);
@@ -560,18 +611,22 @@ wb_shade_fwd_tc_kernel(WbGrid g, WbTc m, const uint8_t* __restrict__ blob, TcIn 
         const float py = wb_addcmul(__ldg(in.origins + 3 * ray + 1), __ldg(in.dirs + 3 * ray + 1), t);
         const float pz = wb_addcmul(__ldg(in.origins + 3 * ray + 2), __ldg(in.dirs + 3 * ray + 2), t);
         // density-decoder input row: grid features (+ position embedding), zero padded to Kp; the two threads of a row split the LODs
-        tile_gather(g, t0, c.r, c.h, px, py, pz);
-        if (c.h == 0) {
-            tile_embed(t0, c.r, m.feat_dim, m.pos_mode, m.pos_freq, px, py, pz);
-            tile_zero(t0, c.r, m.I[0], m.Kp[0]);
-        }
-        if (in.x0_save) {
-            tc_group_sync(1, TC_GROUP);
-            if (valid)
-                for (int ch = c.h; ch < nch0; ch += 2) in.x0_save[(int64_t)ch * in.S + s] = *reinterpret_cast<const uint4*>(t0 + ch * 2048 + c.r * 16);
+        if (TA) {
+            tile_gather_ta(g, c.tmem + ((uint32_t)c.laneq << 16) + (uint32_t)m.work_col[1], c.h, px, py, pz, in.x0_save, in.S, s, valid);
+        } else {
+            tile_gather(g, t0, c.r, c.h, px, py, pz);
+            if (c.h == 0) {
+                tile_embed(t0, c.r, m.feat_dim, m.pos_mode, m.pos_freq, px, py, pz);
+                tile_zero(t0, c.r, m.I[0], m.Kp[0]);
+            }
+            if (in.x0_save) {
+                tc_group_sync(1, TC_GROUP);
+                if (valid)
+                    for (int ch = c.h; ch < nch0; ch += 2) in.x0_save[(int64_t)ch * in.S + s] = *reinterpret_cast<const uint4*>(t0 + ch * 2048 + c.r * 16);
+            }
         }
         float df[16], c3[3];
-        tc_decoders(m, c, in, ray, df, c3);
+        tc_decoders<TA>(m, c, in, ray, df, c3);
         if (valid && c.h == 0) {
             const float r = 1.0f / (1.0f + expf(-c3[0])), gg = 1.0f / (1.0f + expf(-c3[1])), b = 1.0f / (1.0f + expf(-c3[2]));
             shaded[s] = make_float4(r, gg, b, fmaxf(df[0], 0.0f));
@@ -594,6 +649,7 @@ static int tc_launch_ray_embed(const WbTc& m, const wb_rays* rays, void* workspa
 // Tuning knobs (defaults = the measured optimum on B200 for the app/nerf configuration, profiles/README.md); the environment
 // overrides exist for the sweeps and are read once per process.
 static int tc_env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
+static int tc_knob_fwd_tmema() { static const int v = tc_env_int("WB_TC_FWD_TMEMA", 0); return v; }
 static int tc_knob_fwd_ctas() { static const int v = tc_env_int("WB_TC_FWD_CTAS", 3); return v; }
 static int tc_knob_scatter_lpb() { static const int v = tc_env_int("WB_TC_SCATTER_LPB", 16); return v; }
 static int tc_knob_scatter_idx2() { static const int v = tc_env_int("WB_TC_SCATTER_IDX2", 1); return v; }
@@ -605,7 +661,15 @@ int wb_tc_shade_fwd(const wb_nef_desc* nef, const float* blob, const wb_rays* ra
                     int64_t S, float* shaded, void* feat_save, void* workspace, cudaStream_t st)
 {
     WbGrid g; int rc = wb_make_grid(nef, &g); if (rc) return rc;
-    WbTc m; rc = wb_tc_make(nef, false, &m); if (rc) return rc;
+    // EXPERIMENTAL, off by default (WB_TC_FWD_TMEMA=1): activations in tensor memory, A operand read from TMEM (wb_tc.cuh tc_mma_ts).
+    // Applies to the specialised F == 2 'cat' gather without position embedding, whose rows are whole 16-byte chunks.
+    const bool ta = tc_knob_fwd_tmema() && nef->feature_dim == 2 && nef->multiscale == 0 && nef->pos_mode == 0 &&
+                    (nef->num_lods * nef->feature_dim) % 16 == 0;
+    WbTc m; rc = wb_tc_make(nef, false, &m, ta); if (rc) return rc;
+    if (ta) {   // no activation tile in shared memory: the parameter blob and the bias tile move to the front
+        const int tile = m.w_smem_off;
+        m.w_smem_off -= tile; m.ones_off -= tile; m.smem_bytes -= tile;
+    }
     WB_CHECK_ARG(workspace != nullptr, "precision 1 needs the workspace (wb_rf_workspace_bytes)");
     rc = tc_launch_ray_embed(m, rays, workspace, st); if (rc) return rc;
     TcIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S, reinterpret_cast<const uint4*>(workspace), reinterpret_cast<uint4*>(feat_save), nullptr };
@@ -613,14 +677,15 @@ int wb_tc_shade_fwd(const wb_nef_desc* nef, const float* blob, const wb_rays* ra
     // profiles/README.md).  The register bound of the instantiation must match, or the hardware silently runs fewer.
     int per_sm = (227 * 1024) / (m.smem_bytes + 4096); per_sm = max(1, min(per_sm, 512 / m.tmem_cols));
     per_sm = max(2, min(min(per_sm, 4), tc_knob_fwd_ctas()));
-    auto kern = per_sm == 2 ? wb_shade_fwd_tc_kernel<2> : per_sm == 3 ? wb_shade_fwd_tc_kernel<3> : wb_shade_fwd_tc_kernel<4>;
+    auto kern = ta ? (per_sm == 2 ? wb_shade_fwd_tc_kernel<2, true> : per_sm == 3 ? wb_shade_fwd_tc_kernel<3, true> : wb_shade_fwd_tc_kernel<4, true>)
+                   : (per_sm == 2 ? wb_shade_fwd_tc_kernel<2, false> : per_sm == 3 ? wb_shade_fwd_tc_kernel<3, false> : wb_shade_fwd_tc_kernel<4, false>);
     {   // function attributes are driver calls that can wait behind other driver work (e.g. an NVML poll): set them once, not per launch
-        static int done_for[5] = { -1, -1, -1, -1, -1 };
-        if (done_for[per_sm] != m.smem_bytes) {
+        static int done_for[10] = { -1, -1, -1, -1, -1, -1, -1, -1, -1, -1 };
+        if (done_for[per_sm + (ta ? 5 : 0)] != m.smem_bytes) {
             WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, m.smem_bytes));
             WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          min(100, (per_sm * (m.smem_bytes + 4096) * 100) / (228 * 1024) + 1)));
-            done_for[per_sm] = m.smem_bytes;
+            done_for[per_sm + (ta ? 5 : 0)] = m.smem_bytes;
         }
     }
     const int64_t ntiles = (S + TC_ROWS - 1) / TC_ROWS;

@@ -51,6 +51,14 @@ __device__ __forceinline__ uint32_t tc_elect_one()
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
     return pred;
 }
+// A operand read from TENSOR MEMORY (dense fp16: lane = row, two halfs per 32-bit column, K-major only), B from shared memory.
+// EXPERIMENTAL (forward variant behind WB_TC_FWD_TMEMA, see wb_shade_tc.cu): activations never touch shared memory.
+__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+                 :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // make all previously issued MMAs of this thread arrive on an mbarrier when they complete
 __device__ __forceinline__ void tc_commit(uint64_t* bar)
 {
@@ -123,6 +131,21 @@ __device__ __forceinline__ void tc_st16_zero(uint32_t taddr)
                  :: "r"(taddr), "r"(z) : "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+
+// store 4 / 16 consecutive 32-bit columns of this thread's TMEM lane (warp-collective); tc_st_wait() before the hand-over
+__device__ __forceinline__ void tc_st4(uint32_t taddr, uint4 v)
+{
+    __syncwarp();
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" :: "r"(taddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t r[16])
+{
+    __syncwarp();
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- mbarrier ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_mbar_init(uint64_t* bar, uint32_t count)
