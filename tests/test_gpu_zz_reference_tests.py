@@ -34,3 +34,46 @@ def test_extra_channels():
     rb.density.sum().backward()                                                          # differentiable like every other channel
     gb = nef.decoder_density.lout.bias.grad
     assert gb is not None and torch.isfinite(gb).all()
+
+
+@pytest.mark.skipif(__import__("os").environ.get("WB_TEST_TMEMA", "0") != "1",
+                    reason="experimental forward variant (activations in tensor memory): opt in with WB_TEST_TMEMA=1")
+def test_tmem_a_forward_variant_matches_default():
+    """WB_TC_FWD_TMEMA=1 (read once per process, hence the subprocesses): same samples, rgb within fp16 round-off of the default
+    tensor-core forward, identical saved features -> identical gradients path.  Never run in round 1 (no GPU budget left)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import json, os, sys
+import numpy as np, torch
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import wisp_b200 as W
+from oracle import oracle as O
+from gpu_util import nef_from_oracle, packed_grads
+onef = O.make_nef(feature_std=0.2, seed=3)
+spc = O.octree_to_spc(O.points_to_octree(O.lego_like_points(6), 6))
+o, d = O.look_at_rays([-3.0, 0.65, -3.0], [0, 0, 0], 48, 48, 30.0)
+nef, blas = nef_from_oracle(onef, spc)
+tracer = W.PackedRFTracer('ray', 512, bg_color=(0.0, 0.0, 0.0)); tracer.seed = 9; tracer.precision = 1
+rb = W.Pipeline(nef, tracer)(rays=W.Rays(torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda(), 0.0, 10.0), channels=["rgb"])
+rb.rgb.sum().backward()
+gt, gd, gc = packed_grads(nef)
+np.savez(OUT, rgb=rb.rgb.detach().cpu().numpy(), gt=gt, gd=gd, gc=gc, n=tracer.get_prev_num_samples())
+'''
+    outs = []
+    for knob in ("0", "1"):
+        out = os.path.join(root, "gpurun_out", f"tmema_{knob}.npz")
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        env = dict(os.environ, WB_TC_FWD_TMEMA=knob)
+        r = subprocess.run([sys.executable, "-c", code.replace("ROOT", repr(root)).replace("OUT", repr(out))], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-800:]
+        outs.append(np.load(out))
+    a, b = outs
+    assert int(a["n"]) == int(b["n"]) > 1000
+    np.testing.assert_allclose(b["rgb"], a["rgb"], atol=2e-3)
+    for k in ("gt", "gd", "gc"):
+        scale = np.abs(a[k]).max()
+        assert np.abs(a[k] - b[k]).max() <= 3e-2 * scale, k
