@@ -649,6 +649,7 @@ static int tc_launch_ray_embed(const WbTc& m, const wb_rays* rays, void* workspa
 // Tuning knobs (defaults = the measured optimum on B200 for the app/nerf configuration, profiles/README.md); the environment
 // overrides exist for the sweeps and are read once per process.
 static int tc_env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
+static int tc_knob_bwd_groups() { static const int v = tc_env_int("WB_TC_BWD_GROUPS", 2); return v; }
 static int tc_knob_fwd_tmema() { static const int v = tc_env_int("WB_TC_FWD_TMEMA", 0); return v; }
 static int tc_knob_fwd_ctas() { static const int v = tc_env_int("WB_TC_FWD_CTAS", 3); return v; }
 static int tc_knob_scatter_lpb() { static const int v = tc_env_int("WB_TC_SCATTER_LPB", 16); return v; }
@@ -986,6 +987,8 @@ wb_table_scatter_kernel(WbGrid g, TcIn in, const __half* __restrict__ dfeat, int
     }
 }
 
+#include "wb_shade_tc_bwd3.cuh"          // experimental three-group variant (WB_TC_BWD_GROUPS=3), never the default
+
 // decoder backward only: dL/d(shaded) -> weight gradients + dL/dfeat planes in the workspace
 int wb_tc_decoder_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray,
                       int64_t S, const float* g_shaded, const float* scale, const void* feat_saved, void* workspace,
@@ -1000,6 +1003,22 @@ int wb_tc_decoder_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* 
     __half* dfeat = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(workspace) + tc_align256(R * m.Kp[m.nl_d] * 2));
     TcIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S, reinterpret_cast<const uint4*>(workspace), nullptr, reinterpret_cast<const uint4*>(feat_saved) };
     TcGrads G = { grad_dens, grad_col, scale, dfeat, planes, width };
+    TcB3Plan plan;
+    if (tc_knob_bwd_groups() == 3 && tc_b3_plan(m, &plan)) {     // EXPERIMENTAL: three sub-tile groups per SM (wb_shade_tc_bwd3.cuh)
+        WbTc m3 = m;
+        for (int l = 0; l < m.nl_d + m.nl_c; ++l) m3.acc_col[l] += 64;       // work columns 0..191, accumulators behind them
+        static int done3 = -1;
+        if (done3 != plan.smem_bytes) {
+            WB_CUDA(cudaFuncSetAttribute(wb_mlp_bwd3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
+            done3 = plan.smem_bytes;
+        }
+        const int64_t nctas3 = ((S + TC_ROWS - 1) / TC_ROWS + TC_B3_GROUPS - 1) / TC_B3_GROUPS;
+        int64_t grid3 = (int64_t)wb_num_sms(); if (grid3 > nctas3) grid3 = nctas3;
+        wb_mlp_bwd3_tc_kernel<<<(unsigned)grid3, TC_B3_GROUPS * TC_GROUP, plan.smem_bytes, st>>>(m3, plan, reinterpret_cast<const uint8_t*>(blob), in,
+                                                                                          reinterpret_cast<const float4*>(g_shaded), G);
+        WB_LAUNCH_CHECK();
+        return WB_OK;
+    }
     {
         static int done_for = -1;
         if (done_for != m.smem_bytes) {

@@ -1,0 +1,330 @@
+// wb_shade_tc_bwd3.cuh -- EXPERIMENTAL decoder backward with THREE sub-tile groups per SM (WB_TC_BWD_GROUPS=3), included by
+// wb_shade_tc.cu.  Written at the end of round 1 from the measured round costs (profiles/README.md, backlog item (d)); it
+// compiles for sm_100a but HAS NOT RUN ON A GPU YET.  The default stays the two-group kernel (wb_mlp_bwd_tc_kernel).
+//
+// The two-group kernel retains all five activation tiles of a sub-tile (78 KB) + a dY tile (16 KB), so only two sub-tiles fit
+// in shared memory and only two latency chains are in flight per SM.  This variant keeps three uniform buffers P, Q, R
+// (one 64-wide tile + its constant-one slab each) and a small buffer E per group and pays one extra round:
+//
+//   tile start : X0 -> P                                    (saved features)
+//   r0  F0     : P  -> relu -> X1 -> Q
+//   r1  F1     : Q  -> df (registers);  X2 = [df[1:], view] -> R
+//   r2  F2     : R  -> relu -> X3 -> P
+//   r3  F3     : P  -> relu -> X4 -> Q
+//   r4  F4     : Q  -> c3 (registers);  dY4 -> E
+//   r5  B4     : wgrad(X4@Q, dY4@E), dgrad -> mask with X4@Q -> dY3 IN PLACE over X4 -> Q
+//   r6  B3     : wgrad(X3@P, dY3@Q), dgrad -> mask with X3@P -> dY2 in place -> P
+//   r7  B2     : wgrad(X2@R, dY2@P), dgrad -> dY1 (16 wide) -> E;  X0 reloaded -> R
+//   r8  F0'    : R  -> relu -> X1 -> Q                       (the extra round)
+//   r9  B1     : wgrad(X1@Q, dY1@E), dgrad -> mask with X1@Q -> dY0 in place -> Q
+//   r10 B0     : wgrad(X0@R, dY0@Q), dgrad -> dL/dfeat planes (global)
+//
+// In-place dY: a thread reads the relu-mask elements of its own row chunk before it overwrites that chunk; the UMMAs that read the
+// tile have completed (the group waited on them).  Constant-one slabs: P and Q always carry it at slab maxw/8 (never overwritten: the
+// tiles living there are maxw wide, X0 in P carries its own at Kp0/8 and is rewritten at every tile start); R carries it at
+// Kp2/8 (X2) or Kp0/8 (X0), rewritten whenever the tile is placed.
+// Restricted to the app/nerf decoder depth (2 density layers, 3 colour layers), every width <= 64.
+#pragma once
+
+constexpr int TC_B3_GROUPS = 3;
+constexpr int TC_B3_ROUNDS = 11;
+
+struct TcB3Plan { int P, Q, R, E, GB, blob_off, ones_off, smem_bytes; };      // byte offsets (P..E from the group base, GB = group stride)
+
+// host: shared-memory plan; returns false when the configuration is outside the variant's scope
+static bool tc_b3_plan(const WbTc& m, TcB3Plan* p)
+{
+    if (m.nl_d != 2 || m.nl_c != 3) return false;
+    int maxw = 0;
+    for (int l = 0; l < 5; ++l) maxw = max(maxw, max(m.Kp[l], m.Np[l]));
+    if (maxw > 64) return false;
+    const int big = (maxw / 8 + 1) * 2048;                       // a maxw-wide tile + its constant-one slab
+    const int small = (max(m.Np[1], m.Np[4]) / 8) * 2048;        // dY1 / dY4
+    p->P = 0; p->Q = big; p->R = 2 * big; p->E = 3 * big; p->GB = 3 * big + small;
+    p->blob_off = TC_B3_GROUPS * p->GB;
+    p->ones_off = p->blob_off + m.blob_bytes;
+    int end = p->ones_off + 2 * 2048;
+    const int window = (TC_B3_GROUPS - 1) * p->GB + p->R + 16 * 2048;     // 16-slab read window of the weight-grad A operand
+    if (end < window) end = window;
+    p->smem_bytes = end + 64;
+    return p->smem_bytes + 6144 <= 227 * 1024;
+}
+
+// ---- per-CTA issue table: [group][round][chain]  (chain 0, 1: warp 0 in this order; chain 2: warp 1) ----
+__device__ __forceinline__ void tc_b3_build_table(const WbTc& m, const TcB3Plan& p, TcRec* tab, uint8_t* smem, uint32_t tmem)
+{
+    const int e = threadIdx.x;
+    if (e < TC_ROWS) {                                           // Ones[128 x 16] of the bias UMMA
+        uint4 one; one.x = 0x00003C00u; one.y = 0; one.z = 0; one.w = 0;
+        *reinterpret_cast<uint4*>(smem + p.ones_off + e * 16) = one;
+        *reinterpret_cast<uint4*>(smem + p.ones_off + 2048 + e * 16) = make_uint4(0, 0, 0, 0);
+    }
+    if (e >= TC_B3_GROUPS * TC_B3_ROUNDS * 3) return;
+    const int ch = e % 3, rd = (e / 3) % TC_B3_ROUNDS, g = e / (3 * TC_B3_ROUNDS);
+    const uint32_t base = tc_smem_u32(smem), gb = base + g * p.GB;
+    const uint32_t bP = gb + p.P, bQ = gb + p.Q, bR = gb + p.R, bE = gb + p.E;
+    const uint32_t wbase = base + p.blob_off;
+    const uint32_t work = tmem + g * 64;                          // D_work[g]: 64 columns per group, accumulators behind them
+    // round -> (layer, forward?, X buffer, dY buffer)
+    const int  lay[TC_B3_ROUNDS] = { 0, 1, 2, 3, 4, 4, 3, 2, 0, 1, 0 };
+    const bool fwd[TC_B3_ROUNDS] = { true, true, true, true, true, false, false, false, true, false, false };
+    const uint32_t X[TC_B3_ROUNDS] = { bP, bQ, bR, bP, bQ, bQ, bP, bR, bR, bQ, bR };
+    const uint32_t Y[TC_B3_ROUNDS] = { 0, 0, 0, 0, 0, bE, bQ, bP, 0, bE, bQ };
+    const int l = lay[rd], Np = m.Np[l], Kp = m.Kp[l];
+    uint64_t da = 0, db = 0; uint32_t id = 0, d = 0, nk = 0, acc = 0, aadv = 0, badv = 0;
+    if (fwd[rd]) {
+        if (ch == 0) {            // bias: D_work = Ones . Bias_l^T
+            da = tc_desc(base + p.ones_off, 2048, 128); db = tc_desc(wbase + m.b_off[l], Np * 16, 128);
+            id = tc_idesc(128, Np, 0, 0); d = work; nk = m.has_bias ? 1 : 0;
+        } else if (ch == 1) {     // D_work (+)= X_l . W_l^T
+            da = tc_desc(X[rd], 2048, 128); db = tc_desc(wbase + m.w_off[l], Np * 16, 128);
+            id = tc_idesc(128, Np, 0, 0); d = work; nk = Kp / 16; acc = m.has_bias; aadv = 4096 >> 4; badv = (2 * Np * 16) >> 4;
+        }
+    } else {
+        if (ch == 0) {            // acc_l[in, out] += X_l^T . dY_l   (K = 128 samples)
+            da = tc_desc(X[rd], 128, 2048); db = tc_desc(Y[rd], 128, 2048);
+            id = tc_idesc(128, Np, 1, 1); d = tmem + m.acc_col[l]; nk = 8; acc = 1; aadv = 256 >> 4; badv = 256 >> 4;
+        } else if (ch == 2) {     // D_work = dY_l . W_l             (K = out features)
+            da = tc_desc(Y[rd], 2048, 128); db = tc_desc(wbase + m.w_off[l], 128, Np * 16);
+            id = tc_idesc(128, Kp, 0, 1); d = work; nk = Np / 16; aadv = 4096 >> 4; badv = 256 >> 4;
+        }
+    }
+    TcRec r = { (uint32_t)da, (uint32_t)(da >> 32), (uint32_t)db, (uint32_t)(db >> 32), id, d, nk | (acc << 8), aadv | (badv << 16) };
+    tab[(g * TC_B3_ROUNDS + rd) * 3 + ch] = r;
+}
+
+__device__ __forceinline__ void tc_b3_round(TcCtx& c, const TcRec* r3)
+{
+    uint4 qa0 = make_uint4(0, 0, 0, 0), qa1 = qa0, qb0 = qa0, qb1 = qa0;
+    if (c.wig == 0) {
+        const uint4* pa = reinterpret_cast<const uint4*>(r3); const uint4* pb = reinterpret_cast<const uint4*>(r3 + 1);
+        qa0 = pa[0]; qa1 = pa[1]; qb0 = pb[0]; qb1 = pb[1];
+    } else if (c.wig == 1) {
+        const uint4* pa = reinterpret_cast<const uint4*>(r3 + 2);
+        qa0 = pa[0]; qa1 = pa[1];
+    }
+    tc_fence_smem_async();
+    tc_fence_before();
+    tc_group_sync(c.g + 1, TC_GROUP);
+    if (c.wig < TC_ISSUERS) {
+        if (tc_elect_one()) {
+            tc_fence_after();
+            if (((qa1.z | qb1.z) & 0xffu) != 0) { tc_issue_rec(qa0, qa1); tc_issue_rec(qb0, qb1); tc_commit(c.bar); }
+            else tc_mbar_arrive(c.bar);
+        }
+        __syncwarp();
+    }
+    tc_mbar_wait(c.bar, c.phase);
+    c.phase ^= 1u;
+    tc_fence_after();
+}
+
+// relu(D_work[:, 0:Np)) -> fp16 tile `dst` (this thread: its row, its column half)
+__device__ __forceinline__ void tc_b3_relu_to_tile(const TcCtx& c, uint32_t trow, int Np, uint8_t* dst)
+{
+    // 16 columns at a time: this kernel runs 768 threads per SM, i.e. at most 85 registers per thread
+    for (int c0 = c.h * 32; c0 < Np; c0 += 64) {
+        for (int cc = c0; cc < min(c0 + 32, Np); cc += 16) {
+            float v[16]; tc_ld16(trow + cc, v);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                uint4 o;
+                o.x = tc_pack2_relu(v[q * 8], v[q * 8 + 1]); o.y = tc_pack2_relu(v[q * 8 + 2], v[q * 8 + 3]);
+                o.z = tc_pack2_relu(v[q * 8 + 4], v[q * 8 + 5]); o.w = tc_pack2_relu(v[q * 8 + 6], v[q * 8 + 7]);
+                *reinterpret_cast<uint4*>(dst + ((cc >> 3) + q) * 2048 + c.r * 16) = o;
+            }
+        }
+    }
+}
+// dY = D_work[:, 0:Kp) masked by relu'(X) written IN PLACE over the activation tile `tile`
+__device__ __forceinline__ void tc_b3_mask_in_place(const TcCtx& c, uint32_t trow, int Kp, uint8_t* tile)
+{
+    for (int c0 = c.h * 32; c0 < Kp; c0 += 64) {
+        for (int cc = c0; cc < min(c0 + 32, Kp); cc += 16) {
+            float v[16]; tc_ld16(trow + cc, v);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                uint4* slot = reinterpret_cast<uint4*>(tile + ((cc >> 3) + q) * 2048 + c.r * 16);
+                const uint4 a = *slot;
+                const __half2 z2 = __float2half2_rn(0.0f);
+                uint4 o;
+                o.x = tc_pack2(v[q * 8], v[q * 8 + 1]) & __hgt2_mask(*reinterpret_cast<const __half2*>(&a.x), z2);
+                o.y = tc_pack2(v[q * 8 + 2], v[q * 8 + 3]) & __hgt2_mask(*reinterpret_cast<const __half2*>(&a.y), z2);
+                o.z = tc_pack2(v[q * 8 + 4], v[q * 8 + 5]) & __hgt2_mask(*reinterpret_cast<const __half2*>(&a.z), z2);
+                o.w = tc_pack2(v[q * 8 + 6], v[q * 8 + 7]) & __hgt2_mask(*reinterpret_cast<const __half2*>(&a.w), z2);
+                *slot = o;
+            }
+        }
+    }
+}
+__device__ __forceinline__ void tc_b3_one_slab(uint8_t* tile, int slab, int r)
+{
+    uint4 one; one.x = 0x00003C00u; one.y = 0; one.z = 0; one.w = 0;           // fp16 1.0 in feature 0 of the slab
+    *reinterpret_cast<uint4*>(tile + slab * 2048 + r * 16) = one;
+}
+
+__global__ void __launch_bounds__(TC_B3_GROUPS * TC_GROUP, 1)
+wb_mlp_bwd3_tc_kernel(WbTc m, TcB3Plan p, const uint8_t* __restrict__ blob, TcIn in, const float4* __restrict__ g_shaded, TcGrads G)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[TC_B3_GROUPS + 1];
+    __shared__ uint32_t tmem_s;
+    __shared__ TcRec tab[TC_B3_GROUPS * TC_B3_ROUNDS * 3];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TC_B3_GROUPS; ++i) tc_mbar_init(&bars[i], TC_ISSUERS);
+        tc_mbar_init(&bars[TC_B3_GROUPS], 1); tc_mbar_init_fence();
+        tc_mbar_expect_tx(&bars[TC_B3_GROUPS], (uint32_t)m.blob_bytes);
+        tc_bulk_g2s(smem + p.blob_off, blob, (uint32_t)m.blob_bytes, &bars[TC_B3_GROUPS]);
+    }
+    if (threadIdx.x < 32) tc_tmem_alloc(&tmem_s, 512u);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    tc_b3_build_table(m, p, tab, smem, tmem_s);
+    TcCtx c; tc_ctx_init(c, smem, bars, nullptr, tmem_s, 1);
+    uint8_t* gbase = smem + c.g * p.GB;
+    uint8_t* bP = gbase + p.P; uint8_t* bQ = gbase + p.Q; uint8_t* bR = gbase + p.R; uint8_t* bE = gbase + p.E;
+    const TcRec* rec = tab + c.g * TC_B3_ROUNDS * 3;
+    const int maxslab = (p.Q - p.P) / 2048 - 1;                  // slab of the constant-one column of a maxw-wide tile
+    if (c.h == 0) { tc_b3_one_slab(bP, maxslab, c.r); tc_b3_one_slab(bQ, maxslab, c.r); }
+    if (threadIdx.x < 128) {                                     // zero the resident weight-grad accumulators
+        const uint32_t tr = c.tmem + ((uint32_t)c.laneq << 16);
+        for (int l = 0; l < 5; ++l)
+            for (int cc = 0; cc < m.Np[l]; cc += 16) tc_st16_zero(tr + m.acc_col[l] + cc);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    tc_mbar_wait(&bars[TC_B3_GROUPS], 0);
+    const float scale = __ldg(G.scale), inv_scale = 1.0f / scale;
+    const int nch0 = m.Kp[0] / 8, nchc = m.Kp[2] / 8;
+    const int64_t ntiles = (in.S + TC_ROWS - 1) / TC_ROWS;
+    const uint32_t trow = c.tmem + ((uint32_t)c.laneq << 16) + (uint32_t)c.g * 64u;
+    const float z8[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    for (int64_t tile = (int64_t)blockIdx.x * TC_B3_GROUPS + c.g; tile < ntiles; tile += (int64_t)gridDim.x * TC_B3_GROUPS) {
+        int64_t s = tile * TC_ROWS + c.r;
+        const bool valid = s < in.S;
+        if (!valid) s = in.S - 1;
+        const int64_t ray = __ldg(in.rec_ray + s);
+        // X0 -> P
+        for (int ch = c.h; ch < nch0; ch += 2)
+            *reinterpret_cast<uint4*>(bP + ch * 2048 + c.r * 16) = __ldg(in.x0_saved + (int64_t)ch * in.S + s);
+        if (c.h == 0) tc_b3_one_slab(bP, nch0, c.r);
+        // r0: F0 -> X1 -> Q
+        tc_b3_round(c, rec + 0 * 3);
+        tc_b3_relu_to_tile(c, trow, m.Np[0], bQ);
+        // r1: F1 -> df; X2 -> R
+        tc_b3_round(c, rec + 1 * 3);
+        float df0;
+        {
+            float df[16];
+            tc_ld16(trow, df);
+            df0 = df[0];
+            const int nd = m.O[1] - 1;
+            const uint4* re = in.ray_embed + ray * nchc;
+            uint4 q = __ldg(re + c.h);
+            __half* hq = reinterpret_cast<__half*>(&q);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float dv = c.h == 0 ? df[(j + 1) & 15] : df[(j + 9) & 15];
+                if (8 * c.h + j < nd) hq[j] = __float2half_rn(dv);
+            }
+            *reinterpret_cast<uint4*>(bR + c.h * 2048 + c.r * 16) = q;
+            for (int ch = 2 + c.h; ch < nchc; ch += 2) *reinterpret_cast<uint4*>(bR + ch * 2048 + c.r * 16) = __ldg(re + ch);
+            if (c.h == 0) tc_b3_one_slab(bR, nchc, c.r);
+        }
+        // r2: F2 -> X3 -> P ; r3: F3 -> X4 -> Q
+        tc_b3_round(c, rec + 2 * 3);
+        tc_b3_relu_to_tile(c, trow, m.Np[2], bP);
+        tc_b3_round(c, rec + 3 * 3);
+        tc_b3_relu_to_tile(c, trow, m.Np[3], bQ);
+        // r4: F4 -> c3 ; dY4 -> E
+        tc_b3_round(c, rec + 4 * 3);
+        const float4 go = valid ? __ldg(g_shaded + s) : make_float4(0, 0, 0, 0);
+        {
+            float v[16]; tc_ld16(trow, v);
+            if (c.h == 0) {
+                const float r = 1.0f / (1.0f + expf(-v[0])), gg = 1.0f / (1.0f + expf(-v[1])), b = 1.0f / (1.0f + expf(-v[2]));
+                float dy[8] = { go.x * r * (1.0f - r) * scale, go.y * gg * (1.0f - gg) * scale, go.z * b * (1.0f - b) * scale, 0, 0, 0, 0, 0 };
+                tile_store8(bE, c.r, 0, dy);
+            }
+            for (int sl = 1 + c.h; sl < m.Np[4] / 8; sl += 2) tile_store8(bE, c.r, sl, z8);
+        }
+        // r5: B4 -> dY3 in place over X4 (Q) ; r6: B3 -> dY2 in place over X3 (P)
+        tc_b3_round(c, rec + 5 * 3);
+        tc_b3_mask_in_place(c, trow, m.Kp[4], bQ);
+        tc_b3_round(c, rec + 6 * 3);
+        tc_b3_mask_in_place(c, trow, m.Kp[3], bP);
+        // r7: B2 -> dY1 -> E ; X0 -> R
+        tc_b3_round(c, rec + 7 * 3);
+        {
+            float v[16]; tc_ld16(trow, v);
+            const int dout = m.O[1];
+            float gdf[16];
+            gdf[0] = (df0 > 0.0f) ? go.w * scale : 0.0f;         // relu' of density (nerf.py:263)
+#pragma unroll
+            for (int j = 1; j < 16; ++j) gdf[j] = (j < dout) ? v[j - 1] : 0.0f;
+            if (c.h == 0) tile_store8(bE, c.r, 0, gdf); else tile_store8(bE, c.r, 1, gdf + 8);
+            for (int sl = 2 + c.h; sl < m.Np[1] / 8; sl += 2) tile_store8(bE, c.r, sl, z8);
+            for (int ch = c.h; ch < nch0; ch += 2)
+                *reinterpret_cast<uint4*>(bR + ch * 2048 + c.r * 16) = __ldg(in.x0_saved + (int64_t)ch * in.S + s);
+            if (c.h == 0) tc_b3_one_slab(bR, nch0, c.r);
+        }
+        // r8: F0' -> X1 -> Q
+        tc_b3_round(c, rec + 8 * 3);
+        tc_b3_relu_to_tile(c, trow, m.Np[0], bQ);
+        // r9: B1 -> dY0 in place over X1 (Q)
+        tc_b3_round(c, rec + 9 * 3);
+        tc_b3_mask_in_place(c, trow, m.Kp[1], bQ);
+        // r10: B0 -> dL/dfeat planes
+        tc_b3_round(c, rec + 10 * 3);
+        {
+            const int W = G.width, nfe = G.planes * W;
+            for (int f0 = c.h * 16; f0 < nfe; f0 += 32) {
+                float v[16]; tc_ld16(trow + f0, v);
+                if (!valid) continue;
+                if (W == 2) {
+#pragma unroll
+                    for (int qq = 0; qq < 8; ++qq) {
+                        const int pl = (f0 >> 1) + qq;
+                        if (pl < G.planes) reinterpret_cast<__half2*>(G.dfeat)[(int64_t)pl * in.S + s] = __floats2half2_rn(v[2 * qq], v[2 * qq + 1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) {
+                        const int fe = f0 + jj;
+                        if (fe < nfe) G.dfeat[((int64_t)(fe / W) * in.S + s) * W + (fe % W)] = __float2half_rn(v[jj]);
+                    }
+                }
+            }
+        }
+    }
+    // ---- flush weight / bias gradient accumulators (TMEM rows = input feature, row Kp = bias) ----
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x < 128) {
+        const int row = threadIdx.x;
+        const uint32_t tr = c.tmem + ((uint32_t)c.laneq << 16);
+        for (int l = 0; l < 5; ++l) {
+            float* gbase2 = l < m.nl_d ? G.gdens : G.gcol;
+            const int I = m.I[l], O = m.O[l];
+            const int wrow0 = row & ~31;
+            if (wrow0 > m.Kp[l]) continue;
+            for (int cc = 0; cc < m.Np[l]; cc += 16) {
+                float v[16]; tc_ld16(tr + m.acc_col[l] + cc, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int o = cc + j;
+                    if (o >= O) continue;
+                    const float val = v[j] * inv_scale;
+                    if (row < I) { if (val != 0.0f) atomicAdd(gbase2 + m.src_w[l] + o * I + row, val); }
+                    else if (row == m.Kp[l] && m.src_b[l] >= 0) atomicAdd(gbase2 + m.src_b[l] + o, val);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tc_tmem_dealloc(c.tmem, 512u);
+}

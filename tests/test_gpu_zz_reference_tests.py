@@ -36,18 +36,18 @@ def test_extra_channels():
     assert gb is not None and torch.isfinite(gb).all()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("WB_TEST_TMEMA", "0") != "1",
-                    reason="experimental forward variant (activations in tensor memory): opt in with WB_TEST_TMEMA=1")
-def test_tmem_a_forward_variant_matches_default():
-    """WB_TC_FWD_TMEMA=1 (read once per process, hence the subprocesses): same samples, rgb within fp16 round-off of the default
-    tensor-core forward, identical saved features -> identical gradients path.  Never run in round 1 (no GPU budget left)."""
-    import json
+@pytest.mark.skipif(__import__("os").environ.get("WB_TEST_EXPERIMENTAL", "0") != "1",
+                    reason="experimental kernel variants (never run in round 1): opt in with WB_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("knob", ["WB_TC_FWD_TMEMA=1", "WB_TC_BWD_GROUPS=3"])
+def test_experimental_variant_matches_default(knob):
+    """The knobs are read once per process, hence the subprocesses: same samples, rgb within fp16 round-off of the default
+    tensor-core path, gradients within the precision-1 tolerance of each other."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = r'''
-import json, os, sys
+import os, sys
 import numpy as np, torch
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import wisp_b200 as W
@@ -59,15 +59,19 @@ o, d = O.look_at_rays([-3.0, 0.65, -3.0], [0, 0, 0], 48, 48, 30.0)
 nef, blas = nef_from_oracle(onef, spc)
 tracer = W.PackedRFTracer('ray', 512, bg_color=(0.0, 0.0, 0.0)); tracer.seed = 9; tracer.precision = 1
 rb = W.Pipeline(nef, tracer)(rays=W.Rays(torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda(), 0.0, 10.0), channels=["rgb"])
-rb.rgb.sum().backward()
+tgt = torch.sigmoid(torch.randn(o.shape[0], 3, generator=torch.Generator().manual_seed(2))).cuda()
+torch.nn.functional.smooth_l1_loss(rb.rgb, tgt).backward()
 gt, gd, gc = packed_grads(nef)
 np.savez(OUT, rgb=rb.rgb.detach().cpu().numpy(), gt=gt, gd=gd, gc=gc, n=tracer.get_prev_num_samples())
 '''
+    name, value = knob.split("=")
     outs = []
-    for knob in ("0", "1"):
-        out = os.path.join(root, "gpurun_out", f"tmema_{knob}.npz")
+    for on in (False, True):
+        out = os.path.join(root, "gpurun_out", f"exp_{name}_{int(on)}.npz")
         os.makedirs(os.path.dirname(out), exist_ok=True)
-        env = dict(os.environ, WB_TC_FWD_TMEMA=knob)
+        env = dict(os.environ)
+        if on:
+            env[name] = value
         r = subprocess.run([sys.executable, "-c", code.replace("ROOT", repr(root)).replace("OUT", repr(out))], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-800:]
         outs.append(np.load(out))
