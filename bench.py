@@ -78,7 +78,7 @@ def cpu_scene(args):
     return O, onef, spc
 
 
-def cpu_time_step(O, onef, spc, args, nrays, cam_i, seed):
+def cpu_time_step(O, onef, spc, args, nrays, cam_i, seed, keep=None):
     """One bounded sample: `nrays` rays strided uniformly over the res^2 frame of camera cam_i, full config."""
     o, d = O.look_at_rays(orbit_origin(cam_i), CAM_LOOKAT, args.res, args.res, CAM_FOV)
     R = o.shape[0]
@@ -88,7 +88,21 @@ def cpu_time_step(O, onef, spc, args, nrays, cam_i, seed):
     t0 = time.perf_counter()
     st = O.rf_step(spc, onef, o, d, NEAR, FAR, args.num_steps, tgt, loss="huber", bg=(0, 0, 0), seed=seed)
     dt = time.perf_counter() - t0
+    if keep is not None:                      # parity leg of the GPU arm: the oracle's outputs and the inputs that produced them
+        keep.update(st=st, origins=o, dirs=d, target=tgt, seed=seed)
     return dt, st["num_samples"]
+
+
+def use_all_host_threads(O):
+    """The CPU arm always runs on every host core: torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently
+    turn the OpenMP oracle into a single-thread run (round-1 SCALE ratios at N >= 2 were void for that reason)."""
+    n = os.cpu_count() or 1
+    try:
+        n = max(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    O.set_num_threads(n)
+    return O.num_threads()
 
 
 def run_reference(args):
@@ -96,23 +110,25 @@ def run_reference(args):
     if rank != 0:
         return
     O, onef, spc = cpu_scene(args)
-    cores = O.num_threads()
-    nrays = args.cpu_sample_rays or 16384
-    for i in range(args.warmup):
-        cpu_time_step(O, onef, spc, args, max(256, nrays // 8), i, i)
-    tot, samples = 0.0, 0
+    cores = use_all_host_threads(O)
+    nrays = args.cpu_sample_rays or 65536
+    for i in range(args.warmup):              # warm-up at the timed size (page-faults of the 42 MB gradient table, thread pool spin-up)
+        cpu_time_step(O, onef, spc, args, nrays, i, i)
+    times, samples = [], 0
     for i in range(args.steps):
         dt, ns = cpu_time_step(O, onef, spc, args, nrays, args.warmup + i, args.warmup + i)
-        tot += dt; samples += ns
-    value = nrays * args.steps / tot
-    sample = f"{nrays} rays strided over the {args.res}^2 frame per step, full config (n={args.num_steps}); {samples // max(args.steps, 1)} hit samples/step"
+        times.append(dt); samples += ns
+    med = float(np.median(times))             # median of the steps: robust against a noisy neighbour on the shared host
+    value = nrays / med
+    sample = (f"{nrays} rays strided over the {args.res}^2 frame per step, full config (n={args.num_steps}); "
+              f"{samples // max(args.steps, 1)} hit samples/step; value = rays / median step time")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * tot / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": 1e3 * med, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args),
             "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
-            "note": "reference has no CPU tracer and cannot be built here (kaolin un-vendored); this is the oracle port, OpenMP"}
+            "gpu_launches": 0, "step_s": [round(t, 4) for t in times],
+            "note": "reference has no CPU tracer and cannot be built here (kaolin un-vendored); this is the oracle port, OpenMP on all host cores"}
     print(json.dumps(line), flush=True)
 
 

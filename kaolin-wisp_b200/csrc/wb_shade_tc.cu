@@ -479,7 +479,7 @@ __device__ __forceinline__ void tc_round(TcCtx& c, int l, int k0a, int k0b, int 
 
 // Decoders of one 128-sample sub-tile, starting from an X0 tile that the group has already written.
 // Returns (in registers, both column halves) the density-decoder output df[16] and the colour pre-activations c3[3].
-// TA (experimental forward variant): the activation tile lives in tensor memory (m.work_col[1]; lane = row, two halfs per column) and
+// TA (default forward variant for the F == 2 cat grid): the activation tile lives in tensor memory (m.work_col[1]; lane = row, two halfs per column) and
 // feeds the UMMAs as the A operand directly; nothing but the weights is in shared memory.
 template <bool TA = false>
 __device__ __forceinline__ void tc_decoders(const WbTc& m, TcCtx& c, const TcIn& in, int64_t ray, float df[16], float c3[3])
@@ -548,7 +548,7 @@ __device__ __forceinline__ void tc_decoders(const WbTc& m, TcCtx& c, const TcIn&
 // ---------------------------------------------------------------------------------------------------------------
 // forward kernel: CTA = one group = one 128-sample sub-tile at a time; several CTAs per SM overlap gather / UMMA / epilogue
 // ---------------------------------------------------------------------------------------------------------------
-// F == 2 'cat' gather straight into the TMEM activation tile (experimental TMEM-A variant): 4 LODs = 8 features = one 16-byte chunk =
+// F == 2 'cat' gather straight into the TMEM activation tile (TMEM-A variant): 4 LODs = 8 features = one 16-byte chunk =
 // 4 TMEM columns of this thread's lane; the chunk is also what the backward wants saved.
 __device__ __forceinline__ void tile_gather_ta(const WbGrid& g, uint32_t arow, int half, float px, float py, float pz,
                                                uint4* __restrict__ save, int64_t S, int64_t s, bool valid)
@@ -649,8 +649,8 @@ static int tc_launch_ray_embed(const WbTc& m, const wb_rays* rays, void* workspa
 // Tuning knobs (defaults = the measured optimum on B200 for the app/nerf configuration, profiles/README.md); the environment
 // overrides exist for the sweeps and are read once per process.
 static int tc_env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
-static int tc_knob_bwd_groups() { static const int v = tc_env_int("WB_TC_BWD_GROUPS", 2); return v; }
-static int tc_knob_fwd_tmema() { static const int v = tc_env_int("WB_TC_FWD_TMEMA", 0); return v; }
+static int tc_knob_bwd_groups() { static const int v = tc_env_int("WB_TC_BWD_GROUPS", 3); return v; }
+static int tc_knob_fwd_tmema() { static const int v = tc_env_int("WB_TC_FWD_TMEMA", 1); return v; }
 static int tc_knob_fwd_ctas() { static const int v = tc_env_int("WB_TC_FWD_CTAS", 3); return v; }
 static int tc_knob_scatter_lpb() { static const int v = tc_env_int("WB_TC_SCATTER_LPB", 16); return v; }
 static int tc_knob_scatter_idx2() { static const int v = tc_env_int("WB_TC_SCATTER_IDX2", 1); return v; }
@@ -662,7 +662,8 @@ int wb_tc_shade_fwd(const wb_nef_desc* nef, const float* blob, const wb_rays* ra
                     int64_t S, float* shaded, void* feat_save, void* workspace, cudaStream_t st)
 {
     WbGrid g; int rc = wb_make_grid(nef, &g); if (rc) return rc;
-    // EXPERIMENTAL, off by default (WB_TC_FWD_TMEMA=1): activations in tensor memory, A operand read from TMEM (wb_tc.cuh tc_mma_ts).
+    // Default since round 2 (WB_TC_FWD_TMEMA=0 selects the shared-memory tile): activations in tensor memory, A operand read from TMEM
+    // (wb_tc.cuh tc_mma_ts); measured 3.10 -> 2.86 ms on the 1024^2 frame, same results.
     // Applies to the specialised F == 2 'cat' gather without position embedding, whose rows are whole 16-byte chunks.
     const bool ta = tc_knob_fwd_tmema() && nef->feature_dim == 2 && nef->multiscale == 0 && nef->pos_mode == 0 &&
                     (nef->num_lods * nef->feature_dim) % 16 == 0;
@@ -987,7 +988,7 @@ wb_table_scatter_kernel(WbGrid g, TcIn in, const __half* __restrict__ dfeat, int
     }
 }
 
-#include "wb_shade_tc_bwd3.cuh"          // experimental three-group variant (WB_TC_BWD_GROUPS=3), never the default
+#include "wb_shade_tc_bwd3.cuh"          // three-group variant: the default for the app/nerf decoder shape (WB_TC_BWD_GROUPS=2 selects the kernel above)
 
 // decoder backward only: dL/d(shaded) -> weight gradients + dL/dfeat planes in the workspace
 int wb_tc_decoder_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray,
@@ -1004,7 +1005,7 @@ int wb_tc_decoder_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* 
     TcIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S, reinterpret_cast<const uint4*>(workspace), nullptr, reinterpret_cast<const uint4*>(feat_saved) };
     TcGrads G = { grad_dens, grad_col, scale, dfeat, planes, width };
     TcB3Plan plan;
-    if (tc_knob_bwd_groups() == 3 && tc_b3_plan(m, &plan)) {     // EXPERIMENTAL: three sub-tile groups per SM (wb_shade_tc_bwd3.cuh)
+    if (tc_knob_bwd_groups() == 3 && tc_b3_plan(m, &plan)) {     // three sub-tile groups per SM (wb_shade_tc_bwd3.cuh): 4.53 -> 3.69 ms measured
         WbTc m3 = m;
         for (int l = 0; l < m.nl_d + m.nl_c; ++l) m3.acc_col[l] += 64;       // work columns 0..191, accumulators behind them
         static int done3 = -1;

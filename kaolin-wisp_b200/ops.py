@@ -200,14 +200,36 @@ def march_fill_reference_layout(ms: MarchState, device):
     return ridx, samples, depth, deltas, boundary
 
 
-def _bucket(S: int) -> int:
-    """Capacity for a per-sample buffer: S rounded up to 1/8 of its power of two (<= 12.5 % slack, >= 64 Ki samples).
-    The sample count changes with every batch of rays; bucketed sizes let the caching allocator hand the same blocks back
-    instead of going to cudaMalloc / cudaFree (a device sync) whenever S reaches a new maximum."""
+_CAP_FLOOR = 0      # high-water capacity of the per-sample buffers (samples); only grows
+
+
+def reserve_samples(S: int) -> int:
+    """Pre-size the per-sample buffers for batches of up to S hit samples (trainer warm-up: the reference sizes its ray batch
+    from prev_num_samples the same way, multiview_trainer.py:95-109).  Returns the capacity now in force."""
+    global _CAP_FLOOR
+    _CAP_FLOOR = max(_CAP_FLOOR, _bucket_raw(int(S)))
+    return _CAP_FLOOR
+
+
+def _bucket_raw(S: int) -> int:
     if S <= 0:
         return 0
     gran = max(1 << 16, 1 << max(0, S.bit_length() - 4))
     return (S + gran - 1) // gran * gran
+
+
+def _bucket(S: int) -> int:
+    """Capacity for a per-sample buffer: S rounded up to 1/8 of its power of two (<= 12.5 % slack, >= 64 Ki samples), and never
+    below the largest capacity handed out so far.  The sample count changes with every batch of rays; one stable size lets
+    the caching allocator hand the same blocks back instead of going to cudaMalloc / cudaFree (a device sync, ~10 ms) whenever
+    S crosses a bucket boundary.  A batch that outgrows the high-water mark raises it with 1/16 headroom."""
+    global _CAP_FLOOR
+    if S <= 0:
+        return 0
+    b = _bucket_raw(S)
+    if b > _CAP_FLOOR:
+        _CAP_FLOOR = _bucket_raw(S + S // 16)
+    return _CAP_FLOOR
 
 
 def _empty_s(S: int, tail: tuple, dtype, device):

@@ -115,3 +115,116 @@ def find_depth_bound(query: np.ndarray, curr_idxes: np.ndarray, depth: np.ndarra
                 break
             i += 1
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# NeuralSDF.sdf + PackedSDFTracer.trace restated in numpy (TEST INFRASTRUCTURE; pinned by tests/golden/sdf_octree*.npz,
+# which the reference's own classes produced through oracle/ref_import.py)
+# ------------------------------------------------------------------------------------------------------------------
+def make_sdf_case(level=5, num_lods=3, feature_dim=8, hidden_dim=16, multiscale="sum", res=20, seed=7, feature_std=0.05,
+                  cam=(-2.0, 0.9, -1.6), fov=40.0, radius=0.52):
+    """Synthetic app/nglod scene: octahedron-surface octree, OctreeGrid features, NeuralSDF(position_input, 1 hidden layer)
+    whose decoder is (|x|+|y|+|z|)/sqrt(3) - 0.3 plus a small feature-driven perturbation (as oracle/make_golden.py:gen_sdf)."""
+    rng = np.random.default_rng(seed)
+    p = rng.standard_normal((400000, 3)); p = p / np.abs(p).sum(-1, keepdims=True) * radius
+    q = np.unique(np.floor(np.clip((2 ** level) * (p + 1.0) / 2.0, 0, 2 ** level - 1)).astype(np.int16), axis=0)
+    octree = O.points_to_octree(q, level)
+    spc = O.octree_to_spc(octree)
+    _, pyr, trinkets, _ = make_trilinear_spc(spc)
+    base = level - num_lods + 1
+    active = [base + i for i in range(num_lods)]
+    feats = [(rng.standard_normal((int(pyr[0, l]) + 1, feature_dim)) * feature_std).astype(np.float32) for l in active]
+    in_dim = 3 + (feature_dim if multiscale == "sum" else feature_dim * num_lods)
+    b = 1.0 / np.sqrt(in_dim)
+    W0 = (rng.uniform(-b, b, (hidden_dim, in_dim)) * 0.05).astype(np.float32)
+    W0[:6, :3] = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1.0]], np.float32)
+    b0 = np.zeros(hidden_dim, np.float32)
+    bh = 1.0 / np.sqrt(hidden_dim)
+    W1 = (rng.uniform(-bh, bh, (1, hidden_dim)) * 0.05).astype(np.float32); W1[0, :6] = 1.0 / np.sqrt(3.0)
+    b1 = np.full(1, -0.3, np.float32)
+    o, d = O.look_at_rays(list(cam), [0, 0, 0], res, res, fov)
+    return dict(octree=octree, spc=spc, level=level, trinkets=trinkets, pyramid_dual=pyr, active_lods=active, feats=feats, multiscale=multiscale,
+                W=[W0, W1], b=[b0, b1], origins=o, dirs=d, feature_dim=feature_dim, hidden_dim=hidden_dim)
+
+
+def neural_sdf(case, coords: np.ndarray, lod_idx=None) -> np.ndarray:
+    """NeuralSDF.sdf (neural_sdf.py:120-155), pos_embedder='none' + position_input: decoder(cat([coords, grid feats])) -> [N,1]."""
+    if coords.shape[0] == 0:
+        return np.zeros((0, 1), np.float32)
+    lod_idx = len(case["active_lods"]) - 1 if lod_idx is None else lod_idx
+    f = octree_grid_interpolate(case["spc"], case["trinkets"], case["feats"], case["active_lods"], coords.astype(np.float32), lod_idx, case["multiscale"])
+    h = np.concatenate([coords.astype(np.float32), f.astype(np.float32)], -1)
+    Ws, bs = case["W"], case["b"]
+    for W, b in zip(Ws[:-1], bs[:-1]):
+        h = np.maximum(h @ W.T + b, 0.0).astype(np.float32)
+    return (h @ Ws[-1].T + bs[-1]).astype(np.float32)
+
+
+def sdf_trace(case, num_steps=64, step_size=1.0, min_dis=1e-4, lod_idx=None, dist_max=6.0, with_normals=True, return_debug=False):
+    """PackedSDFTracer.trace (packed_sdf_tracer.py:78-174), statement by statement, on numpy arrays.
+    Kept quirks: `t += dist` also advances packs that already terminated (so depth drifts by dist per executed iteration after
+    the hit while xyz does not); the loop ends when no pack is alive anywhere; find_depth_bound's bounds (see above)."""
+    spc, o, d = case["spc"], case["origins"], case["dirs"]
+    lod_idx = len(case["active_lods"]) - 1 if lod_idx is None else lod_idx
+    rt = O.raytrace(spc, o, d, case["active_lods"][lod_idx])
+    ridx, depth = rt["ridx"], rt["depth"].copy()
+    R = o.shape[0]
+    out = dict(xyz=np.zeros((R, 3), np.float32), depth=np.zeros((R, 1), np.float32), hit=np.zeros(R, bool), normal=np.zeros((R, 3), np.float32),
+               rgb=np.zeros((R, 3), np.float32), alpha=np.zeros((R, 1), np.float32))
+    if ridx.shape[0] == 0:
+        if with_normals:
+            out["rgb"][:] = 0.5
+        return out
+    depth[:, 0:1] += np.float32(1e-5)                                         # :91
+    first = np.ones(ridx.shape[0], bool); first[1:] = ridx[1:] != ridx[:-1]   # mark_pack_boundaries
+    curr = np.nonzero(first)[0].astype(np.int32)
+    first_ridx = ridx[first].astype(np.int64)
+    no, nd = o[first_ridx], d[first_ridx]
+    P = first_ridx.shape[0]
+    mask = np.ones(P, bool); hit = np.zeros(P, bool)
+    t = depth[first][:, 0:1].copy()
+    fma = lambda tt: (nd.astype(np.float64) * tt.astype(np.float64) + no.astype(np.float64)).astype(np.float32)   # addcmul == fma
+    x = fma(t)
+    dist = np.zeros_like(t)
+    step = np.float32(step_size)
+    dist[mask] = neural_sdf(case, x[mask], lod_idx) * np.float32(1.0) * step
+    dist_prev = dist.copy()
+    iters = 0
+    for i in range(num_steps):
+        iters += 1
+        t = t + dist
+        x = np.where(mask[:, None], fma(t), x)
+        hit = np.where(mask, np.abs(dist)[:, 0] < np.float32(min_dis * 1.0), hit)
+        hit = hit | np.where(mask, np.abs(dist + dist_prev)[:, 0] * np.float32(0.5) < np.float32((min_dis * 5) * 1.0), hit)
+        mask = np.where(mask, (t < np.float32(dist_max))[:, 0], mask)
+        mask = mask & ~hit
+        if not mask.any():
+            break
+        dist_prev = np.where(mask[:, None], dist, dist_prev)
+        nxt = find_depth_bound(t, curr, depth)
+        mask = mask & (nxt != -1)
+        aabb = nxt != curr
+        curr = np.where(mask, nxt, curr)
+        t = np.where((mask & aabb)[:, None], depth[curr.astype(np.int64), 0:1], t)
+        x = np.where(mask[:, None], fma(t), x)
+        if not mask.any():
+            break
+        dist[mask] = neural_sdf(case, x[mask], lod_idx) * np.float32(1.0) * step
+    hb = np.zeros(R, bool); hb[first_ridx] = hit
+    out["hit"] = hb
+    out["xyz"][hb] = x[hit]; out["depth"][hb] = t[hit]
+    if with_normals:
+        eps = np.float32(0.005)
+        xh = x[hit]
+        g = []
+        for a in range(3):
+            e = np.zeros(3, np.float32); e[a] = eps
+            g.append(neural_sdf(case, xh + e) - neural_sdf(case, xh - e))     # lod_idx=None -> finest LOD (gradients.py:29-45)
+        grad = np.concatenate(g, -1) / np.float32(0.005 * 2.0) if xh.shape[0] else np.zeros((0, 3), np.float32)
+        nrm = np.sqrt((grad.astype(np.float32) ** 2).sum(-1, keepdims=True))
+        out["normal"][hb] = grad / np.maximum(nrm, np.float32(1e-5))
+        out["rgb"][:] = (out["normal"] + 1.0) / 2.0
+    out["alpha"][hb] = 1.0
+    if return_debug:
+        out["iters"] = iters
+    return out

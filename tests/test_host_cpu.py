@@ -132,14 +132,26 @@ def test_precision_support_query_is_host_side():
 
 
 def test_bucketed_capacities():
-    """Per-sample buffers are carved from capacities with at most 1/8 slack that repeat across nearby sample counts."""
-    from wisp_b200.ops import _bucket
-    assert _bucket(0) == 0 and _bucket(1) == 1 << 16 and _bucket((1 << 16) + 1) == 2 << 16
+    """Per-sample buffers are carved from capacities with at most 1/8 slack that repeat across nearby sample counts, and the
+    capacity in force never shrinks (one stable size per training run: no cudaMalloc when S crosses a bucket boundary)."""
+    from wisp_b200 import ops
+    b = ops._bucket_raw
+    assert b(0) == 0 and b(1) == 1 << 16 and b((1 << 16) + 1) == 2 << 16
     for S in (15_592_267, 15_667_821, 12_191_426, 333_000_000, 70_001):
-        c = _bucket(S)
-        assert S <= c <= S * 1.125 + (1 << 16)
-    assert _bucket(15_592_267) == _bucket(15_667_821)            # neighbouring frames of the orbit share their blocks
-    assert len({_bucket(s) for s in range(15_000_000, 16_000_000, 10_007)}) <= 2
+        assert S <= b(S) <= S * 1.125 + (1 << 16)
+    assert b(15_592_267) == b(15_667_821)
+    old = ops._CAP_FLOOR
+    try:
+        ops._CAP_FLOOR = 0
+        c0 = ops._bucket(15_000_000)
+        assert 15_000_000 <= c0 <= 15_000_000 * 1.2
+        assert {ops._bucket(s) for s in range(12_000_000, 15_900_000, 100_003)} == {c0}     # smaller and slightly larger batches reuse it
+        c1 = ops._bucket(20_000_000)
+        assert c1 >= 20_000_000 and ops._bucket(15_000_000) == c1                            # grows, never shrinks
+        assert ops.reserve_samples(30_000_000) >= 30_000_000 and ops._bucket(1) >= 30_000_000
+        assert ops._bucket(0) == 0
+    finally:
+        ops._CAP_FLOOR = old
 
 
 def test_bench_reference_arm_contract():
