@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--precision", type=int, default=1, help="0: fp32 decoders, 1: fp16 tensor-core decoders (reference enable_amp)")
     ap.add_argument("--cpu-sample-rays", type=int, default=0, help="rays in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
+                    help="BASELINE.json config: 2 = HashGrid NeRF fwd+bwd (headline), 3 = nglod OctreeGrid SDF sphere trace, 4 = TriplanarGrid NeRF")
     return ap.parse_args()
 
 
@@ -185,13 +187,20 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, (world, args.gpus)
 
-    # ---- model: identical random init on every rank ----
+    # ---- model: identical init on every rank, taken from the oracle's seeded numpy init so that the CPU restatement and the GPU
+    # model are the SAME network (the parity leg below compares them on the cpu_baseline sample) ----
     torch.manual_seed(0)
+    onef0 = O.make_nef(feature_std=1e-4, seed=0)                      # config 2 shapes; pure numpy (no oracle library call)
     pts = torch.from_numpy(O.lego_like_points(7))
     blas = W.OctreeAS.from_quantized_points(pts.to(dev), 7) if args.scene == "lego" else W.OctreeAS.make_dense(7, device=dev)
     grid = W.HashGrid.from_geometric(blas, feature_dim=2, num_lods=16, multiscale_type='cat', feature_std=1e-4, codebook_bitwidth=19,
                                      min_grid_res=16, max_grid_res=512)
     nef = W.NeuralRadianceField(grid, view_embedder='positional', view_multires=4, hidden_dim=64, num_layers=1, bias=True).to(dev)
+    with torch.no_grad():
+        grid.codebook.feats.copy_(torch.from_numpy(onef0.table))
+        for dec, Ws, bs in ((nef.decoder_density, onef0.dens_W, onef0.dens_b), (nef.decoder_color, onef0.col_W, onef0.col_b)):
+            for l, Wm, bm in zip(list(dec.layers) + [dec.lout], Ws, bs):
+                l.weight.copy_(torch.from_numpy(np.ascontiguousarray(Wm))); l.bias.copy_(torch.from_numpy(np.ascontiguousarray(bm)))
     tracer = W.PackedRFTracer(raymarch_type='ray', num_steps=args.num_steps, bg_color=(0.0, 0.0, 0.0))
     tracer.precision = args.precision
     pipe = W.Pipeline(nef, tracer)
@@ -245,6 +254,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- parity at bench scale, on the benched path: the GPU step vs the CPU restatement on the cpu_baseline sample (same rays,
+    # same jitter seed, same weights, full config) BEFORE any training step; also times the CPU run -> cpu_baseline ----
+    parity, cpu_base = None, None
+    if rank == 0 and not args.no_cpu_baseline:
+        parity, cpu_base = parity_leg(args, O, W, torch, dev, spc_np=None, onef=onef0, pipe=pipe, tracer=tracer, nef=nef)
+    W.ops.reserve_samples(int(1.08 * 16.0e6 * (args.res / 1024.0) ** 2 * (args.num_steps / 2048.0)) if args.scene == "lego" else 0)
     sampler = ClockSampler(local)          # started before the warm-up so that samples exist for short timed regions; it keeps
     if rank == 0:                          # running (one nvidia-smi process, 200 ms period) through both timed loops
         sampler.start()
@@ -392,13 +407,9 @@ def run_ours(args):
             "samples_per_step_per_gpu": S_step, "samples_per_sec": total_samples / (ms * 1e-3), "stage_ms": mean_ms,
             "step_ms": step_ms, "cudaMalloc_calls_in_timed_region": int(dev_allocs), "render_only": render}
 
-    if not args.no_cpu_baseline:
-        Oc, onef, spc = cpu_scene(args)
-        dt0, _ = cpu_time_step(Oc, onef, spc, args, 2048, 0, 0)                     # probe, then size the sample to ~12 s of CPU work
-        nr = args.cpu_sample_rays or int(min(R, max(4096, 2048 * 12.0 / max(dt0, 1e-3))))
-        dt, ns = cpu_time_step(Oc, onef, spc, args, nr, args.warmup, 1000 + args.warmup)
-        line["cpu_baseline"] = {"value": nr / dt, "unit": "rays/s", "cores": Oc.num_threads(), "kind": "port",
-                                "sample": f"{nr} rays strided over the {args.res}^2 frame, full config, {ns} hit samples, {dt:.1f} s"}
+    if cpu_base is not None:
+        line["cpu_baseline"] = cpu_base
+        line["parity"] = parity
     if args.trace_host:
         print("step, premarch ms, zero_grad+forward ms, loss ms, backward ms, reduce+opt ms, cudaMallocs so far", file=sys.stderr)
         for row in host_trace:
@@ -408,9 +419,349 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+
+# ------------------------------------------------------------------------------------------------------------------
+# parity at bench scale (rank 0, outside every timed region)
+# ------------------------------------------------------------------------------------------------------------------
+PARITY_TOL = {0: {"rgb": 1e-4, "loss": 1e-5, "grad": 2e-3}, 1: {"rgb": 2e-3, "loss": 2e-3, "grad": 3e-2}}    # DESIGN.md "Tolerances"
+
+
+def parity_leg(args, O, W, torch, dev, spc_np, onef, pipe, tracer, nef):
+    """The CPU restatement and the GPU pipeline on the same bounded sample of the benched frame: per-ray rgb, the huber loss and the
+    gradients of one step.  Raises if a tolerance is exceeded: a fast step whose result differs from the reference's is not a result."""
+    use_all_host_threads(O)
+    spc = O.octree_to_spc(O.points_to_octree(O.lego_like_points(7), 7) if args.scene == "lego" else O.dense_octree(7))
+    R = args.res * args.res
+    dt0, _ = cpu_time_step(O, onef, spc, args, 2048, 0, 0)                          # probe, then size the sample to ~12 s of CPU work
+    nr = args.cpu_sample_rays or int(min(R, max(4096, 2048 * 12.0 / max(dt0, 1e-3))))
+    keep = {}
+    dt, ns = cpu_time_step(O, onef, spc, args, nr, args.warmup, 1000 + args.warmup, keep=keep)
+    cpu_base = {"value": nr / dt, "unit": "rays/s", "cores": O.num_threads(), "kind": "port",
+                "sample": f"{nr} rays strided over the {args.res}^2 frame, full config, {ns} hit samples, {dt:.1f} s"}
+    st = keep["st"]
+    for p_ in nef.parameters():
+        p_.grad = None
+    tracer.seed = keep["seed"]
+    o, d, tgt = (torch.from_numpy(keep[k]).to(dev) for k in ("origins", "dirs", "target"))
+    rb = pipe(rays=W.Rays(o, d, dist_min=NEAR, dist_max=FAR), lod_idx=None, channels=["rgb"])
+    loss = torch.nn.functional.smooth_l1_loss(rb.rgb, tgt, reduction='none').mean()
+    loss.backward()
+    torch.cuda.synchronize()
+
+    def rel(a, b):
+        return float(np.abs(a - b).max() / max(float(np.abs(b).max()), 1e-30))
+    flat = lambda dec: torch.cat([t.grad.reshape(-1) for l in list(dec.layers) + [dec.lout] for t in (l.weight, l.bias)]).cpu().numpy()
+    out = {"rays": int(nr), "samples": int(ns), "samples_match": bool(tracer.get_prev_num_samples() == st["num_samples"]),
+           "precision": int(args.precision),
+           "rgb_max_abs_err": float(np.abs(rb.rgb.detach().cpu().numpy() - st["rgb"]).max()),
+           "loss_gpu": float(loss), "loss_cpu": float(st["loss"]), "loss_rel_err": abs(float(loss) - st["loss"]) / max(abs(st["loss"]), 1e-30),
+           "table_grad_rel_err": rel(nef.grid.codebook.feats.grad.cpu().numpy(), st["table"]),
+           "density_decoder_grad_rel_err": rel(flat(nef.decoder_density), st["dens"]),
+           "color_decoder_grad_rel_err": rel(flat(nef.decoder_color), st["col"]),
+           "tolerance": PARITY_TOL[int(args.precision)], "checked_against": "oracle/wisp_oracle.c wo_rf_step (fp32), same rays / seed / weights"}
+    tol = out["tolerance"]
+    ok = (out["samples_match"] and out["rgb_max_abs_err"] <= tol["rgb"] and out["loss_rel_err"] <= tol["loss"]
+          and max(out["table_grad_rel_err"], out["density_decoder_grad_rel_err"], out["color_decoder_grad_rel_err"]) <= tol["grad"])
+    out["ok"] = bool(ok)
+    for p_ in nef.parameters():
+        p_.grad = None
+    if not ok:
+        print(json.dumps({"parity_failure": out}), file=sys.stderr, flush=True)
+        raise SystemExit("bench.py: GPU result differs from the CPU restatement beyond the stated tolerance (see stderr)")
+    return out, cpu_base
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE config 3 (app/nglod OctreeGrid SDF sphere trace) and config 4 (TriplanarGrid NeRF): single GPU per rank
+# ------------------------------------------------------------------------------------------------------------------
+def _peaks():
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(pk.get("hbm_gbs", 6650.0)), "MEASURED_PEAKS.json (measured)"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
+def _finish_line(args, torch, dist, world, rank, dev, line_fn, ms, ms_e2e, extra):
+    tms = torch.tensor([ms, ms_e2e] + list(extra), dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = tms.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tms.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        tms = torch.cat([mx[:2], sm[2:]])
+    if rank == 0:
+        print(json.dumps(line_fn(float(tms[0]), float(tms[1]), [float(x) for x in tms[2:]])), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_config3(args):
+    """One step = one 512^2 frame through Pipeline(NeuralSDF(OctreeGrid F=16, 6 LODs, 'sum', 128-wide decoder), PackedSDFTracer(32, 0.8)):
+    native raytrace + ONE persistent sphere-tracing kernel (wb_sdf_trace) + finite-difference normals (nglod_octree.yaml)."""
+    import torch
+    import torch.distributed as dist
+    import wisp_b200 as W
+    from oracle import octree_grid as OG
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from gpu_util import sdf_nef_from_case
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local); dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    res = 512 if args.res == 1024 else args.res
+    nsteps, step_size, min_dis = 32, 0.8, 3e-4
+    case = OG.make_sdf_case(level=7, num_lods=6, feature_dim=16, hidden_dim=128, multiscale="sum", res=64, seed=11, feature_std=0.02)
+    nef = sdf_nef_from_case(case, device=dev)
+    tracer = W.PackedSDFTracer(num_steps=nsteps, step_size=step_size, min_dis=min_dis)
+    pipe = W.Pipeline(nef, tracer)
+    R = res * res
+    total = args.warmup + args.steps
+    from oracle import oracle as O
+    cams = [O.look_at_rays(orbit_origin((i * world + rank) * 3), CAM_LOOKAT, res, res, CAM_FOV) for i in range(total)]
+    cams = [(o * np.float32(0.75), d) for o, d in cams]                              # radius ~3.2: the sphere-like surface fills the frame
+    host = [(torch.from_numpy(np.ascontiguousarray(o)).pin_memory(), torch.from_numpy(d).pin_memory()) for o, d in cams]
+    devr = [(o.to(dev), d.to(dev)) for o, d in host]
+    chans = ["rgb", "depth", "hit", "normal"]
+
+    # parity on a 64^2 slice of the same model (rank 0): the numpy restatement pinned by tests/golden/sdf_octree.npz
+    parity, cpu_base = None, None
+    if rank == 0 and not args.no_cpu_baseline:
+        t0 = time.perf_counter()
+        ref = OG.sdf_trace(case, num_steps=nsteps, step_size=step_size, min_dis=min_dis, dist_max=6.0)
+        dt = time.perf_counter() - t0
+        with torch.no_grad():
+            rb = pipe(rays=W.Rays(torch.from_numpy(case["origins"]).to(dev), torch.from_numpy(case["dirs"]).to(dev), 0.0, 6.0), channels=chans)
+        hit = rb.hit.cpu().numpy(); both = hit & ref["hit"]
+        parity = {"rays": int(hit.size), "hits_cpu": int(ref["hit"].sum()), "hit_flips": int((hit != ref["hit"]).sum()),
+                  "depth_max_abs_err": float(np.abs(rb.depth.cpu().numpy()[both] - ref["depth"][both]).max()) if both.any() else 0.0,
+                  "normal_min_dot": float((rb.normal.cpu().numpy()[both] * ref["normal"][both]).sum(-1).min()) if both.any() else 1.0,
+                  "tolerance": {"hit_flips": "<= 0.2 %", "depth": 1e-4, "normal_dot": 0.99}}
+        parity["ok"] = bool(parity["hit_flips"] <= max(1, hit.size // 500) and parity["depth_max_abs_err"] <= 1e-4 and parity["normal_min_dot"] >= 0.99)
+        if not parity["ok"]:
+            print(json.dumps({"parity_failure": parity}), file=sys.stderr, flush=True)
+            raise SystemExit("bench.py --config 3: GPU sphere trace differs from the restatement beyond the stated tolerance")
+        cpu_base = {"value": hit.size / dt, "unit": "rays/s", "cores": 1, "kind": "port",
+                    "sample": f"{hit.size} rays (64^2 view of the same model), numpy restatement of packed_sdf_tracer.py:78-174 (single thread + OpenMP octree query), {dt:.2f} s"}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    with torch.no_grad():
+        for i in range(args.warmup):
+            pipe(rays=W.Rays(*devr[i], 0.0, 6.0), channels=chans)
+        barrier()
+        W.ops.PROFILE = []
+        l0 = W._cabi.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        evals, hits = [], 0
+        e0.record()
+        for k in range(args.steps):
+            rb = pipe(rays=W.Rays(*devr[args.warmup + k], 0.0, 6.0), channels=chans)
+            evals.append(tracer.prev_num_evals.clone())
+        e1.record()
+        barrier()
+        launches = W._cabi.launch_count() - l0
+        prof, W.ops.PROFILE = W.ops.PROFILE, None
+        hits = int(rb.hit.sum())
+        n_evals = float(sum(int(e) for e in evals))
+        ms = e0.elapsed_time(e1)
+        stage = {}
+        for name, a, b in prof:
+            stage.setdefault(name, []).append(a.elapsed_time(b))
+        # end to end: rays from pinned host memory, the rgb + hit image read back
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        out_rgb = torch.empty((R, 3), dtype=torch.float32).pin_memory(); out_hit = torch.empty(R, dtype=torch.bool).pin_memory()
+        for k in range(args.warmup):
+            o, d = (t.to(dev, non_blocking=True) for t in host[k]); pipe(rays=W.Rays(o, d, 0.0, 6.0), channels=chans)
+        barrier()
+        e2.record()
+        for k in range(args.steps):
+            o, d = (t.to(dev, non_blocking=True) for t in host[args.warmup + k])
+            rb = pipe(rays=W.Rays(o, d, 0.0, 6.0), channels=chans)
+            out_rgb.copy_(rb.rgb, non_blocking=True); out_hit.copy_(rb.hit, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        e3.record()
+        barrier()
+        ms_e2e = e2.elapsed_time(e3)
+    clocks = sampler.stop() if rank == 0 else None
+    hbm, src = _peaks()
+
+    def line(ms, ms_e2e, extra):
+        ev = extra[0]
+        t_trace = float(np.mean(stage.get("sdf_trace", [ms / args.steps])))
+        per_eval = 6 * 8 * 16 * 2 + 6 * 8 * 4                                       # SURVEY 8(d): fp16-equivalent feature bytes + trinkets per LOD
+        ach = (ev / (args.steps * world)) * per_eval / (t_trace * 1e-3) / 1e9
+        return {"metric": "rays/sec sphere-trace 512^2 nglod OctreeGrid SDF (BASELINE config 3)", "value": R * args.steps * world / (ms * 1e-3), "unit": "rays/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32 decoder, f16-rounded octree features (octree_grid.py:147-149)", "data": "synthetic",
+                "config": {"workload": f"app/nglod OctreeGrid level 7, F=16 x 6 LODs 'sum', NeuralSDF 19-128-1, PackedSDFTracer(32 steps, 0.8), {res}^2 rays, "
+                                       "octahedron-shell octree (13 201 level-7 cells), orbit camera, render (no gradients: the tracer is inference-only)",
+                           "rays_per_step_per_gpu": R, "l2": "a different camera every step; the feature levels (3 MB) are L2 resident by design",
+                           "parallelism": f"dp{world} (one view per GPU, no collective)" if world > 1 else "single GPU"},
+                "e2e": {"value": R * args.steps * world / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": R * 24, "d2h_bytes_per_step": R * 13,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": "wb_sdf_trace_kernel", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                             "kernel_ms": t_trace, "algorithmic_per_eval": f"{per_eval} B", "evals_per_launch": ev / (args.steps * world), "peak_source": src,
+                             "note": "HBM-equivalent: the feature levels are L2 resident; the kernel is a latency chain of <= 33 dependent field evaluations per ray"},
+                "stage_ms": {k: float(np.mean(v)) for k, v in stage.items()}, "hits_last_frame": hits, "field_evals_per_frame": ev / (args.steps * world),
+                "cpu_baseline": cpu_base, "parity": parity}
+    _finish_line(args, torch, dist, world, rank, dev, line, ms, ms_e2e, [n_evals])
+
+
+def run_config4(args):
+    """One step = fwd + bwd + Adam on an 800^2 frame through Pipeline(NeuralRadianceField(TriplanarGrid fdim 4, 4 LODs 65^2..513^2,
+    'sum'), PackedRFTracer('voxel', 512)) over an AABB (nerf_triplanar.yaml shapes with log_base_resolution 6): FUSED path."""
+    import torch
+    import torch.distributed as dist
+    import wisp_b200 as W
+    from oracle import oracle as O
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local); dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    res = 800 if args.res == 1024 else args.res
+    nsteps = 512 if args.num_steps == 2048 else args.num_steps
+    torch.manual_seed(0)
+    blas = W.AxisAlignedBBoxAS(device=dev)
+    grid = W.TriplanarGrid(blas, feature_dim=4, log_base_resolution=6, num_lods=4, multiscale_type='sum', feature_std=0.01)
+    nef = W.NeuralRadianceField(grid, view_embedder='positional', view_multires=4, hidden_dim=64, num_layers=1, bias=True).to(dev)
+    tracer = W.PackedRFTracer(raymarch_type='voxel', num_steps=nsteps, bg_color=(1.0, 1.0, 1.0)); tracer.precision = args.precision
+    pipe = W.Pipeline(nef, tracer)
+    params = [p for p in nef.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-3, eps=1e-15, fused=True)
+    reducer = W.parallel.GradientReducer(params)
+    R = res * res
+    total = args.warmup + args.steps
+    g = torch.Generator().manual_seed(2)
+    host = []
+    for i in range(total):
+        o, d = O.look_at_rays(orbit_origin(i * world + rank), CAM_LOOKAT, res, res, CAM_FOV)
+        host.append((torch.from_numpy(o).pin_memory(), torch.from_numpy(d).pin_memory(), torch.sigmoid(torch.randn(R, 3, generator=g)).pin_memory()))
+    devb = [tuple(t.to(dev) for t in b) for b in host]
+
+    # parity (rank 0): fused tensor-core path vs the unfused route (native triplane kernel pinned to the reference golden + torch decoders)
+    parity = None
+    if rank == 0 and not args.no_cpu_baseline:
+        o, d, t = (x[:: max(1, R // 16384)][:16384].contiguous() for x in devb[0])
+        outs = []
+        for fused in (False, True):
+            for p_ in params:
+                p_.grad = None
+            if not fused:
+                nef.fused_spec = lambda lod_idx=None: None
+            tracer.seed = 3
+            tracer.precision = args.precision if fused else 0
+            rb = pipe(rays=W.Rays(o, d, NEAR, FAR), channels=["rgb"])
+            torch.nn.functional.smooth_l1_loss(rb.rgb, t).backward()
+            outs.append((rb.rgb.detach().clone(), {n: p_.grad.clone() for n, p_ in nef.named_parameters()}))
+            if not fused:
+                del nef.fused_spec
+        tracer.precision = args.precision
+        tol = PARITY_TOL[int(args.precision)]
+        gerr = max(float((outs[1][1][n] - gr).abs().max() / gr.abs().max().clamp_min(1e-30)) for n, gr in outs[0][1].items())
+        parity = {"rays": int(o.shape[0]), "rgb_max_abs_err": float((outs[1][0] - outs[0][0]).abs().max()), "grad_max_rel_err": gerr, "tolerance": tol,
+                  "checked_against": "unfused route: wb_triplane kernel (pinned to tests/golden/triplanar.npz) + torch nn.Linear decoders, fp32"}
+        parity["ok"] = bool(parity["rgb_max_abs_err"] <= tol["rgb"] and gerr <= tol["grad"])
+        for p_ in params:
+            p_.grad = None
+        if not parity["ok"]:
+            print(json.dumps({"parity_failure": parity}), file=sys.stderr, flush=True)
+            raise SystemExit("bench.py --config 4: fused path differs from the unfused route beyond the stated tolerance")
+
+    def step(i, o, d, t):
+        opt.zero_grad(set_to_none=True)
+        tracer.seed = 1000 + i * world + rank
+        rb = pipe(rays=W.Rays(o, d, dist_min=NEAR, dist_max=FAR), channels=["rgb"])
+        loss = torch.nn.functional.smooth_l1_loss(rb.rgb, t, reduction='none').mean()
+        loss.backward()
+        reducer.reduce()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    W.ops.reserve_samples(R * nsteps)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for i in range(args.warmup):
+        step(i, *devb[i])
+    barrier()
+    W.ops.PROFILE = []
+    l0 = W._cabi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    S_total = 0
+    e0.record()
+    for k in range(args.steps):
+        step(args.warmup + k, *devb[args.warmup + k]); S_total += tracer.get_prev_num_samples()
+    e1.record()
+    barrier()
+    launches = W._cabi.launch_count() - l0
+    prof, W.ops.PROFILE = W.ops.PROFILE, None
+    ms = e0.elapsed_time(e1)
+    stage = {}
+    for name, a, b in prof:
+        stage.setdefault(name, []).append(a.elapsed_time(b))
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pre = W.parallel.HostPrefetcher(host[:args.warmup], dev)
+    for k, b in enumerate(pre):
+        step(k, *b)
+    barrier()
+    e2.record()
+    last = None
+    pre = W.parallel.HostPrefetcher(host[args.warmup:], dev)
+    for k, b in enumerate(pre):
+        last = float(step(args.warmup + k, *b).item())
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    clocks = sampler.stop() if rank == 0 else None
+    hbm, src = _peaks()
+
+    def line(ms, ms_e2e, extra):
+        S_step = extra[0] / (args.steps * world)
+        mean = {k: float(np.mean(v)) for k, v in stage.items()}
+        per = 4 * 3 * 4 * 4 * 4                                                   # SURVEY 8(d): L * 3 planes * 4 texels * fdim * 4 B = 768 B/sample
+        roofs = []
+        for st_name, kern, mult in (("shade_fwd", "wb_shade_fwd_tc_kernel<GX>" if args.precision == 1 else "wb_shade_fwd_kernel", 1),
+                                    ("table_scatter", "wb_featx_scatter_kernel", 2), ("decoder_bwd", "wb_mlp_bwd3_tc_kernel", 0)):
+            if st_name in mean and mult:
+                a = S_step * per * mult / (mean[st_name] * 1e-3) / 1e9
+                roofs.append({"bound": "hbm", "kernel": kern, "achieved": a, "peak": hbm, "unit": "GB/s", "frac": a / hbm, "traffic": None,
+                              "kernel_ms": mean[st_name], "algorithmic_per_sample": f"{per * mult} B", "samples_per_launch": S_step})
+        roof = dict(max(roofs, key=lambda r: r["kernel_ms"])) if roofs else None
+        if roof:
+            roof["peak_source"] = src
+            roof["note"] = "HBM-equivalent: the planes (12.6 MB) are L2 resident"
+        return {"metric": "rays/sec (fwd+bwd) 800^2 TriplanarGrid NeRF (BASELINE config 4)", "value": R * args.steps * world / (ms * 1e-3), "unit": "rays/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32" if args.precision == 0 else "f16(tensor)+f32 accumulate", "data": "synthetic",
+                "config": {"workload": f"TriplanarGrid fdim 4, 4 LODs 65^2..513^2 'sum', 2-layer-64 MLP, AABB, 'voxel' {nsteps} steps, {res}^2 rays, fwd+bwd+Adam, fused path",
+                           "rays_per_step_per_gpu": R, "l2": "per-step sample records + saved features (> 10 GB) exceed the 126 MB L2; a different camera every step",
+                           "parallelism": f"dp{world} (one view per GPU per step, NCCL all-reduce of gradients)" if world > 1 else "single GPU"},
+                "e2e": {"value": R * args.steps * world / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": R * 36, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / args.steps, "last_loss": last},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "rooflines": roofs, "stage_ms": mean,
+                "samples_per_step_per_gpu": S_step, "samples_per_sec": extra[0] / (ms * 1e-3), "parity": parity,
+                "cpu_baseline": None if args.no_cpu_baseline else {"value": None, "unit": "rays/s", "cores": 0, "kind": "port",
+                                                                   "sample": "no CPU restatement of the triplanar field in oracle/ (torch F.grid_sample is the pin); see --config 2 for the CPU arm"}}
+    _finish_line(args, torch, dist, world, rank, dev, line, ms, ms_e2e, [float(S_total)])
+
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.config == 3:
+        run_config3(a)
+    elif a.config == 4:
+        run_config4(a)
     else:
         run_ours(a)

@@ -67,6 +67,21 @@ typedef struct wb_nef_desc {
     int32_t col_dims[WB_MAX_LAYERS + 1];
     const float* dens_params;
     const float* col_params;
+    /* ---- feature grids other than the hash grid (fused path only; zero for the hash grid) ----
+     * grid_kind 1 = TriplanarGrid (triplanar_grid.py:24-150): num_lods = LODs used (lod_idx + 1), feature_dim = 3 * fdim
+     *   (the width of one LOD's [plane, fdim] block), resolutions[l] = 2^(log_base_resolution + l) (plane side - 1),
+     *   grid_ptrs = 3*num_lods planes (fmx, fmy, fmz of LOD 0, LOD 1, ...), each [1, fdim, res+1, res+1] fp32.
+     * grid_kind 2 = OctreeGrid (octree_grid.py:24-226): num_lods = LODs used, feature_dim = F, grid_ptrs = features[0..num_lods)
+     *   each [pyramid_dual[0,l]+1, F] fp32; oct/points/trinkets/base_lod/half_round as in wb_octree_interp_fwd.
+     * For both: lod_idx = num_lods (nothing is zeroed), table / resolutions-as-hash / begin_idxes / codebook_size unused.
+     * grid_grads: same shapes as grid_ptrs, accumulated into by the backward entry points (their grad_table may be NULL). */
+    int32_t grid_kind;
+    int32_t base_lod, half_round;
+    const float* const* grid_ptrs;          /* HOST array of device pointers */
+    float* const* grid_grads;               /* HOST array of device pointers (backward only) */
+    const struct wb_octree* oct;            /* grid_kind 2 */
+    const int16_t* points;
+    const int32_t* trinkets;
 } wb_nef_desc;
 
 /* Rays (wisp/core/rays.py:19-36).  near/far: scalars, or per-ray arrays when near_v != NULL. */
@@ -194,6 +209,58 @@ int wb_find_depth_bound(const float* query, const int32_t* curr_idxes, const flo
                         int32_t* out, wb_stream s);
 
 /* ------------------------------------------------------------------------------------------------
+ * NeuralSDF(OctreeGrid) and the sphere tracer of app/nglod (BASELINE config 3)
+ *   wb_sdf_eval  replaces NeuralSDF.sdf (wisp/models/nefs/neural_sdf.py:120-155): OctreeGrid.interpolate
+ *                (octree_grid.py:130-219) + position embedding + BasicDecoder, one launch, fp32 decoder.
+ *   wb_sdf_trace replaces the whole loop of PackedSDFTracer.trace (wisp/tracers/packed_sdf_tracer.py:78-174) including
+ *                wisp._C.render.find_depth_bound_cuda (find_depth_bound_cuda.cu:16-45) and finitediff_gradient
+ *                (wisp/ops/differential/gradients.py:29-45): ONE persistent cooperative kernel.  Input: the nuggets of
+ *                wb_raytrace_fill at level base_lod + lod_idx (raw depths: the kernel adds the reference's 1e-5 to the
+ *                entries itself) and the per-ray nugget offsets of wb_scan_counts.  Outputs are per ray; the caller
+ *                initialises them (zeros; rgb = 0.5 when want_normals, packed_sdf_tracer.py:168) and the kernel
+ *                writes the rays that hit: xyz [R,3], depth [R], hit u8 [R], normal [R,3], rgb [R,3], alpha [R].
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct wb_sdf_desc {
+    /* OctreeGrid (octree_grid.py:58-104): level-local trinkets, one feature tensor per active LOD */
+    const int16_t* points;                  /* blas.points int16 [T,3]                               */
+    const int32_t* trinkets;                /* grid.trinkets int32 [T,8]                             */
+    const float* const* feats;              /* HOST array of num_lods device pointers [rows_l, F] f32 */
+    int32_t feature_dim, base_lod, num_lods;
+    int32_t multiscale;                     /* 0 'cat', 1 'sum'                                      */
+    int32_t half_round;                     /* feats.half() ... .float() of the call site (:147-149) */
+    /* NeuralSDF (neural_sdf.py:30-99): position embedding FIRST, then grid features                   */
+    int32_t pos_mode, pos_freq;             /* 0 none, 1 identity, 2 positional, 3 positional+input  */
+    int32_t num_layers, hidden_dim;         /* BasicDecoder(bias=True): num_layers hidden layers, relu, 1 output */
+    const float* params;                    /* packed [W0, b0, ..., Wout, bout], nn.Linear layout      */
+} wb_sdf_desc;
+int wb_sdf_eval(const wb_octree* oct, const wb_sdf_desc* nef, int32_t lod_idx, const float* coords, int64_t N, float* sdf, wb_stream s);
+/* Per-pack state of the sphere tracer (pack = ray with >= 1 nugget).  All device pointers, allocated by the caller for R rays;
+ * nothing needs initialising.  state bit 0 = alive (the reference's `mask`), bit 1 = hit. */
+typedef struct wb_sdf_state {
+    int32_t* flags;                         /* [R]    ray has nuggets                                  */
+    int64_t* pack_off;                      /* [R+1]  exclusive scan of flags; pack_off[R] = #packs    */
+    void* scan_ws; int64_t scan_ws_bytes;   /* wb_scan_workspace_bytes(R)                              */
+    int32_t* pack_ray;                      /* [R]    ray of pack p                                    */
+    float* t; float* dist; float* dist_prev;/* [R]    depth along the ray, last / previous sdf step    */
+    float* x;                               /* [R,3]  current point                                    */
+    int32_t* cursor0; int32_t* cursor1;     /* [R]    nugget cursor, double buffered                   */
+    uint8_t* state;                         /* [R]                                                     */
+    int32_t* iterflags;                     /* [2*num_steps+4] any-pack-alive flags of every iteration; [2*num_steps+2] = field evaluations of wb_sdf_trace */
+} wb_sdf_state;
+int wb_sdf_trace(const wb_octree* oct, const wb_sdf_desc* nef, int32_t lod_idx, const wb_rays* rays,
+                 const float* nug_depth, int64_t Ng, const int64_t* ray_offsets,
+                 int32_t num_steps, float step_size, float min_dis, int32_t want_normals, const wb_sdf_state* state,
+                 float* xyz, float* depth, uint8_t* hit, float* normal, float* rgb, float* alpha, wb_stream s);
+/* The same state machine one phase per launch, for fields this library cannot evaluate itself (NeuralSDF over a hash or
+ * triplanar grid, app/nglod/configs/nglod_hash.yaml): the caller evaluates its field at state->x of the alive packs and writes
+ * state->dist between the phases.  phase 0: pack list (then read pack_off[R])  1: initial t, x, cursor, alive   2: step 1 of
+ * iteration `iteration` (packed_sdf_tracer.py:120-131)   3: step 2 (:133-141)   4: outputs of the packs that hit.
+ * iterflags[2*iteration + (phase == 3)] != 0 afterwards iff a pack is still alive (the loop's `break` tests). */
+int wb_sdf_phase(int32_t phase, const wb_rays* rays, const float* nug_depth, int64_t Ng, const int64_t* ray_offsets,
+                 int32_t num_steps, int32_t iteration, float min_dis, const wb_sdf_state* state,
+                 float* xyz, float* depth, uint8_t* hit, float* alpha, wb_stream s);
+
+/* ------------------------------------------------------------------------------------------------
  * Packed compositing -- replaces kaolin.render.spc.{exponential_integration, sum_reduce} + the buffer
  *   scatter of PackedRFTracer.trace (wisp/tracers/packed_rf_tracer.py:136-165).
  *   shaded: float4 [S] = (r, g, b, sigma); offsets int64 [R+1]; depth/deltas [S].
@@ -247,6 +314,10 @@ int wb_rf_shade_bwd(const wb_nef_desc* nef, const float* blob, int32_t precision
                     const void* feat_saved, void* workspace,
                     float* grad_table, float* grad_dens, float* grad_col, wb_stream s);
 
+/* scale = 2^clamp(floor(log2(64 / max(absmax, 1e-30))), -20, 60): the loss scale wb_rf_decoder_bwd / wb_rf_table_scatter expect,
+ * derived on the device from wb_composite_bwd's absmax. */
+int wb_rf_loss_scale(const float* absmax, float* scale, wb_stream s);
+
 /* The two stages of the precision-1 backward, callable separately (wb_rf_shade_bwd runs them back to back):
  * wb_rf_decoder_bwd writes the weight gradients and leaves dL/dfeat (fp16 planes) in the workspace; wb_rf_table_scatter
  * turns those planes into hash-table updates with warp-level merging of samples that share a cell. */
@@ -255,6 +326,18 @@ int wb_rf_decoder_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* 
                       float* grad_dens, float* grad_col, wb_stream s);
 int wb_rf_table_scatter(const wb_nef_desc* nef, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray, int64_t S,
                         const float* loss_scale, void* workspace, float* grad_table, wb_stream s);
+
+/* ------------------------------------------------------------------------------------------------
+ * NeuralRadianceField.prune (wisp/models/nefs/nerf.py:175-212), the elementwise halves around the density probe:
+ *   wb_prune_samples : one probe point per finest-level cell, samples = ((points + u) / 2^level) * 2 - 1 (:189-192) and a unit
+ *                      direction; u = explicit [N,3] draw, or NULL for the counter stream keyed by (seed, cell, axis).  Also writes
+ *                      rec_t = 0 and rec_ray = i so that wb_rf_shade_fwd evaluates the field at the probe points (rays of length 0).
+ *   wb_prune_update  : occupancy = max(sigma, occupancy * decay) (:186,:196); keep = occupancy > min_density (:198);
+ *                      shaded = float4 [N] written by wb_rf_shade_fwd (sigma in .w).
+ * ---------------------------------------------------------------------------------------------- */
+int wb_prune_samples(const int16_t* points, int64_t N, int32_t level, const float* u, uint32_t seed,
+                     float* samples, float* dirs, float* rec_t, int32_t* rec_ray, wb_stream s);
+int wb_prune_update(const float* shaded, int64_t N, float decay, float min_density, float* occupancy, uint8_t* keep, wb_stream s);
 
 /* ------------------------------------------------------------------------------------------------
  * Diagnostics: one-tile tcgen05 GEMM that pins the shared-memory operand layouts of the tensor-core decoder

@@ -32,6 +32,9 @@ class NefDesc(C.Structure):
         ("dens_layers", C.c_int32), ("dens_dims", C.c_int32 * (WB_MAX_LAYERS + 1)),
         ("col_layers", C.c_int32), ("col_dims", C.c_int32 * (WB_MAX_LAYERS + 1)),
         ("dens_params", C.c_void_p), ("col_params", C.c_void_p),
+        ("grid_kind", C.c_int32), ("base_lod", C.c_int32), ("half_round", C.c_int32),
+        ("grid_ptrs", C.POINTER(C.c_void_p)), ("grid_grads", C.POINTER(C.c_void_p)),
+        ("oct", C.c_void_p), ("points", C.c_void_p), ("trinkets", C.c_void_p),
     ]
 
 
@@ -49,15 +52,29 @@ class OctreeDesc(C.Structure):
                 ("coarse_bits", C.c_void_p), ("coarse_level", C.c_int32)]
 
 
+class SdfDesc(C.Structure):
+    """struct wb_sdf_desc."""
+    _fields_ = [("points", C.c_void_p), ("trinkets", C.c_void_p), ("feats", C.POINTER(C.c_void_p)),
+                ("feature_dim", C.c_int32), ("base_lod", C.c_int32), ("num_lods", C.c_int32), ("multiscale", C.c_int32), ("half_round", C.c_int32),
+                ("pos_mode", C.c_int32), ("pos_freq", C.c_int32), ("num_layers", C.c_int32), ("hidden_dim", C.c_int32), ("params", C.c_void_p)]
+
+
+class SdfState(C.Structure):
+    """struct wb_sdf_state."""
+    _fields_ = [("flags", C.c_void_p), ("pack_off", C.c_void_p), ("scan_ws", C.c_void_p), ("scan_ws_bytes", C.c_int64), ("pack_ray", C.c_void_p),
+                ("t", C.c_void_p), ("dist", C.c_void_p), ("dist_prev", C.c_void_p), ("x", C.c_void_p), ("cursor0", C.c_void_p), ("cursor1", C.c_void_p),
+                ("state", C.c_void_p), ("iterflags", C.c_void_p)]
+
+
 EXPORTS = [
     "wb_last_error", "wb_version", "wb_device_check", "wb_launch_count",
     "wb_octree_generate_points", "wb_octree_build_bits", "wb_octree_build_coarse", "wb_query",
     "wb_raymarch_ray_count", "wb_scan_workspace_bytes", "wb_scan_counts", "wb_raymarch_ray_fill",
     "wb_raytrace_count", "wb_raytrace_fill", "wb_raymarch_voxel_fill", "wb_raymarch_uniform_count", "wb_raymarch_uniform_fill",
     "wb_hashgrid_fwd", "wb_hashgrid_bwd", "wb_triplane_fwd", "wb_triplane_bwd",
-    "wb_octree_interp_fwd", "wb_octree_interp_bwd", "wb_find_depth_bound", "wb_composite_fwd", "wb_composite_bwd",
+    "wb_octree_interp_fwd", "wb_octree_interp_bwd", "wb_find_depth_bound", "wb_sdf_eval", "wb_sdf_trace", "wb_sdf_phase", "wb_composite_fwd", "wb_composite_bwd",
     "wb_rf_march_fill", "wb_rf_param_blob_floats", "wb_rf_precision_supported", "wb_rf_pack_params", "wb_rf_shade_fwd", "wb_rf_shade_bwd",
-    "wb_rf_workspace_bytes", "wb_rf_feat_bytes", "wb_rf_decoder_bwd", "wb_rf_table_scatter", "wb_tc_selftest",
+    "wb_rf_workspace_bytes", "wb_rf_feat_bytes", "wb_rf_decoder_bwd", "wb_rf_table_scatter", "wb_rf_loss_scale", "wb_prune_samples", "wb_prune_update", "wb_tc_selftest",
 ]
 
 _lib: Optional[C.CDLL] = None

@@ -130,3 +130,20 @@ extern "C" int wb_composite_bwd(const float* shaded, const float* depth, const f
     WB_LAUNCH_CHECK();
     return WB_OK;
 }
+
+// Power-of-two loss scale of the fp16 decoder backward from max |g_shaded| (wb_composite_bwd's absmax): the largest gradient lands
+// near 64 in fp16.  One thread; replaces five elementwise torch launches of round 1 and still needs no host sync.
+__global__ void wb_loss_scale_kernel(const float* __restrict__ absmax, float* __restrict__ scale)
+{
+    const float amax = fmaxf(*absmax, 1e-30f);
+    float k = floorf(log2f(64.0f / amax));
+    k = fminf(fmaxf(k, -20.0f), 60.0f);
+    *scale = __int_as_float(((int)k + 127) << 23);
+}
+extern "C" int wb_rf_loss_scale(const float* absmax, float* scale, wb_stream s)
+{
+    WB_CHECK_ARG(absmax && scale, "null pointer");
+    wb_loss_scale_kernel<<<1, 1, 0, (cudaStream_t)s>>>(absmax, scale);
+    WB_LAUNCH_CHECK();
+    return WB_OK;
+}

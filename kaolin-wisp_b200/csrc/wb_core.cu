@@ -1,5 +1,6 @@
 // wb_core.cu -- error channel, launch accounting and descriptor validation of libwispb200.
 #include "wb_common.cuh"
+#include "wb_featx.cuh"
 #include <stdarg.h>
 #include <atomic>
 #include <math.h>
@@ -39,12 +40,19 @@ extern "C" int wb_device_check(int device) {
 int wb_make_grid(const wb_nef_desc* d, WbGrid* g) {
     WB_CHECK_ARG(d != nullptr, "null descriptor");
     WB_CHECK_ARG(d->num_lods >= 1 && d->num_lods <= WB_MAX_LODS, "num_lods out of range");
+    WB_CHECK_ARG(d->multiscale == 0 || d->multiscale == 1, "multiscale must be 0 ('cat') or 1 ('sum')");
+    memset(g, 0, sizeof(*g));
+    g->L = d->num_lods; g->F = d->feature_dim; g->multiscale = d->multiscale; g->lod_idx = d->lod_idx;
+    if (d->grid_kind != 0) {                 // triplanar / octree: the features come from wb_featx_gather (WbGridX), not from a table
+        WB_CHECK_ARG(d->grid_kind == 1 || d->grid_kind == 2, "grid_kind must be 0 (hash), 1 (triplanar) or 2 (octree)");
+        WB_CHECK_ARG(d->feature_dim >= 1 && d->feature_dim <= 64, "feature width out of range");
+        g->lod_idx = d->num_lods;
+        return WB_OK;
+    }
     WB_CHECK_ARG(d->feature_dim >= 1 && d->feature_dim <= 8, "feature_dim must be in [1,8]");
     WB_CHECK_ARG(d->codebook_size > 0 && (d->codebook_size & (d->codebook_size - 1)) == 0, "codebook_size must be a power of two");
     WB_CHECK_ARG(d->table != nullptr, "null table");
-    WB_CHECK_ARG(d->multiscale == 0 || d->multiscale == 1, "multiscale must be 0 ('cat') or 1 ('sum')");
-    g->table = d->table; g->L = d->num_lods; g->F = d->feature_dim; g->Tmask = (uint32_t)d->codebook_size - 1u;
-    g->multiscale = d->multiscale; g->lod_idx = d->lod_idx;
+    g->table = d->table; g->Tmask = (uint32_t)d->codebook_size - 1u;
     const int64_t T = d->codebook_size;
     for (int l = 0; l < d->num_lods; ++l) {
         int res = d->resolutions[l];
@@ -56,6 +64,34 @@ int wb_make_grid(const wb_nef_desc* d, WbGrid* g) {
         g->begin[l] = d->begin_idxes[l];
     }
     g->begin[d->num_lods] = d->begin_idxes[d->num_lods];
+    return WB_OK;
+}
+
+int wb_make_gridx(const wb_nef_desc* d, bool backward, WbGridX* x) {
+    WB_CHECK_ARG(d != nullptr, "null descriptor");
+    memset(x, 0, sizeof(*x));
+    x->kind = d->grid_kind;
+    if (d->grid_kind == 0) return WB_OK;
+    WB_CHECK_ARG(d->grid_kind == 1 || d->grid_kind == 2, "grid_kind must be 0 (hash), 1 (triplanar) or 2 (octree)");
+    WB_CHECK_ARG(d->num_lods >= 1 && d->num_lods <= WB_X_MAX_LODS, "triplanar / octree grids: at most 12 LODs on the fused path");
+    WB_CHECK_ARG(d->grid_ptrs != nullptr && (!backward || d->grid_grads != nullptr), "null grid_ptrs / grid_grads");
+    x->nl = d->num_lods; x->sum = d->multiscale;
+    const int np = d->grid_kind == 1 ? 3 * d->num_lods : d->num_lods;
+    for (int i = 0; i < np; ++i) {
+        WB_CHECK_ARG(d->grid_ptrs[i] != nullptr && (!backward || d->grid_grads[i] != nullptr), "null grid tensor");
+        x->ptr[i] = d->grid_ptrs[i]; x->gptr[i] = backward ? d->grid_grads[i] : nullptr;
+    }
+    if (d->grid_kind == 1) {
+        WB_CHECK_ARG(d->feature_dim % 3 == 0 && d->feature_dim / 3 <= WB_X_MAX_C, "triplanar: feature_dim = 3 * fdim, fdim <= 8");
+        x->C = d->feature_dim / 3;
+        for (int l = 0; l < d->num_lods; ++l) { WB_CHECK_ARG(d->resolutions[l] >= 1, "plane resolution must be >= 1"); x->res[l] = d->resolutions[l]; }
+    } else {
+        WB_CHECK_ARG(d->feature_dim <= WB_X_MAX_F, "octree: feature_dim <= 32 on the fused path");
+        WB_CHECK_ARG(d->oct && d->oct->octree && d->oct->prefix && d->points && d->trinkets, "octree grid: null octree / points / trinkets");
+        WB_CHECK_ARG(d->base_lod >= 0 && d->base_lod + d->num_lods - 1 <= d->oct->max_level && d->base_lod + d->num_lods - 1 <= 15, "octree grid: LOD range outside the octree");
+        x->C = d->feature_dim; x->octree = d->oct->octree; x->prefix = d->oct->prefix; x->points = d->points; x->trinkets = d->trinkets;
+        x->base_lod = d->base_lod; x->half_round = d->half_round;
+    }
     return WB_OK;
 }
 

@@ -177,7 +177,7 @@ template <int FT, int PT>
 __device__ __forceinline__ float sdf_eval(const WbOct& oc, const WbSdf& m, const float* __restrict__ sw, int nl, float x, float y, float z)
 {
     const int H = m.H;
-    if (FT > 0 && PT == 1 && m.nh == 1) {
+    if constexpr (FT > 0 && PT == 1) {                    // dispatch guarantees nh == 1, 'sum', identity position input
         constexpr int IN = 3 + (FT > 0 ? FT : 1), INP = (IN + 3) & ~3;
         float in[INP];
         in[0] = x; in[1] = y; in[2] = z;
@@ -197,7 +197,7 @@ __device__ __forceinline__ float sdf_eval(const WbOct& oc, const WbSdf& m, const
             out = fmaf(wo[j], fmaxf(a, 0.0f), out);
         }
         return out;
-    }
+    } else {
     float in[WB_SDF_MAX_IN];
     const int pd = sdf_embed(m.pos_mode, m.pos_freq, x, y, z, in);
     sdf_features<0>(oc, m, nl, x, y, z, in + pd);
@@ -225,6 +225,7 @@ __device__ __forceinline__ float sdf_eval(const WbOct& oc, const WbSdf& m, const
     float out = p[H];
     for (int j = 0; j < H; ++j) out = fmaf(p[j], cur[j], out);
     return out;
+    }
 }
 
 template <int FT, int PT>
@@ -243,8 +244,7 @@ wb_sdf_eval_kernel(WbOct oc, WbSdf m, int nl, const float* __restrict__ coords, 
 struct WbSdfTrace {
     const float* origins; const float* dirs; int64_t R; float dist_max;
     const float2* nug_depth; int64_t Ng; const int64_t* ray_offsets;     // raw raytrace depths (entry, exit); nuggets of ray r: [off[r], off[r+1])
-    const int64_t* pack_off;                                               // [R+1] exclusive scan of (ray has nuggets)
-    int32_t* pack_ray; float* t; float* dist; float* dist_prev; float* x; int32_t* cursor[2]; uint8_t* state; int32_t* iterflags;
+    wb_sdf_state S;                                                        // per-pack state, owned by the caller
     int num_steps, nl, want_normals; float step_size, min_dis, min_dis5;
     float* o_xyz; float* o_depth; uint8_t* o_hit; float* o_normal; float* o_rgb; float* o_alpha;
 };
@@ -256,6 +256,86 @@ __global__ void wb_sdf_flag_kernel(const int64_t* __restrict__ ray_offsets, int6
     if (r < R) flags[r] = ray_offsets[r + 1] > ray_offsets[r] ? 1 : 0;
 }
 
+__device__ __forceinline__ void sdf_point(const WbSdfTrace& T, int64_t r, float t, float& x, float& y, float& z)
+{
+    x = wb_addcmul(__ldg(T.origins + 3 * r), __ldg(T.dirs + 3 * r), t);                 // torch.addcmul(nug_o, nug_d, t) (:104,:122,:140)
+    y = wb_addcmul(__ldg(T.origins + 3 * r + 1), __ldg(T.dirs + 3 * r + 1), t);
+    z = wb_addcmul(__ldg(T.origins + 3 * r + 2), __ldg(T.dirs + 3 * r + 2), t);
+}
+// packs = rays with at least one nugget, in ray order (mark_pack_boundaries + nonzero, :93-94)
+__device__ __forceinline__ void sdf_pack_list(const WbSdfTrace& T, int64_t tid, int64_t nthr)
+{
+    for (int64_t r = tid; r < T.R; r += nthr)
+        if (T.S.pack_off[r + 1] > T.S.pack_off[r]) T.S.pack_ray[T.S.pack_off[r]] = (int32_t)r;
+}
+// initial state of pack p (:96-113) except its first distance; returns the start point
+__device__ __forceinline__ void sdf_init_pack(const WbSdfTrace& T, int64_t p, float& x, float& y, float& z)
+{
+    const int64_t r = T.S.pack_ray[p];
+    const int32_t first = (int32_t)T.ray_offsets[r];
+    const float t = __fadd_rn(__ldg(&T.nug_depth[first]).x, 1e-5f);                     // depth[..., 0:1] += 1e-5 (:91)
+    sdf_point(T, r, t, x, y, z);
+    T.S.t[p] = t; T.S.x[3 * p] = x; T.S.x[3 * p + 1] = y; T.S.x[3 * p + 2] = z;
+    T.S.cursor0[p] = first; T.S.state[p] = SDF_ALIVE;
+}
+// step 1: march by the SDF (:120-131); returns whether the pack is still alive
+__device__ __forceinline__ bool sdf_march_pack(const WbSdfTrace& T, int64_t p)
+{
+    uint8_t st = T.S.state[p];
+    const float d = T.S.dist[p];
+    const float t = __fadd_rn(T.S.t[p], d);                                             // unmasked in the reference: dead packs drift too
+    T.S.t[p] = t;
+    if (!(st & SDF_ALIVE)) return false;
+    float x, y, z; sdf_point(T, T.S.pack_ray[p], t, x, y, z);
+    T.S.x[3 * p] = x; T.S.x[3 * p + 1] = y; T.S.x[3 * p + 2] = z;
+    const bool h = (fabsf(d) < T.min_dis) || (__fmul_rn(fabsf(__fadd_rn(d, T.S.dist_prev[p])), 0.5f) < T.min_dis5);
+    st = h ? (uint8_t)(st | SDF_HIT) : (uint8_t)(st & ~SDF_HIT);
+    if (!(t < T.dist_max) || h) st &= (uint8_t)~SDF_ALIVE;
+    if (st & SDF_ALIVE) T.S.dist_prev[p] = d;
+    T.S.state[p] = st;
+    return (st & SDF_ALIVE) != 0;
+}
+// step 2: jump to the next occupied cell (:133-141); returns whether the pack is still alive (then x holds its new point)
+__device__ __forceinline__ bool sdf_jump_pack(const WbSdfTrace& T, int64_t p, int64_t P, const int32_t* __restrict__ cin, int32_t* __restrict__ cout,
+                                              float& x, float& y, float& z)
+{
+    uint8_t st = T.S.state[p];
+    const int32_t cur = cin[p];
+    float t = T.S.t[p];
+    int32_t nxt = -1;
+    if (cur > -1) {                                                                     // find_depth_bound, for every pack (cu:24-43)
+        uint32_t i = (uint32_t)cur;
+        const uint32_t mx = (p == P - 1) ? (uint32_t)P : (uint32_t)cin[p + 1];         // reference quirks kept (cu:28-29)
+        while (i < mx && (int64_t)i < T.Ng) {
+            const float2 dd = __ldg(&T.nug_depth[i]);
+            const float en = __fadd_rn(dd.x, 1e-5f);
+            if ((t >= en && t <= dd.y) || t < en) { nxt = (int32_t)i; break; }
+            ++i;
+        }
+    }
+    bool alive = false;
+    int32_t ncur = cur;
+    if (st & SDF_ALIVE) {
+        if (nxt == -1) st &= (uint8_t)~SDF_ALIVE;
+        else {
+            if (nxt != cur) { t = __fadd_rn(__ldg(&T.nug_depth[nxt]).x, 1e-5f); T.S.t[p] = t; }
+            ncur = nxt;
+            sdf_point(T, T.S.pack_ray[p], t, x, y, z);
+            T.S.x[3 * p] = x; T.S.x[3 * p + 1] = y; T.S.x[3 * p + 2] = z;
+            alive = true;
+        }
+        T.S.state[p] = st;
+    }
+    cout[p] = ncur;
+    return alive;
+}
+// outputs (:149-174) of a pack that hit, normals excluded
+__device__ __forceinline__ void sdf_write_hit(const WbSdfTrace& T, int64_t p, int64_t r)
+{
+    T.o_xyz[3 * r] = T.S.x[3 * p]; T.o_xyz[3 * r + 1] = T.S.x[3 * p + 1]; T.o_xyz[3 * r + 2] = T.S.x[3 * p + 2];
+    T.o_depth[r] = T.S.t[p]; T.o_hit[r] = 1; T.o_alpha[r] = 1.0f;
+}
+
 template <int FT, int PT>
 __global__ void __launch_bounds__(WB_SDF_THREADS)
 wb_sdf_trace_kernel(WbOct oc, WbSdf m, WbSdfTrace T)
@@ -264,124 +344,96 @@ wb_sdf_trace_kernel(WbOct oc, WbSdf m, WbSdfTrace T)
     cg::grid_group grid = cg::this_grid();
     sdf_stage(m, sw);
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
-    const int64_t P = T.pack_off[T.R];
-    // packs = rays with at least one nugget, in ray order (mark_pack_boundaries + nonzero, :93-94)
-    for (int64_t r = tid; r < T.R; r += nthr)
-        if (T.pack_off[r + 1] > T.pack_off[r]) T.pack_ray[T.pack_off[r]] = (int32_t)r;
+    const int64_t P = T.S.pack_off[T.R];
+    sdf_pack_list(T, tid, nthr);
     grid.sync();
-    // initial state (:96-113)
+    int evals = 0;                                    // field evaluations of this thread (bench.py: algorithmic bytes of the launch)
     for (int64_t p = tid; p < P; p += nthr) {
-        const int64_t r = T.pack_ray[p];
-        const int32_t first = (int32_t)T.ray_offsets[r];
-        const float t = __fadd_rn(__ldg(&T.nug_depth[first]).x, 1e-5f);                 // depth[..., 0:1] += 1e-5 (:91)
-        const float ox = __ldg(T.origins + 3 * r), oy = __ldg(T.origins + 3 * r + 1), oz = __ldg(T.origins + 3 * r + 2);
-        const float dx = __ldg(T.dirs + 3 * r), dy = __ldg(T.dirs + 3 * r + 1), dz = __ldg(T.dirs + 3 * r + 2);
-        const float x = wb_addcmul(ox, dx, t), y = wb_addcmul(oy, dy, t), z = wb_addcmul(oz, dz, t);
-        const float d = __fmul_rn(__fmul_rn(sdf_eval<FT, PT>(oc, m, sw, T.nl, x, y, z), 1.0f), T.step_size);
-        T.t[p] = t; T.dist[p] = d; T.dist_prev[p] = d; T.x[3 * p] = x; T.x[3 * p + 1] = y; T.x[3 * p + 2] = z;
-        T.cursor[0][p] = first; T.state[p] = SDF_ALIVE;
+        ++evals;
+        float x, y, z; sdf_init_pack(T, p, x, y, z);
+        const float d = __fmul_rn(__fmul_rn(sdf_eval<FT, PT>(oc, m, sw, T.nl, x, y, z), 1.0f), T.step_size);   // sdf * invres * step_size (:109)
+        T.S.dist[p] = d; T.S.dist_prev[p] = d;
     }
     grid.sync();
     int cb = 0;
     for (int it = 0; it < T.num_steps; ++it) {
-        // ---- step 1: march by the SDF (:120-131) ----
         int any = 0;
-        for (int64_t p = tid; p < P; p += nthr) {
-            uint8_t st = T.state[p];
-            const float d = T.dist[p];
-            const float t = __fadd_rn(T.t[p], d);                                       // unmasked in the reference: dead packs drift too
-            T.t[p] = t;
-            if (st & SDF_ALIVE) {
-                const int64_t r = T.pack_ray[p];
-                T.x[3 * p] = wb_addcmul(__ldg(T.origins + 3 * r), __ldg(T.dirs + 3 * r), t);
-                T.x[3 * p + 1] = wb_addcmul(__ldg(T.origins + 3 * r + 1), __ldg(T.dirs + 3 * r + 1), t);
-                T.x[3 * p + 2] = wb_addcmul(__ldg(T.origins + 3 * r + 2), __ldg(T.dirs + 3 * r + 2), t);
-                const bool h = (fabsf(d) < T.min_dis) || (__fmul_rn(fabsf(__fadd_rn(d, T.dist_prev[p])), 0.5f) < T.min_dis5);
-                st = h ? (uint8_t)(st | SDF_HIT) : (uint8_t)(st & ~SDF_HIT);
-                if (!(t < T.dist_max) || h) st &= (uint8_t)~SDF_ALIVE;
-                if (st & SDF_ALIVE) { T.dist_prev[p] = d; any = 1; }
-                T.state[p] = st;
-            }
-        }
-        if (__syncthreads_or(any) && threadIdx.x == 0) atomicOr(T.iterflags + 2 * it, 1);
+        for (int64_t p = tid; p < P; p += nthr) any |= sdf_march_pack(T, p) ? 1 : 0;
+        if (__syncthreads_or(any) && threadIdx.x == 0) atomicOr(T.S.iterflags + 2 * it, 1);
         grid.sync();
-        if (__ldcg(T.iterflags + 2 * it) == 0) break;
-        // ---- step 2: jump to the next occupied cell (:133-147) ----
+        if (__ldcg(T.S.iterflags + 2 * it) == 0) break;                                 // `if not mask.any(): break` (:129)
         any = 0;
-        const int32_t* cin = T.cursor[cb]; int32_t* cout = T.cursor[cb ^ 1];
+        const int32_t* cin = cb ? T.S.cursor1 : T.S.cursor0; int32_t* cout = cb ? T.S.cursor0 : T.S.cursor1;
         for (int64_t p = tid; p < P; p += nthr) {
-            uint8_t st = T.state[p];
-            const int32_t cur = cin[p];
-            float t = T.t[p];
-            int32_t nxt = -1;
-            if (cur > -1) {                                                             // find_depth_bound, for every pack (cu:24-43)
-                uint32_t i = (uint32_t)cur;
-                const uint32_t mx = (p == P - 1) ? (uint32_t)P : (uint32_t)cin[p + 1];
-                while (i < mx && (int64_t)i < T.Ng) {
-                    const float2 dd = __ldg(&T.nug_depth[i]);
-                    const float en = __fadd_rn(dd.x, 1e-5f);
-                    if ((t >= en && t <= dd.y) || t < en) { nxt = (int32_t)i; break; }
-                    ++i;
-                }
+            float x, y, z;
+            if (sdf_jump_pack(T, p, P, cin, cout, x, y, z)) {
+                ++evals;
+                T.S.dist[p] = __fmul_rn(__fmul_rn(sdf_eval<FT, PT>(oc, m, sw, T.nl, x, y, z), 1.0f), T.step_size);   // (:145-146)
+                any = 1;
             }
-            int32_t ncur = cur;
-            if (st & SDF_ALIVE) {
-                if (nxt == -1) st &= (uint8_t)~SDF_ALIVE;
-                else {
-                    if (nxt != cur) { t = __fadd_rn(__ldg(&T.nug_depth[nxt]).x, 1e-5f); T.t[p] = t; }
-                    ncur = nxt;
-                    const int64_t r = T.pack_ray[p];
-                    const float x = wb_addcmul(__ldg(T.origins + 3 * r), __ldg(T.dirs + 3 * r), t);
-                    const float y = wb_addcmul(__ldg(T.origins + 3 * r + 1), __ldg(T.dirs + 3 * r + 1), t);
-                    const float z = wb_addcmul(__ldg(T.origins + 3 * r + 2), __ldg(T.dirs + 3 * r + 2), t);
-                    T.x[3 * p] = x; T.x[3 * p + 1] = y; T.x[3 * p + 2] = z;
-                    T.dist[p] = __fmul_rn(__fmul_rn(sdf_eval<FT, PT>(oc, m, sw, T.nl, x, y, z), 1.0f), T.step_size);
-                    any = 1;
-                }
-                T.state[p] = st;
-            }
-            cout[p] = ncur;
         }
         cb ^= 1;
-        if (__syncthreads_or(any) && threadIdx.x == 0) atomicOr(T.iterflags + 2 * it + 1, 1);
+        if (__syncthreads_or(any) && threadIdx.x == 0) atomicOr(T.S.iterflags + 2 * it + 1, 1);
         grid.sync();
-        if (__ldcg(T.iterflags + 2 * it + 1) == 0) break;
+        if (__ldcg(T.S.iterflags + 2 * it + 1) == 0) break;                             // (:143)
     }
-    // ---- outputs (:149-174): hit packs only; the buffers were initialised by the caller ----
     for (int64_t p = tid; p < P; p += nthr) {
-        if (!(T.state[p] & SDF_HIT)) continue;
-        const int64_t r = T.pack_ray[p];
-        const float x = T.x[3 * p], y = T.x[3 * p + 1], z = T.x[3 * p + 2];
-        T.o_xyz[3 * r] = x; T.o_xyz[3 * r + 1] = y; T.o_xyz[3 * r + 2] = z;
-        T.o_depth[r] = T.t[p]; T.o_hit[r] = 1; T.o_alpha[r] = 1.0f;
+        if (!(T.S.state[p] & SDF_HIT)) continue;
+        const int64_t r = T.S.pack_ray[p];
+        sdf_write_hit(T, p, r);
         if (T.want_normals) {
+            evals += 6;
+            const float x = T.S.x[3 * p], y = T.S.x[3 * p + 1], z = T.S.x[3 * p + 2];
             const float eps = 0.005f, den = (float)(0.005 * 2.0);
             const int nlf = m.num_lods;                                                // lod_idx = None -> finest LOD (gradients.py / neural_sdf.py:136-137)
-            float gx = sdf_eval<FT, PT>(oc, m, sw, nlf, x + eps, y, z) - sdf_eval<FT, PT>(oc, m, sw, nlf, x - eps, y, z);
-            float gy = sdf_eval<FT, PT>(oc, m, sw, nlf, x, y + eps, z) - sdf_eval<FT, PT>(oc, m, sw, nlf, x, y - eps, z);
-            float gz = sdf_eval<FT, PT>(oc, m, sw, nlf, x, y, z + eps) - sdf_eval<FT, PT>(oc, m, sw, nlf, x, y, z - eps);
-            gx = __fdiv_rn(gx, den); gy = __fdiv_rn(gy, den); gz = __fdiv_rn(gz, den);
+            float g3[3];
+#pragma unroll 1
+            for (int a = 0; a < 3; ++a) {                                               // f(x + eps e_a) - f(x - eps e_a)
+                const float ex = a == 0 ? eps : 0.0f, ey = a == 1 ? eps : 0.0f, ez = a == 2 ? eps : 0.0f;
+                float fp = 0.0f, fm = 0.0f;
+#pragma unroll 1
+                for (int sgn = 0; sgn < 2; ++sgn) {
+                    const float v = sgn == 0 ? sdf_eval<FT, PT>(oc, m, sw, nlf, x + ex, y + ey, z + ez)
+                                             : sdf_eval<FT, PT>(oc, m, sw, nlf, x - ex, y - ey, z - ez);
+                    if (sgn == 0) fp = v; else fm = v;
+                }
+                g3[a] = fp - fm;
+            }
+            float gx = __fdiv_rn(g3[0], den), gy = __fdiv_rn(g3[1], den), gz = __fdiv_rn(g3[2], den);
             const float nrm = fmaxf(sqrtf(gx * gx + gy * gy + gz * gz), 1e-5f);         // F.normalize(p=2, eps=1e-5)
             gx = __fdiv_rn(gx, nrm); gy = __fdiv_rn(gy, nrm); gz = __fdiv_rn(gz, nrm);
             T.o_normal[3 * r] = gx; T.o_normal[3 * r + 1] = gy; T.o_normal[3 * r + 2] = gz;
             T.o_rgb[3 * r] = (gx + 1.0f) / 2.0f; T.o_rgb[3 * r + 1] = (gy + 1.0f) / 2.0f; T.o_rgb[3 * r + 2] = (gz + 1.0f) / 2.0f;
         }
     }
+    evals = __reduce_add_sync(0xffffffffu, evals);
+    if ((threadIdx.x & 31) == 0 && evals) atomicAdd(T.S.iterflags + 2 * T.num_steps + 2, evals);
+}
+
+// The same state machine one phase per launch, for neural fields whose SDF is evaluated outside this library (NeuralSDF over a
+// hash or triplanar grid): the caller evaluates the field at S.x of the alive packs between the phases.
+//   phase 0: pack list   1: initial state   2: step 1 (march)   3: step 2 (jump)   4: outputs of the packs that hit
+__global__ void __launch_bounds__(WB_SDF_THREADS)
+wb_sdf_phase_kernel(WbSdfTrace T, int phase, int it, int cb)
+{
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+    const int64_t P = T.S.pack_off[T.R];
+    if (phase == 0) { sdf_pack_list(T, tid, nthr); return; }
+    int any = 0;
+    for (int64_t p = tid; p < P; p += nthr) {
+        float x, y, z;
+        if (phase == 1) sdf_init_pack(T, p, x, y, z);
+        else if (phase == 2) any |= sdf_march_pack(T, p) ? 1 : 0;
+        else if (phase == 3) any |= sdf_jump_pack(T, p, P, cb ? T.S.cursor1 : T.S.cursor0, cb ? T.S.cursor0 : T.S.cursor1, x, y, z) ? 1 : 0;
+        else if (T.S.state[p] & SDF_HIT) sdf_write_hit(T, p, T.S.pack_ray[p]);
+    }
+    if (phase == 2 || phase == 3)
+        if (__syncthreads_or(any) && threadIdx.x == 0) atomicOr(T.S.iterflags + 2 * it + (phase == 3 ? 1 : 0), 1);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
-static int64_t sdf_al(int64_t b) { return (b + 255) / 256 * 256; }
-
-extern "C" int64_t wb_sdf_workspace_bytes(int64_t R, int32_t num_steps)
-{
-    if (R < 0 || num_steps < 0) return -1;
-    const int64_t scan = wb_scan_workspace_bytes(R);
-    return sdf_al(4 * R) + sdf_al(8 * (R + 1)) + sdf_al(scan) + sdf_al(4 * R) + 3 * sdf_al(4 * R) + sdf_al(12 * R) + 2 * sdf_al(4 * R) + sdf_al(R)
-         + sdf_al(4 * (2 * (int64_t)num_steps + 4)) + 256;
-}
-
 static bool sdf_fast_shape(const WbSdf& m) { return m.multiscale == 1 && m.F == 16 && m.pos_mode == 1 && m.nh == 1; }
 
 extern "C" int wb_sdf_eval(const wb_octree* oct, const wb_sdf_desc* nef, int32_t lod_idx, const float* coords, int64_t N, float* out, wb_stream s)
@@ -401,58 +453,77 @@ extern "C" int wb_sdf_eval(const wb_octree* oct, const wb_sdf_desc* nef, int32_t
     return WB_OK;
 }
 
+static int sdf_make_trace(const wb_rays* rays, const float* nug_depth, int64_t Ng, const int64_t* ray_offsets, int32_t num_steps, float step_size,
+                          float min_dis, const wb_sdf_state* st, WbSdfTrace* T)
+{
+    WB_CHECK_ARG(rays != nullptr && rays->origins && rays->dirs && nug_depth && ray_offsets, "null pointer");
+    WB_CHECK_ARG(rays->near_v == nullptr, "the SDF tracer compares t with a scalar dist_max (packed_sdf_tracer.py:127)");
+    WB_CHECK_ARG(st && st->flags && st->pack_off && st->scan_ws && st->pack_ray && st->t && st->dist && st->dist_prev && st->x && st->cursor0 && st->cursor1 &&
+                 st->state && st->iterflags, "null pointer in wb_sdf_state");
+    WB_CHECK_ARG(num_steps >= 0 && num_steps <= 4096, "num_steps out of range");
+    WB_CHECK_ARG(st->scan_ws_bytes >= wb_scan_workspace_bytes(rays->num_rays), "scan workspace too small (wb_scan_workspace_bytes)");
+    memset(T, 0, sizeof(*T));
+    T->origins = rays->origins; T->dirs = rays->dirs; T->R = rays->num_rays; T->dist_max = rays->dist_max;
+    T->nug_depth = reinterpret_cast<const float2*>(nug_depth); T->Ng = Ng; T->ray_offsets = ray_offsets; T->S = *st;
+    T->num_steps = num_steps; T->step_size = step_size;
+    T->min_dis = (float)((double)min_dis * 1.0); T->min_dis5 = (float)(((double)min_dis * 5.0) * 1.0);     // min_dis * invres, (min_dis*5) * invres (:123-126)
+    return WB_OK;
+}
+// rays with nuggets -> exclusive scan (pack_off); iteration flags cleared
+static int sdf_scan_packs(const WbSdfTrace& T, int32_t num_steps, cudaStream_t st)
+{
+    WB_CUDA(cudaMemsetAsync(T.S.iterflags, 0, 4 * (2 * (size_t)num_steps + 4), st));
+    wb_sdf_flag_kernel<<<(unsigned)((T.R + 255) / 256), 256, 0, st>>>(T.ray_offsets, T.R, T.S.flags);
+    WB_LAUNCH_CHECK();
+    return wb_scan_counts(T.S.flags, T.R, T.S.pack_off, T.S.scan_ws, T.S.scan_ws_bytes, (wb_stream)st);
+}
+
 extern "C" int wb_sdf_trace(const wb_octree* oct, const wb_sdf_desc* nef, int32_t lod_idx, const wb_rays* rays,
                             const float* nug_depth, int64_t Ng, const int64_t* ray_offsets,
-                            int32_t num_steps, float step_size, float min_dis, int32_t want_normals,
-                            void* workspace, int64_t workspace_bytes,
+                            int32_t num_steps, float step_size, float min_dis, int32_t want_normals, const wb_sdf_state* state,
                             float* xyz, float* depth, uint8_t* hit, float* normal, float* rgb, float* alpha, wb_stream s)
 {
     WB_CHECK_ARG(rays != nullptr, "null rays");
-    const int64_t R = rays->num_rays;
-    if (R == 0 || Ng == 0) return WB_OK;
+    if (rays->num_rays == 0 || Ng == 0) return WB_OK;
     WbSdf m; int rc = wb_make_sdf(nef, &m); if (rc) return rc;
     WB_CHECK_ARG(lod_idx >= 0 && lod_idx < m.num_lods, "lod_idx out of range");
     WB_CHECK_ARG(m.multiscale == 1 || lod_idx == m.num_lods - 1, "'cat' grids feed the decoder all LODs: lod_idx must be num_lods-1");
     WbOct oc; rc = wb_make_oct(oct, m.base_lod + m.num_lods - 1, &oc); if (rc) return rc;
-    WB_CHECK_ARG(rays->origins && rays->dirs && nug_depth && ray_offsets && workspace, "null pointer");
-    WB_CHECK_ARG(rays->near_v == nullptr, "the SDF tracer compares t with a scalar dist_max (packed_sdf_tracer.py:127)");
+    WbSdfTrace T; rc = sdf_make_trace(rays, nug_depth, Ng, ray_offsets, num_steps, step_size, min_dis, state, &T); if (rc) return rc;
     WB_CHECK_ARG(xyz && depth && hit && alpha && (!want_normals || (normal && rgb)), "null output");
-    WB_CHECK_ARG(num_steps >= 0 && num_steps <= 4096, "num_steps out of range");
-    WB_CHECK_ARG(workspace_bytes >= wb_sdf_workspace_bytes(R, num_steps), "workspace too small (wb_sdf_workspace_bytes)");
-    cudaStream_t st = (cudaStream_t)s;
-    uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
-    auto take = [&](int64_t bytes) { uint8_t* p = w; w += sdf_al(bytes); return p; };
-    int32_t* flags = reinterpret_cast<int32_t*>(take(4 * R));
-    int64_t* pack_off = reinterpret_cast<int64_t*>(take(8 * (R + 1)));
-    const int64_t scan_b = wb_scan_workspace_bytes(R);
-    void* scan_ws = take(scan_b);
-    WbSdfTrace T;
-    T.origins = rays->origins; T.dirs = rays->dirs; T.R = R; T.dist_max = rays->dist_max;
-    T.nug_depth = reinterpret_cast<const float2*>(nug_depth); T.Ng = Ng; T.ray_offsets = ray_offsets; T.pack_off = pack_off;
-    T.pack_ray = reinterpret_cast<int32_t*>(take(4 * R));
-    T.t = reinterpret_cast<float*>(take(4 * R)); T.dist = reinterpret_cast<float*>(take(4 * R)); T.dist_prev = reinterpret_cast<float*>(take(4 * R));
-    T.x = reinterpret_cast<float*>(take(12 * R));
-    T.cursor[0] = reinterpret_cast<int32_t*>(take(4 * R)); T.cursor[1] = reinterpret_cast<int32_t*>(take(4 * R));
-    T.state = take(R);
-    T.iterflags = reinterpret_cast<int32_t*>(take(4 * (2 * (int64_t)num_steps + 4)));
-    T.num_steps = num_steps; T.nl = lod_idx + 1; T.want_normals = want_normals ? 1 : 0;
-    T.step_size = step_size; T.min_dis = (float)((double)min_dis * 1.0); T.min_dis5 = (float)(((double)min_dis * 5.0) * 1.0);
+    T.nl = lod_idx + 1; T.want_normals = want_normals ? 1 : 0;
     T.o_xyz = xyz; T.o_depth = depth; T.o_hit = hit; T.o_normal = normal; T.o_rgb = rgb; T.o_alpha = alpha;
-    WB_CUDA(cudaMemsetAsync(T.iterflags, 0, 4 * (2 * (size_t)num_steps + 4), st));
-    wb_sdf_flag_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(ray_offsets, R, flags);
-    WB_LAUNCH_CHECK();
-    rc = wb_scan_counts(flags, R, pack_off, scan_ws, scan_b, s); if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)s;
+    rc = sdf_scan_packs(T, num_steps, st); if (rc) return rc;
     const int smem = m.smem_floats * 4;
-    const bool fast = sdf_fast_shape(m);
-    const void* kern = fast ? (const void*)wb_sdf_trace_kernel<16, 1> : (const void*)wb_sdf_trace_kernel<0, 0>;
+    const void* kern = sdf_fast_shape(m) ? (const void*)wb_sdf_trace_kernel<16, 1> : (const void*)wb_sdf_trace_kernel<0, 0>;
     if (smem > 48 * 1024) WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int per_sm = 0;
     WB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WB_SDF_THREADS, smem));
     WB_CHECK_ARG(per_sm >= 1, "sphere-trace kernel does not fit on an SM");
     int64_t ctas = (int64_t)wb_num_sms() * per_sm;                       // cooperative launch: every CTA resident
-    const int64_t need = (R + WB_SDF_THREADS - 1) / WB_SDF_THREADS; if (ctas > need) ctas = need;
+    const int64_t need = (T.R + WB_SDF_THREADS - 1) / WB_SDF_THREADS; if (ctas > need) ctas = need;
     void* args[] = { &oc, &m, &T };
     WB_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)ctas), dim3(WB_SDF_THREADS), args, (size_t)smem, st));
     wb_count_launch();
+    return WB_OK;
+}
+
+extern "C" int wb_sdf_phase(int32_t phase, const wb_rays* rays, const float* nug_depth, int64_t Ng, const int64_t* ray_offsets,
+                            int32_t num_steps, int32_t iteration, float min_dis, const wb_sdf_state* state,
+                            float* xyz, float* depth, uint8_t* hit, float* alpha, wb_stream s)
+{
+    WB_CHECK_ARG(rays != nullptr, "null rays");
+    WB_CHECK_ARG(phase >= 0 && phase <= 4 && iteration >= 0 && iteration < (num_steps > 0 ? num_steps : 1), "bad phase / iteration");
+    if (rays->num_rays == 0 || Ng == 0) return WB_OK;
+    WbSdfTrace T; int rc = sdf_make_trace(rays, nug_depth, Ng, ray_offsets, num_steps, 1.0f, min_dis, state, &T); if (rc) return rc;
+    WB_CHECK_ARG(phase != 4 || (xyz && depth && hit && alpha), "null output");
+    T.o_xyz = xyz; T.o_depth = depth; T.o_hit = hit; T.o_alpha = alpha;
+    cudaStream_t st = (cudaStream_t)s;
+    if (phase == 0) { rc = sdf_scan_packs(T, num_steps, st); if (rc) return rc; }
+    int64_t ctas = (T.R + WB_SDF_THREADS - 1) / WB_SDF_THREADS; const int64_t cap = (int64_t)wb_num_sms() * 8; if (ctas > cap) ctas = cap;
+    // cursors alternate between the two buffers once per executed jump phase: iteration `it` reads buffer it & 1
+    wb_sdf_phase_kernel<<<(unsigned)ctas, WB_SDF_THREADS, 0, st>>>(T, phase, iteration, iteration & 1);
+    WB_LAUNCH_CHECK();
     return WB_OK;
 }

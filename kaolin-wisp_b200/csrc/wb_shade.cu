@@ -15,6 +15,7 @@
 // register tiles), bias-grad and data-grad, and finally scatters dL/dfeat to the hash table with vector
 // reductions (red.global.add.v2.f32).  No S-sized activation tensor ever exists in HBM.
 #include "wb_common.cuh"
+#include "wb_featx.cuh"
 #include <math.h>
 
 #define WB_ML 16          // max linear layers over both decoders
@@ -294,7 +295,7 @@ struct WbShadeIn {
 };
 
 // forward of one sample through both decoders; activations at act (already offset by tid).  Returns sigma, rgb.
-__device__ __forceinline__ void wb_sample_forward(const WbGrid& g, const WbMlp& m, const float* __restrict__ W,
+__device__ __forceinline__ void wb_sample_forward(const WbGrid& g, const WbGridX& gx, const WbMlp& m, const float* __restrict__ W,
                                                   const WbShadeIn& in, int64_t s, float* act, int NTP,
                                                   float& sigma, float& r, float& gg, float& b)
 {
@@ -304,7 +305,8 @@ __device__ __forceinline__ void wb_sample_forward(const WbGrid& g, const WbMlp& 
     const float dx = __ldg(in.dirs + 3 * (int64_t)ray), dy = __ldg(in.dirs + 3 * (int64_t)ray + 1), dz = __ldg(in.dirs + 3 * (int64_t)ray + 2);
     const float px = wb_addcmul(ox, dx, t), py = wb_addcmul(oy, dy, t), pz = wb_addcmul(oz, dz, t);
     float* x0 = act + m.act_in[0] * NTP;
-    wb_gather(g, px, py, pz, x0, NTP);
+    if (gx.kind == 0) wb_gather(g, px, py, pz, x0, NTP);
+    else wb_featx_gather(gx, px, py, pz, [&](int f, float v) { x0[f * NTP] = v; });     // triplanar / octree grid
     wb_embed(m.pos_mode, m.pos_freq, px, py, pz, x0 + m.feat_dim * NTP, NTP);
     for (int k = m.I[0]; k < m.Ipad[0]; ++k) x0[k * NTP] = 0.0f;
     for (int l = 0; l < m.nl_d; ++l)
@@ -330,7 +332,7 @@ __device__ __forceinline__ void wb_sample_forward(const WbGrid& g, const WbMlp& 
 // ---------------------------------------------------------------------------------------------------------
 template <int NT>
 __global__ void __launch_bounds__(NT)
-wb_shade_fwd_kernel(WbGrid g, WbMlp m, const float* __restrict__ blob, WbShadeIn in, float4* __restrict__ shaded)
+wb_shade_fwd_kernel(WbGrid g, WbGridX gx, WbMlp m, const float* __restrict__ blob, WbShadeIn in, float4* __restrict__ shaded)
 {
     extern __shared__ __align__(16) float smem[];
     constexpr int NTP = NT + 1;
@@ -343,14 +345,14 @@ wb_shade_fwd_kernel(WbGrid g, WbMlp m, const float* __restrict__ blob, WbShadeIn
         const int64_t s = tile * NT + threadIdx.x;
         if (s < in.S) {
             float sigma, r, gg, b;
-            wb_sample_forward(g, m, W, in, s, act, NTP, sigma, r, gg, b);
+            wb_sample_forward(g, gx, m, W, in, s, act, NTP, sigma, r, gg, b);
             shaded[s] = make_float4(r, gg, b, sigma);
         }
     }
 }
 
 template <int NT>
-static int wb_shade_fwd_launch(const WbGrid& g, const WbMlp& m, const float* blob, const WbShadeIn& in, float* shaded, cudaStream_t st)
+static int wb_shade_fwd_launch(const WbGrid& g, const WbGridX& gx, const WbMlp& m, const float* blob, const WbShadeIn& in, float* shaded, cudaStream_t st)
 {
     const size_t smem = (size_t)(m.fwd_floats + m.act_cols * (NT + 1)) * sizeof(float);
     if (smem > 227 * 1024) return 1;
@@ -358,7 +360,7 @@ static int wb_shade_fwd_launch(const WbGrid& g, const WbMlp& m, const float* blo
     const int64_t ntiles = (in.S + NT - 1) / NT;
     int per_sm = (int)((227 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 8) per_sm = 8;
     int64_t grid = (int64_t)wb_num_sms() * per_sm; if (grid > ntiles) grid = ntiles;
-    wb_shade_fwd_kernel<NT><<<(unsigned)grid, NT, smem, st>>>(g, m, blob, in, reinterpret_cast<float4*>(shaded));
+    wb_shade_fwd_kernel<NT><<<(unsigned)grid, NT, smem, st>>>(g, gx, m, blob, in, reinterpret_cast<float4*>(shaded));
     WB_LAUNCH_CHECK();
     return WB_OK;
 }
@@ -371,11 +373,12 @@ extern "C" int wb_rf_shade_fwd(const wb_nef_desc* nef, const float* blob, int32_
     WB_CHECK_ARG(blob && rays && rays->origins && rays->dirs && rec_t && rec_ray && shaded, "null pointer");
     if (precision == 1) return wb_tc_shade_fwd(nef, blob, rays, rec_t, rec_ray, S, shaded, feat_save, workspace, (cudaStream_t)s);
     WbGrid g; int rc = wb_make_grid(nef, &g); if (rc) return rc;
+    WbGridX gx; rc = wb_make_gridx(nef, false, &gx); if (rc) return rc;
     WbMlp m; rc = wb_make_mlp(nef, false, &m); if (rc) return rc;
     WbShadeIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S };
-    rc = wb_shade_fwd_launch<128>(g, m, blob, in, shaded, (cudaStream_t)s);
-    if (rc == 1) rc = wb_shade_fwd_launch<64>(g, m, blob, in, shaded, (cudaStream_t)s);
-    if (rc == 1) rc = wb_shade_fwd_launch<32>(g, m, blob, in, shaded, (cudaStream_t)s);
+    rc = wb_shade_fwd_launch<128>(g, gx, m, blob, in, shaded, (cudaStream_t)s);
+    if (rc == 1) rc = wb_shade_fwd_launch<64>(g, gx, m, blob, in, shaded, (cudaStream_t)s);
+    if (rc == 1) rc = wb_shade_fwd_launch<32>(g, gx, m, blob, in, shaded, (cudaStream_t)s);
     if (rc == 1) { wb_set_error("wb_rf_shade_fwd: decoder too large for shared memory"); return WB_ERR_INVALID; }
     return rc;
 }
@@ -455,7 +458,7 @@ struct WbShadeGrads { float* gtable; float* gdens; float* gcol; };
 
 template <int NT>
 __global__ void __launch_bounds__(NT)
-wb_shade_bwd_kernel(WbGrid g, WbMlp m, const float* __restrict__ blob, WbShadeIn in, const float4* __restrict__ g_shaded, WbShadeGrads G)
+wb_shade_bwd_kernel(WbGrid g, WbGridX gx, WbMlp m, const float* __restrict__ blob, WbShadeIn in, const float4* __restrict__ g_shaded, WbShadeGrads G)
 {
     extern __shared__ __align__(16) float smem[];
     constexpr int NTP = NT + 1;
@@ -471,7 +474,7 @@ wb_shade_bwd_kernel(WbGrid g, WbMlp m, const float* __restrict__ blob, WbShadeIn
         const bool valid = s < in.S;
         if (!valid) s = in.S - 1;                            // keep shared columns finite; its gradient is zeroed below
         float sigma, r, gg, b;
-        wb_sample_forward(g, m, W, in, s, act, NTP, sigma, r, gg, b);
+        wb_sample_forward(g, gx, m, W, in, s, act, NTP, sigma, r, gg, b);
         float4 go = valid ? __ldg(g_shaded + s) : make_float4(0, 0, 0, 0);
         // ---- colour decoder ----
         float* gout = gA + threadIdx.x; float* gin = gB + threadIdx.x;
@@ -522,7 +525,8 @@ wb_shade_bwd_kernel(WbGrid g, WbMlp m, const float* __restrict__ blob, WbShadeIn
             const float py = wb_addcmul(__ldg(in.origins + 3 * (int64_t)ray + 1), __ldg(in.dirs + 3 * (int64_t)ray + 1), t);
             const float pz = wb_addcmul(__ldg(in.origins + 3 * (int64_t)ray + 2), __ldg(in.dirs + 3 * (int64_t)ray + 2), t);
             const int L = g.L, F = g.F;
-            const int lmax = g.multiscale == 0 ? min(L, g.lod_idx) : L;
+            const int lmax = gx.kind != 0 ? 0 : g.multiscale == 0 ? min(L, g.lod_idx) : L;
+            if (gx.kind != 0) wb_featx_scatter(gx, px, py, pz, [&](int f) { return gout[f * NTP]; });     // triplanar / octree grid
             for (int l = 0; l < lmax; ++l) {
                 uint32_t idx[8]; float cf[8];
                 wb_corner_setup(g, l, px, py, pz, idx, cf);
@@ -548,7 +552,7 @@ wb_shade_bwd_kernel(WbGrid g, WbMlp m, const float* __restrict__ blob, WbShadeIn
 }
 
 template <int NT>
-static int wb_shade_bwd_launch(const WbGrid& g, const WbMlp& m, const float* blob, const WbShadeIn& in, const float* g_shaded,
+static int wb_shade_bwd_launch(const WbGrid& g, const WbGridX& gx, const WbMlp& m, const float* blob, const WbShadeIn& in, const float* g_shaded,
                                const WbShadeGrads& G, cudaStream_t st)
 {
     const size_t smem = (size_t)(m.act_cols + 2 * m.maxw) * (NT + 1) * sizeof(float);
@@ -557,7 +561,7 @@ static int wb_shade_bwd_launch(const WbGrid& g, const WbMlp& m, const float* blo
     const int64_t ntiles = (in.S + NT - 1) / NT;
     int per_sm = (int)((227 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 8) per_sm = 8;
     int64_t grid = (int64_t)wb_num_sms() * per_sm; if (grid > ntiles) grid = ntiles;
-    wb_shade_bwd_kernel<NT><<<(unsigned)grid, NT, smem, st>>>(g, m, blob, in, reinterpret_cast<const float4*>(g_shaded), G);
+    wb_shade_bwd_kernel<NT><<<(unsigned)grid, NT, smem, st>>>(g, gx, m, blob, in, reinterpret_cast<const float4*>(g_shaded), G);
     WB_LAUNCH_CHECK();
     return WB_OK;
 }
@@ -570,15 +574,16 @@ extern "C" int wb_rf_shade_bwd(const wb_nef_desc* nef, const float* blob, int32_
     WB_CHECK_ARG(precision == 0 || precision == 1, "precision must be 0 (fp32) or 1 (fp16 tensor cores)");
     if (S == 0) return WB_OK;
     WB_CHECK_ARG(blob && rays && rays->origins && rays->dirs && rec_t && rec_ray && g_shaded, "null pointer");
-    WB_CHECK_ARG(grad_table && grad_dens && grad_col, "null gradient buffer");
+    WB_CHECK_ARG((grad_table || nef->grid_kind != 0) && grad_dens && grad_col, "null gradient buffer");
     if (precision == 1) return wb_tc_shade_bwd(nef, blob, rays, rec_t, rec_ray, S, g_shaded, loss_scale, feat_saved, workspace, grad_table, grad_dens, grad_col, (cudaStream_t)s);
     WbGrid g; int rc = wb_make_grid(nef, &g); if (rc) return rc;
+    WbGridX gx; rc = wb_make_gridx(nef, true, &gx); if (rc) return rc;
     WbMlp m; rc = wb_make_mlp(nef, true, &m); if (rc) return rc;
     WbShadeIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S };
     WbShadeGrads G = { grad_table, grad_dens, grad_col };
-    rc = wb_shade_bwd_launch<128>(g, m, blob, in, g_shaded, G, (cudaStream_t)s);
-    if (rc == 1) rc = wb_shade_bwd_launch<64>(g, m, blob, in, g_shaded, G, (cudaStream_t)s);
-    if (rc == 1) rc = wb_shade_bwd_launch<32>(g, m, blob, in, g_shaded, G, (cudaStream_t)s);
+    rc = wb_shade_bwd_launch<128>(g, gx, m, blob, in, g_shaded, G, (cudaStream_t)s);
+    if (rc == 1) rc = wb_shade_bwd_launch<64>(g, gx, m, blob, in, g_shaded, G, (cudaStream_t)s);
+    if (rc == 1) rc = wb_shade_bwd_launch<32>(g, gx, m, blob, in, g_shaded, G, (cudaStream_t)s);
     if (rc == 1) { wb_set_error("wb_rf_shade_bwd: decoder too large for shared memory"); return WB_ERR_INVALID; }
     return rc;
 }

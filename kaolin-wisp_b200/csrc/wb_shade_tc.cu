@@ -29,6 +29,7 @@
 // Gradients are carried in fp16 under a power-of-two loss scale supplied on the device (no host sync) and unscaled in fp32
 // at the two exits (table scatter, weight-gradient flush).
 #include "wb_common.cuh"
+#include "wb_featx.cuh"
 #include "wb_tc.cuh"
 #include <math.h>
 
@@ -577,9 +578,10 @@ __device__ __forceinline__ void tile_gather_ta(const WbGrid& g, uint32_t arow, i
     tc_st_wait();
 }
 
-template <int MINB, bool TA>         // MINB: resident CTAs per SM the register allocation is bounded for; TA: activations in tensor memory
+template <int MINB, bool TA, bool GX = false>   // MINB: resident CTAs per SM the register allocation is bounded for; TA: activations in tensor
+                                                // memory; GX: triplanar / octree feature grid (wb_featx.cuh) instead of the hash grid
 __global__ void __launch_bounds__(TC_GROUP, MINB)
-wb_shade_fwd_tc_kernel(WbGrid g, WbTc m, const uint8_t* __restrict__ blob, TcIn in, float4* __restrict__ shaded)
+wb_shade_fwd_tc_kernel(WbGrid g, WbGridX gx, WbTc m, const uint8_t* __restrict__ blob, TcIn in, float4* __restrict__ shaded)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[2];
@@ -614,7 +616,8 @@ wb_shade_fwd_tc_kernel(WbGrid g, WbTc m, const uint8_t* __restrict__ blob, TcIn 
         if (TA) {
             tile_gather_ta(g, c.tmem + ((uint32_t)c.laneq << 16) + (uint32_t)m.work_col[1], c.h, px, py, pz, in.x0_save, in.S, s, valid);
         } else {
-            tile_gather(g, t0, c.r, c.h, px, py, pz);
+            if (!GX) tile_gather(g, t0, c.r, c.h, px, py, pz);
+            else if (c.h == 0) wb_featx_gather(gx, px, py, pz, [&](int f, float v) { tile_store1(t0, c.r, f, v); });
             if (c.h == 0) {
                 tile_embed(t0, c.r, m.feat_dim, m.pos_mode, m.pos_freq, px, py, pz);
                 tile_zero(t0, c.r, m.I[0], m.Kp[0]);
@@ -662,10 +665,11 @@ int wb_tc_shade_fwd(const wb_nef_desc* nef, const float* blob, const wb_rays* ra
                     int64_t S, float* shaded, void* feat_save, void* workspace, cudaStream_t st)
 {
     WbGrid g; int rc = wb_make_grid(nef, &g); if (rc) return rc;
+    WbGridX gx; rc = wb_make_gridx(nef, false, &gx); if (rc) return rc;
     // Default since round 2 (WB_TC_FWD_TMEMA=0 selects the shared-memory tile): activations in tensor memory, A operand read from TMEM
     // (wb_tc.cuh tc_mma_ts); measured 3.10 -> 2.86 ms on the 1024^2 frame, same results.
     // Applies to the specialised F == 2 'cat' gather without position embedding, whose rows are whole 16-byte chunks.
-    const bool ta = tc_knob_fwd_tmema() && nef->feature_dim == 2 && nef->multiscale == 0 && nef->pos_mode == 0 &&
+    const bool ta = tc_knob_fwd_tmema() && nef->grid_kind == 0 && nef->feature_dim == 2 && nef->multiscale == 0 && nef->pos_mode == 0 &&
                     (nef->num_lods * nef->feature_dim) % 16 == 0;
     WbTc m; rc = wb_tc_make(nef, false, &m, ta); if (rc) return rc;
     if (ta) {   // no activation tile in shared memory: the parameter blob and the bias tile move to the front
@@ -679,20 +683,21 @@ int wb_tc_shade_fwd(const wb_nef_desc* nef, const float* blob, const wb_rays* ra
     // profiles/README.md).  The register bound of the instantiation must match, or the hardware silently runs fewer.
     int per_sm = (227 * 1024) / (m.smem_bytes + 4096); per_sm = max(1, min(per_sm, 512 / m.tmem_cols));
     per_sm = max(2, min(min(per_sm, 4), tc_knob_fwd_ctas()));
-    auto kern = ta ? (per_sm == 2 ? wb_shade_fwd_tc_kernel<2, true> : per_sm == 3 ? wb_shade_fwd_tc_kernel<3, true> : wb_shade_fwd_tc_kernel<4, true>)
+    if (gx.kind != 0) per_sm = 2;                   // the generic grids keep more state per thread: 128 registers, 2 CTAs per SM
+    auto kern = gx.kind != 0 ? wb_shade_fwd_tc_kernel<2, false, true> : ta ? (per_sm == 2 ? wb_shade_fwd_tc_kernel<2, true> : per_sm == 3 ? wb_shade_fwd_tc_kernel<3, true> : wb_shade_fwd_tc_kernel<4, true>)
                    : (per_sm == 2 ? wb_shade_fwd_tc_kernel<2, false> : per_sm == 3 ? wb_shade_fwd_tc_kernel<3, false> : wb_shade_fwd_tc_kernel<4, false>);
     {   // function attributes are driver calls that can wait behind other driver work (e.g. an NVML poll): set them once, not per launch
         static int done_for[10] = { -1, -1, -1, -1, -1, -1, -1, -1, -1, -1 };
-        if (done_for[per_sm + (ta ? 5 : 0)] != m.smem_bytes) {
+        if (done_for[gx.kind != 0 ? 9 : per_sm + (ta ? 5 : 0)] != m.smem_bytes) {
             WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, m.smem_bytes));
             WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          min(100, (per_sm * (m.smem_bytes + 4096) * 100) / (228 * 1024) + 1)));
-            done_for[per_sm + (ta ? 5 : 0)] = m.smem_bytes;
+            done_for[gx.kind != 0 ? 9 : per_sm + (ta ? 5 : 0)] = m.smem_bytes;
         }
     }
     const int64_t ntiles = (S + TC_ROWS - 1) / TC_ROWS;
     int64_t grid = (int64_t)wb_num_sms() * per_sm; if (grid > ntiles) grid = ntiles;
-    kern<<<(unsigned)grid, TC_GROUP, m.smem_bytes, st>>>(g, m, reinterpret_cast<const uint8_t*>(blob), in, reinterpret_cast<float4*>(shaded));
+    kern<<<(unsigned)grid, TC_GROUP, m.smem_bytes, st>>>(g, gx, m, reinterpret_cast<const uint8_t*>(blob), in, reinterpret_cast<float4*>(shaded));
     WB_LAUNCH_CHECK();
     return WB_OK;
 }
@@ -988,6 +993,23 @@ wb_table_scatter_kernel(WbGrid g, TcIn in, const __half* __restrict__ dfeat, int
     }
 }
 
+// dL/dfeat planes -> triplanar planes / octree feature levels (kinds 1, 2): one thread per sample
+__global__ void __launch_bounds__(256)
+wb_featx_scatter_kernel(WbGridX gx, TcIn in, const __half* __restrict__ dfeat, int width, const float* __restrict__ scale_p)
+{
+    const float inv_scale = 1.0f / __ldg(scale_p);
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < in.S; s += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t ray = __ldg(in.rec_ray + s);
+        const float t = __ldg(in.rec_t + s);
+        const float px = wb_addcmul(__ldg(in.origins + 3 * ray), __ldg(in.dirs + 3 * ray), t);
+        const float py = wb_addcmul(__ldg(in.origins + 3 * ray + 1), __ldg(in.dirs + 3 * ray + 1), t);
+        const float pz = wb_addcmul(__ldg(in.origins + 3 * ray + 2), __ldg(in.dirs + 3 * ray + 2), t);
+        wb_featx_scatter(gx, px, py, pz, [&](int f) {                       // feature f lives in plane f / width at column f % width
+            return __half2float(dfeat[((int64_t)(f / width) * in.S + s) * width + (f % width)]) * inv_scale;
+        });
+    }
+}
+
 #include "wb_shade_tc_bwd3.cuh"          // three-group variant: the default for the app/nerf decoder shape (WB_TC_BWD_GROUPS=2 selects the kernel above)
 
 // decoder backward only: dL/d(shaded) -> weight gradients + dL/dfeat planes in the workspace
@@ -1039,12 +1061,19 @@ int wb_tc_table_scatter(const wb_nef_desc* nef, const wb_rays* rays, const float
                         const float* scale, void* workspace, float* grad_table, cudaStream_t st)
 {
     WbGrid g; int rc = wb_make_grid(nef, &g); if (rc) return rc;
+    WbGridX gx; rc = wb_make_gridx(nef, true, &gx); if (rc) return rc;
     WbTc m; rc = wb_tc_make(nef, true, &m); if (rc) return rc;
-    WB_CHECK_ARG(scale != nullptr && workspace != nullptr && grad_table != nullptr, "null pointer");
+    WB_CHECK_ARG(scale != nullptr && workspace != nullptr && (grad_table != nullptr || gx.kind != 0), "null pointer");
     int planes, width; tc_dfeat_shape(nef, &planes, &width);
     const int64_t R = rays->num_rays;
     const __half* dfeat = reinterpret_cast<const __half*>(reinterpret_cast<const uint8_t*>(workspace) + tc_align256(R * m.Kp[m.nl_d] * 2));
     TcIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S, nullptr, nullptr, nullptr };
+    if (gx.kind != 0) {
+        int64_t bx = (S + 255) / 256; const int64_t cap = (int64_t)wb_num_sms() * 16; if (bx > cap) bx = cap;
+        wb_featx_scatter_kernel<<<(unsigned)bx, 256, 0, st>>>(gx, in, dfeat, width, scale);
+        WB_LAUNCH_CHECK();
+        return WB_OK;
+    }
     const int levels = g.multiscale == 0 ? planes : g.L;
     if (levels > 0) {
         // LODs per CTA row: the sample position / record loads are shared by `lpb` LODs (measured sweep in profiles/README.md)

@@ -122,3 +122,59 @@ extern "C" int wb_query(const wb_octree* oct, const float* coords, int64_t N, in
     WB_LAUNCH_CHECK();
     return WB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// NeuralRadianceField.prune (wisp/models/nefs/nerf.py:175-212): the two elementwise halves around the density probe.
+//   wb_prune_samples: one probe point per finest-level cell, samples = ((points + u) / res) * 2 - 1 (:189-192), op by op in
+//     fp32 as the reference's torch kernels, and a uniform direction on the sphere (wisp/ops/geometric.py:25-39; the density
+//     does not depend on it).  u: explicit [N,3] tensor (parity tests replay the reference's draw) or the counter-based stream
+//     keyed by (seed, cell, axis) -- the same seed on every rank gives the same probe points, so pruned octrees agree across
+//     GPUs without a broadcast.
+//   wb_prune_update: occupancy = max(density, occupancy * decay) (:186,:196), keep = occupancy > min_density (:198).
+// The probe itself is the fused shade kernel (wb_rf_shade_fwd with the probe points as zero-length rays).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void wb_prune_samples_kernel(const int16_t* __restrict__ points, int64_t N, float res, const float* __restrict__ u, uint32_t seed,
+                                        float* __restrict__ samples, float* __restrict__ dirs, float* __restrict__ rec_t, int32_t* __restrict__ rec_ray)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const uint32_t key = wb_ray_key(seed, (uint32_t)i);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float ua = u ? __ldg(u + 3 * i + a) : wb_jitter(key, (uint32_t)a);
+        float v = __fadd_rn((float)points[3 * i + a], ua);
+        v = __fdiv_rn(v, res);
+        samples[3 * i + a] = __fsub_rn(__fmul_rn(v, 2.0f), 1.0f);
+    }
+    const float u0 = wb_jitter(key, 3u), u1 = wb_jitter(key, 4u);
+    const float z = 1.0f - 2.0f * u0, r = sqrtf(fmaxf(1.0f - z * z, 0.0f)), phi = 6.283185307179586f * u1;
+    dirs[3 * i] = r * cosf(phi); dirs[3 * i + 1] = r * sinf(phi); dirs[3 * i + 2] = z;
+    rec_t[i] = 0.0f; rec_ray[i] = (int32_t)i;                      // probe point i = ray i at depth 0: fma(dir, 0, origin) == origin
+}
+extern "C" int wb_prune_samples(const int16_t* points, int64_t N, int32_t level, const float* u, uint32_t seed,
+                                float* samples, float* dirs, float* rec_t, int32_t* rec_ray, wb_stream s)
+{
+    if (N == 0) return WB_OK;
+    WB_CHECK_ARG(points && samples && dirs && rec_t && rec_ray, "null pointer");
+    WB_CHECK_ARG(level >= 0 && level <= 15 && N < ((int64_t)1 << 31), "level / N out of range");
+    wb_prune_samples_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)s>>>(points, N, (float)(1 << level), u, seed, samples, dirs, rec_t, rec_ray);
+    WB_LAUNCH_CHECK();
+    return WB_OK;
+}
+__global__ void wb_prune_update_kernel(const float4* __restrict__ shaded, int64_t N, float decay, float min_density,
+                                       float* __restrict__ occupancy, uint8_t* __restrict__ keep)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float occ = fmaxf(__ldg(shaded + i).w, __fmul_rn(occupancy[i], decay));
+    occupancy[i] = occ;
+    keep[i] = occ > min_density ? 1 : 0;
+}
+extern "C" int wb_prune_update(const float* shaded, int64_t N, float decay, float min_density, float* occupancy, uint8_t* keep, wb_stream s)
+{
+    if (N == 0) return WB_OK;
+    WB_CHECK_ARG(shaded && occupancy && keep, "null pointer");
+    wb_prune_update_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)s>>>(reinterpret_cast<const float4*>(shaded), N, decay, min_density, occupancy, keep);
+    WB_LAUNCH_CHECK();
+    return WB_OK;
+}

@@ -6,6 +6,7 @@
 // Coordinate handling restates ATen's grid sampler (GridSampler.h: unnormalize, reflect_coordinates, clip, bilinear
 // with in-bounds masking); plane pairing: x-plane <- (y,z), y-plane <- (x,z), z-plane <- (x,y) (:217-222).
 #include "wb_common.cuh"
+#include "wb_featx.cuh"          // wb_reflect / wb_tp_coord: ATen grid-sampler coordinate handling
 
 struct WbTriplane {
     int num_lods, fdim;
@@ -13,21 +14,6 @@ struct WbTriplane {
     const float* planes[WB_MAX_LODS][3];  // fmx, fmy, fmz of every LOD, each [1, fdim, res+1, res+1]
     float* gplanes[WB_MAX_LODS][3];       // gradients (backward)
 };
-
-__device__ __forceinline__ float wb_reflect(float in, float span)
-{   // reflect_coordinates(in, 0, 2*span) for align_corners=True
-    if (span <= 0.0f) return 0.0f;
-    in = fabsf(in);
-    const float extra = fmodf(in, span);
-    const int flips = (int)floorf(in / span);
-    return (flips & 1) ? span - extra : extra;
-}
-__device__ __forceinline__ float wb_tp_coord(float c, int size)
-{
-    float x = ((c + 1.0f) * 0.5f) * (float)(size - 1);          // grid_sampler_unnormalize, align_corners=True
-    x = wb_reflect(x, (float)(size - 1));
-    return fminf((float)(size - 1), fmaxf(x, 0.0f));            // clip_coordinates
-}
 
 template <bool BWD>
 __global__ void __launch_bounds__(256)

@@ -17,7 +17,6 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .grids import HashGrid
 
 
 class PositionalEmbedder(nn.Module):
@@ -68,12 +67,7 @@ class BasicDecoder(nn.Module):
 
     def packed_params(self):
         """[W0, b0?, W1, b1?, ...] -- the order the C ABI expects (include/wispb200.h)."""
-        out = []
-        for l in list(self.layers) + [self.lout]:
-            out.append(l.weight)
-            if l.bias is not None:
-                out.append(l.bias)
-        return out
+        return ops.decoder_params(self)
 
     def dims(self):
         return [self.input_dim] + [self.hidden_dim] * self.num_layers + [self.output_dim]
@@ -170,33 +164,18 @@ class NeuralRadianceField(BaseNeuralField):
             return get_positional_embedder(frequencies=frequencies, include_input=include_input)
         raise NotImplementedError(f'Unsupported embedder type for NeuralRadianceField: {embedder_type}')
 
-    def prune(self):
-        """Prunes the blas based on the current state (nerf.py:175-212): decay the running occupancy, query the density at one
-        random point per finest-level cell (native hash-grid kernel + decoder_density), keep the cells above `prune_min_density`
-        and rebuild the occupancy structure from them.  The next raymarch rebuilds the native bit masks (OctreeAS.tensors())."""
-        if self.prune_density_decay is None or self.prune_min_density is None:
-            return
-        if self.grid is None:
+    def prune(self, jitter=None, seed=None):
+        """Prunes the blas based on the current state (nerf.py:175-212): decay the running occupancy, probe the density at one
+        jittered point per finest-level cell, keep the cells above `prune_min_density`, rebuild the occupancy structure from them.
+        All of it runs on the native path (ops.prune_field: probe points, fused gather + decoders, occupancy update); the next
+        raymarch rebuilds the native bit masks (OctreeAS.tensors()).  `jitter` ([cells, 3] in [0,1)) replays a given draw; `seed`
+        selects the counter-based stream (default: the prune-call count, identical on all ranks)."""
+        if self.prune_density_decay is None or self.prune_min_density is None or self.grid is None:
             return
         if not hasattr(self.grid, "occupancy") or not hasattr(self.grid, "dense_points"):
             raise NotImplementedError(f'Pruning not implemented for grid type {self.grid.__class__.__name__}')
-        dev = self.grid.codebook.feats.device if hasattr(self.grid, "codebook") else next(self.parameters()).device
-        self.grid.occupancy = self.grid.occupancy.to(dev) * self.prune_density_decay
-        points = self.grid.dense_points.to(dev)
-        res = 2.0 ** self.grid.blas.max_level
-        samples = torch.rand(points.shape[0], 3, device=points.device)
-        samples = (points.float() + samples) / res * 2.0 - 1.0
-        sample_views = torch.from_numpy(sample_unif_sphere(samples.shape[0])).float().to(points.device)
-        with torch.no_grad():
-            density = self.forward(coords=samples, ray_d=sample_views, channels="density")
-        self.grid.occupancy = torch.stack([density[:, 0], self.grid.occupancy], -1).max(dim=-1)[0]
-        _points = points[self.grid.occupancy > self.prune_min_density]
-        if _points.shape[0] == 0:
-            return
-        if not hasattr(self.grid.blas.__class__, "from_quantized_points"):
-            raise Exception(f"The BLAS {self.grid.blas.__class__.__name__} does not support initialization "
-                            "from_quantized_points, which is required for pruning.")
-        self.grid.blas = self.grid.blas.__class__.from_quantized_points(_points, self.grid.blas.max_level)
+        if not ops.prune_field(self, jitter=jitter, seed=seed):
+            raise NotImplementedError("prune(): this field configuration is outside the native path (ops.nef_spec)")
 
     def register_forward_functions(self):
         self._register_forward_function(self.rgba, ["density", "rgb"])
@@ -228,27 +207,9 @@ class NeuralRadianceField(BaseNeuralField):
         return 15 + self.view_embed_dim
 
     # ---- fused path ----------------------------------------------------------------------------------------
-    @staticmethod
-    def _embed_mode(kind: str, include_input: bool, freq: int):
-        if kind == 'none' and not include_input:
-            return 0, 0
-        if kind == 'identity' or (kind == 'none' and include_input):
-            return 1, 0
-        return (3 if include_input else 2), freq
-
     def fused_spec(self, lod_idx: Optional[int] = None) -> Optional[ops.NefSpec]:
-        """Description of this field for wb_rf_*; None when the configuration is outside the fused path."""
-        g = self.grid
-        if not isinstance(g, HashGrid) or g.feature_dim > 8:
-            return None
-        if lod_idx is None:
-            lod_idx = len(g.active_lods) - 1
-        pm, pf = self._embed_mode(self.pos_embedder_type, self.position_input, self.pos_multires)
-        vm, vf = self._embed_mode(self.view_embedder_type, True, self.view_multires)
-        return ops.NefSpec(resolutions=list(g.resolutions), begin_idxes=[int(b) for b in g.codebook.begin_idxes.tolist()],
-                           codebook_size=g.codebook_size, feature_dim=g.feature_dim, multiscale=g.multiscale_type, lod_idx=int(lod_idx),
-                           pos_mode=pm, pos_freq=pf, view_mode=vm, view_freq=vf, has_bias=bool(self.bias),
-                           dens_dims=self.decoder_density.dims(), col_dims=self.decoder_color.dims())
+        """Description of this field for wb_rf_* (ops.nef_spec); None when the configuration is outside the fused path."""
+        return ops.nef_spec(self, lod_idx)
 
 
 class NeuralSDF(BaseNeuralField):
@@ -283,12 +244,18 @@ class NeuralSDF(BaseNeuralField):
         return lambda coords, lod_idx=None: fn(coords, lod_idx)[channel]
 
     def sdf(self, coords, lod_idx=None):
-        """neural_sdf.py:120-155."""
+        """neural_sdf.py:120-155.  Without autograd (the sphere tracer, the SDF slices of the trainer's validation) the whole
+        evaluation -- octree descent, trilinear blend of every LOD, position input, decoder -- is one native launch (wb_sdf_eval);
+        with autograd it is the native grid kernel + torch decoder."""
         shape = coords.shape
         if shape[0] == 0:
             return dict(sdf=torch.zeros_like(coords)[..., 0:1])
         if lod_idx is None:
             lod_idx = self.grid.num_lods - 1
+        if not torch.is_grad_enabled() and coords.is_cuda and not torch.is_autocast_enabled():
+            fused = ops.sdf_eval(self, coords, lod_idx)
+            if fused is not None:
+                return dict(sdf=fused.reshape(*shape[:-1], 1))
         if len(shape) == 2:
             coords = coords[:, None]
         num_samples = coords.shape[1]

@@ -462,6 +462,172 @@ def finitediff_gradient(x: torch.Tensor, f, eps: float = 0.005) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------------------------
+# NeuralSDF(OctreeGrid) + sphere tracing (app/nglod)
+# --------------------------------------------------------------------------------------------------------------
+def _sdf_embed_mode(nef):
+    """(pos_mode, pos_freq) of a NeuralSDF (neural_sdf.py:86-99): 0 none, 1 identity, 2 positional, 3 positional + input."""
+    pe = getattr(nef, "pos_embedder", None)
+    if pe is None:
+        return 0, 0
+    if isinstance(pe, torch.nn.Identity):
+        return 1, 0
+    nf = int(getattr(pe, "num_freq", 0))
+    if nf <= 0 or not getattr(pe, "log_sampling", True) or int(round(float(getattr(pe, "max_freq_log2", nf - 1)))) != nf - 1:
+        return None                                        # only get_positional_embedder(frequencies) bands (2^0 .. 2^(f-1))
+    return (3 if getattr(pe, "include_input", True) else 2), nf
+
+
+def sdf_field(nef):
+    """-> (SdfDesc, OctreeTensors, keepalive) for a NeuralSDF over an OctreeGrid ('linear'), or None when the field is outside
+    what wb_sdf_eval / wb_sdf_trace evaluate natively (other grids, activations, skip connections, > 128 wide)."""
+    g, dec = getattr(nef, "grid", None), getattr(nef, "decoder", None)
+    if g is None or dec is None or not all(hasattr(g, a) for a in ("trinkets", "features", "base_lod", "num_lods", "multiscale_type", "blas")):
+        return None
+    if getattr(g, "interpolation_type", "linear") != "linear" or getattr(dec, "skip", None):
+        return None
+    if getattr(nef, "activation_type", "relu") != "relu" or getattr(dec, "activation", torch.relu) not in (torch.relu, torch.nn.functional.relu):
+        return None
+    layers = list(dec.layers) + [dec.lout]
+    if not all(isinstance(l, torch.nn.Linear) and l.bias is not None for l in layers):
+        return None
+    H, nh = layers[0].out_features, len(layers) - 1
+    if not (1 <= nh <= 4 and H <= 128 and layers[-1].out_features == 1 and all(l.out_features == H for l in layers[:-1])):
+        return None
+    if nh > 1 and H % 4:
+        return None
+    em = _sdf_embed_mode(nef)
+    if em is None or g.feature_dim > 64:
+        return None
+    dev = g.features[0].device
+    blas = g.blas
+    oct = blas.tensors() if hasattr(blas, "tensors") else None
+    if oct is None:                                        # a reference OctreeAS patched by install()
+        from .install import _octree_tensors
+        oct = _octree_tensors(blas)
+    if g.trinkets.device != dev:
+        g.trinkets = g.trinkets.to(dev)
+    feats = [A.f32c(f.detach()) for f in g.features]
+    params = torch.cat([t.detach().reshape(-1).float() for l in layers for t in (l.weight, l.bias)]).contiguous()
+    trinkets = g.trinkets.int().contiguous()
+    d = A.SdfDesc()
+    ptrs = (C.c_void_p * len(feats))(*[f.data_ptr() for f in feats])
+    d.points, d.trinkets, d.feats = oct.points.data_ptr(), trinkets.data_ptr(), ptrs
+    d.feature_dim, d.base_lod, d.num_lods = int(g.feature_dim), int(g.base_lod), int(g.num_lods)
+    d.multiscale = 1 if g.multiscale_type == 'sum' else 0
+    d.half_round = int(getattr(g, "half_features", True))
+    d.pos_mode, d.pos_freq = em
+    d.num_layers, d.hidden_dim, d.params = nh, H, params.data_ptr()
+    pos_dim = 0 if em[0] == 0 else 3 if em[0] == 1 else 6 * em[1] + (3 if em[0] == 3 else 0)
+    if layers[0].in_features != pos_dim + (g.feature_dim if d.multiscale else g.feature_dim * g.num_lods):
+        return None
+    return d, oct, [ptrs, feats, params, trinkets]
+
+
+def sdf_eval(nef, coords: torch.Tensor, lod_idx: Optional[int] = None) -> Optional[torch.Tensor]:
+    """NeuralSDF.sdf (neural_sdf.py:120-155) in one launch -> [N, 1]; None when the field is not natively supported."""
+    fd = sdf_field(nef)
+    if fd is None:
+        return None
+    d, oct, keep = fd
+    if lod_idx is None:
+        lod_idx = d.num_lods - 1
+    if d.multiscale == 0 and lod_idx != d.num_lods - 1:
+        return None
+    A.require_device(coords)
+    c = A.f32c(coords).reshape(-1, 3)
+    out = torch.empty((c.shape[0], 1), dtype=torch.float32, device=c.device)
+    od = oct.desc()
+    with _stage("sdf_eval"):
+        A.check(A.lib().wb_sdf_eval(C.byref(od), C.byref(d), C.c_int32(lod_idx), A.ptr(c), C.c_int64(c.shape[0]), A.ptr(out), A.stream()))
+    return out
+
+
+class _SdfState:
+    """Per-pack state tensors of the sphere tracer (struct wb_sdf_state), owned by PyTorch."""
+
+    def __init__(self, R: int, num_steps: int, dev):
+        L = A.lib()
+        i32 = lambda n: torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        f32 = lambda n: torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+        self.flags, self.pack_ray, self.cursor0, self.cursor1 = i32(R), i32(R), i32(R), i32(R)
+        self.pack_off = torch.empty(R + 1, dtype=torch.int64, device=dev)
+        self.scan_ws = torch.empty(max(int(L.wb_scan_workspace_bytes(C.c_int64(R))), 1), dtype=torch.uint8, device=dev)
+        self.t, self.dist, self.dist_prev, self.x = f32(R), f32(R), f32(R), f32(3 * R)
+        self.state = torch.empty(max(R, 1), dtype=torch.uint8, device=dev)
+        self.iterflags = i32(2 * num_steps + 4)
+        s = A.SdfState()
+        s.flags, s.pack_off, s.scan_ws, s.scan_ws_bytes, s.pack_ray = self.flags.data_ptr(), self.pack_off.data_ptr(), self.scan_ws.data_ptr(), self.scan_ws.numel(), self.pack_ray.data_ptr()
+        s.t, s.dist, s.dist_prev, s.x = self.t.data_ptr(), self.dist.data_ptr(), self.dist_prev.data_ptr(), self.x.data_ptr()
+        s.cursor0, s.cursor1, s.state, s.iterflags = self.cursor0.data_ptr(), self.cursor1.data_ptr(), self.state.data_ptr(), self.iterflags.data_ptr()
+        self.c = s
+
+
+def _sdf_buffers(R: int, dev, want_normals: bool):
+    """Output buffers as the reference initialises them (packed_sdf_tracer.py:149-168)."""
+    z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
+    out = dict(xyz=z(R, 3), depth=z(R, 1), hit=torch.zeros(R, dtype=torch.bool, device=dev), normal=z(R, 3), alpha=z(R, 1))
+    out["rgb"] = torch.full((R, 3), 0.5, dtype=torch.float32, device=dev) if want_normals else z(R, 3)    # rgb = (normal + 1) / 2 for every ray
+    return out
+
+
+def sdf_trace(nef, oct: OctreeTensors, origins, dirs, dist_max, level: int, lod_idx: int, num_steps: int, step_size: float, min_dis: float,
+              want_normals: bool):
+    """PackedSDFTracer.trace (packed_sdf_tracer.py:78-174): raytrace + ONE persistent sphere-tracing kernel (wb_sdf_trace) when the
+    field is a NeuralSDF(OctreeGrid); otherwise the same state machine phase by phase (wb_sdf_phase) with the field evaluated through
+    its own forward().  -> dict(xyz, depth, hit, normal, rgb, alpha) per ray."""
+    A.require_device(origins)
+    R, dev, L = origins.shape[0], origins.device, A.lib()
+    _, _, nug_depth, ray_off = raytrace(oct, origins, dirs, level)
+    Ng = nug_depth.shape[0]
+    out = _sdf_buffers(R, dev, want_normals)
+    if Ng == 0 or R == 0:
+        return out, None
+    if torch.is_tensor(dist_max):
+        if dist_max.numel() != 1:
+            raise A.WispB200Error("PackedSDFTracer compares t with a scalar dist_max (packed_sdf_tracer.py:127)")
+        dist_max = float(dist_max)
+    rays, keep = A.make_rays(origins, dirs, 0.0, float(dist_max))
+    st = _SdfState(R, num_steps, dev)
+    od = oct.desc()
+    fd = sdf_field(nef)
+    if fd is not None and not (fd[0].multiscale == 0 and lod_idx != fd[0].num_lods - 1):
+        d, _, keep2 = fd
+        with _stage("sdf_trace"):
+            A.check(L.wb_sdf_trace(C.byref(od), C.byref(d), C.c_int32(lod_idx), C.byref(rays), A.ptr(nug_depth), C.c_int64(Ng), A.ptr(ray_off),
+                                   C.c_int32(num_steps), C.c_float(step_size), C.c_float(min_dis), C.c_int32(int(want_normals)), C.byref(st.c),
+                                   A.ptr(out["xyz"]), A.ptr(out["depth"]), A.ptr(out["hit"]), A.ptr(out["normal"]), A.ptr(out["rgb"]), A.ptr(out["alpha"]), A.stream()))
+        out["_evals"] = st.iterflags[2 * num_steps + 2: 2 * num_steps + 3]      # device counter: field evaluations of this launch
+        return out, None
+
+    # ---- generic field: the state machine runs natively, the field through its own forward() between the phases ----
+    def phase(ph, it=0):
+        A.check(L.wb_sdf_phase(C.c_int32(ph), C.byref(rays), A.ptr(nug_depth), C.c_int64(Ng), A.ptr(ray_off), C.c_int32(num_steps), C.c_int32(it),
+                               C.c_float(min_dis), C.byref(st.c), A.ptr(out["xyz"]), A.ptr(out["depth"]), A.ptr(out["hit"]), A.ptr(out["alpha"]), A.stream()))
+
+    def field(x):
+        return nef(coords=x, lod_idx=lod_idx, channels="sdf").reshape(-1).float() * 1.0 * step_size
+
+    with torch.no_grad():
+        phase(0)
+        P = int(st.pack_off[-1].item())
+        phase(1)
+        x = st.x[:3 * P].view(P, 3)
+        st.dist[:P] = field(x)
+        st.dist_prev[:P] = st.dist[:P]
+        for it in range(num_steps):
+            phase(2, it)
+            if int(st.iterflags[2 * it].item()) == 0:
+                break
+            phase(3, it)
+            if int(st.iterflags[2 * it + 1].item()) == 0:
+                break
+            alive = torch.nonzero(st.state[:P] & 1)[:, 0]
+            st.dist[alive] = field(x[alive])
+        phase(4)
+    return out, st
+
+
+# --------------------------------------------------------------------------------------------------------------
 # packed compositing
 # --------------------------------------------------------------------------------------------------------------
 def _bg3(bg) -> "C.Array":
@@ -505,9 +671,14 @@ class CompositeFn(torch.autograd.Function):
 # --------------------------------------------------------------------------------------------------------------
 # fused render path
 # --------------------------------------------------------------------------------------------------------------
+GRID_KINDS = {"hash": 0, "triplanar": 1, "octree": 2}
+
+
 @dataclass
 class NefSpec:
-    """Static description of a NeuralRadianceField(HashGrid) that the fused path supports."""
+    """Static description of a NeuralRadianceField that the fused path supports.  kind 'hash': HashGrid (resolutions, begin_idxes,
+    codebook_size); 'triplanar': TriplanarGrid (resolutions = plane side - 1 of the LODs used, feature_dim = 3 * fdim);
+    'octree': OctreeGrid (feature_dim = F, base_lod).  For the last two num_lods counts the LODs 0..lod_idx actually used."""
     resolutions: List[int]
     begin_idxes: List[int]
     codebook_size: int
@@ -521,9 +692,34 @@ class NefSpec:
     has_bias: bool
     dens_dims: List[int]
     col_dims: List[int]
+    kind: str = "hash"
+    num_lods: int = 0
+    base_lod: int = 0
+    half_round: bool = True
 
-    def desc(self, table: torch.Tensor, dens_flat: torch.Tensor, col_flat: torch.Tensor) -> A.NefDesc:
-        d = A.make_grid_desc(table, self.resolutions, self.begin_idxes, self.codebook_size, self.multiscale, self.lod_idx)
+    def desc(self, grid: Sequence[torch.Tensor], dens_flat: torch.Tensor, col_flat: torch.Tensor, oct: Optional[OctreeTensors] = None,
+             trinkets: Optional[torch.Tensor] = None, grads: Optional[Sequence[torch.Tensor]] = None):
+        """-> (NefDesc, keepalive).  grid: [table] | planes (fmx, fmy, fmz per LOD) | feature levels."""
+        keep = []
+        if self.kind == "hash":
+            d = A.make_grid_desc(grid[0], self.resolutions, self.begin_idxes, self.codebook_size, self.multiscale, self.lod_idx)
+        else:
+            d = A.NefDesc()
+            d.grid_kind = GRID_KINDS[self.kind]
+            d.num_lods, d.feature_dim, d.codebook_size = self.num_lods, self.feature_dim, 0
+            d.multiscale, d.lod_idx = (0 if self.multiscale == "cat" else 1), self.num_lods
+            for i, r in enumerate(self.resolutions):
+                d.resolutions[i] = int(r)
+            ptrs = (C.c_void_p * len(grid))(*[t.data_ptr() for t in grid])
+            d.grid_ptrs = ptrs; keep.append(ptrs)
+            if grads is not None:
+                gptrs = (C.c_void_p * len(grads))(*[t.data_ptr() for t in grads])
+                d.grid_grads = gptrs; keep.append(gptrs)
+            if self.kind == "octree":
+                od = oct.desc()
+                keep.append(od)
+                d.oct, d.points, d.trinkets = C.addressof(od), oct.points.data_ptr(), trinkets.data_ptr()
+                d.base_lod, d.half_round = self.base_lod, int(self.half_round)
         d.pos_mode, d.pos_freq, d.view_mode, d.view_freq = self.pos_mode, self.pos_freq, self.view_mode, self.view_freq
         d.has_bias = int(self.has_bias)
         d.dens_layers = len(self.dens_dims) - 1
@@ -535,28 +731,165 @@ class NefSpec:
         for i, v in enumerate(self.col_dims):
             d.col_dims[i] = v
         d.dens_params, d.col_params = dens_flat.data_ptr(), col_flat.data_ptr()
-        return d
+        return d, keep
 
 
 def _flatten(params: Sequence[torch.Tensor]) -> torch.Tensor:
     return torch.cat([p.detach().reshape(-1).float() for p in params]) if params else torch.zeros(0)
 
 
+def _embedder_mode(emb):
+    """(mode, freq) of an embedder object (nerf.py:110-141): None -> (0, 0); nn.Identity -> (1, 0); PositionalEmbedder with the
+    get_positional_embedder bands 2^0..2^(f-1) -> (3 | 2, f); anything else (e.g. the tcnn spherical harmonics) -> None."""
+    if emb is None:
+        return 0, 0
+    if isinstance(emb, torch.nn.Identity):
+        return 1, 0
+    nf = getattr(emb, "num_freq", None)
+    if nf is None or not getattr(emb, "log_sampling", True):
+        return None
+    nf = int(nf)
+    if nf < 1 or int(round(float(getattr(emb, "max_freq_log2", nf - 1)))) != nf - 1 or int(getattr(emb, "out_dim", 0)) not in (6 * nf, 3 + 6 * nf):
+        return None
+    return (3 if getattr(emb, "include_input", True) else 2), nf
+
+
+def _decoder_layers(dec):
+    """Linear layers of a BasicDecoder(relu, no skip) (basic_decoders.py:59-101), or None."""
+    if getattr(dec, "skip", None) or getattr(dec, "activation", torch.relu) not in (torch.relu, torch.nn.functional.relu):
+        return None
+    layers = list(dec.layers) + [dec.lout]
+    if not all(isinstance(l, torch.nn.Linear) for l in layers):
+        return None
+    return layers
+
+
+def decoder_params(dec) -> List[torch.Tensor]:
+    """[W0, b0?, W1, b1?, ...] -- the order the C ABI expects (include/wispb200.h)."""
+    out = []
+    for l in list(dec.layers) + [dec.lout]:
+        out.append(l.weight)
+        if l.bias is not None:
+            out.append(l.bias)
+    return out
+
+
+def raymarch_level(grid, lod_idx: int) -> int:
+    """Octree level the tracer marches (BLASGrid.raymarch overrides: hash_grid.py:235-240 max_level, octree_grid.py:221-226 base_lod,
+    triplanar_grid.py:145-150 level 0)."""
+    if hasattr(grid, "codebook"):
+        return grid.blas.max_level
+    if hasattr(grid, "trinkets"):
+        return grid.base_lod
+    return 0
+
+
+def nef_spec(nef, lod_idx: Optional[int] = None) -> Optional[NefSpec]:
+    """Describe a NeuralRadianceField -- this package's mirror or the reference's own class (install()) -- for the fused path, or
+    None when something is outside it (embedders other than none/identity/positional, activations other than relu, skip
+    connections, grids other than Hash/Triplanar/Octree 'linear')."""
+    g = getattr(nef, "grid", None)
+    if g is None or getattr(nef, "activation_type", "relu") != "relu" or getattr(nef, "layer_type", "linear") not in ("linear", "none"):
+        return None
+    ld, lc = _decoder_layers(nef.decoder_density), _decoder_layers(nef.decoder_color)
+    pe, ve = _embedder_mode(getattr(nef, "pos_embedder", None)), _embedder_mode(getattr(nef, "view_embedder", None))
+    if ld is None or lc is None or pe is None or ve is None:
+        return None
+    if lod_idx is None:
+        lod_idx = len(g.active_lods) - 1
+    lod_idx = int(lod_idx)
+    has_bias = ld[0].bias is not None
+    if any((l.bias is not None) != has_bias for l in ld + lc):
+        return None
+    dims = lambda ls: [ls[0].in_features] + [l.out_features for l in ls]
+    common = dict(multiscale=g.multiscale_type, pos_mode=pe[0], pos_freq=pe[1], view_mode=ve[0], view_freq=ve[1], has_bias=has_bias,
+                  dens_dims=dims(ld), col_dims=dims(lc))
+    if g.multiscale_type not in ("cat", "sum"):
+        return None
+    if hasattr(g, "codebook"):                                   # HashGrid
+        if g.feature_dim > 8 or getattr(g, "coord_dim", 3) != 3:
+            return None
+        begin = getattr(g, "_wb_begin", None)
+        if begin is None or len(begin) != len(g.resolutions) + 1:
+            begin = [int(b) for b in g.codebook.begin_idxes.tolist()]       # one-off device read, cached on the grid
+            try:
+                g._wb_begin = begin
+            except Exception:
+                pass
+        return NefSpec(resolutions=[int(r) for r in g.resolutions], begin_idxes=begin, codebook_size=int(g.codebook_size),
+                       feature_dim=int(g.feature_dim), lod_idx=lod_idx, kind="hash", num_lods=len(g.resolutions), **common)
+    nl = lod_idx + 1
+    if nl > 12 or getattr(g, "interpolation_type", "linear") != "linear":
+        return None
+    if hasattr(g, "trinkets"):                                    # OctreeGrid (the VQAD CodebookOctreeGrid keeps indices, not features)
+        if g.feature_dim > 32 or hasattr(g, "dictionary"):
+            return None
+        spec = NefSpec(resolutions=[], begin_idxes=[], codebook_size=0, feature_dim=int(g.feature_dim), lod_idx=lod_idx, kind="octree",
+                       num_lods=nl, base_lod=int(g.base_lod), half_round=bool(getattr(g, "half_features", True)), **common)
+    elif all(hasattr(f, "fmx") for f in getattr(g, "features", [])) and len(getattr(g, "features", [])) > 0:      # TriplanarGrid
+        fdim = g.features[0].fmx.shape[1]
+        if fdim > 8 or any(getattr(f, "padding_mode", "reflection") != "reflection" for f in g.features):
+            return None
+        spec = NefSpec(resolutions=[int(g.features[i].fmx.shape[-1]) - 1 for i in range(nl)], begin_idxes=[], codebook_size=0,
+                       feature_dim=3 * int(fdim), lod_idx=lod_idx, kind="triplanar", num_lods=nl, **common)
+    else:
+        return None
+    feat = spec.feature_dim if (g.multiscale_type == "sum" or (spec.kind == "octree" and nl == 1)) else nl * spec.feature_dim
+    pos_dim = 0 if pe[0] == 0 else 3 if pe[0] == 1 else 6 * pe[1] + (3 if pe[0] == 3 else 0)
+    if spec.dens_dims[0] != feat + pos_dim:                      # e.g. 'cat' evaluated below its finest LOD: the reference fails in nn.Linear
+        return None
+    return spec
+
+
+def grid_tensors(nef, spec: NefSpec) -> List[torch.Tensor]:
+    """The grid's trainable tensors in the order NefSpec.desc expects."""
+    g = nef.grid
+    if spec.kind == "hash":
+        return [g.codebook.feats]
+    if spec.kind == "triplanar":
+        out = []
+        for i in range(spec.num_lods):
+            f = g.features[i]
+            out += [f.fmx, f.fmy, f.fmz]
+        return out
+    return [g.features[i] for i in range(spec.num_lods)]
+
+
+def _grid_context(nef, spec: NefSpec):
+    """(OctreeTensors, trinkets) of an octree-grid field, else (None, None)."""
+    if spec.kind != "octree":
+        return None, None
+    g = nef.grid
+    dev = g.features[0].device
+    if g.trinkets.device != dev:
+        g.trinkets = g.trinkets.to(dev)
+    blas = g.blas
+    if hasattr(blas, "tensors"):
+        oct = blas.tensors()
+    else:
+        from .install import _octree_tensors
+        oct = _octree_tensors(blas)
+    return oct, g.trinkets.int().contiguous()
+
+
 class RFTraceFn(torch.autograd.Function):
-    """PackedRFTracer.trace + NeuralRadianceField.rgba + HashGrid.interpolate as one native pipeline:
+    """PackedRFTracer.trace + NeuralRadianceField.rgba + grid.interpolate as one native pipeline:
          march(count/scan/fill) -> shade (gather + decoders fused) -> composite        (forward)
-         composite_bwd -> shade_bwd (decoder recompute, table scatter)                  (backward)
-    Inputs: table, then the decoder parameters in packing order [W0, b0?, W1, b1?, ...] for density then colour.
+         composite_bwd -> shade_bwd (decoder recompute, grid scatter)                   (backward)
+    Inputs: the grid tensors (NefSpec order), then the decoder parameters in packing order [W0, b0?, W1, b1?, ...] for density
+    then colour.
     """
 
     @staticmethod
-    def forward(ctx, ms: MarchState, spec: NefSpec, n_dens: int, bg, precision: int, want_grad: bool, table, *params):
-        A.require_device(table)
+    def forward(ctx, ms: MarchState, spec: NefSpec, n_grid: int, n_dens: int, bg, precision: int, want_grad: bool, octctx, *tensors):
+        grid, params = tensors[:n_grid], tensors[n_grid:]
+        A.require_device(grid[0])
         L = A.lib()
-        dev = table.device
-        tb = A.f32c(table.detach())
+        dev = grid[0].device
+        gt = [A.f32c(t.detach()) for t in grid]
         dens_flat, col_flat = _flatten(params[:n_dens]), _flatten(params[n_dens:])
-        desc = spec.desc(tb, dens_flat, col_flat)
+        oct, trinkets = octctx if octctx is not None else (None, None)
+        desc, keep = spec.desc(gt, dens_flat, col_flat, oct, trinkets)
         nblob = int(L.wb_rf_param_blob_floats(C.byref(desc), C.c_int32(precision)))
         if nblob < 0:
             raise A.WispB200Error(L.wb_last_error().decode())
@@ -567,7 +900,7 @@ class RFTraceFn(torch.autograd.Function):
         shaded = _empty_s(S, (4,), torch.float32, dev)
         # grad mode is always off inside Function.forward and needs_input_grad ignores torch.no_grad(): the caller (rf_trace)
         # tells us whether a backward pass can follow, so that inference neither saves features nor needs the backward tiles
-        need_grad = bool(want_grad) and any(ctx.needs_input_grad[6:])
+        need_grad = bool(want_grad) and any(ctx.needs_input_grad[8:])
         Scap = _bucket(S)                                  # byte sizes for the bucketed capacity (layouts still use S)
         wsb = int(L.wb_rf_workspace_bytes(C.byref(desc), C.c_int32(precision), C.c_int64(R), C.c_int64(Scap), C.c_int32(0)))
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if wsb > 0 else None
@@ -586,20 +919,23 @@ class RFTraceFn(torch.autograd.Function):
         with _stage("composite_fwd"):
             A.check(L.wb_composite_fwd(A.ptr(shaded), A.ptr(rec_t), A.ptr(rec_delta), A.ptr(ms.offsets), C.c_int64(R), bgv,
                                        A.ptr(rgb), A.ptr(depth), A.ptr(alpha), A.ptr(hit), A.stream()))
-        ctx.ms, ctx.spec, ctx.n_dens, ctx.bg, ctx.precision = ms, spec, n_dens, bgv, precision
+        ctx.ms, ctx.spec, ctx.n_grid, ctx.n_dens, ctx.bg, ctx.precision, ctx.octctx = ms, spec, n_grid, n_dens, bgv, precision, octctx
         ctx.param_shapes = [p.shape for p in params]
         ctx.feat = feat
-        ctx.save_for_backward(tb, dens_flat, col_flat, blob, rec_t, rec_delta, rec_ray, shaded)
+        ctx.save_for_backward(dens_flat, col_flat, blob, rec_t, rec_delta, rec_ray, shaded, *gt)
         ctx.mark_non_differentiable(hit)
         return rgb, depth, alpha, hit
 
     @staticmethod
     def backward(ctx, g_rgb, g_depth, g_alpha, _g_hit):
-        tb, dens_flat, col_flat, blob, rec_t, rec_delta, rec_ray, shaded = ctx.saved_tensors
+        dens_flat, col_flat, blob, rec_t, rec_delta, rec_ray, shaded, *gt = ctx.saved_tensors
         ms, spec = ctx.ms, ctx.spec
         L = A.lib()
         S, R = ms.total, ms.rays.num_rays
-        desc = spec.desc(tb, dens_flat, col_flat)
+        oct, trinkets = ctx.octctx if ctx.octctx is not None else (None, None)
+        g_grid = [torch.zeros_like(t) for t in gt]
+        desc, keep = spec.desc(gt, dens_flat, col_flat, oct, trinkets, grads=g_grid)
+        g_table = g_grid[0] if spec.kind == "hash" else None
         g_sh = _empty_s(S, (4,), torch.float32, shaded.device)
         gd = A.f32c(g_depth).reshape(-1) if g_depth is not None else None
         ga = A.f32c(g_alpha).reshape(-1) if g_alpha is not None else None
@@ -608,18 +944,15 @@ class RFTraceFn(torch.autograd.Function):
         with _stage("composite_bwd"):
             A.check(L.wb_composite_bwd(A.ptr(shaded), A.ptr(rec_t), A.ptr(rec_delta), A.ptr(ms.offsets), C.c_int64(R), ctx.bg,
                                        A.ptr(grgb), A.ptr(gd), A.ptr(ga), A.ptr(g_sh), A.ptr(absmax), A.stream()))
-        g_table = torch.zeros_like(tb)
         g_dens = torch.zeros_like(dens_flat)
         g_col = torch.zeros_like(col_flat)
         scale = None
         if ctx.precision == 1 and S > 0:
             # power-of-two loss scale computed on the device (no host sync): largest |gradient| -> ~64 in fp16
-            amax = absmax[0].clamp_min(1e-30)              # max |g_shaded|, gathered by the compositing backward itself
-            # 2^k assembled from the exponent bits (torch.exp2 is a jiterator op: NVRTC compile at first use)
-            k = torch.floor(torch.log2(64.0 / amax)).clamp(-20.0, 60.0).to(torch.int32)
-            scale = ((k + 127) << 23).view(torch.float32).reshape(1).contiguous()
+            scale = torch.empty(1, dtype=torch.float32, device=shaded.device)
+            A.check(L.wb_rf_loss_scale(A.ptr(absmax), A.ptr(scale), A.stream()))
         wsb = int(L.wb_rf_workspace_bytes(C.byref(desc), C.c_int32(ctx.precision), C.c_int64(R), C.c_int64(_bucket(S)), C.c_int32(1)))
-        ws = torch.empty(wsb, dtype=torch.uint8, device=tb.device) if wsb > 0 else None
+        ws = torch.empty(wsb, dtype=torch.uint8, device=shaded.device) if wsb > 0 else None
         if ctx.precision == 1 and S > 0:
             with _stage("decoder_bwd"):
                 A.check(L.wb_rf_decoder_bwd(C.byref(desc), A.ptr(blob), C.byref(ms.rays), A.ptr(rec_t), A.ptr(rec_ray), C.c_int64(S), A.ptr(g_sh),
@@ -637,18 +970,130 @@ class RFTraceFn(torch.autograd.Function):
             for shp in shapes:
                 n = int(torch.Size(shp).numel())
                 grads.append(flat[o:o + n].reshape(shp)); o += n
-        return (None, None, None, None, None, None, g_table, *grads)
+        return (None, None, None, None, None, None, None, None, *g_grid, *grads)
 
 
-def precision_supported(spec, nef, precision: int, backward: bool) -> bool:
-    """Host-side query (wb_rf_precision_supported): can this decoder configuration run at `precision`?"""
-    tb = A.f32c(nef.grid.codebook.feats.detach())
-    dens, col = _flatten(nef.decoder_density.packed_params()), _flatten(nef.decoder_color.packed_params())
-    desc = spec.desc(tb, dens, col)
-    return bool(A.lib().wb_rf_precision_supported(C.byref(desc), C.c_int32(precision), C.c_int32(1 if backward else 0)))
+_SUPPORT_CACHE: dict = {}
+
+
+def precision_supported(spec: NefSpec, nef, precision: int, backward: bool) -> bool:
+    """Host-side query (wb_rf_precision_supported): can this decoder configuration run at `precision`?  Depends only on the
+    static description, so the answer is memoised (the tracer asks once per trace() call)."""
+    if precision == 0:
+        return True
+    key = (spec.kind, spec.feature_dim, spec.num_lods, spec.multiscale, spec.lod_idx, spec.pos_mode, spec.pos_freq, spec.view_mode, spec.view_freq,
+           spec.has_bias, tuple(spec.dens_dims), tuple(spec.col_dims), int(precision), bool(backward))
+    ans = _SUPPORT_CACHE.get(key)
+    if ans is None:
+        # the query looks at widths only: stand-in one-element tensors, no parameter flattening
+        dummy = torch.zeros(1)
+        d = A.NefDesc()
+        d.grid_kind = GRID_KINDS[spec.kind]
+        d.num_lods = spec.num_lods if spec.kind != "hash" else len(spec.resolutions)
+        d.feature_dim, d.multiscale = spec.feature_dim, (0 if spec.multiscale == "cat" else 1)
+        d.lod_idx = spec.lod_idx if spec.kind == "hash" else d.num_lods
+        d.pos_mode, d.pos_freq, d.view_mode, d.view_freq, d.has_bias = spec.pos_mode, spec.pos_freq, spec.view_mode, spec.view_freq, int(spec.has_bias)
+        d.dens_layers, d.col_layers = len(spec.dens_dims) - 1, len(spec.col_dims) - 1
+        if d.dens_layers > A.WB_MAX_LAYERS or d.col_layers > A.WB_MAX_LAYERS:
+            return False
+        for i, v in enumerate(spec.dens_dims):
+            d.dens_dims[i] = v
+        for i, v in enumerate(spec.col_dims):
+            d.col_dims[i] = v
+        d.dens_params = d.col_params = dummy.data_ptr()
+        ans = bool(A.lib().wb_rf_precision_supported(C.byref(d), C.c_int32(precision), C.c_int32(1 if backward else 0)))
+        _SUPPORT_CACHE[key] = ans
+    return ans
+
+
+def rf_trace_nef(ms: MarchState, spec: NefSpec, nef, bg, precision: int = 0):
+    """Fused trace of `nef` (mirror or reference class) over the marched samples -> rgb [R,3], depth [R,1], alpha [R,1], hit [R]."""
+    grid = grid_tensors(nef, spec)
+    dens, col = decoder_params(nef.decoder_density), decoder_params(nef.decoder_color)
+    octctx = _grid_context(nef, spec) if spec.kind == "octree" else None
+    return RFTraceFn.apply(ms, spec, len(grid), len(dens), bg, precision, torch.is_grad_enabled(), octctx, *grid, *dens, *col)
 
 
 def rf_trace(ms: MarchState, spec: NefSpec, table: torch.Tensor, dens_params: Sequence[torch.Tensor],
              col_params: Sequence[torch.Tensor], bg, precision: int = 0):
-    """-> rgb [R,3], depth [R,1], alpha [R,1], hit [R]."""
-    return RFTraceFn.apply(ms, spec, len(dens_params), bg, precision, torch.is_grad_enabled(), table, *dens_params, *col_params)
+    """Hash-grid form with explicit tensors -> rgb [R,3], depth [R,1], alpha [R,1], hit [R]."""
+    return RFTraceFn.apply(ms, spec, 1, len(dens_params), bg, precision, torch.is_grad_enabled(), None, table, *dens_params, *col_params)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# NeuralRadianceField.prune
+# --------------------------------------------------------------------------------------------------------------
+_PRUNE_CALLS = 0
+
+
+def prune_field(nef, jitter: Optional[torch.Tensor] = None, seed: Optional[int] = None, group=None) -> bool:
+    """NeuralRadianceField.prune (nerf.py:175-212) on the native path: probe points (wb_prune_samples) -> density through the fused
+    shade kernel (grid gather + decoders, no torch nn.Linear) -> occupancy decay / max / threshold (wb_prune_update) -> octree
+    rebuilt from the surviving cells.  Returns False (nothing touched) when the field is outside the fused path, so that callers
+    can fall back to the reference body; True otherwise (including the reference's early returns).
+
+    Rank consistency: the probe points come from a counter-based stream keyed by `seed` (default: the number of
+    prune calls so far, identical on every rank), and with torch.distributed initialised the updated occupancy is broadcast from
+    rank 0 before thresholding, so every rank rebuilds the same octree even if the parameters have drifted by a rounding."""
+    global _PRUNE_CALLS
+    if getattr(nef, "prune_density_decay", None) is None or getattr(nef, "prune_min_density", None) is None:
+        return True
+    g = getattr(nef, "grid", None)
+    if g is None:
+        return True
+    if not hasattr(g, "occupancy") or not hasattr(g, "dense_points"):
+        return False
+    spec = nef_spec(nef, None)
+    if spec is None:
+        return False
+    grid = grid_tensors(nef, spec)
+    dev = grid[0].device
+    if dev.type != "cuda":
+        return False
+    A.require_device(grid[0])
+    L = A.lib()
+    points = g.dense_points.to(dev).contiguous()
+    if points.dtype != torch.int16:
+        points = points.to(torch.int16)
+    N = points.shape[0]
+    level = g.blas.max_level
+    occ = A.f32c(g.occupancy.to(dev)).clone()
+    if seed is None:
+        seed = 0x5EED0000 + _PRUNE_CALLS
+    _PRUNE_CALLS += 1
+    u = None if jitter is None else A.f32c(jitter.to(dev))
+    if u is not None and tuple(u.shape) != (N, 3):
+        raise A.WispB200Error(f"prune jitter must be [{N}, 3]")
+    samples = torch.empty((N, 3), dtype=torch.float32, device=dev); dirs = torch.empty_like(samples)
+    rec_t = torch.empty(N, dtype=torch.float32, device=dev); rec_ray = torch.empty(N, dtype=torch.int32, device=dev)
+    with _stage("prune_samples"):
+        A.check(L.wb_prune_samples(A.ptr(points), C.c_int64(N), C.c_int32(level), A.ptr(u), C.c_uint32(seed & 0xFFFFFFFF), A.ptr(samples), A.ptr(dirs),
+                                   A.ptr(rec_t), A.ptr(rec_ray), A.stream()))
+    gt = [A.f32c(t.detach()) for t in grid]
+    dens_flat, col_flat = _flatten(decoder_params(nef.decoder_density)), _flatten(decoder_params(nef.decoder_color))
+    oct, trinkets = _grid_context(nef, spec)
+    desc, keep_alive = spec.desc(gt, dens_flat, col_flat, oct, trinkets)
+    blob = torch.empty(int(L.wb_rf_param_blob_floats(C.byref(desc), C.c_int32(0))), dtype=torch.float32, device=dev)
+    A.check(L.wb_rf_pack_params(C.byref(desc), C.c_int32(0), A.ptr(blob), A.stream()))
+    rays, keep_rays = A.make_rays(samples, dirs, 0.0, 0.0)
+    shaded = torch.empty((N, 4), dtype=torch.float32, device=dev)
+    with _stage("prune_density"):             # fp32 decoders: the reference probes under torch.no_grad() outside autocast
+        A.check(L.wb_rf_shade_fwd(C.byref(desc), A.ptr(blob), C.c_int32(0), C.byref(rays), A.ptr(rec_t), A.ptr(rec_ray), C.c_int64(N), A.ptr(shaded),
+                                  None, None, A.stream()))
+    keep = torch.empty(N, dtype=torch.bool, device=dev)
+    with _stage("prune_update"):
+        A.check(L.wb_prune_update(A.ptr(shaded), C.c_int64(N), C.c_float(float(nef.prune_density_decay)), C.c_float(float(nef.prune_min_density)),
+                                  A.ptr(occ), A.ptr(keep), A.stream()))
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(occ, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        keep = occ > float(nef.prune_min_density)
+    g.occupancy = occ
+    kept = points[keep]
+    if kept.shape[0] == 0:
+        return True
+    cls = g.blas.__class__
+    if not hasattr(cls, "from_quantized_points"):
+        raise Exception(f"The BLAS {cls.__name__} does not support initialization from_quantized_points, which is required for pruning.")
+    g.blas = cls.from_quantized_points(kept, level)
+    return True

@@ -54,10 +54,11 @@ class PackedRFTracer(nn.Module):
         if self._march_stream is None:
             self._march_stream = torch.cuda.Stream(device=dev)
         cur = torch.cuda.current_stream(dev)
+        level = ops.raymarch_level(nef.grid, nef.grid.num_lods - 1)
+        blas.tensors().ensure_bits(level)                   # built on the caller's stream BEFORE the side stream starts waiting on it
         self._march_stream.wait_stream(cur)                 # the rays (and octree masks) are ready on the caller's stream ...
         if ready is not None:
             self._march_stream.wait_event(ready)            # ... or when `ready` fires (e.g. HostPrefetcher.staged_event)
-        blas.tensors().ensure_bits(blas.max_level)
         with torch.cuda.stream(self._march_stream):
             key = (rays.origins.shape[0], n)
             if getattr(self, "_primed", None) != key:
@@ -68,13 +69,21 @@ class PackedRFTracer(nn.Module):
                           torch.empty(R + 1, dtype=torch.int64, device=dev)) for _ in range(3)]
                 del spare
                 self._primed = key
-            pm = ops.march_count(blas.tensors(), rays.origins, rays.dirs, rays.dist_min, rays.dist_max, n, blas.max_level,
+            pm = ops.march_count(blas.tensors(), rays.origins, rays.dirs, rays.dist_min, rays.dist_max, n, level,
                                  seed=seed, defer_total=True)
         for t in (rays.origins, rays.dirs):
             t.record_stream(self._march_stream)
         if len(self._pending) >= 4:
             self._pending.clear()
-        self._pending[(rays.origins.data_ptr(), rays.dirs.data_ptr(), rays.origins.shape[0], seed & 0xFFFFFFFF, n, id(blas))] = pm
+        self._pending[self._march_key(rays, seed, n, blas)] = pm
+
+    @staticmethod
+    def _march_key(rays, seed, n, blas):
+        """Identity of a pre-marched batch: the ray tensors (storage + version: an in-place overwrite invalidates it), the ray
+        interval, the jitter seed, the step count and the occupancy structure (object + its octree storage, which prune() replaces)."""
+        nf = tuple((x.data_ptr(), x._version) if torch.is_tensor(x) else float(x) for x in (rays.dist_min, rays.dist_max))
+        return (rays.origins.data_ptr(), rays.dirs.data_ptr(), rays.origins._version, rays.dirs._version, rays.origins.shape[0], nf,
+                seed & 0xFFFFFFFF, n, id(blas), blas.octree.data_ptr())
 
     def get_prev_num_samples(self):
         return self.prev_num_samples
@@ -121,19 +130,17 @@ class PackedRFTracer(nn.Module):
             raise TypeError(f"Raymarch sampler type: {raymarch_type} is not supported by OctreeAS.")       # octree_as.py:427
         if spec is not None and not extra_channels:
             blas = nef.grid.blas
+            level = ops.raymarch_level(nef.grid, lod_idx)
             if raymarch_type == 'ray':
-                pm = self._pending.pop((rays.origins.data_ptr(), rays.dirs.data_ptr(), N, seed & 0xFFFFFFFF, num_steps, id(blas)), None) \
-                    if (self._pending and jitter is None) else None
+                pm = self._pending.pop(self._march_key(rays, seed, num_steps, blas), None) if (self._pending and jitter is None) else None
                 ms = pm.finalize() if pm is not None else \
-                    ops.march_count(blas.tensors(), rays.origins, rays.dirs, rays.dist_min, rays.dist_max, num_steps, blas.max_level,
+                    ops.march_count(blas.tensors(), rays.origins, rays.dirs, rays.dist_min, rays.dist_max, num_steps, level,
                                     jitter=jitter, seed=seed)
             else:
-                ms, _ = ops.march_nuggets(blas.tensors(), rays.origins, rays.dirs, blas.max_level, num_steps, raymarch_type,
+                ms, _ = ops.march_nuggets(blas.tensors(), rays.origins, rays.dirs, level, num_steps, raymarch_type,
                                           reference_layout=False, jitter=jitter, seed=seed)
             self.prev_num_samples = ms.total
-            rgb, depth, alpha, hit = ops.rf_trace(ms, spec, nef.grid.codebook.feats, nef.decoder_density.packed_params(),
-                                                  nef.decoder_color.packed_params(), self.bg_color,
-                                                  precision=self._resolve_precision(spec, nef))
+            rgb, depth, alpha, hit = ops.rf_trace_nef(ms, spec, nef, self.bg_color, precision=self._resolve_precision(spec, nef))
             return RenderBuffer(depth=depth if "depth" in channels else None, hit=hit, rgb=rgb, alpha=alpha)
 
         # ---- unfused route: same operators, nef evaluated through its own forward() ----
@@ -166,8 +173,8 @@ class PackedRFTracer(nn.Module):
 
 class PackedSDFTracer(nn.Module):
     """wisp.tracers.PackedSDFTracer (packed_sdf_tracer.py:20-174): sphere tracing over the nugget list of OctreeAS.raytrace with
-    find_depth_bound jumping between occupied cells; normals by central differences.  Same control flow as the reference; the
-    raytrace, the nugget cursor and the grid interpolation are native kernels."""
+    find_depth_bound jumping between occupied cells; normals by central differences.  The reference's Python loop of masked
+    torch ops is one persistent cooperative kernel here (csrc/wb_sdf.cu)."""
 
     def __init__(self, num_steps=64, step_size=1.0, min_dis=1e-4):
         super().__init__()
@@ -197,69 +204,26 @@ class PackedSDFTracer(nn.Module):
         return self.trace(nef, rays, requested, extra, **args)
 
     def trace(self, nef, rays, channels, extra_channels, lod_idx=None, num_steps=64, step_size=1.0, min_dis=1e-4):
+        """packed_sdf_tracer.py:57-174.  The nuggets come from the native raytrace; the sphere-tracing loop, the nugget cursor
+        and the finite-difference normals are ONE persistent kernel (ops.sdf_trace -> wb_sdf_trace) for NeuralSDF(OctreeGrid);
+        for other fields the per-pack state machine still runs natively and only the field is evaluated through its forward()."""
         assert nef.grid is not None and "this tracer requires a grid"
         if lod_idx is None:
             lod_idx = nef.grid.num_lods - 1
-        invres = 1.0
-        rt = nef.grid.raytrace(rays, nef.grid.active_lods[lod_idx], with_exit=True)
-        ridx, pidx, depth = rt.ridx, rt.pidx, rt.depth
-        dev = rays.origins.device
-        depth[..., 0:1] += 1e-5                                                 # packed_sdf_tracer.py:91
-        first_hit = torch.ones_like(ridx, dtype=torch.bool)
-        if ridx.shape[0] > 1:
-            first_hit[1:] = ridx[1:] != ridx[:-1]                               # mark_pack_boundaries
-        curr_idxes = torch.nonzero(first_hit)[..., 0].int()
-        first_ridx = ridx[first_hit].long()
-        nug_o, nug_d = rays.origins[first_ridx], rays.dirs[first_ridx]
-        mask = torch.ones([first_ridx.shape[0]], device=dev).bool()
-        hit = torch.zeros_like(mask).bool()
-        t = depth[first_hit][..., 0:1]
-        x = torch.addcmul(nug_o, nug_d, t)
-        dist = torch.zeros_like(t)
-        dist_max = rays.dist_max
-        with torch.no_grad():
-            sdf = nef(coords=x[mask], lod_idx=lod_idx, channels="sdf") * invres * step_size
-            dist[mask] = sdf.to(dist.dtype)
-            dist[~mask] = 20
-            dist_prev = dist.clone()
-            for i in range(num_steps):
-                t += dist
-                x = torch.where(mask.view(mask.shape[0], 1), torch.addcmul(nug_o, nug_d, t), x)
-                hit = torch.where(mask, torch.abs(dist)[..., 0] < min_dis * invres, hit)
-                hit |= torch.where(mask, torch.abs(dist + dist_prev)[..., 0] * 0.5 < (min_dis * 5) * invres, hit)
-                mask = torch.where(mask, (t < dist_max)[..., 0], mask)
-                mask &= ~hit
-                if not mask.any():
-                    break
-                dist_prev = torch.where(mask.view(mask.shape[0], 1), dist, dist_prev)
-                next_idxes = ops.find_depth_bound(t, depth, first_hit, curr_idxes=curr_idxes)
-                mask &= (next_idxes != -1)
-                aabb_mask = (next_idxes != curr_idxes)
-                curr_idxes = torch.where(mask, next_idxes, curr_idxes)
-                t = torch.where((mask & aabb_mask).view(mask.shape[0], 1), depth[curr_idxes.long(), 0:1], t)
-                x = torch.where(mask.view(mask.shape[0], 1), torch.addcmul(nug_o, nug_d, t), x)
-                if not mask.any():
-                    break
-                sdf = nef(coords=x[mask], lod_idx=lod_idx, channels="sdf") * invres * step_size
-                dist[mask] = sdf.to(dist.dtype)
-        x_buffer = torch.zeros_like(rays.origins)
-        depth_buffer = torch.zeros_like(rays.origins[..., 0:1])
-        hit_buffer = torch.zeros_like(rays.origins[..., 0]).bool()
-        normal_buffer = torch.zeros_like(rays.origins)
-        rgb_buffer = torch.zeros(*rays.origins.shape[:-1], 3, device=dev)
-        alpha_buffer = torch.zeros(*rays.origins.shape[:-1], 1, device=dev)
-        hit_buffer[first_ridx] = hit
+        want_normals = "rgb" in channels or "normal" in channels
+        blas = nef.grid.blas
+        out, st = ops.sdf_trace(nef, blas.tensors(), rays.origins, rays.dirs, rays.dist_max, nef.grid.active_lods[lod_idx], lod_idx,
+                                num_steps, step_size, min_dis, want_normals)
+        hit = out["hit"]
+        self.prev_num_evals = out.get("_evals")                          # device int32 [1] (fused kernel only): field evaluations of the trace
+        if st is not None and want_normals and bool(hit.any()):          # generic field: central differences through its forward()
+            grad = ops.finitediff_gradient(out["xyz"][hit], nef.get_forward_function("sdf"))
+            out["normal"][hit] = torch.nn.functional.normalize(grad, p=2, dim=-1, eps=1e-5)
+            out["rgb"] = (out["normal"] + 1.0) / 2.0
         extra_outputs = {}
-        for channel in extra_channels:
-            feats = nef(coords=x[hit], lod_idx=lod_idx, channels=channel)
-            extra_buffer = torch.zeros(*rays.origins.shape[:-1], feats.shape[-1], device=dev)
-            extra_buffer[hit_buffer] = feats.to(extra_buffer.dtype)
-            extra_outputs[channel] = extra_buffer
-        x_buffer[hit_buffer] = x[hit]
-        depth_buffer[hit_buffer] = t[hit]
-        if "rgb" in channels or "normal" in channels:
-            grad = ops.finitediff_gradient(x[hit], nef.get_forward_function("sdf"))
-            normal_buffer[hit_buffer] = torch.nn.functional.normalize(grad, p=2, dim=-1, eps=1e-5)
-            rgb_buffer[..., :3] = (normal_buffer + 1.0) / 2.0
-        alpha_buffer[hit_buffer] = 1.0
-        return RenderBuffer(xyz=x_buffer, depth=depth_buffer, hit=hit_buffer, normal=normal_buffer, rgb=rgb_buffer, alpha=alpha_buffer, **extra_outputs)
+        for channel in extra_channels:                                    # queried at the surface points (:153-156)
+            feats = nef(coords=out["xyz"][hit], lod_idx=lod_idx, channels=channel)
+            buf = torch.zeros(*rays.origins.shape[:-1], feats.shape[-1], device=feats.device)
+            buf[hit] = feats.to(buf.dtype)
+            extra_outputs[channel] = buf
+        return RenderBuffer(xyz=out["xyz"], depth=out["depth"], hit=hit, normal=out["normal"], rgb=out["rgb"], alpha=out["alpha"], **extra_outputs)

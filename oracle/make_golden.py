@@ -221,6 +221,51 @@ def gen_sdf():
     print("sdf_octree", out["sum_feats"].shape, out["cat_feats"].shape)
 
 
+def gen_prune():
+    """NeuralRadianceField.prune (nerf.py:175-212) executed by the reference class on CPU: occupancy decay, jittered density probe of
+    every finest-level cell through the reference's HashGrid + decoders, threshold, octree rebuild (from_quantized_points).
+    torch.rand is replaced by a recorded draw; `.cuda()` is the identity (no GPU in the build container)."""
+    from wisp.accelstructs import OctreeAS
+    from wisp.models.grids import HashGrid
+    from wisp.models.nefs import NeuralRadianceField
+    torch.manual_seed(5)
+    level = 4
+    oct_np = O.dense_octree(level)
+    blas = OctreeAS(torch.from_numpy(oct_np))
+    grid = HashGrid.from_geometric(blas, feature_dim=2, num_lods=6, multiscale_type='cat', feature_std=0.8, codebook_bitwidth=11,
+                                   min_grid_res=4, max_grid_res=48)
+    nef = NeuralRadianceField(grid, view_embedder='positional', view_multires=4, hidden_dim=32, num_layers=1, bias=True,
+                              prune_density_decay=0.6, prune_min_density=0.0)
+    N = grid.dense_points.shape[0]
+    rng = np.random.default_rng(21)
+    u = rng.random((N, 3), dtype=np.float32)
+    occ0 = (rng.random(N, dtype=np.float32) * 1.5).astype(np.float32)
+    grid.occupancy = torch.from_numpy(occ0.copy())
+    # threshold at the median of what the update will produce, so that about half of the cells survive
+    orig_rand, orig_cuda = torch.rand, torch.Tensor.cuda
+    torch.rand = lambda *a, **k: torch.from_numpy(u)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        with torch.no_grad():
+            samples = (grid.dense_points.float() + torch.from_numpy(u)) / (2.0 ** level) * 2.0 - 1.0
+            dens = nef(coords=samples, ray_d=torch.zeros_like(samples) + 0.5, channels="density")[:, 0]
+        nef.prune_min_density = float(np.median(np.maximum(dens.numpy(), occ0 * 0.6)))
+        dW, db = _mlp_params(nef.decoder_density)
+        cW, cb = _mlp_params(nef.decoder_color)
+        onef = O.Nef([int(r) for r in grid.resolutions], 2, 11, grid.codebook.feats.detach().numpy().copy(), dW, db, cW, cb, multiscale="cat", view_mode=3, view_freq=4)
+        icfg, resa, begin, table, pd, pc = onef.pack()
+        nef.prune()
+    finally:
+        torch.rand, torch.Tensor.cuda = orig_rand, orig_cuda
+    new_occ = grid.occupancy.numpy()
+    keep = new_occ > nef.prune_min_density
+    np.savez_compressed(os.path.join(OUT, "prune.npz"), octree=oct_np, level=level, u=u, occupancy0=occ0, decay=0.6, min_density=nef.prune_min_density,
+                        icfg=icfg, res=resa, begin=begin, table=table, dens_params=pd, col_params=pc,
+                        density=dens.numpy(), occupancy1=new_occ, keep=keep, new_octree=grid.blas.octree.numpy(),
+                        new_max_level=grid.blas.max_level)
+    print("prune: cells", N, "kept", int(keep.sum()), "new octree bytes", grid.blas.octree.shape[0])
+
+
 def main():
     warnings.filterwarnings("ignore")
     ref_import.install()
@@ -229,6 +274,7 @@ def main():
     gen_raymarch_nuggets()
     gen_triplanar()
     gen_sdf()
+    gen_prune()
     # A: miniature of BASELINE config 2 (cat, bias, positional view embedding, sparse lego-like octree)
     gen_rf_trace("rf_trace_cat", level=5, res=None, hw=24, n_steps=96, num_lods=6, bw=11, min_res=4, max_res=48, hidden=32,
                  num_layers=1, bias=True, multiscale="cat", view_embedder="positional", near=0.0, far=10.0, bg=(1.0, 1.0, 1.0))

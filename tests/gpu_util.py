@@ -36,3 +36,19 @@ def packed_grads(nef):
                 parts.append(l.bias.grad.reshape(-1))
         return torch.cat(parts).cpu().numpy()
     return nef.grid.codebook.feats.grad.cpu().numpy(), flat(nef.decoder_density), flat(nef.decoder_color)
+
+
+def sdf_nef_from_case(case, device="cuda"):
+    """oracle.octree_grid.make_sdf_case -> W.NeuralSDF(OctreeGrid) with identical octree, features and decoder."""
+    blas = W.OctreeAS(torch.from_numpy(case["octree"]).to(device))
+    grid = W.OctreeGrid(blas, feature_dim=case["feature_dim"], num_lods=len(case["active_lods"]), multiscale_type=case["multiscale"], feature_std=0.0)
+    assert grid.active_lods == list(case["active_lods"])
+    assert np.array_equal(grid.trinkets.cpu().numpy(), case["trinkets"])
+    nef = W.NeuralSDF(grid, pos_embedder='none', position_input=True, hidden_dim=case["hidden_dim"], num_layers=len(case["W"]) - 1).to(device)
+    with torch.no_grad():
+        for f, ref in zip(grid.features, case["feats"]):
+            f.copy_(torch.from_numpy(ref))
+        lin = list(nef.decoder.layers) + [nef.decoder.lout]
+        for l, Wm, b in zip(lin, case["W"], case["b"]):
+            l.weight.copy_(torch.from_numpy(Wm)); l.bias.copy_(torch.from_numpy(b))
+    return nef

@@ -310,43 +310,47 @@ def test_premarch_is_the_same_march(W, golden_dir):
         assert o[2] == outs[0][2] and np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])
 
 
-def test_nef_prune_rebuilds_occupancy(W):
-    """NeuralRadianceField.prune() (nerf.py:175-212): occupancy decay, one random density probe per cell, threshold, new OctreeAS.
-    Checked against a line-by-line restatement run with the same RNG state; the marcher then only samples kept cells."""
-    level = 5
-    blas = W.OctreeAS.make_dense(level, device="cuda")
-    torch.manual_seed(1)
-    grid = W.HashGrid.from_geometric(blas, feature_dim=2, num_lods=8, multiscale_type='cat', feature_std=0.5, codebook_bitwidth=12,
-                                     min_grid_res=8, max_grid_res=64)
-    nef = W.NeuralRadianceField(grid, view_embedder='positional', view_multires=2, hidden_dim=32, num_layers=1, bias=True,
-                                prune_density_decay=0.5, prune_min_density=1.02).cuda()
-    with torch.no_grad():
-        nef.decoder_density.lout.weight.mul_(8.0)             # spread the densities around the threshold
-    nef.grid.occupancy = torch.rand(nef.grid.num_cells)
-    occ0 = nef.grid.occupancy.clone()
-    # --- restatement (same RNG draws as prune(): torch.rand on the device, then np.random.rand) ---
-    torch.manual_seed(7); np.random.seed(7)
-    pts = nef.grid.dense_points.cuda()
-    smp = (pts.float() + torch.rand(pts.shape[0], 3, device="cuda")) / 2.0 ** level * 2.0 - 1.0
-    u = np.random.rand(2, pts.shape[0]); z = 1 - 2 * u[0]; r = np.sqrt(1.0 - z * z); phi = 2 * np.pi * u[1]
-    views = torch.from_numpy(np.array([r * np.cos(phi), r * np.sin(phi), z]).transpose()).float().cuda()
-    with torch.no_grad():
-        dens = nef(coords=smp, ray_d=views, channels="density")
-    occ_exp = torch.maximum(dens[:, 0], occ0.cuda() * 0.5)
-    keep = occ_exp > 1.02
-    assert 0 < int(keep.sum()) < pts.shape[0]                 # a non-trivial prune
-    # --- the method ---
-    torch.manual_seed(7); np.random.seed(7)
-    nef.prune()
-    assert torch.allclose(nef.grid.occupancy, occ_exp)
+def test_nef_prune_golden(W, golden_dir):
+    """NeuralRadianceField.prune() against what the REFERENCE class did (tests/golden/prune.npz: nerf.py:175-212 run through
+    oracle/ref_import.py with a recorded torch.rand draw): same occupancy, same surviving cells, byte-identical rebuilt octree.
+    Then properties of the native path: the marcher only samples kept cells; the default counter-based probe stream is
+    deterministic per seed (what makes pruning rank-consistent); a second prune keeps decaying."""
+    from golden_util import load_case
+    from gpu_util import nef_from_oracle
+    g, onef, spc = load_case(os.path.join(golden_dir, "prune.npz"))
+    level = int(g["level"])
+
+    def fresh():
+        nef, blas = nef_from_oracle(onef, spc)
+        nef.prune_density_decay, nef.prune_min_density = float(g["decay"]), float(g["min_density"])
+        nef.grid.occupancy = torch.from_numpy(g["occupancy0"].copy())
+        return nef
+    nef = fresh()
+    pts = nef.grid.dense_points.cpu().numpy()
+    nef.prune(jitter=torch.from_numpy(g["u"]))
+    occ = nef.grid.occupancy.cpu().numpy()
+    np.testing.assert_allclose(occ, g["occupancy1"], atol=2e-5, rtol=1e-5)
+    keep = occ > float(g["min_density"])
+    edge = np.abs(g["occupancy1"] - float(g["min_density"])) < 1e-4          # the threshold is the median: a cell may sit on it
+    assert np.array_equal(keep[~edge], g["keep"][~edge]) and 0 < keep.sum() < keep.size
     new = nef.grid.blas
+    if np.array_equal(keep, g["keep"]):
+        assert np.array_equal(new.octree.cpu().numpy(), g["new_octree"]) and new.max_level == int(g["new_max_level"])
     s0, c0 = int(new.pyramid[1, level]), int(new.pyramid[0, level])
     got = set(map(tuple, new.points[s0:s0 + c0].cpu().numpy().tolist()))
-    assert got == set(map(tuple, pts[keep].cpu().numpy().tolist()))
+    assert got == set(map(tuple, pts[keep].tolist()))
     o, d = O.look_at_rays([-3.0, 0.65, -3.0], [0, 0, 0], 24, 24, 30.0)
     mr = new.raymarch(W.Rays(dev(o), dev(d), dist_min=0.0, dist_max=8.0), 'ray', 128, seed=3)
     cells = torch.floor((mr.samples + 1.0) * 0.5 * 2 ** level).clamp(0, 2 ** level - 1).to(torch.int16).cpu().numpy()
     assert mr.samples.shape[0] > 0 and set(map(tuple, cells.tolist())) <= got
+    # counter-based probe stream: same seed -> same result, other seed -> (slightly) different occupancy
+    a, b, c = fresh(), fresh(), fresh()
+    a.prune(seed=5); b.prune(seed=5); c.prune(seed=6)
+    assert torch.equal(a.grid.occupancy, b.grid.occupancy) and np.array_equal(a.grid.blas.octree.cpu().numpy(), b.grid.blas.octree.cpu().numpy())
+    assert not torch.equal(a.grid.occupancy, c.grid.occupancy)
+    occ_a = a.grid.occupancy.clone()
+    a.prune(seed=5)
+    assert bool((a.grid.occupancy >= occ_a * float(g["decay"]) - 1e-6).all())
 
 
 def test_wide_decoders_under_autocast_stay_native(W):
@@ -649,6 +653,65 @@ def test_triplanar_nerf_voxel_trace(W):
     np.testing.assert_allclose(rb.rgb.detach().cpu().numpy(), exp, atol=2e-4)
 
 
+def _trace_with_grads(W, nef, tracer, rays, fused, precision):
+    """One forward + backward of the tracer; fused=False forces the unfused route (native grid kernel + torch nn.Linear decoders:
+    autograd gives the reference gradients).  -> rgb, depth, alpha, {param name: grad}."""
+    for p_ in nef.parameters():
+        p_.grad = None
+    tracer.precision = precision
+    if not fused:
+        nef.fused_spec = lambda lod_idx=None: None
+    try:
+        assert (nef.fused_spec() is not None) == fused
+        rb = tracer(nef, rays=rays, channels=["rgb", "depth", "alpha", "hit"])
+        tgt = torch.sigmoid(torch.randn(rays.origins.shape[0], 3, generator=torch.Generator().manual_seed(4))).cuda()
+        (torch.nn.functional.smooth_l1_loss(rb.rgb, tgt) + 0.1 * rb.alpha.mean() + 0.01 * rb.depth.mean()).backward()
+    finally:
+        if not fused:
+            del nef.fused_spec
+    grads = {n: p_.grad.detach().clone() for n, p_ in nef.named_parameters() if p_.grad is not None}
+    return rb.rgb.detach(), rb.depth.detach(), rb.alpha.detach(), grads
+
+
+@pytest.mark.parametrize("kind", ["triplanar_sum", "triplanar_cat", "octree_sum", "octree_cat"])
+def test_fused_triplanar_octree_nerf(W, kind):
+    """NeuralRadianceField over TriplanarGrid / OctreeGrid through the FUSED pipeline (gather inside the shade kernels, decoders on
+    the fp32 SIMT kernels or the tensor cores -- no nn.Linear) against the unfused route, whose grid kernels are pinned to the
+    reference classes' goldens and whose decoders are torch's.  Config-4 shapes for the triplanar grid (4 LODs 65^2..513^2 x 4
+    channels, 'voxel' marching of the AABB, 64-wide decoders); nerf_octree.yaml shapes in miniature for the octree grid."""
+    torch.manual_seed(2)
+    o, d = O.look_at_rays([-3.0, 0.65, -3.0], [0, 0, 0], 40, 40, 30.0)
+    rays = W.Rays(dev(o), dev(d), 0.0, 10.0)
+    ms = kind.split("_")[1]
+    if kind.startswith("triplanar"):
+        blas = W.AxisAlignedBBoxAS(device="cuda")
+        grid = W.TriplanarGrid(blas, feature_dim=4, log_base_resolution=6, num_lods=4, multiscale_type=ms, feature_std=0.3)
+        tracer = W.PackedRFTracer('voxel', 48, bg_color=(1.0, 1.0, 1.0))
+    else:
+        blas = W.OctreeAS.from_quantized_points(torch.from_numpy(O.lego_like_points(6)).cuda(), 6)
+        grid = W.OctreeGrid(blas, feature_dim=8, num_lods=4, multiscale_type=ms, feature_std=0.3)
+        tracer = W.PackedRFTracer('ray', 192, bg_color=(1.0, 1.0, 1.0))
+    nef = W.NeuralRadianceField(grid, view_embedder='positional', view_multires=4, hidden_dim=64, num_layers=1, bias=True).cuda()
+    spec = nef.fused_spec()
+    assert spec is not None and spec.kind == kind.split("_")[0]
+    tracer.seed = 11
+    ref = _trace_with_grads(W, nef, tracer, rays, fused=False, precision=0)
+    n_ref = tracer.get_prev_num_samples()
+    assert n_ref > 5000 and float(ref[2].max()) > 0.2
+    for precision, (tol_rgb, tol_depth, tol_g) in ((0, (1e-4, 5e-4, 2e-3)), (1, (2e-3, 2e-2, 3e-2))):
+        tracer.seed = 11
+        got = _trace_with_grads(W, nef, tracer, rays, fused=True, precision=precision)
+        assert tracer.get_prev_num_samples() == n_ref
+        assert float((got[0] - ref[0]).abs().max()) <= tol_rgb, (precision, "rgb")
+        assert float((got[1] - ref[1]).abs().max()) <= tol_depth, (precision, "depth")
+        assert float((got[2] - ref[2]).abs().max()) <= tol_rgb, (precision, "alpha")
+        assert set(got[3]) == set(ref[3])
+        for n, gr in ref[3].items():
+            scale = float(gr.abs().max())
+            assert scale > 0, n
+            assert float((got[3][n] - gr).abs().max()) <= tol_g * scale, (precision, n)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # OctreeGrid / NeuralSDF / PackedSDFTracer (BASELINE config 3 path)
 # ---------------------------------------------------------------------------------------------------------------
@@ -714,22 +777,81 @@ def test_find_depth_bound_vs_oracle(W):
 
 
 def test_sdf_tracer_golden(W, golden_dir):
-    """PackedSDFTracer.trace (sphere tracing + find_depth_bound + finite-difference normals) vs the reference tracer."""
+    """PackedSDFTracer.trace (persistent kernel: sphere tracing + nugget cursor + finite-difference normals) vs the reference
+    tracer run by the reference's own classes.  The decoder sums in a different order than torch's CPU GEMM, so a ray whose
+    |sdf| lands within fp32 round-off of a threshold may flip: at most 1 of the 400 rays, everything else must agree."""
     g = np.load(os.path.join(golden_dir, "sdf_octree.npz"))
     nef, grid, blas = _sdf_from_golden(W, g, "sum")
     tracer = W.PackedSDFTracer(num_steps=24, step_size=0.8, min_dis=1e-3)
     rb = tracer(nef, rays=W.Rays(dev(g["origins"]), dev(g["dirs"]), dist_min=0.0, dist_max=6.0), lod_idx=2,
                 channels=["rgb", "depth", "hit", "normal", "alpha", "xyz"])
     hit, ref_hit = rb.hit.cpu().numpy(), g["t_hit"]
-    # fp16 feature rounding can flip a ray that ends within min_dis of the threshold: allow 2 % disagreement, compare the rest
-    agree = hit == ref_hit
-    assert agree.mean() >= 0.98 and ref_hit.sum() > 20
+    assert (hit != ref_hit).sum() <= 1 and ref_hit.sum() > 20
     both = hit & ref_hit
-    np.testing.assert_allclose(rb.depth.cpu().numpy()[both], g["t_depth"][both], atol=5e-3)
-    np.testing.assert_allclose(rb.xyz.cpu().numpy()[both], g["t_xyz"][both], atol=5e-3)
-    np.testing.assert_allclose(rb.alpha.cpu().numpy()[both], g["t_alpha"][both])
-    dotn = (rb.normal.detach().cpu().numpy()[both] * g["t_normal"][both]).sum(-1)
-    assert np.median(dotn) > 0.99
+    np.testing.assert_allclose(rb.depth.cpu().numpy()[both], g["t_depth"][both], atol=2e-4)
+    np.testing.assert_allclose(rb.xyz.cpu().numpy()[both], g["t_xyz"][both], atol=2e-4)
+    np.testing.assert_allclose(rb.alpha.cpu().numpy(), np.where(hit[:, None], 1.0, 0.0))
+    np.testing.assert_allclose(rb.normal.detach().cpu().numpy()[both], g["t_normal"][both], atol=2e-2)
+    miss = ~hit & ~ref_hit
+    np.testing.assert_allclose(rb.rgb.cpu().numpy()[miss], g["t_rgb"][miss])            # rgb = (0 + 1) / 2 where nothing was hit
+
+
+def _config3_case():
+    from oracle import octree_grid as OG
+    # BASELINE config 3 shapes (nglod_octree.yaml): level-7 octree, OctreeGrid(F=16, 6 LODs, 'sum'), NeuralSDF(128 wide, 1 layer)
+    return OG, OG.make_sdf_case(level=7, num_lods=6, feature_dim=16, hidden_dim=128, multiscale="sum", res=64, seed=11, feature_std=0.02)
+
+
+def test_sdf_eval_config3_vs_oracle(W):
+    """wb_sdf_eval (descent + 6 LODs x 8 corners x 16 features + position input + 19-128-1 decoder in one launch) vs numpy."""
+    from gpu_util import sdf_nef_from_case
+    OG, case = _config3_case()
+    nef = sdf_nef_from_case(case)
+    rng = np.random.default_rng(5)
+    pts = case["spc"].points[case["spc"].pyramid[1, 7]: case["spc"].pyramid[1, 7] + case["spc"].pyramid[0, 7]].astype(np.float32)
+    near = ((pts[rng.integers(0, pts.shape[0], 6000)] + rng.random((6000, 3)).astype(np.float32)) / 64.0 - 1.0).astype(np.float32)
+    coords = np.concatenate([near, rng.uniform(-1.05, 1.05, (2000, 3)).astype(np.float32)])
+    with torch.no_grad():
+        for lod in (5, 2, 0):
+            got = nef(coords=dev(coords), lod_idx=lod, channels="sdf").cpu().numpy()
+            ref = OG.neural_sdf(case, coords, lod)
+            np.testing.assert_allclose(got, ref, atol=2e-5, rtol=1e-5)
+        # the no-grad fast path and the autograd route (grid kernel + torch decoder) are the same function
+        with torch.enable_grad():
+            slow = nef(coords=dev(coords), lod_idx=5, channels="sdf").detach().cpu().numpy()
+        np.testing.assert_allclose(nef(coords=dev(coords), lod_idx=5, channels="sdf").cpu().numpy(), slow, atol=2e-5)
+
+
+def test_sdf_trace_config3_vs_oracle(W):
+    """Sphere tracing at BASELINE config-3 shapes (64^2-ray slice of the 512^2 frame, 32 steps, step 0.8): every quirk of the
+    reference loop is observable here -- terminated packs keep drifting by `dist` until the LAST pack terminates, so depth != |xyz - o|."""
+    from gpu_util import sdf_nef_from_case
+    OG, case = _config3_case()
+    nef = sdf_nef_from_case(case)
+    ref = OG.sdf_trace(case, num_steps=32, step_size=0.8, min_dis=3e-3, dist_max=6.0, return_debug=True)
+    tracer = W.PackedSDFTracer(num_steps=32, step_size=0.8, min_dis=3e-3)
+    rays = W.Rays(dev(case["origins"]), dev(case["dirs"]), dist_min=0.0, dist_max=6.0)
+    rb = tracer(nef, rays=rays, channels=["rgb", "depth", "hit", "normal", "alpha", "xyz"])
+    hit = rb.hit.cpu().numpy()
+    flips = int((hit != ref["hit"]).sum())
+    assert ref["hit"].sum() > 500 and flips <= max(1, hit.size // 500), (flips, int(ref["hit"].sum()))    # <= 0.2 %
+    both = hit & ref["hit"]
+    np.testing.assert_allclose(rb.depth.cpu().numpy()[both], ref["depth"][both], atol=1e-4)
+    np.testing.assert_allclose(rb.xyz.cpu().numpy()[both], ref["xyz"][both], atol=1e-4)
+    dotn = (rb.normal.cpu().numpy()[both] * ref["normal"][both]).sum(-1)
+    assert np.quantile(dotn, 0.01) > 0.999
+    # the phase-by-phase route (fields the library cannot evaluate itself) is the same state machine
+    orig = W.ops.sdf_field
+    try:
+        W.ops.sdf_field = lambda nef_: None
+        rb2 = tracer(nef, rays=rays, channels=["rgb", "depth", "hit", "normal", "alpha", "xyz"])
+    finally:
+        W.ops.sdf_field = orig
+    h2 = rb2.hit.cpu().numpy()
+    assert int((h2 != hit).sum()) <= max(1, hit.size // 500)
+    b2 = h2 & hit
+    np.testing.assert_allclose(rb2.depth.cpu().numpy()[b2], rb.depth.cpu().numpy()[b2], atol=1e-4)
+    np.testing.assert_allclose(rb2.normal.cpu().numpy()[b2], rb.normal.cpu().numpy()[b2], atol=2e-2)
 
 
 # ---------------------------------------------------------------------------------------------------------------

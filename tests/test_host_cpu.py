@@ -4,6 +4,7 @@ refuse to run without a B200 (no CPU fallback)."""
 import ctypes as C
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -179,3 +180,82 @@ def test_bench_reference_arm_contract():
     out1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                           capture_output=True, text=True, timeout=300, env=env)
     assert out1.returncode == 0 and out1.stdout.strip() == ""
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/wisp"), reason="needs the reference checkout (build container only)")
+def test_install_patches_the_real_wisp_classes():
+    """wisp_b200.install.install() against the UNMODIFIED reference classes (imported on CPU through oracle/ref_import.py, in a
+    subprocess because the import stubs are process-wide): every patched method keeps its signature, the tracer keeps the
+    attributes other wisp code reads and survives copy.deepcopy, ops.nef_spec / ops.sdf_field read the reference's own
+    NeuralRadianceField / NeuralSDF objects, unsupported configurations are declined (-> original method), wide decoders
+    under autocast resolve to the fp32 kernels, and uninstall() restores the originals."""
+    import subprocess
+    code = r"""
+import copy, inspect, sys, warnings
+warnings.filterwarnings("ignore")
+sys.path.insert(0, ROOT)
+import torch
+from oracle import ref_import, oracle as O
+ref_import.install()
+import wisp.ops.grid as grid_ops
+from wisp.accelstructs import OctreeAS
+from wisp.models.grids import HashGrid, OctreeGrid, TriplanarGrid
+from wisp.models.nefs import NeuralRadianceField, NeuralSDF
+from wisp.tracers import PackedRFTracer, PackedSDFTracer
+targets = [(OctreeAS, n) for n in ("query", "raytrace", "_raymarch_ray", "_raymarch_voxel", "_raymarch_uniform")] + \
+          [(TriplanarGrid, "interpolate"), (OctreeGrid, "interpolate"), (PackedRFTracer, "trace"), (PackedSDFTracer, "trace"),
+           (NeuralSDF, "sdf"), (NeuralRadianceField, "prune"), (grid_ops, "hashgrid")]
+before = {(c.__name__, n): getattr(c, n) for c, n in targets}
+import wisp_b200 as W
+from wisp_b200 import install as I, ops
+assert I.install() is True
+for c, n in targets:
+    new, old = getattr(c, n), before[(c.__name__, n)]
+    assert new is not old, (c, n)
+    assert list(inspect.signature(new).parameters) == list(inspect.signature(old).parameters), (c, n)
+    assert new.__name__ == n
+tracer = PackedRFTracer(raymarch_type='ray', num_steps=16, bg_color=(0.0, 0.0, 0.0))
+t2 = copy.deepcopy(tracer)
+assert t2.num_steps == 16 and t2.raymarch_type == 'ray' and hasattr(t2, "bg_color") and t2.get_prev_num_samples() is None
+assert tracer.get_supported_channels() == {"depth", "hit", "rgb", "alpha"}
+blas = OctreeAS(torch.from_numpy(O.dense_octree(3)))
+hg = HashGrid.from_geometric(blas, feature_dim=2, num_lods=4, multiscale_type='cat', feature_std=0.1, codebook_bitwidth=10, min_grid_res=4, max_grid_res=32)
+nef = NeuralRadianceField(hg, view_embedder='positional', view_multires=4, hidden_dim=64, num_layers=1, bias=True)
+spec = ops.nef_spec(nef, 3)
+assert spec is not None and spec.kind == "hash" and spec.view_mode == 3 and spec.view_freq == 4 and spec.pos_mode == 0
+assert spec.dens_dims == [8, 64, 16] and spec.col_dims == [42, 64, 64, 3] and spec.has_bias and spec.resolutions == [int(r) for r in hg.resolutions]
+assert ops.precision_supported(spec, nef, 1, True)
+wide = NeuralRadianceField(hg, view_embedder='positional', view_multires=4, hidden_dim=128, num_layers=1, bias=False)
+sw = ops.nef_spec(wide, 3)
+assert sw is not None and not sw.has_bias and ops.precision_supported(sw, wide, 1, False) and not ops.precision_supported(sw, wide, 1, True)
+ident = NeuralRadianceField(hg, view_embedder='none', pos_embedder='positional', pos_multires=3, position_input=True, hidden_dim=32)
+si = ops.nef_spec(ident, 3)
+assert si.view_mode == 1 and si.pos_mode == 3 and si.pos_freq == 3 and si.dens_dims[0] == 8 + 3 + 18
+nef.view_embedder = torch.nn.Linear(3, 27)                      # something the native path does not know (cf. 'tcnn')
+assert ops.nef_spec(nef, 3) is None
+tg = TriplanarGrid(blas, feature_dim=4, log_base_resolution=3, num_lods=2, multiscale_type='sum', feature_std=0.1)
+st = ops.nef_spec(NeuralRadianceField(tg, view_embedder='positional', view_multires=4, hidden_dim=32), 1)
+assert st.kind == "triplanar" and st.feature_dim == 12 and st.resolutions == [8, 16] and ops.raymarch_level(tg, 1) == 0
+og = OctreeGrid(blas, feature_dim=8, num_lods=2, multiscale_type='cat', feature_std=0.1)
+so = ops.nef_spec(NeuralRadianceField(og, view_embedder='positional', view_multires=4, hidden_dim=32), 1)
+assert so.kind == "octree" and so.base_lod == og.base_lod == 2 and so.dens_dims[0] == 16 and ops.raymarch_level(og, 1) == 2
+assert ops.raymarch_level(hg, 3) == 3
+sdf = NeuralSDF(OctreeGrid(blas, feature_dim=16, num_lods=2, multiscale_type='sum', feature_std=0.1), pos_embedder='none', position_input=True, hidden_dim=128, num_layers=1)
+fd = ops.sdf_field(sdf)
+assert fd is not None and fd[0].hidden_dim == 128 and fd[0].feature_dim == 16 and fd[0].pos_mode == 1 and fd[0].multiscale == 1
+assert ops.sdf_field(NeuralSDF(hg, pos_embedder='none', position_input=True, hidden_dim=32)) is None       # SDF over a hash grid: phase-by-phase route
+# no CPU fallback behind the patches either
+from wisp.core import Rays
+try:
+    blas.query(torch.zeros(4, 3))
+    raise SystemExit("query on CPU tensors must raise")
+except W.WispB200Error:
+    pass
+I.uninstall()
+for c, n in targets:
+    assert getattr(c, n) is before[(c.__name__, n)], (c, n)
+print("INSTALL-OK")
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code.replace("ROOT", repr(root))], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "INSTALL-OK" in r.stdout, (r.stdout[-500:], r.stderr[-1500:])

@@ -168,3 +168,31 @@ def test_oracle_step_vs_torch_twin_other_shapes(shape):
     for got, ref, nm in ((st["table"], gt, "table"), (st["dens"], gd, "dens"), (st["col"], gc, "col")):
         scale = max(np.abs(ref).max(), 1e-12)
         assert np.abs(got - ref).max() <= 2e-4 * scale + 1e-9, (nm, np.abs(got - ref).max(), scale)
+
+
+def test_sdf_trace_restatement_matches_reference_tracer(golden_dir):
+    """oracle.octree_grid.sdf_trace (numpy restatement of packed_sdf_tracer.py:78-174) against the RenderBuffer the reference's
+    own PackedSDFTracer produced (tests/golden/sdf_octree.npz, oracle/make_golden.py:gen_sdf)."""
+    from oracle import octree_grid as OG
+    g = np.load(os.path.join(golden_dir, "sdf_octree.npz"))
+    spc = O.octree_to_spc(g["octree"])
+    _, pyr, tr, _ = OG.make_trilinear_spc(spc)
+    case = dict(spc=spc, trinkets=tr, pyramid_dual=pyr, active_lods=[3, 4, 5], feats=[g[f"sum_feat{i}"] for i in range(3)], multiscale="sum",
+                W=[g["sum_W0"], g["sum_W1"]], b=[g["sum_b0"], g["sum_b1"]], origins=g["origins"], dirs=g["dirs"])
+    out = OG.sdf_trace(case, num_steps=24, step_size=0.8, min_dis=1e-3, lod_idx=2, dist_max=6.0)
+    assert np.array_equal(out["hit"], g["t_hit"]) and g["t_hit"].sum() > 20
+    for k, tol in (("depth", 2e-5), ("xyz", 2e-6), ("normal", 2e-4), ("rgb", 1e-4), ("alpha", 0.0)):
+        assert np.abs(out[k] - g["t_" + k]).max() <= tol, k
+
+
+def test_prune_density_probe_matches_reference_class(golden_dir):
+    """The density the reference NeuralRadianceField returned at prune()'s probe points (tests/golden/prune.npz) == oracle nef_rgba."""
+    g, onef, spc = load_case(os.path.join(golden_dir, "prune.npz"))
+    lvl = int(g["level"])
+    pts = spc.points[spc.pyramid[1, lvl]: spc.pyramid[1, lvl] + spc.pyramid[0, lvl]].astype(np.float32)
+    smp = ((pts + g["u"]) / np.float32(2 ** lvl) * np.float32(2.0) - np.float32(1.0)).astype(np.float32)
+    _, dens = O.nef_rgba(onef, smp, np.zeros_like(smp) + 0.5)
+    np.testing.assert_allclose(dens[:, 0], g["density"], atol=2e-6)
+    occ = np.maximum(dens[:, 0], g["occupancy0"] * np.float32(g["decay"]))
+    np.testing.assert_allclose(occ, g["occupancy1"], atol=2e-6)
+    assert np.array_equal(O.points_to_octree(pts[g["keep"]].astype(np.int16), lvl), g["new_octree"])
