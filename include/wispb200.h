@@ -328,6 +328,43 @@ int wb_rf_table_scatter(const wb_nef_desc* nef, const wb_rays* rays, const float
                         const float* loss_scale, void* workspace, float* grad_table, wb_stream s);
 
 /* ------------------------------------------------------------------------------------------------
+ * Trainer step glue: MultiviewTrainer.step (wisp/trainers/multiview_trainer.py:111-180) and
+ * BaseTrainer.init_optimizer (wisp/trainers/base_trainer.py:205-235).
+ *   wb_composite_bwd_loss : wb_composite_bwd with the image loss and its gradient evaluated inside: rgb_pred = wb_composite_fwd's
+ *       rgb, target = ground truth [R,3]; loss_type 0 = l2 (mse_loss), 1 = l1, 2 = huber (smooth_l1_loss), reduction =
+ *       sum * inv_count; *loss_out (device float, zeroed by the caller) receives the loss value.
+ *   wb_adam_step : torch.optim.Adam (amsgrad off) over up to 64 tensors in one launch; per-segment lr and weight decay carry the
+ *       reference's parameter groups; grad_scale multiplies every gradient first (1/world after an all-reduce(sum)); zero_grad != 0
+ *       clears each gradient as it is consumed.  desc_dev: device scratch, desc_pinned: page-locked host scratch, both
+ *       wb_adam_desc_bytes() bytes, owned by the caller for as long as steps are in flight.
+ * ---------------------------------------------------------------------------------------------- */
+int wb_composite_bwd_loss(const float* shaded, const float* depth, const float* deltas, const int64_t* offsets, int64_t R,
+                          const float* bg, const float* rgb_pred, const float* target, int32_t loss_type, float inv_count,
+                          float* g_shaded, float* absmax, float* loss_out, wb_stream s);
+typedef struct wb_adam_segment {
+    float* param; float* grad; float* exp_avg; float* exp_avg_sq;
+    int64_t numel;
+    float lr, weight_decay;
+} wb_adam_segment;
+int64_t wb_adam_desc_bytes(void);
+int wb_adam_step(const wb_adam_segment* segs, int32_t nseg, float beta1, float beta2, float eps, int32_t step, float grad_scale,
+                 int32_t zero_grad, void* desc_dev, void* desc_pinned, wb_stream s);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ray generation (camera -> rays on the device); origin/view/right/up/cam_pos/rotation are HOST pointers (launch parameters).
+ *   wb_raygen_lookat  : _look_at + _generate_rays (wisp/trainers/tracker/offline_renderer.py:23-89) over normalized_grid
+ *                       (wisp/ops/geometric.py:65-99, use_aspect=True, no jitter); view/right/up are the normalised camera frame
+ *                       the reference derives from (from, to); ortho != 0 selects mode='ortho'.  origins / dirs: [H*W, 3].
+ *   wb_raygen_pinhole : generate_pinhole_rays (wisp/ops/raygen/raygen.py:40-85) with the pixel grid of
+ *                       generate_centered_pixel_coords (:24-31); the Kaolin camera is passed as numbers: position, camera-to-world
+ *                       rotation (row-major 3x3), principal point x0/y0, tan(fov/2) per axis, image size, ray-grid size.
+ * ---------------------------------------------------------------------------------------------- */
+int wb_raygen_lookat(const float* origin, const float* view, const float* right, const float* up, float tan_half_fov,
+                     int32_t height, int32_t width, int32_t ortho, float* origins, float* dirs, wb_stream s);
+int wb_raygen_pinhole(const float* cam_pos, const float* cam_to_world_rot, float x0, float y0, float tan_half_fov_h, float tan_half_fov_v,
+                      int32_t img_height, int32_t img_width, int32_t res_y, int32_t res_x, float* origins, float* dirs, wb_stream s);
+
+/* ------------------------------------------------------------------------------------------------
  * NeuralRadianceField.prune (wisp/models/nefs/nerf.py:175-212), the elementwise halves around the density probe:
  *   wb_prune_samples : one probe point per finest-level cell, samples = ((points + u) / 2^level) * 2 - 1 (:189-192) and a unit
  *                      direction; u = explicit [N,3] draw, or NULL for the counter stream keyed by (seed, cell, axis).  Also writes

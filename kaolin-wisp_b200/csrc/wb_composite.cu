@@ -59,20 +59,42 @@ extern "C" int wb_composite_fwd(const float* shaded, const float* depth, const f
 // backward:  g_k = dL/dw_k = g_rgb.c_k + g_depth*t_k + (g_alpha - g_rgb.bg)
 //            dL/dtau_k = g_k*T_{k+1} - sum_{j>k} g_j w_j      dL/dc_k = g_rgb*w_k      dL/dsigma_k = dL/dtau_k*delta_k
 // pass 1 accumulates G = sum_j g_j w_j, pass 2 uses G - prefix_incl.
+// LOSS: the trainer's image loss (multiview_trainer.py:140-154) is evaluated here instead of by torch: g_rgb holds the PREDICTED rgb
+// (wb_composite_fwd's output), `target` the ground truth, and dL/drgb = loss'(rgb - target) * inv_count is formed per ray in
+// registers; the loss value (sum over rays and channels * inv_count) is accumulated into *loss_out.
+struct WbLoss { const float* target; int type; float inv_count; float* loss_out; };      // type 0 l2 (mse), 1 l1, 2 huber (smooth_l1, beta 1)
+__device__ __forceinline__ float wb_loss_term(int type, float d, float& grad)
+{
+    if (type == 0) { grad = 2.0f * d; return d * d; }
+    if (type == 1) { grad = d > 0.0f ? 1.0f : d < 0.0f ? -1.0f : 0.0f; return fabsf(d); }
+    const float ad = fabsf(d);
+    if (ad < 1.0f) { grad = d; return 0.5f * d * d; }
+    grad = d > 0.0f ? 1.0f : -1.0f; return ad - 0.5f;
+}
+
+template <bool LOSS>
 __global__ void __launch_bounds__(WB_COMP_THREADS)
 wb_composite_bwd_kernel(const float4* __restrict__ shaded, const float* __restrict__ depth, const float* __restrict__ deltas,
                         const int64_t* __restrict__ offsets, int64_t R, float bgr, float bgg, float bgb,
                         const float* __restrict__ g_rgb, const float* __restrict__ g_depth, const float* __restrict__ g_alpha,
-                        float4* __restrict__ g_shaded, float* __restrict__ absmax)
+                        float4* __restrict__ g_shaded, float* __restrict__ absmax, WbLoss LS)
 {
-    float amax = 0.0f;
+    float amax = 0.0f, lsum = 0.0f;
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = warp0; r < R; r += nwarps) {
         const int64_t b = offsets[r], e = offsets[r + 1];
+        float gr, gg, gb;
+        if (LOSS) {
+            float l0 = wb_loss_term(LS.type, __ldg(g_rgb + 3 * r) - __ldg(LS.target + 3 * r), gr);
+            l0 += wb_loss_term(LS.type, __ldg(g_rgb + 3 * r + 1) - __ldg(LS.target + 3 * r + 1), gg);
+            l0 += wb_loss_term(LS.type, __ldg(g_rgb + 3 * r + 2) - __ldg(LS.target + 3 * r + 2), gb);
+            gr *= LS.inv_count; gg *= LS.inv_count; gb *= LS.inv_count;
+            if (lane == 0) lsum += l0;
+        }
         if (e == b) continue;
-        const float gr = __ldg(g_rgb + 3 * r), gg = __ldg(g_rgb + 3 * r + 1), gb = __ldg(g_rgb + 3 * r + 2);
+        if (!LOSS) { gr = __ldg(g_rgb + 3 * r); gg = __ldg(g_rgb + 3 * r + 1); gb = __ldg(g_rgb + 3 * r + 2); }
         const float gd = g_depth ? __ldg(g_depth + r) : 0.0f;
         const float ga = (g_alpha ? __ldg(g_alpha + r) : 0.0f) - (gr * bgr + gg * bgg + gb * bgb);
         float G = 0, carry = 0;
@@ -114,6 +136,7 @@ wb_composite_bwd_kernel(const float4* __restrict__ shaded, const float* __restri
         for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
         if (lane == 0 && amax > 0.0f) atomicMax(reinterpret_cast<unsigned int*>(absmax), __float_as_uint(amax));
     }
+    if (LOSS && lane == 0 && lsum != 0.0f) atomicAdd(LS.loss_out, lsum * LS.inv_count);
 }
 
 extern "C" int wb_composite_bwd(const float* shaded, const float* depth, const float* deltas, const int64_t* offsets, int64_t R,
@@ -124,9 +147,29 @@ extern "C" int wb_composite_bwd(const float* shaded, const float* depth, const f
     WB_CHECK_ARG(offsets && bg && g_rgb, "null pointer");
     const float b3[3] = { bg[0], bg[1], bg[2] };   // host pointer (launch parameter)
     int64_t ctas = (R + 7) / 8; const int64_t cap = (int64_t)wb_num_sms() * 32; if (ctas > cap) ctas = cap;
-    wb_composite_bwd_kernel<<<(unsigned)ctas, WB_COMP_THREADS, 0, (cudaStream_t)s>>>(
+    wb_composite_bwd_kernel<false><<<(unsigned)ctas, WB_COMP_THREADS, 0, (cudaStream_t)s>>>(
         reinterpret_cast<const float4*>(shaded), depth, deltas, offsets, R, b3[0], b3[1], b3[2], g_rgb, g_depth, g_alpha,
-        reinterpret_cast<float4*>(g_shaded), absmax);
+        reinterpret_cast<float4*>(g_shaded), absmax, WbLoss{ nullptr, 0, 0.0f, nullptr });
+    WB_LAUNCH_CHECK();
+    return WB_OK;
+}
+
+// Image loss + its gradient + the compositing backward in one launch: replaces smooth_l1_loss / mse_loss /
+// abs, .mean(), their autograd kernels and the [R,3] gradient tensor of MultiviewTrainer.step (multiview_trainer.py:140-176).
+// loss_out (device float, zeroed by the caller) receives sum(loss(rgb - target)) * inv_count; inv_count = 1 / (3 * rays) for
+// rgb_loss_denom 'rays' (global ray count under data parallelism), 1 / prev_num_samples for 'samples'.
+extern "C" int wb_composite_bwd_loss(const float* shaded, const float* depth, const float* deltas, const int64_t* offsets, int64_t R,
+                                     const float* bg, const float* rgb_pred, const float* target, int32_t loss_type, float inv_count,
+                                     float* g_shaded, float* absmax, float* loss_out, wb_stream s)
+{
+    if (R == 0) return WB_OK;
+    WB_CHECK_ARG(offsets && bg && rgb_pred && target && g_shaded && loss_out, "null pointer");
+    WB_CHECK_ARG(loss_type >= 0 && loss_type <= 2, "loss_type must be 0 (l2), 1 (l1) or 2 (huber)");
+    const float b3[3] = { bg[0], bg[1], bg[2] };
+    int64_t ctas = (R + 7) / 8; const int64_t cap = (int64_t)wb_num_sms() * 32; if (ctas > cap) ctas = cap;
+    wb_composite_bwd_kernel<true><<<(unsigned)ctas, WB_COMP_THREADS, 0, (cudaStream_t)s>>>(
+        reinterpret_cast<const float4*>(shaded), depth, deltas, offsets, R, b3[0], b3[1], b3[2], rgb_pred, nullptr, nullptr,
+        reinterpret_cast<float4*>(g_shaded), absmax, WbLoss{ target, loss_type, inv_count, loss_out });
     WB_LAUNCH_CHECK();
     return WB_OK;
 }

@@ -56,9 +56,39 @@ struct WbTc {
     int work_col[2];                           // TMEM working accumulator of sub-tile 0/1
     int tmem_cols;
     int feat_dim, pos_dim, view_dim, pos_mode, pos_freq, view_mode, view_freq;
+    int fits2;                                 // backward: the two-group kernel (all tiles retained) fits in shared memory
 };
 
 static int tc_round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// ---- three-group decoder backward (wb_shade_tc_bwd3.cuh): shared-memory plan ----
+constexpr int TC_B3_GROUPS = 3;
+struct TcB3Plan { int P, Q, R, E, GB, blob_off, ones_off, smem_bytes; };      // byte offsets (P..E from the group base, GB = group stride)
+
+// host: shared-memory plan; returns false when the configuration is outside the variant's scope
+static bool tc_b3_plan(const WbTc& m, TcB3Plan* p)
+{
+    if (m.nl_d != 2 || m.nl_c != 3) return false;
+    int maxw = 0;
+    for (int l = 0; l < 5; ++l) maxw = max(maxw, max(m.Kp[l], m.Np[l]));
+    if (maxw > 64) return false;
+    // the hidden activation tiles X1, X3, X4 share the buffers P and Q, whose constant-one slab sits behind a maxw-wide tile: the
+    // hidden width must BE the widest tile (true for app/nerf: 64-wide hidden layers over 32 / 42 inputs; a 32-wide decoder over a
+    // 42-wide colour input would read its bias-gradient row from a stale slab)
+    if (m.Kp[1] != maxw || m.Kp[3] != maxw || m.Kp[4] != maxw || m.Np[0] != maxw || m.Np[2] != maxw || m.Np[3] != maxw) return false;
+    const int big = (maxw / 8 + 1) * 2048;                       // a maxw-wide tile + its constant-one slab
+    const int small = (max(m.Np[1], m.Np[4]) / 8) * 2048;        // dY1 / dY4
+    p->P = 0; p->Q = big; p->R = 2 * big; p->E = 3 * big; p->GB = 3 * big + small;
+    p->blob_off = TC_B3_GROUPS * p->GB;
+    p->ones_off = p->blob_off + m.blob_bytes;
+    int end = p->ones_off + 2 * 2048;
+    const int window = (TC_B3_GROUPS - 1) * p->GB + p->R + 16 * 2048;     // 16-slab read window of the weight-grad A operand
+    if (end < window) end = window;
+    p->smem_bytes = end + 64;
+    return p->smem_bytes + 6144 <= 227 * 1024;
+}
+
+
 static int tc_embed_dim(int mode, int freq) { return mode == 0 ? 0 : mode == 1 ? 3 : mode == 2 ? 6 * freq : 3 + 6 * freq; }
 
 // returns WB_OK, or WB_ERR_INVALID with a message when the configuration does not fit the tensor-core path
@@ -115,14 +145,19 @@ int wb_tc_make(const wb_nef_desc* d, bool backward, WbTc* m, bool tmem_a = false
     }
     m->smem_bytes = p + 64;
     // static shared memory of the kernels (issue table, barriers): 3 KB forward, 5 KB backward
-    WB_CHECK_ARG(m->smem_bytes + (backward ? 5632 : 3584) <= 227 * 1024,
-                 backward ? "tensor-core path: decoder backward does not fit in shared memory (use precision 0)"
-                          : "tensor-core path: decoder does not fit in shared memory (use precision 0)");
+    m->fits2 = (m->smem_bytes + (backward ? 5632 : 3584) <= 227 * 1024) ? 1 : 0;
+    if (!m->fits2) {       // the two-group backward retains every activation tile; the three-group kernel's uniform buffers may still fit
+        TcB3Plan plan3;
+        WB_CHECK_ARG(backward && tc_b3_plan(*m, &plan3),
+                     backward ? "tensor-core path: decoder backward does not fit in shared memory (use precision 0)"
+                              : "tensor-core path: decoder does not fit in shared memory (use precision 0)");
+    }
     int col = 0;
     for (int gi = 0; gi < groups; ++gi) { m->work_col[gi] = col; col += maxw; }
     // forward TMEM-A variant (one group): work_col[1] is otherwise unused and holds the first column of the fp16 activation tile
     if (tmem_a && !backward) { m->work_col[1] = col; col += maxw / 2; }  // two halfs per 32-bit column
     if (backward) for (int l = 0; l < nl; ++l) { m->acc_col[l] = col; col += m->Np[l]; }
+    if (backward && !m->fits2) col += 64;      // three-group kernel: a third working accumulator
     WB_CHECK_ARG(col <= 512, "tensor-core path: accumulators do not fit in TMEM (use precision 0)");
     int alloc = 32; while (alloc < col) alloc <<= 1;
     m->tmem_cols = alloc;
@@ -652,6 +687,7 @@ static int tc_launch_ray_embed(const WbTc& m, const wb_rays* rays, void* workspa
 // Tuning knobs (defaults = the measured optimum on B200 for the app/nerf configuration, profiles/README.md); the environment
 // overrides exist for the sweeps and are read once per process.
 static int tc_env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
+static int tc_knob_fuse_scatter() { static const int v = tc_env_int("WB_TC_FUSE_SCATTER", 1); return v; }
 static int tc_knob_bwd_groups() { static const int v = tc_env_int("WB_TC_BWD_GROUPS", 3); return v; }
 static int tc_knob_fwd_tmema() { static const int v = tc_env_int("WB_TC_FWD_TMEMA", 1); return v; }
 static int tc_knob_fwd_ctas() { static const int v = tc_env_int("WB_TC_FWD_CTAS", 3); return v; }
@@ -1013,10 +1049,22 @@ wb_featx_scatter_kernel(WbGridX gx, TcIn in, const __half* __restrict__ dfeat, i
 #include "wb_shade_tc_bwd3.cuh"          // three-group variant: the default for the app/nerf decoder shape (WB_TC_BWD_GROUPS=2 selects the kernel above)
 
 // decoder backward only: dL/d(shaded) -> weight gradients + dL/dfeat planes in the workspace
+// grad_table != NULL asks for the table scatter to be fused into the decoder backward; *fused_out reports whether it was (it is for the
+// app/nerf shape: F == 2 'cat' hash grid, three-group kernel) -- otherwise the caller runs wb_tc_table_scatter afterwards
+int wb_tc_decoder_bwd_ex(const wb_nef_desc* nef, const float* blob, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray,
+                         int64_t S, const float* g_shaded, const float* scale, const void* feat_saved, void* workspace,
+                         float* grad_dens, float* grad_col, float* grad_table, int* fused_out, cudaStream_t st);
 int wb_tc_decoder_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray,
                       int64_t S, const float* g_shaded, const float* scale, const void* feat_saved, void* workspace,
                       float* grad_dens, float* grad_col, cudaStream_t st)
 {
+    return wb_tc_decoder_bwd_ex(nef, blob, rays, rec_t, rec_ray, S, g_shaded, scale, feat_saved, workspace, grad_dens, grad_col, nullptr, nullptr, st);
+}
+int wb_tc_decoder_bwd_ex(const wb_nef_desc* nef, const float* blob, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray,
+                         int64_t S, const float* g_shaded, const float* scale, const void* feat_saved, void* workspace,
+                         float* grad_dens, float* grad_col, float* grad_table, int* fused_out, cudaStream_t st)
+{
+    if (fused_out) *fused_out = 0;
     WbTc m; int rc = wb_tc_make(nef, true, &m); if (rc) return rc;
     WB_CHECK_ARG(scale != nullptr, "precision 1 needs the device loss-scale pointer");
     WB_CHECK_ARG(feat_saved != nullptr && workspace != nullptr, "precision 1 backward needs the saved features and the workspace");
@@ -1027,21 +1075,28 @@ int wb_tc_decoder_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* 
     TcIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S, reinterpret_cast<const uint4*>(workspace), nullptr, reinterpret_cast<const uint4*>(feat_saved) };
     TcGrads G = { grad_dens, grad_col, scale, dfeat, planes, width };
     TcB3Plan plan;
-    if (tc_knob_bwd_groups() == 3 && tc_b3_plan(m, &plan)) {     // three sub-tile groups per SM (wb_shade_tc_bwd3.cuh): 4.53 -> 3.69 ms measured
+    if ((tc_knob_bwd_groups() == 3 || !m.fits2) && tc_b3_plan(m, &plan)) {     // three sub-tile groups per SM (wb_shade_tc_bwd3.cuh): 4.53 -> 3.69 ms measured
         WbTc m3 = m;
         for (int l = 0; l < m.nl_d + m.nl_c; ++l) m3.acc_col[l] += 64;       // work columns 0..191, accumulators behind them
-        static int done3 = -1;
-        if (done3 != plan.smem_bytes) {
-            WB_CUDA(cudaFuncSetAttribute(wb_mlp_bwd3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
-            done3 = plan.smem_bytes;
+        WbGrid g; memset(&g, 0, sizeof(g));
+        const bool fuse = grad_table != nullptr && tc_knob_fuse_scatter() && nef->grid_kind == 0 && nef->feature_dim == 2 && nef->multiscale == 0 &&
+                          planes <= 16;
+        if (fuse) { rc = wb_make_grid(nef, &g); if (rc) return rc; }
+        auto kern3 = fuse ? wb_mlp_bwd3_tc_kernel<true> : wb_mlp_bwd3_tc_kernel<false>;
+        static int done3[2] = { -1, -1 };
+        if (done3[fuse ? 1 : 0] != plan.smem_bytes) {
+            WB_CUDA(cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
+            done3[fuse ? 1 : 0] = plan.smem_bytes;
         }
         const int64_t nctas3 = ((S + TC_ROWS - 1) / TC_ROWS + TC_B3_GROUPS - 1) / TC_B3_GROUPS;
         int64_t grid3 = (int64_t)wb_num_sms(); if (grid3 > nctas3) grid3 = nctas3;
-        wb_mlp_bwd3_tc_kernel<<<(unsigned)grid3, TC_B3_GROUPS * TC_GROUP, plan.smem_bytes, st>>>(m3, plan, reinterpret_cast<const uint8_t*>(blob), in,
-                                                                                          reinterpret_cast<const float4*>(g_shaded), G);
+        kern3<<<(unsigned)grid3, TC_B3_GROUPS * TC_GROUP, plan.smem_bytes, st>>>(m3, plan, reinterpret_cast<const uint8_t*>(blob), in,
+                                                                          reinterpret_cast<const float4*>(g_shaded), G, g, grad_table);
         WB_LAUNCH_CHECK();
+        if (fuse && fused_out) *fused_out = 1;
         return WB_OK;
     }
+    WB_CHECK_ARG(m.fits2, "tensor-core path: decoder backward does not fit in shared memory (use precision 0)");
     {
         static int done_for = -1;
         if (done_for != m.smem_bytes) {
@@ -1094,7 +1149,8 @@ int wb_tc_shade_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* ra
                     int64_t S, const float* g_shaded, const float* scale, const void* feat_saved, void* workspace,
                     float* grad_table, float* grad_dens, float* grad_col, cudaStream_t st)
 {
-    int rc = wb_tc_decoder_bwd(nef, blob, rays, rec_t, rec_ray, S, g_shaded, scale, feat_saved, workspace, grad_dens, grad_col, st);
-    if (rc) return rc;
+    int fused = 0;
+    int rc = wb_tc_decoder_bwd_ex(nef, blob, rays, rec_t, rec_ray, S, g_shaded, scale, feat_saved, workspace, grad_dens, grad_col, grad_table, &fused, st);
+    if (rc || fused) return rc;
     return wb_tc_table_scatter(nef, rays, rec_t, rec_ray, S, scale, workspace, grad_table, st);
 }

@@ -27,29 +27,7 @@
 // Restricted to the app/nerf decoder depth (2 density layers, 3 colour layers), every width <= 64.
 #pragma once
 
-constexpr int TC_B3_GROUPS = 3;
 constexpr int TC_B3_ROUNDS = 11;
-
-struct TcB3Plan { int P, Q, R, E, GB, blob_off, ones_off, smem_bytes; };      // byte offsets (P..E from the group base, GB = group stride)
-
-// host: shared-memory plan; returns false when the configuration is outside the variant's scope
-static bool tc_b3_plan(const WbTc& m, TcB3Plan* p)
-{
-    if (m.nl_d != 2 || m.nl_c != 3) return false;
-    int maxw = 0;
-    for (int l = 0; l < 5; ++l) maxw = max(maxw, max(m.Kp[l], m.Np[l]));
-    if (maxw > 64) return false;
-    const int big = (maxw / 8 + 1) * 2048;                       // a maxw-wide tile + its constant-one slab
-    const int small = (max(m.Np[1], m.Np[4]) / 8) * 2048;        // dY1 / dY4
-    p->P = 0; p->Q = big; p->R = 2 * big; p->E = 3 * big; p->GB = 3 * big + small;
-    p->blob_off = TC_B3_GROUPS * p->GB;
-    p->ones_off = p->blob_off + m.blob_bytes;
-    int end = p->ones_off + 2 * 2048;
-    const int window = (TC_B3_GROUPS - 1) * p->GB + p->R + 16 * 2048;     // 16-slab read window of the weight-grad A operand
-    if (end < window) end = window;
-    p->smem_bytes = end + 64;
-    return p->smem_bytes + 6144 <= 227 * 1024;
-}
 
 // ---- per-CTA issue table: [group][round][chain]  (chain 0, 1: warp 0 in this order; chain 2: warp 1) ----
 __device__ __forceinline__ void tc_b3_build_table(const WbTc& m, const TcB3Plan& p, TcRec* tab, uint8_t* smem, uint32_t tmem)
@@ -164,8 +142,79 @@ __device__ __forceinline__ void tc_b3_one_slab(uint8_t* tile, int slab, int r)
     *reinterpret_cast<uint4*>(tile + slab * 2048 + r * 16) = one;
 }
 
+// One LOD of the hash-table scatter for the 32 consecutive samples of a warp (F == 2): the arithmetic of wb_table_scatter_kernel
+// <2, true, true> (hashgrid_interpolate_cuda.cu:151-160 + run merging + paired 16-byte reductions), callable from the decoder
+// backward's last epilogue so that dL/dfeat never leaves the SM.  s0, s1: this sample's (still loss-scaled) gradient of the LOD's two
+// features.  Warp-collective: every lane of the warp calls it with the same `l`.
+__device__ __forceinline__ void tc_scatter_level_f2(const WbGrid& g, int l, float px, float py, float pz, bool valid, float s0, float s1,
+                                                    float inv_scale, int lane, float* __restrict__ gtable)
+{
+    float* tb = gtable + g.begin[l] * 2;
+    const bool pair_ok = (reinterpret_cast<uintptr_t>(tb) & 15u) == 0;
+    uint32_t idx[8]; float cf[8]; uint64_t key = ~0ull - (uint64_t)lane;    // invalid lanes never merge
+    if (valid) {
+        int ix, iy, iz; float wx, wy, wz, jx, jy, jz;
+        wb_cell(px, g.hres[l], g.hi[l], ix, wx, jx); wb_cell(py, g.hres[l], g.hi[l], iy, wy, jy); wb_cell(pz, g.hres[l], g.hi[l], iz, wz, jz);
+        key = (uint64_t)ix | ((uint64_t)iy << 20) | ((uint64_t)iz << 40);
+        const float xy00 = jx * jy, xy01 = jx * wy, xy10 = wx * jy, xy11 = wx * wy;
+        cf[0] = xy00 * jz; cf[1] = xy00 * wz; cf[2] = xy01 * jz; cf[3] = xy01 * wz;
+        cf[4] = xy10 * jz; cf[5] = xy10 * wz; cf[6] = xy11 * jz; cf[7] = xy11 * wz;
+        wb_corner_indices(g, l, ix, iy, iz, idx);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { idx[j] = 0; cf[j] = 0.0f; }
+    }
+    const uint64_t kprev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = (lane == 0) || (kprev != key);
+    const uint32_t heads = __ballot_sync(0xffffffffu, head);
+    const int run_head = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+    const int dist = lane - run_head;
+    const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
+    const int maxd = __reduce_max_sync(0xffffffffu, dist);
+    float v0[8], v1[8];
+    if (maxd > 0) {     // run sums as loss-scaled fp16 pairs (one shuffle per corner and scan step), unscaled after the scan
+        __half2 h[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(s0 * cf[j], s1 * cf[j]);
+        for (int o = 1; o <= maxd; o <<= 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const __half2 a = __shfl_up_sync(0xffffffffu, h[j], o);
+                if (dist >= o) h[j] = __hadd2(h[j], a);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float2 f = __half22float2(h[j]); v0[j] = f.x * inv_scale; v1[j] = f.y * inv_scale; }
+    } else {
+        const float g0 = s0 * inv_scale, g1 = s1 * inv_scale;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v0[j] = g0 * cf[j]; v1[j] = g1 * cf[j]; }
+    }
+    if (tail && valid) {
+        float2* t2 = reinterpret_cast<float2*>(tb);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t i0 = idx[j], i1 = idx[j + 4];
+            const bool nz0 = (v0[j] != 0.0f || v1[j] != 0.0f), nz1 = (v0[j + 4] != 0.0f || v1[j + 4] != 0.0f);
+            if (pair_ok && ((i0 ^ i1) == 1u)) {
+                if (nz0 || nz1) {
+                    const float4 val = (i0 & 1u) ? make_float4(v0[j + 4], v1[j + 4], v0[j], v1[j]) : make_float4(v0[j], v1[j], v0[j + 4], v1[j + 4]);
+                    atomicAdd(reinterpret_cast<float4*>(t2 + (i0 & ~1u)), val);
+                }
+            } else {
+                if (nz0) atomicAdd(t2 + i0, make_float2(v0[j], v1[j]));
+                if (nz1) atomicAdd(t2 + i1, make_float2(v0[j + 4], v1[j + 4]));
+            }
+        }
+    }
+}
+
+// FUSE: the hash-table scatter runs in the last epilogue of every sub-tile instead of as a second kernel: the 60 B/sample of fp16
+// dL/dfeat planes (written, then re-read with the sample position rebuilt) never reach HBM, and the scatter's shuffles / reductions
+// fill issue slots that the round latencies of the other two groups leave empty.  F == 2 'cat' hash grids only.
+template <bool FUSE>
 __global__ void __launch_bounds__(TC_B3_GROUPS * TC_GROUP, 1)
-wb_mlp_bwd3_tc_kernel(WbTc m, TcB3Plan p, const uint8_t* __restrict__ blob, TcIn in, const float4* __restrict__ g_shaded, TcGrads G)
+wb_mlp_bwd3_tc_kernel(WbTc m, TcB3Plan p, const uint8_t* __restrict__ blob, TcIn in, const float4* __restrict__ g_shaded, TcGrads G, WbGrid g, float* __restrict__ gtable)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[TC_B3_GROUPS + 1];
@@ -277,9 +326,25 @@ wb_mlp_bwd3_tc_kernel(WbTc m, TcB3Plan p, const uint8_t* __restrict__ blob, TcIn
         // r9: B1 -> dY0 in place over X1 (Q)
         tc_b3_round(c, rec + 9 * 3);
         tc_b3_mask_in_place(c, trow, m.Kp[1], bQ);
-        // r10: B0 -> dL/dfeat planes
+        // r10: B0 -> dL/dfeat: scattered into the hash table right here (FUSE) or written as fp16 planes for wb_table_scatter_kernel
+        float px = 0.0f, py = 0.0f, pz = 0.0f;
+        if (FUSE) {                                               // sample position (octree_as.py:283); the loads overlap the round
+            const float t = __ldg(in.rec_t + s);
+            px = wb_addcmul(__ldg(in.origins + 3 * ray), __ldg(in.dirs + 3 * ray), t);
+            py = wb_addcmul(__ldg(in.origins + 3 * ray + 1), __ldg(in.dirs + 3 * ray + 1), t);
+            pz = wb_addcmul(__ldg(in.origins + 3 * ray + 2), __ldg(in.dirs + 3 * ray + 2), t);
+        }
         tc_b3_round(c, rec + 10 * 3);
-        {
+        if (FUSE) {
+            // column half h holds features [16h, 16h+16) = LODs 8h .. 8h+7; a warp = 32 consecutive samples of one half
+            float v[16]; tc_ld16(trow + c.h * 16, v);
+            const int lane = threadIdx.x & 31;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int l = c.h * 8 + q;
+                if (l < G.planes) tc_scatter_level_f2(g, l, px, py, pz, valid, v[2 * q], v[2 * q + 1], inv_scale, lane, gtable);
+            }
+        } else {
             const int W = G.width, nfe = G.planes * W;
             for (int f0 = c.h * 16; f0 < nfe; f0 += 32) {
                 float v[16]; tc_ld16(trow + f0, v);

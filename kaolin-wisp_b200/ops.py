@@ -672,6 +672,7 @@ class CompositeFn(torch.autograd.Function):
 # fused render path
 # --------------------------------------------------------------------------------------------------------------
 GRID_KINDS = {"hash": 0, "triplanar": 1, "octree": 2}
+SPLIT_BWD = __import__("os").environ.get("WB_SPLIT_BWD", "0") == "1"
 
 
 @dataclass
@@ -953,14 +954,14 @@ class RFTraceFn(torch.autograd.Function):
             A.check(L.wb_rf_loss_scale(A.ptr(absmax), A.ptr(scale), A.stream()))
         wsb = int(L.wb_rf_workspace_bytes(C.byref(desc), C.c_int32(ctx.precision), C.c_int64(R), C.c_int64(_bucket(S)), C.c_int32(1)))
         ws = torch.empty(wsb, dtype=torch.uint8, device=shaded.device) if wsb > 0 else None
-        if ctx.precision == 1 and S > 0:
+        if ctx.precision == 1 and S > 0 and SPLIT_BWD:        # the two stages as separate launches (profiling; WB_SPLIT_BWD=1)
             with _stage("decoder_bwd"):
                 A.check(L.wb_rf_decoder_bwd(C.byref(desc), A.ptr(blob), C.byref(ms.rays), A.ptr(rec_t), A.ptr(rec_ray), C.c_int64(S), A.ptr(g_sh),
                                             A.ptr(scale), A.ptr(ctx.feat), A.ptr(ws), A.ptr(g_dens), A.ptr(g_col), A.stream()))
             with _stage("table_scatter"):
                 A.check(L.wb_rf_table_scatter(C.byref(desc), C.byref(ms.rays), A.ptr(rec_t), A.ptr(rec_ray), C.c_int64(S), A.ptr(scale), A.ptr(ws),
                                               A.ptr(g_table), A.stream()))
-        else:
+        else:   # precision 1: decoder backward with the hash-table scatter fused into its last epilogue (one kernel) where the shape allows
             with _stage("shade_bwd"):
                 A.check(L.wb_rf_shade_bwd(C.byref(desc), A.ptr(blob), C.c_int32(ctx.precision), C.byref(ms.rays), A.ptr(rec_t), A.ptr(rec_ray),
                                           C.c_int64(S), A.ptr(g_sh), A.ptr(scale), A.ptr(ctx.feat), A.ptr(ws), A.ptr(g_table), A.ptr(g_dens), A.ptr(g_col), A.stream()))

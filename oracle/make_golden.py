@@ -266,6 +266,31 @@ def gen_prune():
     print("prune: cells", N, "kept", int(keep.sum()), "new octree bytes", grid.blas.octree.shape[0])
 
 
+def gen_raygen():
+    """_look_at / _generate_rays (wisp/trainers/tracker/offline_renderer.py:23-89) + normalized_grid (wisp/ops/geometric.py:65-99),
+    executed from the UNMODIFIED reference source on CPU (the two functions are compiled from the file; the module itself cannot be
+    imported because wisp.trainers pulls the GUI stack)."""
+    import ast
+    import torch.nn.functional as F
+    from wisp.ops.geometric import normalized_grid
+    path = ref_import.REF_ROOT + "/wisp/trainers/tracker/offline_renderer.py"
+    tree = ast.parse(open(path).read())
+    fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("_look_at", "_generate_rays")]
+    ns = dict(torch=torch, F=F, np=np, normalized_grid=normalized_grid)
+    exec(compile(ast.Module(body=fns, type_ignores=[]), path, "exec"), ns)
+    out = {}
+    for name, (f, t, h, w, mode, fov) in dict(square=([-3.0, 0.65, -3.0], [0, 0, 0], 48, 48, 'persp', 30.0),
+                                              wide=([2.0, 1.5, -1.0], [0.1, -0.2, 0.3], 20, 36, 'persp', 55.0),
+                                              tall=([0.5, 2.5, 3.0], [0, 0, 0], 31, 17, 'persp', 90.0),
+                                              ortho=([-1.0, 1.0, 2.0], [0, 0, 0], 16, 24, 'ortho', 40.0)).items():
+        o, d = ns["_look_at"](f, t, h, w, mode=mode, fov=fov, device='cpu')
+        out[name + "_args"] = np.asarray(f + t + [h, w, fov], np.float64)
+        out[name + "_mode"] = mode
+        out[name + "_origins"] = o.numpy(); out[name + "_dirs"] = d.numpy()
+    np.savez_compressed(os.path.join(OUT, "raygen.npz"), **out)
+    print("raygen", {k: v.shape for k, v in out.items() if k.endswith("_dirs")})
+
+
 def main():
     warnings.filterwarnings("ignore")
     ref_import.install()
@@ -275,6 +300,7 @@ def main():
     gen_triplanar()
     gen_sdf()
     gen_prune()
+    gen_raygen()
     # A: miniature of BASELINE config 2 (cat, bias, positional view embedding, sparse lego-like octree)
     gen_rf_trace("rf_trace_cat", level=5, res=None, hw=24, n_steps=96, num_lods=6, bw=11, min_res=4, max_res=48, hidden=32,
                  num_layers=1, bias=True, multiscale="cat", view_embedder="positional", near=0.0, far=10.0, bg=(1.0, 1.0, 1.0))

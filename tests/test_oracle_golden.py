@@ -196,3 +196,12 @@ def test_prune_density_probe_matches_reference_class(golden_dir):
     occ = np.maximum(dens[:, 0], g["occupancy0"] * np.float32(g["decay"]))
     np.testing.assert_allclose(occ, g["occupancy1"], atol=2e-6)
     assert np.array_equal(O.points_to_octree(pts[g["keep"]].astype(np.int16), lvl), g["new_octree"])
+
+
+def test_look_at_rays_matches_reference_source(golden_dir):
+    """oracle.look_at_rays == _look_at of the reference's offline renderer (tests/golden/raygen.npz, generated from the unmodified source)."""
+    g = np.load(os.path.join(golden_dir, "raygen.npz"))
+    for n in ("square", "wide", "tall"):
+        a = g[n + "_args"]
+        o, d = O.look_at_rays(list(a[:3]), list(a[3:6]), int(a[6]), int(a[7]), float(a[8]))
+        assert np.abs(o - g[n + "_origins"]).max() == 0.0 and np.abs(d - g[n + "_dirs"]).max() <= 5e-7, n
