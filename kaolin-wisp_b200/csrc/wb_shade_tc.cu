@@ -75,6 +75,7 @@ static bool tc_b3_plan(const WbTc& m, TcB3Plan* p)
     // the hidden activation tiles X1, X3, X4 share the buffers P and Q, whose constant-one slab sits behind a maxw-wide tile: the
     // hidden width must BE the widest tile (true for app/nerf: 64-wide hidden layers over 32 / 42 inputs; a 32-wide decoder over a
     // 42-wide colour input would read its bias-gradient row from a stale slab)
+    if (m.Np[0] + m.Np[1] + m.Np[2] + m.Np[3] + m.Np[4] > 512 - 3 * 64) return false;      // TMEM: 64 working columns per group + the weight-grad accumulators
     if (m.Kp[1] != maxw || m.Kp[3] != maxw || m.Kp[4] != maxw || m.Np[0] != maxw || m.Np[2] != maxw || m.Np[3] != maxw) return false;
     const int big = (maxw / 8 + 1) * 2048;                       // a maxw-wide tile + its constant-one slab
     const int small = (max(m.Np[1], m.Np[4]) / 8) * 2048;        // dY1 / dY4
@@ -687,7 +688,7 @@ static int tc_launch_ray_embed(const WbTc& m, const wb_rays* rays, void* workspa
 // Tuning knobs (defaults = the measured optimum on B200 for the app/nerf configuration, profiles/README.md); the environment
 // overrides exist for the sweeps and are read once per process.
 static int tc_env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
-static int tc_knob_fuse_scatter() { static const int v = tc_env_int("WB_TC_FUSE_SCATTER", 1); return v; }
+static int tc_knob_fuse_scatter() { static const int v = tc_env_int("WB_TC_FUSE_SCATTER", 2); return v; }     // 0 separate kernel, 1 last epilogue, 2 pipelined
 static int tc_knob_bwd_groups() { static const int v = tc_env_int("WB_TC_BWD_GROUPS", 3); return v; }
 static int tc_knob_fwd_tmema() { static const int v = tc_env_int("WB_TC_FWD_TMEMA", 1); return v; }
 static int tc_knob_fwd_ctas() { static const int v = tc_env_int("WB_TC_FWD_CTAS", 3); return v; }
@@ -1077,16 +1078,18 @@ int wb_tc_decoder_bwd_ex(const wb_nef_desc* nef, const float* blob, const wb_ray
     TcB3Plan plan;
     if ((tc_knob_bwd_groups() == 3 || !m.fits2) && tc_b3_plan(m, &plan)) {     // three sub-tile groups per SM (wb_shade_tc_bwd3.cuh): 4.53 -> 3.69 ms measured
         WbTc m3 = m;
-        for (int l = 0; l < m.nl_d + m.nl_c; ++l) m3.acc_col[l] += 64;       // work columns 0..191, accumulators behind them
+        for (int l = 0; l < m.nl_d + m.nl_c; ++l) m3.acc_col[l] = 3 * 64 + (m.acc_col[l] - m.acc_col[0]);      // work columns 0..191 (64 per group,
+                                                                                            // whatever maxw is), accumulators behind them
         WbGrid g; memset(&g, 0, sizeof(g));
         const bool fuse = grad_table != nullptr && tc_knob_fuse_scatter() && nef->grid_kind == 0 && nef->feature_dim == 2 && nef->multiscale == 0 &&
                           planes <= 16;
         if (fuse) { rc = wb_make_grid(nef, &g); if (rc) return rc; }
-        auto kern3 = fuse ? wb_mlp_bwd3_tc_kernel<true> : wb_mlp_bwd3_tc_kernel<false>;
-        static int done3[2] = { -1, -1 };
-        if (done3[fuse ? 1 : 0] != plan.smem_bytes) {
+        const int fmode = !fuse ? 0 : (tc_knob_fuse_scatter() == 1 ? 1 : 2);
+        auto kern3 = fmode == 2 ? wb_mlp_bwd3_tc_kernel<2> : fmode == 1 ? wb_mlp_bwd3_tc_kernel<1> : wb_mlp_bwd3_tc_kernel<0>;
+        static int done3[3] = { -1, -1, -1 };
+        if (done3[fmode] != plan.smem_bytes) {
             WB_CUDA(cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
-            done3[fuse ? 1 : 0] = plan.smem_bytes;
+            done3[fmode] = plan.smem_bytes;
         }
         const int64_t nctas3 = ((S + TC_ROWS - 1) / TC_ROWS + TC_B3_GROUPS - 1) / TC_B3_GROUPS;
         int64_t grid3 = (int64_t)wb_num_sms(); if (grid3 > nctas3) grid3 = nctas3;

@@ -72,7 +72,10 @@ __device__ __forceinline__ void tc_b3_build_table(const WbTc& m, const TcB3Plan&
     tab[(g * TC_B3_ROUNDS + rd) * 3 + ch] = r;
 }
 
-__device__ __forceinline__ void tc_b3_round(TcCtx& c, const TcRec* r3)
+// `mid` runs on every thread of the group between the issue of the round's UMMAs and the wait for their completion: SIMT work placed
+// there (the pipelined table scatter) executes while the tensor pipe works on this round
+template <class Mid>
+__device__ __forceinline__ void tc_b3_round(TcCtx& c, const TcRec* r3, Mid mid)
 {
     uint4 qa0 = make_uint4(0, 0, 0, 0), qa1 = qa0, qb0 = qa0, qb1 = qa0;
     if (c.wig == 0) {
@@ -93,10 +96,12 @@ __device__ __forceinline__ void tc_b3_round(TcCtx& c, const TcRec* r3)
         }
         __syncwarp();
     }
+    mid();
     tc_mbar_wait(c.bar, c.phase);
     c.phase ^= 1u;
     tc_fence_after();
 }
+__device__ __forceinline__ void tc_b3_round(TcCtx& c, const TcRec* r3) { tc_b3_round(c, r3, [] {}); }
 
 // relu(D_work[:, 0:Np)) -> fp16 tile `dst` (this thread: its row, its column half)
 __device__ __forceinline__ void tc_b3_relu_to_tile(const TcCtx& c, uint32_t trow, int Np, uint8_t* dst)
@@ -209,10 +214,14 @@ __device__ __forceinline__ void tc_scatter_level_f2(const WbGrid& g, int l, floa
     }
 }
 
-// FUSE: the hash-table scatter runs in the last epilogue of every sub-tile instead of as a second kernel: the 60 B/sample of fp16
-// dL/dfeat planes (written, then re-read with the sample position rebuilt) never reach HBM, and the scatter's shuffles / reductions
-// fill issue slots that the round latencies of the other two groups leave empty.  F == 2 'cat' hash grids only.
-template <bool FUSE>
+// FUSE: where the hash-table scatter of a sub-tile's dL/dfeat runs (F == 2 'cat' hash grids only).
+//   0  not here: dL/dfeat leaves as fp16 planes, wb_table_scatter_kernel follows as a second launch (3.70 + 3.72 ms measured).
+//   1  in the last epilogue of the sub-tile (measured 7.10 ms for both: the eight per-LOD scan / reduction chains of a group are a
+//      latency chain of their own and simply lengthen the group's critical path).
+//   2  software-pipelined: the planes are still written (60 B/sample, re-read from L2 by the thread that wrote them), but LOD q of
+//      sub-tile i is scattered inside round q of sub-tile i+1, between the issue of that round's UMMAs and the wait for their
+//      completion -- the scatter's shuffles and reductions run while the tensor pipe works, the UMMA latency hides behind them.
+template <int FUSE>
 __global__ void __launch_bounds__(TC_B3_GROUPS * TC_GROUP, 1)
 wb_mlp_bwd3_tc_kernel(WbTc m, TcB3Plan p, const uint8_t* __restrict__ blob, TcIn in, const float4* __restrict__ g_shaded, TcGrads G, WbGrid g, float* __restrict__ gtable)
 {
@@ -251,6 +260,19 @@ wb_mlp_bwd3_tc_kernel(WbTc m, TcB3Plan p, const uint8_t* __restrict__ blob, TcIn
     const int64_t ntiles = (in.S + TC_ROWS - 1) / TC_ROWS;
     const uint32_t trow = c.tmem + ((uint32_t)c.laneq << 16) + (uint32_t)c.g * 64u;
     const float z8[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    // FUSE == 2: the sample of the previous sub-tile whose gradient this thread still has to scatter
+    bool have_prev = false, pvalid = false; int64_t ps = 0; float ppx = 0.0f, ppy = 0.0f, ppz = 0.0f;
+    const int lane_ = threadIdx.x & 31;
+    const __half2* dfeat2 = reinterpret_cast<const __half2*>(G.dfeat);
+    auto scatter_prev = [&](int q) {           // LOD 8h + q of the previous sub-tile (warp-collective; have_prev is group-uniform)
+        if (FUSE == 2 && have_prev) {
+            const int l = c.h * 8 + q;
+            if (l < G.planes) {
+                const float2 gq = pvalid ? __half22float2(__ldcg(dfeat2 + (int64_t)l * in.S + ps)) : make_float2(0.0f, 0.0f);
+                tc_scatter_level_f2(g, l, ppx, ppy, ppz, pvalid, gq.x, gq.y, inv_scale, lane_, gtable);
+            }
+        }
+    };
     for (int64_t tile = (int64_t)blockIdx.x * TC_B3_GROUPS + c.g; tile < ntiles; tile += (int64_t)gridDim.x * TC_B3_GROUPS) {
         int64_t s = tile * TC_ROWS + c.r;
         const bool valid = s < in.S;
@@ -261,10 +283,10 @@ wb_mlp_bwd3_tc_kernel(WbTc m, TcB3Plan p, const uint8_t* __restrict__ blob, TcIn
             *reinterpret_cast<uint4*>(bP + ch * 2048 + c.r * 16) = __ldg(in.x0_saved + (int64_t)ch * in.S + s);
         if (c.h == 0) tc_b3_one_slab(bP, nch0, c.r);
         // r0: F0 -> X1 -> Q
-        tc_b3_round(c, rec + 0 * 3);
+        tc_b3_round(c, rec + 0 * 3, [&] { scatter_prev(0); });
         tc_b3_relu_to_tile(c, trow, m.Np[0], bQ);
         // r1: F1 -> df; X2 -> R
-        tc_b3_round(c, rec + 1 * 3);
+        tc_b3_round(c, rec + 1 * 3, [&] { scatter_prev(1); });
         float df0;
         {
             float df[16];
@@ -284,12 +306,12 @@ wb_mlp_bwd3_tc_kernel(WbTc m, TcB3Plan p, const uint8_t* __restrict__ blob, TcIn
             if (c.h == 0) tc_b3_one_slab(bR, nchc, c.r);
         }
         // r2: F2 -> X3 -> P ; r3: F3 -> X4 -> Q
-        tc_b3_round(c, rec + 2 * 3);
+        tc_b3_round(c, rec + 2 * 3, [&] { scatter_prev(2); });
         tc_b3_relu_to_tile(c, trow, m.Np[2], bP);
-        tc_b3_round(c, rec + 3 * 3);
+        tc_b3_round(c, rec + 3 * 3, [&] { scatter_prev(3); });
         tc_b3_relu_to_tile(c, trow, m.Np[3], bQ);
         // r4: F4 -> c3 ; dY4 -> E
-        tc_b3_round(c, rec + 4 * 3);
+        tc_b3_round(c, rec + 4 * 3, [&] { scatter_prev(4); });
         const float4 go = valid ? __ldg(g_shaded + s) : make_float4(0, 0, 0, 0);
         {
             float v[16]; tc_ld16(trow, v);
@@ -301,12 +323,12 @@ wb_mlp_bwd3_tc_kernel(WbTc m, TcB3Plan p, const uint8_t* __restrict__ blob, TcIn
             for (int sl = 1 + c.h; sl < m.Np[4] / 8; sl += 2) tile_store8(bE, c.r, sl, z8);
         }
         // r5: B4 -> dY3 in place over X4 (Q) ; r6: B3 -> dY2 in place over X3 (P)
-        tc_b3_round(c, rec + 5 * 3);
+        tc_b3_round(c, rec + 5 * 3, [&] { scatter_prev(5); });
         tc_b3_mask_in_place(c, trow, m.Kp[4], bQ);
-        tc_b3_round(c, rec + 6 * 3);
+        tc_b3_round(c, rec + 6 * 3, [&] { scatter_prev(6); });
         tc_b3_mask_in_place(c, trow, m.Kp[3], bP);
         // r7: B2 -> dY1 -> E ; X0 -> R
-        tc_b3_round(c, rec + 7 * 3);
+        tc_b3_round(c, rec + 7 * 3, [&] { scatter_prev(7); });
         {
             float v[16]; tc_ld16(trow, v);
             const int dout = m.O[1];
@@ -328,21 +350,20 @@ wb_mlp_bwd3_tc_kernel(WbTc m, TcB3Plan p, const uint8_t* __restrict__ blob, TcIn
         tc_b3_mask_in_place(c, trow, m.Kp[1], bQ);
         // r10: B0 -> dL/dfeat: scattered into the hash table right here (FUSE) or written as fp16 planes for wb_table_scatter_kernel
         float px = 0.0f, py = 0.0f, pz = 0.0f;
-        if (FUSE) {                                               // sample position (octree_as.py:283); the loads overlap the round
+        if (FUSE != 0) {                                          // sample position (octree_as.py:283); the loads overlap the round
             const float t = __ldg(in.rec_t + s);
             px = wb_addcmul(__ldg(in.origins + 3 * ray), __ldg(in.dirs + 3 * ray), t);
             py = wb_addcmul(__ldg(in.origins + 3 * ray + 1), __ldg(in.dirs + 3 * ray + 1), t);
             pz = wb_addcmul(__ldg(in.origins + 3 * ray + 2), __ldg(in.dirs + 3 * ray + 2), t);
         }
         tc_b3_round(c, rec + 10 * 3);
-        if (FUSE) {
+        if (FUSE == 1) {
             // column half h holds features [16h, 16h+16) = LODs 8h .. 8h+7; a warp = 32 consecutive samples of one half
             float v[16]; tc_ld16(trow + c.h * 16, v);
-            const int lane = threadIdx.x & 31;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int l = c.h * 8 + q;
-                if (l < G.planes) tc_scatter_level_f2(g, l, px, py, pz, valid, v[2 * q], v[2 * q + 1], inv_scale, lane, gtable);
+                if (l < G.planes) tc_scatter_level_f2(g, l, px, py, pz, valid, v[2 * q], v[2 * q + 1], inv_scale, lane_, gtable);
             }
         } else {
             const int W = G.width, nfe = G.planes * W;
@@ -363,7 +384,12 @@ wb_mlp_bwd3_tc_kernel(WbTc m, TcB3Plan p, const uint8_t* __restrict__ blob, TcIn
                     }
                 }
             }
+            if (FUSE == 2) { have_prev = true; pvalid = valid; ps = s; ppx = px; ppy = py; ppz = pz; }
         }
+    }
+    if (FUSE == 2) {                                              // the last sub-tile of this group has no next round to hide behind
+#pragma unroll 1
+        for (int q = 0; q < 8; ++q) scatter_prev(q);
     }
     // ---- flush weight / bias gradient accumulators (TMEM rows = input feature, row Kp = bias) ----
     tc_fence_before();
