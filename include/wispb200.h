@@ -328,6 +328,20 @@ int wb_rf_table_scatter(const wb_nef_desc* nef, const wb_rays* rays, const float
                         const float* loss_scale, void* workspace, float* grad_table, wb_stream s);
 
 /* ------------------------------------------------------------------------------------------------
+ * CodebookOctreeGrid (VQAD; wisp/models/grids/codebook_grid.py:103-172), row-wise: the softmax / straight-through selection of a
+ * dictionary entry depends only on the corner row, so it runs once per row and LOD instead of once per (sample, corner):
+ *   wb_codebook_rows_fwd : E[row] = sum_k keys[row,k] * dictionary[k]; training != 0: keys = (y_hard - y_soft) + y_soft (:117-123),
+ *                          else one_hot(argmax) (:128-131).  logits [rows, K], dictionary [K, F], E [rows, F]; argmax_out optional.
+ *   wb_codebook_rows_bwd : from dE [rows, F] (what wb_octree_interp_bwd accumulated): g_dictionary [K, F] accumulated into,
+ *                          g_logits [rows, K] written for rows with a non-zero dE (caller zeroes both).
+ * The per-sample blend is wb_octree_interp_fwd / _bwd over E (half_round = 0: the codebook grid blends in fp32, :164-165).
+ * ---------------------------------------------------------------------------------------------- */
+int wb_codebook_rows_fwd(const float* logits, const float* dictionary, int64_t rows, int32_t K, int32_t F, int32_t training,
+                         float* E, int32_t* argmax_out, wb_stream s);
+int wb_codebook_rows_bwd(const float* logits, const float* dictionary, const float* dE, int64_t rows, int32_t K, int32_t F,
+                         float* g_logits, float* g_dictionary, wb_stream s);
+
+/* ------------------------------------------------------------------------------------------------
  * Trainer step glue: MultiviewTrainer.step (wisp/trainers/multiview_trainer.py:111-180) and
  * BaseTrainer.init_optimizer (wisp/trainers/base_trainer.py:205-235).
  *   wb_composite_bwd_loss : wb_composite_bwd with the image loss and its gradient evaluated inside: rgb_pred = wb_composite_fwd's

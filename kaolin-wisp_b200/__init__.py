@@ -8,7 +8,7 @@ from . import _cabi, ops, spc, parallel, raygen                                 
 from ._cabi import WispB200Error                                                # noqa: F401
 from .core import Rays, RenderBuffer                                            # noqa: F401
 from .accelstructs import OctreeAS, AxisAlignedBBoxAS, ASQueryResults, ASRaymarchResults, ASRaytraceResults   # noqa: F401
-from .grids import HashGrid, MultiTable, TriplanarGrid, TriplanarFeatureVolume, OctreeGrid                                         # noqa: F401
+from .grids import HashGrid, MultiTable, TriplanarGrid, TriplanarFeatureVolume, OctreeGrid, CodebookOctreeGrid                                         # noqa: F401
 from .nefs import NeuralRadianceField, NeuralSDF, BasicDecoder, PositionalEmbedder, get_positional_embedder   # noqa: F401
 from .tracers import PackedRFTracer, PackedSDFTracer                                             # noqa: F401
 from .pipeline import Pipeline                                                  # noqa: F401

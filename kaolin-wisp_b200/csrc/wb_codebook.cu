@@ -81,16 +81,18 @@ __global__ void __launch_bounds__(256)
 wb_codebook_rows_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ dict, const float* __restrict__ dE, int64_t rows, int K, int F,
                             float* __restrict__ g_logits, float* __restrict__ g_dict)
 {
-    extern __shared__ float gd[];                              // [K][F] dictionary gradient of this CTA
+    extern __shared__ float gd[];                              // [K][F] dictionary gradient of this CTA, then [8 warps][32] dE rows
     for (int e = threadIdx.x; e < K * F; e += blockDim.x) gd[e] = 0.0f;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = warp0; r < rows; r += nwarps) {
-        float de = lane < F ? __ldg(dE + r * F + lane) : 0.0f;
-        if (__ballot_sync(0xffffffffu, de != 0.0f) == 0u) {     // rows no sample touched: zero gradient (g_logits is pre-zeroed)
-            continue;
-        }
+        const float de = lane < F ? __ldg(dE + r * F + lane) : 0.0f;
+        if (__ballot_sync(0xffffffffu, de != 0.0f) == 0u) continue;     // rows no sample touched: zero gradient (g_logits is pre-zeroed)
+        float* drow = gd + K * F + (threadIdx.x >> 5) * 32;              // this warp's copy of dE[row] (broadcast reads below)
+        __syncwarp();
+        drow[lane] = de;
+        __syncwarp();
         float y[KPL]; int am;
         cb_row_softmax<KPL>(logits + r * K, K, lane, y, am);
         float c[KPL], dot = 0.0f;
@@ -99,13 +101,10 @@ wb_codebook_rows_bwd_kernel(const float* __restrict__ logits, const float* __res
             const int k = lane + 32 * i;
             c[i] = 0.0f;
             if (k < K) {
-                for (int f = 0; f < F; ++f) c[i] = fmaf(__ldg(dict + (int64_t)k * F + f), __shfl_sync(0xffffffffu, de, f), c[i]);
+                for (int f = 0; f < F; ++f) c[i] = fmaf(__ldg(dict + (int64_t)k * F + f), drow[f], c[i]);
                 const float key = ((k == am ? 1.0f : 0.0f) - y[i]) + y[i];
-                if (key != 0.0f) for (int f = 0; f < F; ++f) atomicAdd(gd + k * F + f, key * __shfl_sync(0xffffffffu, de, f));
+                if (key != 0.0f) for (int f = 0; f < F; ++f) atomicAdd(gd + k * F + f, key * drow[f]);
                 dot = fmaf(y[i], c[i], dot);
-            } else {
-                for (int f = 0; f < F; ++f) { (void)__shfl_sync(0xffffffffu, de, f); }
-                for (int f = 0; f < F; ++f) { (void)__shfl_sync(0xffffffffu, de, f); }
             }
         }
         dot = wb_warp_sum(dot);
@@ -136,7 +135,7 @@ extern "C" int wb_codebook_rows_bwd(const float* logits, const float* dictionary
     WB_CHECK_ARG(logits && dictionary && dE && g_logits && g_dictionary, "null pointer");
     WB_CHECK_ARG(K >= 1 && K <= WB_CB_MAXK && F >= 1 && F <= WB_CB_MAXF, "codebook: 1 <= 2^bitwidth <= 1024, feature_dim <= 32");
     int64_t ctas = (rows + 7) / 8; const int64_t cap = (int64_t)wb_num_sms() * 2; if (ctas > cap) ctas = cap;
-    const int smem = K * F * 4;
+    const int smem = (K * F + 8 * 32) * 4;          // dictionary gradient + one dE row per warp
     cudaStream_t st = (cudaStream_t)s;
     auto kern = K <= 256 ? wb_codebook_rows_bwd_kernel<8> : wb_codebook_rows_bwd_kernel<32>;
     if (smem > 48 * 1024) WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -688,7 +688,7 @@ static int tc_launch_ray_embed(const WbTc& m, const wb_rays* rays, void* workspa
 // Tuning knobs (defaults = the measured optimum on B200 for the app/nerf configuration, profiles/README.md); the environment
 // overrides exist for the sweeps and are read once per process.
 static int tc_env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
-static int tc_knob_fuse_scatter() { static const int v = tc_env_int("WB_TC_FUSE_SCATTER", 2); return v; }     // 0 separate kernel, 1 last epilogue, 2 pipelined
+static int tc_knob_fuse_scatter() { static const int v = tc_env_int("WB_TC_FUSE_SCATTER", 1); return v; }     // 0 separate kernel, 1 last epilogue (default), 2 pipelined
 static int tc_knob_bwd_groups() { static const int v = tc_env_int("WB_TC_BWD_GROUPS", 3); return v; }
 static int tc_knob_fwd_tmema() { static const int v = tc_env_int("WB_TC_FWD_TMEMA", 1); return v; }
 static int tc_knob_fwd_ctas() { static const int v = tc_env_int("WB_TC_FWD_CTAS", 3); return v; }
@@ -1084,7 +1084,7 @@ int wb_tc_decoder_bwd_ex(const wb_nef_desc* nef, const float* blob, const wb_ray
         const bool fuse = grad_table != nullptr && tc_knob_fuse_scatter() && nef->grid_kind == 0 && nef->feature_dim == 2 && nef->multiscale == 0 &&
                           planes <= 16;
         if (fuse) { rc = wb_make_grid(nef, &g); if (rc) return rc; }
-        const int fmode = !fuse ? 0 : (tc_knob_fuse_scatter() == 1 ? 1 : 2);
+        const int fmode = !fuse ? 0 : (tc_knob_fuse_scatter() == 2 ? 2 : 1);
         auto kern3 = fmode == 2 ? wb_mlp_bwd3_tc_kernel<2> : fmode == 1 ? wb_mlp_bwd3_tc_kernel<1> : wb_mlp_bwd3_tc_kernel<0>;
         static int done3[3] = { -1, -1, -1 };
         if (done3[fmode] != plan.smem_bytes) {

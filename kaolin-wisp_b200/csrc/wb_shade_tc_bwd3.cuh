@@ -215,12 +215,15 @@ __device__ __forceinline__ void tc_scatter_level_f2(const WbGrid& g, int l, floa
 }
 
 // FUSE: where the hash-table scatter of a sub-tile's dL/dfeat runs (F == 2 'cat' hash grids only).
-//   0  not here: dL/dfeat leaves as fp16 planes, wb_table_scatter_kernel follows as a second launch (3.70 + 3.72 ms measured).
-//   1  in the last epilogue of the sub-tile (measured 7.10 ms for both: the eight per-LOD scan / reduction chains of a group are a
-//      latency chain of their own and simply lengthen the group's critical path).
-//   2  software-pipelined: the planes are still written (60 B/sample, re-read from L2 by the thread that wrote them), but LOD q of
-//      sub-tile i is scattered inside round q of sub-tile i+1, between the issue of that round's UMMAs and the wait for their
-//      completion -- the scatter's shuffles and reductions run while the tensor pipe works, the UMMA latency hides behind them.
+//   0  not here: dL/dfeat leaves as fp16 planes, wb_table_scatter_kernel follows as a second launch (3.70 + 3.72 = 7.46 ms measured
+//      for the pair on the 1024^2 frame).
+//   1  in the last epilogue of the sub-tile (DEFAULT, 7.12 ms): the planes never exist; the win is only their 124 B/sample of traffic
+//      and one launch -- the three groups of a CTA run in lockstep (they convoy on the tensor pipe), so all 24 warps scatter at the same
+//      time and the scatter phase is as issue / reduction-bound as the stand-alone kernel was.
+//   2  software-pipelined (7.34 ms, kept for reference): the planes are still written (and re-read from L2 by the thread that wrote
+//      them), LOD q of sub-tile i is scattered inside round q of sub-tile i+1 between the issue of that round's UMMAs and the wait for
+//      their completion.  It does not pay: a round's wait is barrier / commit / wake-up latency, not UMMA execution time, so there is
+//      little tensor work to hide behind, and the extra plane traffic comes back.
 template <int FUSE>
 __global__ void __launch_bounds__(TC_B3_GROUPS * TC_GROUP, 1)
 wb_mlp_bwd3_tc_kernel(WbTc m, TcB3Plan p, const uint8_t* __restrict__ blob, TcIn in, const float4* __restrict__ g_shaded, TcGrads G, WbGrid g, float* __restrict__ gtable)

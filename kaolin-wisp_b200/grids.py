@@ -230,3 +230,34 @@ class OctreeGrid(nn.Module):
 
     def name(self) -> str:
         return "Octree Grid"
+
+
+class CodebookOctreeGrid(OctreeGrid):
+    """wisp.models.grids.CodebookOctreeGrid (codebook_grid.py:20-172): an OctreeGrid whose corner rows hold logits over a per-LOD
+    dictionary of 2^codebook_bitwidth feature vectors (VQAD).  Parameters as in the reference: `dictionary.N` [2^bw, feature_dim],
+    `features.N` [rows_N, 2^bw].  Evaluation is row-wise (csrc/wb_codebook.cu): selection once per row and LOD, then the ordinary
+    native trilinear blend through the trinkets, in fp32 (the codebook grid does not cast to half, :164-165)."""
+
+    def __init__(self, blas, feature_dim: int, num_lods: int = 1, interpolation_type: str = 'linear', multiscale_type: str = 'cat',
+                 feature_std: float = 0.0, feature_bias: float = 0.0, codebook_bitwidth: int = 8):
+        self.bitwidth = codebook_bitwidth
+        super().__init__(blas, feature_dim, num_lods, interpolation_type, multiscale_type, feature_std, feature_bias)
+        self.dictionary_size = 2 ** self.bitwidth
+        rows = [int(f.shape[0]) for f in self.features]
+        self.dictionary = nn.ParameterList([nn.Parameter(torch.randn(self.dictionary_size, feature_dim) * feature_std) for _ in self.active_lods])
+        self.features = nn.ParameterList([nn.Parameter(torch.randn(r, self.dictionary_size) * feature_std) for r in rows])     # codebook_grid.py:92-96
+        self.half_features = False
+
+    def interpolate(self, coords, lod_idx):
+        """octree_grid.py:165-219 with _index_features replaced by the row-wise selection."""
+        output_shape = coords.shape[:-1]
+        dev = self.features[0].device
+        if self.trinkets.device != dev:
+            self.trinkets = self.trinkets.to(dev)
+        rows = [ops.CodebookRows.apply(self.features[i], self.dictionary[i], self.training) for i in range(lod_idx + 1)]
+        feats = ops.OctreeInterpolate.apply(coords.reshape(-1, 3), self.blas.tensors(), self.trinkets, self.base_lod,
+                                            self.multiscale_type if lod_idx > 0 else 'cat', False, *rows)
+        return feats.reshape(*output_shape, feats.shape[-1])
+
+    def name(self) -> str:
+        return "Codebook Grid"

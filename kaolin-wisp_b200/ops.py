@@ -443,6 +443,35 @@ class OctreeInterpolate(torch.autograd.Function):
         return (None, None, None, None, None, None, *gf)
 
 
+class CodebookRows(torch.autograd.Function):
+    """CodebookOctreeGrid._index_features (codebook_grid.py:103-131) evaluated once per corner ROW: logits [rows, 2^bw], dictionary
+    [2^bw, F] -> E [rows, F] (straight-through softmax selection when `training`, argmax selection otherwise)."""
+
+    @staticmethod
+    def forward(ctx, logits, dictionary, training):
+        A.require_device(logits)
+        lg, dc = A.f32c(logits.detach()), A.f32c(dictionary.detach())
+        rows, K, F = lg.shape[0], lg.shape[1], dc.shape[1]
+        E = torch.empty((rows, F), dtype=torch.float32, device=lg.device)
+        A.check(A.lib().wb_codebook_rows_fwd(A.ptr(lg), A.ptr(dc), C.c_int64(rows), C.c_int32(K), C.c_int32(F), C.c_int32(int(training)), A.ptr(E), None, A.stream()))
+        ctx.save_for_backward(lg, dc)
+        ctx.training = bool(training)
+        return E
+
+    @staticmethod
+    def backward(ctx, dE):
+        lg, dc = ctx.saved_tensors
+        if not ctx.training:            # eval: dictionary[argmax] -- the reference's indexing gives the dictionary a gradient, the logits none
+            am = lg.argmax(-1)
+            gd = torch.zeros_like(dc).index_add_(0, am, A.f32c(dE))
+            return None, gd, None
+        g_lg, g_dc = torch.zeros_like(lg), torch.zeros_like(dc)
+        de = A.f32c(dE)
+        A.check(A.lib().wb_codebook_rows_bwd(A.ptr(lg), A.ptr(dc), A.ptr(de), C.c_int64(lg.shape[0]), C.c_int32(lg.shape[1]), C.c_int32(dc.shape[1]),
+                                             A.ptr(g_lg), A.ptr(g_dc), A.stream()))
+        return g_lg, g_dc, None
+
+
 def find_depth_bound(query: torch.Tensor, nug_depth: torch.Tensor, info=None, curr_idxes: Optional[torch.Tensor] = None) -> torch.Tensor:
     """wisp.ops.geometric.find_depth_bound (geometric.py:15-22)."""
     if curr_idxes is None:

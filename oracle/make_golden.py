@@ -291,6 +291,39 @@ def gen_raygen():
     print("raygen", {k: v.shape for k, v in out.items() if k.endswith("_dirs")})
 
 
+def gen_codebook():
+    """CodebookOctreeGrid.interpolate (codebook_grid.py:103-172 over octree_grid.py:165-219) run by the reference class on CPU, in
+    training mode (straight-through softmax selection, gradients to logits and dictionary) and in eval mode (argmax selection)."""
+    from wisp.accelstructs import OctreeAS
+    from wisp.models.grids import CodebookOctreeGrid
+    torch.manual_seed(9)
+    level = 4
+    oct_np = O.points_to_octree(octahedron_points(level, radius=0.6, n=60000, seed=3), level)
+    blas = OctreeAS(torch.from_numpy(oct_np))
+    out = dict(octree=oct_np, level=level)
+    for ms in ("sum", "cat"):
+        grid = CodebookOctreeGrid(blas, feature_dim=4, num_lods=3, interpolation_type='linear', multiscale_type=ms, feature_std=1.0, codebook_bitwidth=4)
+        pts = blas.points[blas.pyramid[1, level]: blas.pyramid[1, level] + blas.pyramid[0, level]].float()
+        sel = torch.randint(0, pts.shape[0], (300,))
+        coords = (((pts[sel] + torch.rand(300, 3)) / 2 ** level) * 2 - 1).float()
+        coords = torch.cat([coords, torch.rand(60, 3) * 2 - 1])                       # some points outside the occupied cells
+        grid.train()
+        feats = grid.interpolate(coords, 2)
+        go = torch.randn_like(feats)
+        feats.backward(go)
+        d = {f"{ms}_coords": coords.numpy(), f"{ms}_feats_train": feats.detach().numpy(), f"{ms}_go": go.numpy()}
+        for i in range(3):
+            d[f"{ms}_logits{i}"] = grid.features[i].detach().numpy().copy(); d[f"{ms}_dict{i}"] = grid.dictionary[i].detach().numpy().copy()
+            d[f"{ms}_glogits{i}"] = grid.features[i].grad.numpy().copy(); d[f"{ms}_gdict{i}"] = grid.dictionary[i].grad.numpy().copy()
+        grid.eval()
+        with torch.no_grad():
+            d[f"{ms}_feats_eval"] = grid.interpolate(coords, 2).numpy()
+            d[f"{ms}_feats_eval_lod0"] = grid.interpolate(coords, 0).numpy()
+        out.update(d)
+    np.savez_compressed(os.path.join(OUT, "codebook.npz"), **out)
+    print("codebook", out["sum_feats_train"].shape, out["cat_feats_train"].shape, float(np.abs(out["sum_glogits2"]).max()))
+
+
 def main():
     warnings.filterwarnings("ignore")
     ref_import.install()
@@ -301,6 +334,7 @@ def main():
     gen_sdf()
     gen_prune()
     gen_raygen()
+    gen_codebook()
     # A: miniature of BASELINE config 2 (cat, bias, positional view embedding, sparse lego-like octree)
     gen_rf_trace("rf_trace_cat", level=5, res=None, hw=24, n_steps=96, num_lods=6, bw=11, min_res=4, max_res=48, hidden=32,
                  num_layers=1, bias=True, multiscale="cat", view_embedder="positional", near=0.0, far=10.0, bg=(1.0, 1.0, 1.0))

@@ -268,6 +268,14 @@ def _unbatched_interpolate_trilinear(coords, pidx, points, trinkets, feats, leve
     return _InterpTrilinear.apply(coords, pidx, points, trinkets, feats, level)
 
 
+def _coords_to_trilinear_coeffs(coords, points, level):
+    """kaolin.ops.spc.coords_to_trilinear_coeffs: [..., 3] coords and cell points -> [..., 8] coefficients."""
+    from . import octree_grid as OG
+    shp = coords.shape[:-1]
+    cf = OG.trilinear_coeffs(_np(coords).reshape(-1, 3).astype(np.float32), _np(points).reshape(-1, 3), level)
+    return torch.from_numpy(cf).reshape(*shp, 8)
+
+
 def _find_depth_bound_cuda(query, curr_idxes, depth):
     from . import octree_grid as OG
     return torch.from_numpy(OG.find_depth_bound(_np(query), _np(curr_idxes), _np(depth)))
@@ -310,6 +318,7 @@ def install():
     spc_ops.unbatched_make_dual = _unbatched_make_dual
     spc_ops.unbatched_make_trinkets = _unbatched_make_trinkets
     spc_ops.unbatched_interpolate_trilinear = _unbatched_interpolate_trilinear
+    spc_ops.coords_to_trilinear_coeffs = _coords_to_trilinear_coeffs
     wisp_C_render.find_depth_bound_cuda = _find_depth_bound_cuda
     wisp_C.render = wisp_C_render
     spc_render.sum_reduce = _sum_reduce

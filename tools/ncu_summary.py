@@ -17,13 +17,18 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_tensor.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread', 'launch__occupancy_limit_shared_mem',
-        'launch__occupancy_limit_registers', 'launch__grid_size', 'launch__block_size', 'sm__cycles_elapsed.max', 'smsp__inst_executed.sum']
+        'launch__occupancy_limit_registers', 'launch__grid_size', 'launch__block_size', 'sm__cycles_elapsed.max', 'smsp__inst_executed.sum',
+        'lts__t_bytes.sum', 'lts__t_sectors_op_red.sum', 'lts__t_sectors_op_atom.sum', 'l1tex__t_bytes.sum', 'sm__inst_executed_pipe_lsu.sum']
 
 
 def raw(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(out.splitlines()))
-    return rows[0], rows[1], rows[2:]
+    if rep.endswith(".csv"):          # raw page already exported on the GPU box (tools/profile_gpu.sh)
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = [r for r in csv.reader(out.splitlines()) if r]
+    st = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+    return rows[st], rows[st + 1], rows[st + 2:]
 
 
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
@@ -33,9 +38,13 @@ def main(tag):
     import json
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     traffic = {}
-    for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"prof_*_{tag}.ncu-rep"))):
-        hdr, units, vals = raw(rep)
-        name = os.path.basename(rep)[5:-8][:-(len(tag) + 1)]
+    reps = sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"prof_*_{tag}.ncu-rep"))) + sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"prof_*_{tag}.csv")))
+    for rep in reps:
+        try:
+            hdr, units, vals = raw(rep)
+        except StopIteration:
+            print("skip (no data)", rep); continue
+        name = os.path.splitext(os.path.basename(rep))[0][5:][:-(len(tag) + 1)]
         with open(os.path.join(ROOT, "profiles", f"{tag}_{name}.txt"), "w") as f:
             f.write(f"# ncu --set full --clock-control none --import-source on (one launch)  source: gpurun_out/{os.path.basename(rep)}\n")
             for v in vals:

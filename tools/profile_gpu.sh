@@ -1,14 +1,23 @@
 #!/bin/bash
 # Profiling recipe (run under gpurun, ONE GPU): launch list + one full ncu capture per hot kernel.
-# Outputs land in gpurun_out/; `python tools/ncu_summary.py TAG` turns them into profiles/TAG_*.txt.
+#   bash tools/profile_gpu.sh TAG [kernel regex ...]
+# Outputs land in gpurun_out/ as CSV raw pages (the .ncu-rep files are deleted on the box: gpurun_out/ is capped at 64 MiB);
+# `python tools/ncu_summary.py TAG` turns them into profiles/TAG_*.txt.
 set -u
 mkdir -p gpurun_out
-TAG=${1:-r01}
+TAG=${1:-r02}
 shift
-KERNELS=${@:-wb_mlp_bwd_tc_kernel wb_table_scatter_kernel wb_shade_fwd_tc_kernel wb_march_count_kernel}
+KERNELS=${@:-wb_mlp_bwd3_tc_kernel wb_shade_fwd_tc_kernel wb_march_count_kernel wb_composite_bwd_kernel}
 BENCH="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${TAG}.csv $BENCH > gpurun_out/launches_${TAG}.log 2>&1
 for K in $KERNELS; do
-  ncu --set full --clock-control none --import-source on -k regex:$K -s 1 -c 1 -o gpurun_out/prof_${K}_${TAG} -f $BENCH > gpurun_out/prof_${K}_${TAG}.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:$K -s 1 -c 1 -o /tmp/prof_${K}_${TAG} -f $BENCH > gpurun_out/prof_${K}_${TAG}.log 2>&1
+  ncu -i /tmp/prof_${K}_${TAG}.ncu-rep --page raw --csv > gpurun_out/prof_${K}_${TAG}.csv 2>/dev/null
+  rm -f /tmp/prof_${K}_${TAG}.ncu-rep
 done
-ls -la gpurun_out | tail -12
+# config 3: the persistent sphere tracer
+B3="python bench.py --config 3 --steps 1 --warmup 1 --no-cpu-baseline"
+ncu --set full --clock-control none --import-source on -k regex:wb_sdf_trace_kernel -s 1 -c 1 -o /tmp/prof_sdf_${TAG} -f $B3 > gpurun_out/prof_wb_sdf_trace_kernel_${TAG}.log 2>&1
+ncu -i /tmp/prof_sdf_${TAG}.ncu-rep --page raw --csv > gpurun_out/prof_wb_sdf_trace_kernel_${TAG}.csv 2>/dev/null
+rm -f /tmp/prof_sdf_${TAG}.ncu-rep
+du -sh gpurun_out; ls -la gpurun_out | tail -14
