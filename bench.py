@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--step-api", default="native", choices=["native", "autograd"],
                     help="native: wisp_b200.MultiviewStep (the trainer step as one native sequence: fused loss, one-launch Adam); "
                          "autograd: Pipeline call + torch loss + loss.backward() + torch fused Adam (the round-1 step)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = N views per step (1024^2 rays per GPU, the default the driver runs); strong = ONE view per step tiled over "
+                         "the N GPUs (rows rank::N each), SURVEY 8(e) inference-style partitioning")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
                     help="BASELINE.json config: 2 = HashGrid NeRF fwd+bwd (headline), 3 = nglod OctreeGrid SDF sphere trace, 4 = TriplanarGrid NeRF")
     return ap.parse_args()
@@ -56,7 +59,7 @@ def parse():
 def workload_config(args):
     return {"workload": f"app/nerf HashGrid 16-level F=2 T=2^19, 2-layer-64 MLP, {args.res}^2 rays x {args.num_steps} steps ('ray'), "
                         f"{'lego-like level-7 octree' if args.scene == 'lego' else 'dense level-7 octree'}, fwd+bwd+Adam",
-            "rays_per_step_per_gpu": args.res * args.res, "num_steps": args.num_steps, "scene": args.scene,
+            "rays_per_step_per_gpu": args.res * args.res // (args.gpus if getattr(args, "scaling", "weak") == "strong" else 1), "num_steps": args.num_steps, "scene": args.scene,
             "camera": {"origin": CAM_ORIGIN, "lookat": CAM_LOOKAT, "fov": CAM_FOV, "near": NEAR, "far": FAR},
             "loss": "huber/rays", "optimizer": ("Adam on table + decoders: one native launch (wb_adam_step)" if args.step_api == "native"
                                                 else "Adam(fused, torch) on table + decoders"),
@@ -228,8 +231,8 @@ def run_ours(args):
     g = torch.Generator().manual_seed(2)
     for i in range(nsteps_total):
         os_, ds_ = [], []
-        for c in range(world):
-            o, d = O.look_at_rays(orbit_origin(i * world + c), CAM_LOOKAT, args.res, args.res, CAM_FOV)
+        for c in range(world if args.scaling == "weak" else 1):
+            o, d = O.look_at_rays(orbit_origin(i * world + c if args.scaling == "weak" else i), CAM_LOOKAT, args.res, args.res, CAM_FOV)
             o, d = o.reshape(args.res, args.res, 3)[rank::world], d.reshape(args.res, args.res, 3)[rank::world]
             os_.append(o.reshape(-1, 3)); ds_.append(d.reshape(-1, 3))
         o, d = np.ascontiguousarray(np.concatenate(os_)), np.ascontiguousarray(np.concatenate(ds_))
@@ -382,7 +385,7 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    rays_total = R * args.steps * world
+    rays_total = R * args.steps * world          # R = rays per rank per step (weak: res^2, strong: res^2 / world)
     value = rays_total / (ms * 1e-3)
     e2e_value = rays_total / (ms_e2e * 1e-3)
     S_step = total_samples / (args.steps * world)
@@ -437,7 +440,7 @@ def run_ours(args):
                         "bandwidth and DRAM `traffic` is far below the algorithmic bytes (no wasted re-reads); see DESIGN.md section 4")
 
     line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32" if args.precision == 0 else "f16(tensor)+f32 accumulate", "data": "synthetic", "config": workload_config(args),
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": R * (24 + 12), "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
                     "step_ms": e2e_step_ms, "last_loss": loss_host},

@@ -35,6 +35,17 @@ def _worker(rank, world, port, out):
     gathered = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(gathered, t)
     ok = ok and int(gathered[0][0]) == 0 and int(gathered[0][1]) == int(gathered[1][0]) and int(gathered[1][1]) == 1024 * 1024 + 3
+    # the trainer step's gradient exchange (MultiviewStep._all_reduce): sum over ranks of the grid buffers, and ONE small collective for
+    # decoder gradients + loss; the 1/world of the mean is in the loss gradient already (inv_count uses the global ray count)
+    from types import SimpleNamespace
+    from wisp_b200.trainers import MultiviewStep
+    st = SimpleNamespace(g_grid=[torch.full((1000, 2), float(rank + 1)), torch.full((10,), 2.0 * (rank + 1))], g_dens=torch.full((37,), float(rank)),
+                         g_col=torch.arange(11.0) * (rank + 1), g_rest=[torch.full((3, 3), 5.0 + rank)], group=None)
+    loss = torch.tensor([0.25 * (rank + 1)])
+    MultiviewStep._all_reduce(st, loss)
+    ok = ok and bool(torch.allclose(st.g_grid[0], torch.full((1000, 2), 3.0)) and torch.allclose(st.g_grid[1], torch.full((10,), 6.0))
+                     and torch.allclose(st.g_dens, torch.full((37,), 1.0)) and torch.allclose(st.g_col, torch.arange(11.0) * 3)
+                     and torch.allclose(st.g_rest[0], torch.full((3, 3), 11.0)) and abs(float(loss) - 0.75) < 1e-6)
     out[rank] = ok
     dist.destroy_process_group()
 
@@ -57,5 +68,9 @@ def test_shard_range_partitions_exactly():
 
 
 def test_install_is_noop_without_wisp():
+    """Without an importable wisp nothing is patched (the patch body itself is exercised against the real classes in
+    tests/test_host_cpu.py::test_install_patches_the_real_wisp_classes)."""
+    import sys
     from wisp_b200 import install
-    assert install.install() in (False, True)
+    if "wisp" not in sys.modules:
+        assert install.install() is False and not install._ORIG
