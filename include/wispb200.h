@@ -314,6 +314,11 @@ int wb_rf_shade_bwd(const wb_nef_desc* nef, const float* blob, int32_t precision
                     const void* feat_saved, void* workspace,
                     float* grad_table, float* grad_dens, float* grad_col, wb_stream s);
 
+/* Precision 1: wb_rf_shade_fwd writes the per-ray colour-input rows (view embedding) at the start of its workspace; a caller that hands
+ * the SAME workspace (sized with backward = 1) and the same rays to the backward can say so right before that call and save the
+ * launch that would rebuild them.  Applies to the next wb_rf_shade_bwd / wb_rf_decoder_bwd of the calling thread only. */
+int wb_rf_workspace_holds_ray_rows(int32_t yes);
+
 /* scale = 2^clamp(floor(log2(64 / max(absmax, 1e-30))), -20, 60): the loss scale wb_rf_decoder_bwd / wb_rf_table_scatter expect,
  * derived on the device from wb_composite_bwd's absmax. */
 int wb_rf_loss_scale(const float* absmax, float* scale, wb_stream s);

@@ -9,6 +9,9 @@
 
 constexpr int WB_COMP_THREADS = 256;
 
+// A warp owns 32 CONSECUTIVE rays: lane i reads the sample range of ray r0 + i (one coalesced load instead of a dependent broadcast load
+// per ray), rays without samples are finished by their lane alone, the others are composited one after the other by the whole warp
+// (lane = sample, warp-shuffle scan with a running carry); every lane then writes its own ray's outputs (coalesced).
 __global__ void __launch_bounds__(WB_COMP_THREADS)
 wb_composite_fwd_kernel(const float4* __restrict__ shaded, const float* __restrict__ depth, const float* __restrict__ deltas,
                         const int64_t* __restrict__ offsets, int64_t R, float bgr, float bgg, float bgb,
@@ -17,28 +20,34 @@ wb_composite_fwd_kernel(const float4* __restrict__ shaded, const float* __restri
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = warp0; r < R; r += nwarps) {
-        const int64_t b = offsets[r], e = offsets[r + 1];
-        float cr = 0, cg = 0, cb = 0, dd = 0, aa = 0, carry = 0;
-        for (int64_t k0 = b; k0 < e; k0 += 32) {
-            const int64_t k = k0 + lane;
-            float tau = 0, t = 0; float4 sh = make_float4(0, 0, 0, 0);
-            if (k < e) { sh = __ldg(shaded + k); tau = sh.w * __ldg(deltas + k); t = __ldg(depth + k); }
-            const float incl = wb_warp_incl_scan(tau, lane);
-            const float T = expf(-(carry + (incl - tau)));
-            const float w = (k < e) ? T * (1.0f - expf(-tau)) : 0.0f;
-            cr = fmaf(w, sh.x, cr); cg = fmaf(w, sh.y, cg); cb = fmaf(w, sh.z, cb); dd = fmaf(w, t, dd); aa += w;
-            carry += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        cr = wb_warp_sum(cr); cg = wb_warp_sum(cg); cb = wb_warp_sum(cb); dd = wb_warp_sum(dd); aa = wb_warp_sum(aa);
-        if (lane == 0) {
-            if (e > b) {   // rgb[ridx_hit] = bg*(1-alpha) + ray_colors (:165)
-                rgb[3 * r] = bgr * (1.0f - aa) + cr; rgb[3 * r + 1] = bgg * (1.0f - aa) + cg; rgb[3 * r + 2] = bgb * (1.0f - aa) + cb;
-            } else {       // rgb = zeros + bg (:143)
-                rgb[3 * r] = bgr; rgb[3 * r + 1] = bgg; rgb[3 * r + 2] = bgb;
+    for (int64_t r0 = warp0 * 32; r0 < R; r0 += nwarps * 32) {
+        const int64_t rm = r0 + lane;
+        const int64_t mb = rm < R ? __ldg(offsets + rm) : 0, me = rm < R ? __ldg(offsets + rm + 1) : 0;
+        float o_r = bgr, o_g = bgg, o_b = bgb, o_d = 0.0f, o_a = 0.0f;           // rgb = zeros + bg for rays without samples (:143)
+        uint32_t todo = __ballot_sync(0xffffffffu, me > mb);
+        while (todo) {
+            const int j = __ffs(todo) - 1; todo &= todo - 1;
+            const int64_t b = __shfl_sync(0xffffffffu, mb, j), e = __shfl_sync(0xffffffffu, me, j);
+            float cr = 0, cg = 0, cb = 0, dd = 0, aa = 0, carry = 0;
+            for (int64_t k0 = b; k0 < e; k0 += 32) {
+                const int64_t k = k0 + lane;
+                float tau = 0, t = 0; float4 sh = make_float4(0, 0, 0, 0);
+                if (k < e) { sh = __ldg(shaded + k); tau = sh.w * __ldg(deltas + k); t = __ldg(depth + k); }
+                const float incl = wb_warp_incl_scan(tau, lane);
+                const float T = expf(-(carry + (incl - tau)));
+                const float w = (k < e) ? T * (1.0f - expf(-tau)) : 0.0f;
+                cr = fmaf(w, sh.x, cr); cg = fmaf(w, sh.y, cg); cb = fmaf(w, sh.z, cb); dd = fmaf(w, t, dd); aa += w;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
             }
-            if (depth_out) depth_out[r] = dd;
-            alpha[r] = aa; hit[r] = aa > 0.0f ? 1 : 0;
+            cr = wb_warp_sum(cr); cg = wb_warp_sum(cg); cb = wb_warp_sum(cb); dd = wb_warp_sum(dd); aa = wb_warp_sum(aa);
+            if (lane == j) {     // rgb[ridx_hit] = bg*(1-alpha) + ray_colors (:165)
+                o_r = bgr * (1.0f - aa) + cr; o_g = bgg * (1.0f - aa) + cg; o_b = bgb * (1.0f - aa) + cb; o_d = dd; o_a = aa;
+            }
+        }
+        if (rm < R) {
+            rgb[3 * rm] = o_r; rgb[3 * rm + 1] = o_g; rgb[3 * rm + 2] = o_b;
+            if (depth_out) depth_out[rm] = o_d;
+            alpha[rm] = o_a; hit[rm] = o_a > 0.0f ? 1 : 0;
         }
     }
 }
@@ -49,7 +58,7 @@ extern "C" int wb_composite_fwd(const float* shaded, const float* depth, const f
     if (R == 0) return WB_OK;
     WB_CHECK_ARG(offsets && bg && rgb && alpha && hit, "null pointer");
     const float b3[3] = { bg[0], bg[1], bg[2] };   // host pointer (launch parameter)
-    int64_t ctas = (R + 7) / 8; const int64_t cap = (int64_t)wb_num_sms() * 32; if (ctas > cap) ctas = cap;
+    int64_t ctas = (R + 255) / 256; const int64_t cap = (int64_t)wb_num_sms() * 32; if (ctas > cap) ctas = cap;      // 8 warps x 32 rays per CTA pass
     wb_composite_fwd_kernel<<<(unsigned)ctas, WB_COMP_THREADS, 0, (cudaStream_t)s>>>(
         reinterpret_cast<const float4*>(shaded), depth, deltas, offsets, R, b3[0], b3[1], b3[2], rgb, depth_out, alpha, hit);
     WB_LAUNCH_CHECK();
@@ -83,52 +92,62 @@ wb_composite_bwd_kernel(const float4* __restrict__ shaded, const float* __restri
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = warp0; r < R; r += nwarps) {
-        const int64_t b = offsets[r], e = offsets[r + 1];
-        float gr, gg, gb;
-        if (LOSS) {
-            float l0 = wb_loss_term(LS.type, __ldg(g_rgb + 3 * r) - __ldg(LS.target + 3 * r), gr);
-            l0 += wb_loss_term(LS.type, __ldg(g_rgb + 3 * r + 1) - __ldg(LS.target + 3 * r + 1), gg);
-            l0 += wb_loss_term(LS.type, __ldg(g_rgb + 3 * r + 2) - __ldg(LS.target + 3 * r + 2), gb);
-            gr *= LS.inv_count; gg *= LS.inv_count; gb *= LS.inv_count;
-            if (lane == 0) lsum += l0;
-        }
-        if (e == b) continue;
-        if (!LOSS) { gr = __ldg(g_rgb + 3 * r); gg = __ldg(g_rgb + 3 * r + 1); gb = __ldg(g_rgb + 3 * r + 2); }
-        const float gd = g_depth ? __ldg(g_depth + r) : 0.0f;
-        const float ga = (g_alpha ? __ldg(g_alpha + r) : 0.0f) - (gr * bgr + gg * bgg + gb * bgb);
-        float G = 0, carry = 0;
-        for (int64_t k0 = b; k0 < e; k0 += 32) {
-            const int64_t k = k0 + lane;
-            float tau = 0, gk = 0; float4 sh;
-            if (k < e) { sh = __ldg(shaded + k); tau = sh.w * __ldg(deltas + k); gk = gr * sh.x + gg * sh.y + gb * sh.z + gd * __ldg(depth + k) + ga; }
-            const float incl = wb_warp_incl_scan(tau, lane);
-            const float T = expf(-(carry + (incl - tau)));
-            const float w = (k < e) ? T * (1.0f - expf(-tau)) : 0.0f;
-            G = fmaf(gk, w, G);
-            carry += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        G = wb_warp_sum(G);
-        carry = 0; float gw_carry = 0;
-        for (int64_t k0 = b; k0 < e; k0 += 32) {
-            const int64_t k = k0 + lane;
-            float tau = 0, gk = 0, dl = 0; float4 sh = make_float4(0, 0, 0, 0);
-            if (k < e) { sh = __ldg(shaded + k); dl = __ldg(deltas + k); tau = sh.w * dl; gk = gr * sh.x + gg * sh.y + gb * sh.z + gd * __ldg(depth + k) + ga; }
-            const float incl = wb_warp_incl_scan(tau, lane);
-            const float T = expf(-(carry + (incl - tau)));
-            const float Tn = expf(-(carry + incl));                 // T_{k+1}
-            const float w = (k < e) ? T * (1.0f - expf(-tau)) : 0.0f;
-            const float gw = gk * w;
-            const float gw_incl = wb_warp_incl_scan(gw, lane);
-            const float suffix = G - (gw_carry + gw_incl);          // sum_{j>k} g_j w_j
-            const float gtau = gk * Tn - suffix;
-            if (k < e) {
-                const float4 gs = make_float4(gr * w, gg * w, gb * w, gtau * dl);
-                g_shaded[k] = gs;
-                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(gs.x), fabsf(gs.y)), fmaxf(fabsf(gs.z), fabsf(gs.w))));
+    for (int64_t r0 = warp0 * 32; r0 < R; r0 += nwarps * 32) {         // 32 consecutive rays per warp, as in the forward kernel
+        const int64_t rm = r0 + lane;
+        const int64_t mb = rm < R ? __ldg(offsets + rm) : 0, me = rm < R ? __ldg(offsets + rm + 1) : 0;
+        float mgr = 0.0f, mgg = 0.0f, mgb = 0.0f, mgd = 0.0f, mga = 0.0f;    // this lane's ray: dL/d(rgb, depth, alpha)
+        if (rm < R) {
+            if (LOSS) {
+                float l0 = wb_loss_term(LS.type, __ldg(g_rgb + 3 * rm) - __ldg(LS.target + 3 * rm), mgr);
+                l0 += wb_loss_term(LS.type, __ldg(g_rgb + 3 * rm + 1) - __ldg(LS.target + 3 * rm + 1), mgg);
+                l0 += wb_loss_term(LS.type, __ldg(g_rgb + 3 * rm + 2) - __ldg(LS.target + 3 * rm + 2), mgb);
+                mgr *= LS.inv_count; mgg *= LS.inv_count; mgb *= LS.inv_count;
+                lsum += l0;
+            } else if (me > mb) {
+                mgr = __ldg(g_rgb + 3 * rm); mgg = __ldg(g_rgb + 3 * rm + 1); mgb = __ldg(g_rgb + 3 * rm + 2);
+                mgd = g_depth ? __ldg(g_depth + rm) : 0.0f; mga = g_alpha ? __ldg(g_alpha + rm) : 0.0f;
             }
-            carry += __shfl_sync(0xffffffffu, incl, 31);
-            gw_carry += __shfl_sync(0xffffffffu, gw_incl, 31);
+        }
+        uint32_t todo = __ballot_sync(0xffffffffu, me > mb);
+        while (todo) {
+            const int j = __ffs(todo) - 1; todo &= todo - 1;
+            const int64_t b = __shfl_sync(0xffffffffu, mb, j), e = __shfl_sync(0xffffffffu, me, j);
+            const float gr = __shfl_sync(0xffffffffu, mgr, j), gg = __shfl_sync(0xffffffffu, mgg, j), gb = __shfl_sync(0xffffffffu, mgb, j);
+            const float gd = __shfl_sync(0xffffffffu, mgd, j);
+            const float ga = __shfl_sync(0xffffffffu, mga, j) - (gr * bgr + gg * bgg + gb * bgb);
+            float G = 0, carry = 0;
+            for (int64_t k0 = b; k0 < e; k0 += 32) {
+                const int64_t k = k0 + lane;
+                float tau = 0, gk = 0; float4 sh;
+                if (k < e) { sh = __ldg(shaded + k); tau = sh.w * __ldg(deltas + k); gk = gr * sh.x + gg * sh.y + gb * sh.z + gd * __ldg(depth + k) + ga; }
+                const float incl = wb_warp_incl_scan(tau, lane);
+                const float T = expf(-(carry + (incl - tau)));
+                const float w = (k < e) ? T * (1.0f - expf(-tau)) : 0.0f;
+                G = fmaf(gk, w, G);
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            G = wb_warp_sum(G);
+            carry = 0; float gw_carry = 0;
+            for (int64_t k0 = b; k0 < e; k0 += 32) {
+                const int64_t k = k0 + lane;
+                float tau = 0, gk = 0, dl = 0; float4 sh = make_float4(0, 0, 0, 0);
+                if (k < e) { sh = __ldg(shaded + k); dl = __ldg(deltas + k); tau = sh.w * dl; gk = gr * sh.x + gg * sh.y + gb * sh.z + gd * __ldg(depth + k) + ga; }
+                const float incl = wb_warp_incl_scan(tau, lane);
+                const float T = expf(-(carry + (incl - tau)));
+                const float Tn = expf(-(carry + incl));                 // T_{k+1}
+                const float w = (k < e) ? T * (1.0f - expf(-tau)) : 0.0f;
+                const float gw = gk * w;
+                const float gw_incl = wb_warp_incl_scan(gw, lane);
+                const float suffix = G - (gw_carry + gw_incl);          // sum_{j>k} g_j w_j
+                const float gtau = gk * Tn - suffix;
+                if (k < e) {
+                    const float4 gs = make_float4(gr * w, gg * w, gb * w, gtau * dl);
+                    g_shaded[k] = gs;
+                    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(gs.x), fabsf(gs.y)), fmaxf(fabsf(gs.z), fabsf(gs.w))));
+                }
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+                gw_carry += __shfl_sync(0xffffffffu, gw_incl, 31);
+            }
         }
     }
     if (absmax != nullptr) {      // non-negative floats order like their bit patterns: one atomicMax per warp (NaN/Inf sort above finite values)
@@ -136,7 +155,7 @@ wb_composite_bwd_kernel(const float4* __restrict__ shaded, const float* __restri
         for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
         if (lane == 0 && amax > 0.0f) atomicMax(reinterpret_cast<unsigned int*>(absmax), __float_as_uint(amax));
     }
-    if (LOSS && lane == 0 && lsum != 0.0f) atomicAdd(LS.loss_out, lsum * LS.inv_count);
+    if (LOSS) { lsum = wb_warp_sum(lsum); if (lane == 0 && lsum != 0.0f) atomicAdd(LS.loss_out, lsum * LS.inv_count); }
 }
 
 extern "C" int wb_composite_bwd(const float* shaded, const float* depth, const float* deltas, const int64_t* offsets, int64_t R,
@@ -146,7 +165,7 @@ extern "C" int wb_composite_bwd(const float* shaded, const float* depth, const f
     if (R == 0) return WB_OK;
     WB_CHECK_ARG(offsets && bg && g_rgb, "null pointer");
     const float b3[3] = { bg[0], bg[1], bg[2] };   // host pointer (launch parameter)
-    int64_t ctas = (R + 7) / 8; const int64_t cap = (int64_t)wb_num_sms() * 32; if (ctas > cap) ctas = cap;
+    int64_t ctas = (R + 255) / 256; const int64_t cap = (int64_t)wb_num_sms() * 32; if (ctas > cap) ctas = cap;
     wb_composite_bwd_kernel<false><<<(unsigned)ctas, WB_COMP_THREADS, 0, (cudaStream_t)s>>>(
         reinterpret_cast<const float4*>(shaded), depth, deltas, offsets, R, b3[0], b3[1], b3[2], g_rgb, g_depth, g_alpha,
         reinterpret_cast<float4*>(g_shaded), absmax, WbLoss{ nullptr, 0, 0.0f, nullptr });
@@ -166,7 +185,7 @@ extern "C" int wb_composite_bwd_loss(const float* shaded, const float* depth, co
     WB_CHECK_ARG(offsets && bg && rgb_pred && target && g_shaded && loss_out, "null pointer");
     WB_CHECK_ARG(loss_type >= 0 && loss_type <= 2, "loss_type must be 0 (l2), 1 (l1) or 2 (huber)");
     const float b3[3] = { bg[0], bg[1], bg[2] };
-    int64_t ctas = (R + 7) / 8; const int64_t cap = (int64_t)wb_num_sms() * 32; if (ctas > cap) ctas = cap;
+    int64_t ctas = (R + 255) / 256; const int64_t cap = (int64_t)wb_num_sms() * 32; if (ctas > cap) ctas = cap;
     wb_composite_bwd_kernel<true><<<(unsigned)ctas, WB_COMP_THREADS, 0, (cudaStream_t)s>>>(
         reinterpret_cast<const float4*>(shaded), depth, deltas, offsets, R, b3[0], b3[1], b3[2], rgb_pred, nullptr, nullptr,
         reinterpret_cast<float4*>(g_shaded), absmax, WbLoss{ target, loss_type, inv_count, loss_out });

@@ -614,7 +614,54 @@ __device__ __forceinline__ void tile_gather_ta(const WbGrid& g, uint32_t arow, i
     tc_st_wait();
 }
 
-template <int MINB, bool TA, bool GX = false>   // MINB: resident CTAs per SM the register allocation is bounded for; TA: activations in tensor
+// Software-pipelined form of tile_gather_ta (WB_TC_FWD_PIPE=1): the eight corner loads of LOD k are issued, THEN the cell / index /
+// coefficient arithmetic of LOD k+1 runs (~200 instructions), and only then are LOD k's corners blended -- the gather's L1/L2 latency
+// (long_scoreboard: 5.2 stalls per issue, profiles/r02e) overlaps ALU work of the same warp.  Needs more registers than the plain form.
+__device__ __forceinline__ void tile_gather_ta_pipe(const WbGrid& g, uint32_t arow, int half, float px, float py, float pz,
+                                                    uint4* __restrict__ save, int64_t S, int64_t s, bool valid)
+{
+    const int nlev = min(g.L, g.lod_idx);                        // LODs >= lod_idx are zeroed (hash_grid.py:226-229)
+    uint32_t idx[8]; float cf[8]; float2 c[8];
+    int lnext = 4 * half;
+    bool have = false;
+    if (lnext < nlev) {
+        wb_corner_setup(g, lnext, px, py, pz, idx, cf);
+        const float2* tb = reinterpret_cast<const float2*>(g.table + g.begin[lnext] * 2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c[j] = __ldg(tb + idx[j]);
+        have = true;
+    }
+    for (int l0 = 4 * half; l0 < g.L; l0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int l = l0 + q;
+            if (l >= nlev || !have) { v[2 * q] = 0.0f; v[2 * q + 1] = 0.0f; continue; }
+            float cfl[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cfl[j] = cf[j];
+            const int ln = ((l & 3) == 3) ? l + 5 : l + 1;         // this thread's next LOD: 4h, 4h+1, 4h+2, 4h+3, 4h+8, ...
+            const bool more = ln < nlev;
+            if (more) wb_corner_setup(g, ln, px, py, pz, idx, cf);
+            float a0 = c[0].x * cfl[0], a1 = c[0].y * cfl[0];
+#pragma unroll
+            for (int j = 1; j < 8; ++j) { a0 = fmaf(c[j].x, cfl[j], a0); a1 = fmaf(c[j].y, cfl[j], a1); }
+            v[2 * q] = a0; v[2 * q + 1] = a1;
+            if (more) {
+                const float2* tb = reinterpret_cast<const float2*>(g.table + g.begin[ln] * 2);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) c[j] = __ldg(tb + idx[j]);
+            }
+            have = more;
+        }
+        uint4 qv; qv.x = tc_pack2(v[0], v[1]); qv.y = tc_pack2(v[2], v[3]); qv.z = tc_pack2(v[4], v[5]); qv.w = tc_pack2(v[6], v[7]);
+        tc_st4(arow + (uint32_t)(l0 >> 2) * 4u, qv);
+        if (save != nullptr && valid) save[(int64_t)(l0 >> 2) * S + s] = qv;
+    }
+    tc_st_wait();
+}
+
+template <int MINB, bool TA, bool GX = false, bool PIPE = false>   // MINB: resident CTAs per SM the register allocation is bounded for; TA: activations in tensor
                                                 // memory; GX: triplanar / octree feature grid (wb_featx.cuh) instead of the hash grid
 __global__ void __launch_bounds__(TC_GROUP, MINB)
 wb_shade_fwd_tc_kernel(WbGrid g, WbGridX gx, WbTc m, const uint8_t* __restrict__ blob, TcIn in, float4* __restrict__ shaded)
@@ -650,7 +697,8 @@ wb_shade_fwd_tc_kernel(WbGrid g, WbGridX gx, WbTc m, const uint8_t* __restrict__
         const float pz = wb_addcmul(__ldg(in.origins + 3 * ray + 2), __ldg(in.dirs + 3 * ray + 2), t);
         // density-decoder input row: grid features (+ position embedding), zero padded to Kp; the two threads of a row split the LODs
         if (TA) {
-            tile_gather_ta(g, c.tmem + ((uint32_t)c.laneq << 16) + (uint32_t)m.work_col[1], c.h, px, py, pz, in.x0_save, in.S, s, valid);
+            if (PIPE) tile_gather_ta_pipe(g, c.tmem + ((uint32_t)c.laneq << 16) + (uint32_t)m.work_col[1], c.h, px, py, pz, in.x0_save, in.S, s, valid);
+            else tile_gather_ta(g, c.tmem + ((uint32_t)c.laneq << 16) + (uint32_t)m.work_col[1], c.h, px, py, pz, in.x0_save, in.S, s, valid);
         } else {
             if (!GX) tile_gather(g, t0, c.r, c.h, px, py, pz);
             else if (c.h == 0) wb_featx_gather(gx, px, py, pz, [&](int f, float v) { tile_store1(t0, c.r, f, v); });
@@ -676,6 +724,10 @@ wb_shade_fwd_tc_kernel(WbGrid g, WbGridX gx, WbTc m, const uint8_t* __restrict__
     if (threadIdx.x < 32) tc_tmem_dealloc(c.tmem, (uint32_t)m.tmem_cols);
 }
 
+// set by wb_rf_workspace_holds_ray_rows(): the next backward of this thread finds the per-ray colour-input rows in its workspace already
+static thread_local int g_tc_skip_embed = 0;
+extern "C" int wb_rf_workspace_holds_ray_rows(int32_t yes) { g_tc_skip_embed = yes ? 1 : 0; return WB_OK; }
+
 static int tc_launch_ray_embed(const WbTc& m, const wb_rays* rays, void* workspace, cudaStream_t st)
 {
     const int64_t R = rays->num_rays;
@@ -691,6 +743,7 @@ static int tc_env_int(const char* name, int dflt) { const char* v = getenv(name)
 static int tc_knob_fuse_scatter() { static const int v = tc_env_int("WB_TC_FUSE_SCATTER", 1); return v; }     // 0 separate kernel, 1 last epilogue (default), 2 pipelined
 static int tc_knob_bwd_groups() { static const int v = tc_env_int("WB_TC_BWD_GROUPS", 3); return v; }
 static int tc_knob_fwd_tmema() { static const int v = tc_env_int("WB_TC_FWD_TMEMA", 1); return v; }
+static int tc_knob_fwd_pipe() { static const int v = tc_env_int("WB_TC_FWD_PIPE", 0); return v; }
 static int tc_knob_fwd_ctas() { static const int v = tc_env_int("WB_TC_FWD_CTAS", 3); return v; }
 static int tc_knob_scatter_lpb() { static const int v = tc_env_int("WB_TC_SCATTER_LPB", 16); return v; }
 static int tc_knob_scatter_idx2() { static const int v = tc_env_int("WB_TC_SCATTER_IDX2", 1); return v; }
@@ -721,15 +774,18 @@ int wb_tc_shade_fwd(const wb_nef_desc* nef, const float* blob, const wb_rays* ra
     int per_sm = (227 * 1024) / (m.smem_bytes + 4096); per_sm = max(1, min(per_sm, 512 / m.tmem_cols));
     per_sm = max(2, min(min(per_sm, 4), tc_knob_fwd_ctas()));
     if (gx.kind != 0) per_sm = 2;                   // the generic grids keep more state per thread: 128 registers, 2 CTAs per SM
-    auto kern = gx.kind != 0 ? wb_shade_fwd_tc_kernel<2, false, true> : ta ? (per_sm == 2 ? wb_shade_fwd_tc_kernel<2, true> : per_sm == 3 ? wb_shade_fwd_tc_kernel<3, true> : wb_shade_fwd_tc_kernel<4, true>)
+    const bool pipe = ta && tc_knob_fwd_pipe() != 0 && per_sm <= 3;
+    auto kern = gx.kind != 0 ? wb_shade_fwd_tc_kernel<2, false, true>
+              : pipe ? (per_sm == 2 ? wb_shade_fwd_tc_kernel<2, true, false, true> : wb_shade_fwd_tc_kernel<3, true, false, true>)
+              : ta ? (per_sm == 2 ? wb_shade_fwd_tc_kernel<2, true> : per_sm == 3 ? wb_shade_fwd_tc_kernel<3, true> : wb_shade_fwd_tc_kernel<4, true>)
                    : (per_sm == 2 ? wb_shade_fwd_tc_kernel<2, false> : per_sm == 3 ? wb_shade_fwd_tc_kernel<3, false> : wb_shade_fwd_tc_kernel<4, false>);
     {   // function attributes are driver calls that can wait behind other driver work (e.g. an NVML poll): set them once, not per launch
-        static int done_for[10] = { -1, -1, -1, -1, -1, -1, -1, -1, -1, -1 };
-        if (done_for[gx.kind != 0 ? 9 : per_sm + (ta ? 5 : 0)] != m.smem_bytes) {
+        static int done_for[16] = { -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1 };
+        if (done_for[gx.kind != 0 ? 9 : pipe ? 10 + per_sm : per_sm + (ta ? 5 : 0)] != m.smem_bytes) {
             WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, m.smem_bytes));
             WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          min(100, (per_sm * (m.smem_bytes + 4096) * 100) / (228 * 1024) + 1)));
-            done_for[gx.kind != 0 ? 9 : per_sm + (ta ? 5 : 0)] = m.smem_bytes;
+            done_for[gx.kind != 0 ? 9 : pipe ? 10 + per_sm : per_sm + (ta ? 5 : 0)] = m.smem_bytes;
         }
     }
     const int64_t ntiles = (S + TC_ROWS - 1) / TC_ROWS;
@@ -1069,7 +1125,8 @@ int wb_tc_decoder_bwd_ex(const wb_nef_desc* nef, const float* blob, const wb_ray
     WbTc m; int rc = wb_tc_make(nef, true, &m); if (rc) return rc;
     WB_CHECK_ARG(scale != nullptr, "precision 1 needs the device loss-scale pointer");
     WB_CHECK_ARG(feat_saved != nullptr && workspace != nullptr, "precision 1 backward needs the saved features and the workspace");
-    rc = tc_launch_ray_embed(m, rays, workspace, st); if (rc) return rc;
+    if (g_tc_skip_embed) g_tc_skip_embed = 0;          // the forward's workspace (same rays) is being reused: the rows are there
+    else { rc = tc_launch_ray_embed(m, rays, workspace, st); if (rc) return rc; }
     int planes, width; tc_dfeat_shape(nef, &planes, &width);
     const int64_t R = rays->num_rays;
     __half* dfeat = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(workspace) + tc_align256(R * m.Kp[m.nl_d] * 2));

@@ -95,8 +95,8 @@ class MultiviewStep:
             self.params = [p for _, p in named if p.requires_grad]
         self.opt = NativeAdam(tensors, betas=betas, eps=eps)
         dev = tensors[0][0].device
-        self.loss_buf = torch.zeros(1, dtype=torch.float32, device=dev)
-        self.absmax = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._scalars = torch.zeros(2, dtype=torch.float32, device=dev)       # loss accumulator | max |g_shaded|: cleared by ONE fill per step
+        self.loss_buf, self.absmax = self._scalars[0:1], self._scalars[1:2]
         self.scale = torch.ones(1, dtype=torch.float32, device=dev)
         self.last_stage = {}
 
@@ -172,7 +172,7 @@ class MultiviewStep:
         with ops._stage("composite_fwd"):
             A.check(L.wb_composite_fwd(A.ptr(shaded), A.ptr(rec_t), A.ptr(rec_delta), A.ptr(ms.offsets), C.c_int64(R), bgv, A.ptr(rgb), None, A.ptr(alpha),
                                        A.ptr(hit), A.stream()))
-        self.loss_buf.zero_(); self.absmax.zero_()
+        self._scalars.zero_()
         # rgb_loss.mean() over the GLOBAL batch: every rank contributes sum / (3 * R * world); 'samples' divides by the local count
         inv = 1.0 / (3.0 * R * world) if self.loss_denom == "rays" else 1.0 / (max(S, 1) * world)
         with ops._stage("composite_bwd"):
@@ -182,6 +182,7 @@ class MultiviewStep:
         if S > 0:
             if precision == 1:
                 A.check(L.wb_rf_loss_scale(A.ptr(self.absmax), A.ptr(self.scale), A.stream()))
+                L.wb_rf_workspace_holds_ray_rows(C.c_int32(1))      # same workspace, same rays as the forward above
             with ops._stage("shade_bwd"):      # precision 1: decoder backward + table scatter in one kernel where the shape allows
                 A.check(L.wb_rf_shade_bwd(C.byref(desc), A.ptr(blob), C.c_int32(precision), C.byref(ms.rays), A.ptr(rec_t), A.ptr(rec_ray), C.c_int64(S), A.ptr(g_sh),
                                           A.ptr(self.scale) if precision == 1 else None, A.ptr(feat), A.ptr(ws), A.ptr(g_table), A.ptr(self.g_dens), A.ptr(self.g_col), A.stream()))
