@@ -124,6 +124,9 @@ def require_device(t: torch.Tensor) -> None:
     if not t.is_cuda:
         raise WispB200Error("wisp_b200 kernels need CUDA tensors on a B200 (sm_100a); there is no CPU fallback")
     idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if idx != torch.cuda.current_device():
+        raise WispB200Error(f"tensor on cuda:{idx} but the current device is cuda:{torch.cuda.current_device()}: call under torch.cuda.device({idx}) "
+                            "(the library launches on the current device; one process per GPU is the supported layout)")
     if idx not in _checked_devices:
         check(lib().wb_device_check(C.c_int(idx)))
         _checked_devices.add(idx)
@@ -139,8 +142,10 @@ def ptr(t: Optional[torch.Tensor]):
     return C.c_void_p(t.data_ptr())
 
 
-def stream() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream(t: Optional[torch.Tensor] = None) -> C.c_void_p:
+    """The current torch stream (of `t`'s device when given).  The library launches on the CURRENT CUDA device: one process per GPU
+    (torchrun + torch.cuda.set_device) is the supported layout; tensors on another device must be used under torch.cuda.device(...)."""
+    return C.c_void_p((torch.cuda.current_stream(t.device) if t is not None else torch.cuda.current_stream()).cuda_stream)
 
 
 def f32c(t: torch.Tensor) -> torch.Tensor:

@@ -26,7 +26,10 @@ void wb_count_launch(int n = 1);
         wb_set_error("%s: kernel launch failed: %s", __func__, cudaGetErrorString(e__)); return WB_ERR_CUDA; } \
         wb_count_launch(); } while (0)
 
-int wb_num_sms();          // cached multiprocessor count of the current device
+int wb_num_sms();          // multiprocessor count of the CURRENT device (cached per device)
+int wb_cur_device();       // cudaGetDevice: function attributes (dynamic shared memory size) are per device -- the once-only caches
+                           // around cudaFuncSetAttribute fold it into their key (WB_ATTR_KEY)
+#define WB_ATTR_KEY(bytes) ((int64_t)(bytes) * 64 + wb_cur_device())
 
 // ---------------------------------------------------------------------------------------------
 // Jitter contract: counter-based stream keyed by (seed, ray, step).

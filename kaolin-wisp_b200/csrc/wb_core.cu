@@ -13,13 +13,16 @@ void wb_set_error(const char* fmt, ...) {
 }
 void wb_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int wb_cur_device() { int dev = 0; cudaGetDevice(&dev); return dev < 0 ? 0 : (dev & 63); }
 int wb_num_sms() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0; cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    static std::atomic<int> sms[64];
+    const int dev = wb_cur_device();
+    int v = sms[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        sms[dev].store(v, std::memory_order_relaxed);
     }
-    return sms;
+    return v;
 }
 
 extern "C" const char* wb_last_error(void) { return g_err; }

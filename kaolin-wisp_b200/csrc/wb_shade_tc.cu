@@ -780,12 +780,12 @@ int wb_tc_shade_fwd(const wb_nef_desc* nef, const float* blob, const wb_rays* ra
               : ta ? (per_sm == 2 ? wb_shade_fwd_tc_kernel<2, true> : per_sm == 3 ? wb_shade_fwd_tc_kernel<3, true> : wb_shade_fwd_tc_kernel<4, true>)
                    : (per_sm == 2 ? wb_shade_fwd_tc_kernel<2, false> : per_sm == 3 ? wb_shade_fwd_tc_kernel<3, false> : wb_shade_fwd_tc_kernel<4, false>);
     {   // function attributes are driver calls that can wait behind other driver work (e.g. an NVML poll): set them once, not per launch
-        static int done_for[16] = { -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1 };
-        if (done_for[gx.kind != 0 ? 9 : pipe ? 10 + per_sm : per_sm + (ta ? 5 : 0)] != m.smem_bytes) {
+        static int64_t done_for[16] = { -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1 };
+        if (done_for[gx.kind != 0 ? 9 : pipe ? 10 + per_sm : per_sm + (ta ? 5 : 0)] != WB_ATTR_KEY(m.smem_bytes)) {
             WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, m.smem_bytes));
             WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          min(100, (per_sm * (m.smem_bytes + 4096) * 100) / (228 * 1024) + 1)));
-            done_for[gx.kind != 0 ? 9 : pipe ? 10 + per_sm : per_sm + (ta ? 5 : 0)] = m.smem_bytes;
+            done_for[gx.kind != 0 ? 9 : pipe ? 10 + per_sm : per_sm + (ta ? 5 : 0)] = WB_ATTR_KEY(m.smem_bytes);
         }
     }
     const int64_t ntiles = (S + TC_ROWS - 1) / TC_ROWS;
@@ -1143,10 +1143,10 @@ int wb_tc_decoder_bwd_ex(const wb_nef_desc* nef, const float* blob, const wb_ray
         if (fuse) { rc = wb_make_grid(nef, &g); if (rc) return rc; }
         const int fmode = !fuse ? 0 : (tc_knob_fuse_scatter() == 2 ? 2 : 1);
         auto kern3 = fmode == 2 ? wb_mlp_bwd3_tc_kernel<2> : fmode == 1 ? wb_mlp_bwd3_tc_kernel<1> : wb_mlp_bwd3_tc_kernel<0>;
-        static int done3[3] = { -1, -1, -1 };
-        if (done3[fmode] != plan.smem_bytes) {
+        static int64_t done3[3] = { -1, -1, -1 };
+        if (done3[fmode] != WB_ATTR_KEY(plan.smem_bytes)) {
             WB_CUDA(cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
-            done3[fmode] = plan.smem_bytes;
+            done3[fmode] = WB_ATTR_KEY(plan.smem_bytes);
         }
         const int64_t nctas3 = ((S + TC_ROWS - 1) / TC_ROWS + TC_B3_GROUPS - 1) / TC_B3_GROUPS;
         int64_t grid3 = (int64_t)wb_num_sms(); if (grid3 > nctas3) grid3 = nctas3;
@@ -1158,10 +1158,10 @@ int wb_tc_decoder_bwd_ex(const wb_nef_desc* nef, const float* blob, const wb_ray
     }
     WB_CHECK_ARG(m.fits2, "tensor-core path: decoder backward does not fit in shared memory (use precision 0)");
     {
-        static int done_for = -1;
-        if (done_for != m.smem_bytes) {
+        static int64_t done_for = -1;
+        if (done_for != WB_ATTR_KEY(m.smem_bytes)) {
             WB_CUDA(cudaFuncSetAttribute(wb_mlp_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, m.smem_bytes));
-            done_for = m.smem_bytes;
+            done_for = WB_ATTR_KEY(m.smem_bytes);
         }
     }
     const int64_t nctas = ((S + TC_ROWS - 1) / TC_ROWS + TC_BWD_GROUPS - 1) / TC_BWD_GROUPS;

@@ -333,6 +333,14 @@ def march_nuggets(oct: OctreeTensors, origins, dirs, level: int, num_samples: in
 # --------------------------------------------------------------------------------------------------------------
 # hash grid interpolate (unfused drop-in for wisp.ops.grid.hashgrid)
 # --------------------------------------------------------------------------------------------------------------
+def _no_coords_grad(ctx, i: int) -> None:
+    """The native grid kernels return no gradient with respect to the sample coordinates (Kaolin's trilinear interpolation does not
+    either; the reference's hash-grid grad_coords branch, hashgrid_interpolate_cuda.cu:163-210, is not replicated): refuse loudly instead of
+    silently cutting the graph (eikonal losses, autodiff normals must stay on the reference path)."""
+    if ctx.needs_input_grad[i]:
+        raise A.WispB200Error("wisp_b200 grid kernels do not provide gradients with respect to coords (coords.requires_grad is set)")
+
+
 class HashGridInterpolate(torch.autograd.Function):
     """wisp.ops.grid.HashGridInterpolate (ops/grid.py:77-126) over wb_hashgrid_fwd / wb_hashgrid_bwd.
     Differences by design: all LODs in one launch; the table is read as fp32 master (no per-call .half() copy,
@@ -342,6 +350,7 @@ class HashGridInterpolate(torch.autograd.Function):
     def forward(ctx, coords, resolutions, codebook_bitwidth, lod_idx, codebook, codebook_first_idx):
         if codebook.shape[-1] % 2 == 1:
             raise Exception("The codebook feature dimension needs to be a multiple of 2.")   # ops/grid.py:83-84
+        _no_coords_grad(ctx, 0)
         assert coords.shape[-1] == 3, "only the 3D hash grid is on the accelerated path"
         A.require_device(codebook)
         c = A.f32c(coords)
@@ -385,6 +394,7 @@ class TriplaneInterpolate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, coords, num_lods, *planes):
         A.require_device(planes[0])
+        _no_coords_grad(ctx, 0)
         c = A.f32c(coords)
         N, fdim = c.shape[0], planes[0].shape[1]
         pl = [A.f32c(p.detach()) for p in planes[:3 * num_lods]]
@@ -418,6 +428,7 @@ class OctreeInterpolate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, coords, oct, trinkets, base_lod, multiscale, half_round, *feats):
         A.require_device(feats[0])
+        _no_coords_grad(ctx, 0)
         c = A.f32c(coords)
         N, F, nl = c.shape[0], feats[0].shape[1], len(feats)
         fl = [A.f32c(f.detach()) for f in feats]
