@@ -95,9 +95,12 @@ __device__ __forceinline__ void wb_oct_walk(const WbGridX& x, float cx, float cy
 }
 
 // Features of one sample: emit(feature index in the decoder input, value) is called exactly once per feature.
+// [k0, k1): the LODs this call evaluates (default: all).  A caller that splits the LODs of a sample over two threads gets, per call,
+// the 'cat' features of its LODs, or for 'sum' grids the PARTIAL sums over its LODs (emit(f, partial)), which it adds up itself.
 template <class Emit>
-__device__ __forceinline__ void wb_featx_gather(const WbGridX& x, float cx, float cy, float cz, Emit emit)
+__device__ __forceinline__ void wb_featx_gather(const WbGridX& x, float cx, float cy, float cz, Emit emit, int k0 = 0, int k1 = 1 << 30)
 {
+    if (k1 > x.nl) k1 = x.nl;
     if (x.kind == 1) {
         const int C = x.C;
         float acc[3][WB_X_MAX_C];
@@ -105,7 +108,7 @@ __device__ __forceinline__ void wb_featx_gather(const WbGridX& x, float cx, floa
         for (int p = 0; p < 3; ++p)
 #pragma unroll
             for (int c = 0; c < WB_X_MAX_C; ++c) acc[p][c] = 0.0f;
-        for (int l = 0; l < x.nl; ++l) {
+        for (int l = k0; l < k1; ++l) {
             const int size = x.res[l] + 1; const int64_t hw = (int64_t)size * size;
 #pragma unroll
             for (int p = 0; p < 3; ++p) {
@@ -138,9 +141,11 @@ __device__ __forceinline__ void wb_featx_gather(const WbGridX& x, float cx, floa
         for (int f = 0; f < WB_X_MAX_F; ++f) acc[f] = 0.0f;
         int reached = x.base_lod;                     // 'cat': LODs below `reached` have been emitted
         wb_oct_walk(x, cx, cy, cz, [&](int l, int node) {
+            const int k = l - x.base_lod;
+            reached = l + 1;
+            if (k < k0 || k >= k1) return;
             float cf[8]; int tk[8];
             wb_oct_cell(x, node, l, cx, cy, cz, cf, tk);
-            const int k = l - x.base_lod;
             const float* ft = x.ptr[k];
 #pragma unroll
             for (int f = 0; f < WB_X_MAX_F; ++f) {
@@ -156,13 +161,12 @@ __device__ __forceinline__ void wb_featx_gather(const WbGridX& x, float cx, floa
                     if (sum) acc[f] += a; else emit(k * F + f, a);
                 }
             }
-            reached = l + 1;
         });
         if (sum) {
 #pragma unroll
             for (int f = 0; f < WB_X_MAX_F; ++f) if (f < F) emit(f, acc[f]);
         } else {
-            for (int k = reached - x.base_lod; k < x.nl; ++k)       // LODs the point never reached: zeros (pidx == -1)
+            for (int k = max(reached - x.base_lod, k0); k < k1; ++k)       // LODs the point never reached: zeros (pidx == -1)
                 for (int f = 0; f < F; ++f) emit(k * F + f, 0.0f);
         }
     }

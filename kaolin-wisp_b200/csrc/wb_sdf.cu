@@ -186,7 +186,29 @@ __device__ __forceinline__ float sdf_eval(const WbOct& oc, const WbSdf& m, const
         for (int k = IN; k < INP; ++k) in[k] = 0.0f;
         const float* b0 = sw + H * INP; const float* wo = b0 + H;
         float out = wo[H];
-        for (int j = 0; j < H; ++j) {
+        // four hidden units at a time: four independent FMA chains instead of one 20-deep dependent chain per unit (the evaluation is a
+        // latency chain per thread: few packs are alive per CTA, nothing else hides the FMA latency)
+        int j = 0;
+        for (; j + 4 <= H; j += 4) {
+            float a0 = b0[j], a1 = b0[j + 1], a2 = b0[j + 2], a3 = b0[j + 3];
+            const float4* w0 = reinterpret_cast<const float4*>(sw + j * INP);
+            const float4* w1 = reinterpret_cast<const float4*>(sw + (j + 1) * INP);
+            const float4* w2 = reinterpret_cast<const float4*>(sw + (j + 2) * INP);
+            const float4* w3 = reinterpret_cast<const float4*>(sw + (j + 3) * INP);
+#pragma unroll
+            for (int q = 0; q < INP / 4; ++q) {
+                const float4 u0 = w0[q], u1 = w1[q], u2 = w2[q], u3 = w3[q];
+                const float x0 = in[4 * q], x1 = in[4 * q + 1], x2 = in[4 * q + 2], x3 = in[4 * q + 3];
+                a0 = fmaf(u0.x, x0, a0); a1 = fmaf(u1.x, x0, a1); a2 = fmaf(u2.x, x0, a2); a3 = fmaf(u3.x, x0, a3);
+                a0 = fmaf(u0.y, x1, a0); a1 = fmaf(u1.y, x1, a1); a2 = fmaf(u2.y, x1, a2); a3 = fmaf(u3.y, x1, a3);
+                a0 = fmaf(u0.z, x2, a0); a1 = fmaf(u1.z, x2, a1); a2 = fmaf(u2.z, x2, a2); a3 = fmaf(u3.z, x2, a3);
+                a0 = fmaf(u0.w, x3, a0); a1 = fmaf(u1.w, x3, a1); a2 = fmaf(u2.w, x3, a2); a3 = fmaf(u3.w, x3, a3);
+            }
+            // the output layer sums in unit order, as the single-chain form did
+            out = fmaf(wo[j], fmaxf(a0, 0.0f), out); out = fmaf(wo[j + 1], fmaxf(a1, 0.0f), out);
+            out = fmaf(wo[j + 2], fmaxf(a2, 0.0f), out); out = fmaf(wo[j + 3], fmaxf(a3, 0.0f), out);
+        }
+        for (; j < H; ++j) {
             const float4* wr = reinterpret_cast<const float4*>(sw + j * INP);
             float a = b0[j];
 #pragma unroll

@@ -62,11 +62,12 @@ class PackedRFTracer(nn.Module):
         with torch.cuda.stream(self._march_stream):
             key = (rays.origins.shape[0], n)
             if getattr(self, "_primed", None) != key:
-                # first pre-march of this shape: reserve three sets of march buffers in the side stream's allocator pool, so that
-                # the steady state (one set being filled, one consumed, one waiting for its cross-stream events) never calls cudaMalloc
+                # first pre-march of this shape: reserve four sets of march buffers in the side stream's allocator pool, so that
+                # the steady state (one set being filled, one consumed, up to two waiting for their cross-stream events to retire)
+                # never calls cudaMalloc (three sets left an occasional cudaMalloc in a timed step, BENCH_r01)
                 R, nw = key[0], (n + 31) // 32
                 spare = [(torch.empty((R, nw), dtype=torch.int32, device=dev), torch.empty(R, dtype=torch.int32, device=dev),
-                          torch.empty(R + 1, dtype=torch.int64, device=dev)) for _ in range(3)]
+                          torch.empty(R + 1, dtype=torch.int64, device=dev)) for _ in range(4)]
                 del spare
                 self._primed = key
             pm = ops.march_count(blas.tensors(), rays.origins, rays.dirs, rays.dist_min, rays.dist_max, n, level,
