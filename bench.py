@@ -488,7 +488,7 @@ def parity_leg(args, O, W, torch, dev, spc_np, onef, pipe, tracer, nef, stepper=
     tracer.seed = keep["seed"]
     o, d, tgt = (torch.from_numpy(keep[k]).to(dev) for k in ("origins", "dirs", "target"))
     if stepper is not None:       # the benched step itself (MultiviewStep): its loss, its rgb and its gradient buffers, before they are cleared
-        loss = stepper.step(W.Rays(o, d, dist_min=NEAR, dist_max=FAR), tgt, seed=keep["seed"], zero_grad=False, local_only=True)
+        loss = stepper.step(W.Rays(o, d, dist_min=NEAR, dist_max=FAR), tgt, seed=keep["seed"], zero_grad=False, local_only=True, update=False)
         torch.cuda.synchronize()
         rgb_gpu = stepper.last_rgb.cpu().numpy()
         g_table, g_dens, g_col = stepper.g_grid[0].cpu().numpy(), stepper.g_dens.cpu().numpy(), stepper.g_col.cpu().numpy()

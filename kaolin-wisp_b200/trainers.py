@@ -125,9 +125,10 @@ class MultiviewStep:
 
     # ---- the step ------------------------------------------------------------------------------------------------------
     def step(self, rays: Rays, img_gts: torch.Tensor, seed: Optional[int] = None, next_rays: Optional[Rays] = None, next_seed: Optional[int] = None,
-             next_ready=None, zero_grad: bool = True, local_only: bool = False) -> torch.Tensor:
+             next_ready=None, zero_grad: bool = True, local_only: bool = False, update: bool = True) -> torch.Tensor:
         """One optimisation step on (rays, img_gts [R,3]); returns the loss as a device scalar (no host sync).  `next_rays` (+ seed)
-        lets the march of the following batch overlap this step (PackedRFTracer.premarch)."""
+        lets the march of the following batch overlap this step (PackedRFTracer.premarch).  `update=False` stops after the backward
+        (gradients left in g_grid / g_dens / g_col, parameters and optimiser state untouched: gradient checks, bench.py's parity leg)."""
         tr = self.tracer
         if seed is None:
             seed = tr.seed
@@ -191,8 +192,9 @@ class MultiviewStep:
         if world > 1:
             with ops._stage("all_reduce"):
                 self._all_reduce(loss)
-        with ops._stage("adam"):
-            self.opt.step(self.g_grid + [self.g_dens, self.g_col] + self.g_rest, grad_scale=1.0, zero_grad=zero_grad)
+        if update:
+            with ops._stage("adam"):
+                self.opt.step(self.g_grid + [self.g_dens, self.g_col] + self.g_rest, grad_scale=1.0, zero_grad=zero_grad)
         return loss[0]
 
     def _all_reduce(self, loss):

@@ -32,20 +32,21 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header(tmp_path):
-    """Compile include/wispb200.h with the C compiler and compare sizeof/offsetof with the ctypes mirrors."""
+    """Compile include/wispb200.h with the C compiler and compare sizeof/offsetof of EVERY descriptor struct with the ctypes mirrors."""
     import subprocess
+    A = W._cabi
+    structs = {"wb_nef_desc": A.NefDesc, "wb_rays": A.RaysDesc, "wb_octree": A.OctreeDesc, "wb_sdf_desc": A.SdfDesc, "wb_sdf_state": A.SdfState,
+               "wb_adam_segment": A.AdamSegment}
+    lines, mine = [], []
+    for cname, cls in structs.items():
+        lines.append(f'printf("%zu\\n", sizeof({cname}));'); mine.append(C.sizeof(cls))
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("%zu\\n", offsetof({cname}, {fname}));'); mine.append(getattr(cls, fname).offset)
     src = tmp_path / "lay.c"
-    src.write_text('''#include <stdio.h>
-#include <stddef.h>
-#include "wispb200.h"
-int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(wb_nef_desc), offsetof(wb_nef_desc, begin_idxes), offsetof(wb_nef_desc, table),
-  offsetof(wb_nef_desc, dens_dims), offsetof(wb_nef_desc, col_params), sizeof(wb_rays), offsetof(wb_rays, near_v), sizeof(wb_octree), offsetof(wb_octree, bits_level)); return 0; }''')
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "wispb200.h"\nint main(void){ ' + " ".join(lines) + ' return 0; }')
     exe = tmp_path / "lay"
     subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     vals = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
-    A = W._cabi
-    mine = [C.sizeof(A.NefDesc), A.NefDesc.begin_idxes.offset, A.NefDesc.table.offset, A.NefDesc.dens_dims.offset, A.NefDesc.col_params.offset,
-            C.sizeof(A.RaysDesc), A.RaysDesc.near_v.offset, C.sizeof(A.OctreeDesc), A.OctreeDesc.bits_level.offset]
     assert mine == vals
 
 
