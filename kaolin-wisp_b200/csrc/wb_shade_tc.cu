@@ -1214,9 +1214,9 @@ int wb_tc_decoder_bwd_ex(const wb_nef_desc* nef, const float* blob, const wb_ray
         const bool fuse = grad_table != nullptr && tc_knob_fuse_scatter() && nef->grid_kind == 0 && nef->feature_dim == 2 && nef->multiscale == 0 &&
                           planes <= 16;
         if (fuse) { rc = wb_make_grid(nef, &g); if (rc) return rc; }
-        const int fmode = !fuse ? 0 : (tc_knob_fuse_scatter() == 2 ? 2 : 1);
-        auto kern3 = fmode == 2 ? wb_mlp_bwd3_tc_kernel<2> : fmode == 1 ? wb_mlp_bwd3_tc_kernel<1> : wb_mlp_bwd3_tc_kernel<0>;
-        static int64_t done3[3] = { -1, -1, -1 };
+        const int fmode = !fuse ? 0 : (tc_knob_fuse_scatter() == 2 ? 2 : tc_knob_fuse_scatter() == 3 ? 3 : 1);
+        auto kern3 = fmode == 3 ? wb_mlp_bwd3_tc_kernel<3> : fmode == 2 ? wb_mlp_bwd3_tc_kernel<2> : fmode == 1 ? wb_mlp_bwd3_tc_kernel<1> : wb_mlp_bwd3_tc_kernel<0>;
+        static int64_t done3[4] = { -1, -1, -1, -1 };
         if (done3[fmode] != WB_ATTR_KEY(plan.smem_bytes)) {
             WB_CUDA(cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
             done3[fmode] = WB_ATTR_KEY(plan.smem_bytes);

@@ -220,6 +220,9 @@ __device__ __forceinline__ void tc_scatter_level_f2(const WbGrid& g, int l, floa
 //   1  in the last epilogue of the sub-tile (DEFAULT, 7.12 ms): the planes never exist; the win is only their 124 B/sample of traffic
 //      and one launch -- the three groups of a CTA run in lockstep (they convoy on the tensor pipe), so all 24 warps scatter at the same
 //      time and the scatter phase is as issue / reduction-bound as the stand-alone kernel was.
+//   3  as 1, but the scatter phase is a critical section of the CTA (a shared-memory token): the groups' reduction phases are forced
+//      apart, so that while one group issues its ~5 k lane-reductions (the scatter runs at ~0.8 of the per-SM REDG issue rate: 6.3e8
+//      lane-reductions per step, ncu r02e) the other two are in their latency-bound decoder rounds instead of queueing on the same pipe.
 //   2  software-pipelined (7.34 ms, kept for reference): the planes are still written (and re-read from L2 by the thread that wrote
 //      them), LOD q of sub-tile i is scattered inside round q of sub-tile i+1 between the issue of that round's UMMAs and the wait for
 //      their completion.  It does not pay: a round's wait is barrier / commit / wake-up latency, not UMMA execution time, so there is
@@ -231,8 +234,10 @@ wb_mlp_bwd3_tc_kernel(WbTc m, TcB3Plan p, const uint8_t* __restrict__ blob, TcIn
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[TC_B3_GROUPS + 1];
     __shared__ uint32_t tmem_s;
+    __shared__ int scatter_token;                                // FUSE == 3: which group (1..3) is scattering, 0 = nobody
     __shared__ TcRec tab[TC_B3_GROUPS * TC_B3_ROUNDS * 3];
     if (threadIdx.x == 0) {
+        scatter_token = 0;
         for (int i = 0; i < TC_B3_GROUPS; ++i) tc_mbar_init(&bars[i], TC_ISSUERS);
         tc_mbar_init(&bars[TC_B3_GROUPS], 1); tc_mbar_init_fence();
         tc_mbar_expect_tx(&bars[TC_B3_GROUPS], (uint32_t)m.blob_bytes);
@@ -360,13 +365,23 @@ wb_mlp_bwd3_tc_kernel(WbTc m, TcB3Plan p, const uint8_t* __restrict__ blob, TcIn
             pz = wb_addcmul(__ldg(in.origins + 3 * ray + 2), __ldg(in.dirs + 3 * ray + 2), t);
         }
         tc_b3_round(c, rec + 10 * 3);
-        if (FUSE == 1) {
+        if (FUSE == 1 || FUSE == 3) {
             // column half h holds features [16h, 16h+16) = LODs 8h .. 8h+7; a warp = 32 consecutive samples of one half
             float v[16]; tc_ld16(trow + c.h * 16, v);
+            if (FUSE == 3) {      // one group scatters at a time: the reduction-heavy phases of the three groups cannot coincide (see below)
+                if ((threadIdx.x & (TC_GROUP - 1)) == 0) {
+                    while (atomicCAS(&scatter_token, 0, c.g + 1) != 0) __nanosleep(200);
+                }
+                tc_group_sync(c.g + 1, TC_GROUP);
+            }
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int l = c.h * 8 + q;
                 if (l < G.planes) tc_scatter_level_f2(g, l, px, py, pz, valid, v[2 * q], v[2 * q + 1], inv_scale, lane_, gtable);
+            }
+            if (FUSE == 3) {
+                tc_group_sync(c.g + 1, TC_GROUP);
+                if ((threadIdx.x & (TC_GROUP - 1)) == 0) atomicExch(&scatter_token, 0);
             }
         } else {
             const int W = G.width, nfe = G.planes * W;
