@@ -155,6 +155,12 @@ int wb_raymarch_ray_fill(const wb_rays* rays, int32_t num_samples, const float* 
 int wb_raytrace_count(const wb_octree* oct, int32_t level, const wb_rays* rays, int32_t* counts, wb_stream s);
 int wb_raytrace_fill(const wb_octree* oct, int32_t level, const wb_rays* rays, const int64_t* offsets,
                      int32_t* ridx, int32_t* pidx, float* depth, wb_stream s);
+/* The same pair with ONE octree traversal: the count pass keeps the first cache_k nuggets of every ray in `cache`
+ * (wb_raytrace_cache_bytes(R, cache_k) bytes), the fill copies them and re-traverses only rays with more than cache_k nuggets. */
+int64_t wb_raytrace_cache_bytes(int64_t R, int32_t cache_k);
+int wb_raytrace_count_cached(const wb_octree* oct, int32_t level, const wb_rays* rays, int32_t* counts, void* cache, int32_t cache_k, wb_stream s);
+int wb_raytrace_fill_cached(const wb_octree* oct, int32_t level, const wb_rays* rays, const int64_t* offsets, const void* cache, int32_t cache_k,
+                            int32_t* ridx, int32_t* pidx, float* depth, wb_stream s);
 /* num_samples per nugget; jitter: explicit [Ng, num_samples] or NULL for the counter stream keyed by (seed, nugget, k). */
 int wb_raymarch_voxel_fill(const wb_rays* rays, const int32_t* nug_ridx, const float* nug_depth, int64_t Ng, int32_t num_samples,
                            const float* jitter, uint32_t seed, int64_t* ridx, float* samples, float* depth, float* deltas,

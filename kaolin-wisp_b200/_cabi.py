@@ -76,7 +76,7 @@ EXPORTS = [
     "wb_last_error", "wb_version", "wb_device_check", "wb_launch_count",
     "wb_octree_generate_points", "wb_octree_build_bits", "wb_octree_build_coarse", "wb_query",
     "wb_raymarch_ray_count", "wb_scan_workspace_bytes", "wb_scan_counts", "wb_raymarch_ray_fill",
-    "wb_raytrace_count", "wb_raytrace_fill", "wb_raymarch_voxel_fill", "wb_raymarch_uniform_count", "wb_raymarch_uniform_fill",
+    "wb_raytrace_count", "wb_raytrace_fill", "wb_raytrace_cache_bytes", "wb_raytrace_count_cached", "wb_raytrace_fill_cached", "wb_raymarch_voxel_fill", "wb_raymarch_uniform_count", "wb_raymarch_uniform_fill",
     "wb_hashgrid_fwd", "wb_hashgrid_bwd", "wb_triplane_fwd", "wb_triplane_bwd",
     "wb_octree_interp_fwd", "wb_octree_interp_bwd", "wb_find_depth_bound", "wb_sdf_eval", "wb_sdf_trace", "wb_sdf_phase", "wb_composite_fwd", "wb_composite_bwd",
     "wb_rf_march_fill", "wb_rf_param_blob_floats", "wb_rf_precision_supported", "wb_rf_pack_params", "wb_rf_shade_fwd", "wb_rf_shade_bwd",
@@ -110,6 +110,7 @@ def lib() -> C.CDLL:
         L.wb_rf_workspace_bytes.restype = C.c_int64
         L.wb_rf_feat_bytes.restype = C.c_int64
         L.wb_adam_desc_bytes.restype = C.c_int64
+        L.wb_raytrace_cache_bytes.restype = C.c_int64
         _lib = L
     return _lib
 

@@ -28,21 +28,40 @@ __device__ __forceinline__ bool wb_slab(const float o[3], const float d[3], int 
     t0 = en; t1 = tx; return true;
 }
 
-template <bool FILL>
+// MODE 0: count.  1: fill (second traversal).  2: count AND keep the first K nuggets of every ray in a cache laid out [K][R] (nugget-major:
+// the 32 rays of a warp write neighbouring words).  3: fill from that cache; only rays with more than K nuggets are traversed again.
+// Modes 2 + 3 replace the two full depth-first traversals of 0 + 1 by one (the traversal is a chain of dependent byte loads per ray and
+// dominates both passes: 0.29 ms each for the 512^2 rays of the SDF configuration).
+struct WbNugCache { int32_t* pidx; float2* depth; int K; };
+
+template <int MODE>
 __global__ void __launch_bounds__(128)
 wb_raytrace_kernel(WbOct oc, const float* __restrict__ origins, const float* __restrict__ dirs, int64_t R,
                    int32_t* __restrict__ counts, const int64_t* __restrict__ offsets,
-                   int32_t* __restrict__ ridx, int32_t* __restrict__ pidx, float* __restrict__ depth)
+                   int32_t* __restrict__ ridx, int32_t* __restrict__ pidx, float* __restrict__ depth, WbNugCache cache)
 {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
+    constexpr bool FILL = (MODE == 1 || MODE == 3);
+    int64_t pos = FILL ? offsets[r] : 0;
+    if (MODE == 3) {
+        const int n = (int)(offsets[r + 1] - pos);
+        if (n <= cache.K) {                                   // the whole ray is in the cache: copy, no traversal
+            for (int i = 0; i < n; ++i) {
+                const float2 dd = cache.depth[(int64_t)i * R + r];
+                ridx[pos + i] = (int32_t)r; pidx[pos + i] = cache.pidx[(int64_t)i * R + r];
+                depth[2 * (pos + i)] = dd.x; depth[2 * (pos + i) + 1] = dd.y;
+            }
+            return;
+        }
+    }
     const float o[3] = { origins[3 * r], origins[3 * r + 1], origins[3 * r + 2] };
     const float d[3] = { dirs[3 * r], dirs[3 * r + 1], dirs[3 * r + 2] };
     const int mask = (d[0] < 0.0f ? 4 : 0) | (d[1] < 0.0f ? 2 : 0) | (d[2] < 0.0f ? 1 : 0);
     // stack entry: node index + packed (level:4 | x:16 | y:16 | z:16)
     int32_t st_node[7 * 15 + 2]; uint64_t st_cell[7 * 15 + 2];
     int sp = 1; st_node[0] = 0; st_cell[0] = 0;
-    int cnt = 0; int64_t pos = FILL ? offsets[r] : 0;
+    int cnt = 0;
     while (sp > 0) {
         --sp;
         const int32_t node = st_node[sp]; const uint64_t cell = st_cell[sp];
@@ -51,6 +70,7 @@ wb_raytrace_kernel(WbOct oc, const float* __restrict__ origins, const float* __r
         if (!wb_slab(o, d, cx, cy, cz, l, t0, t1)) continue;
         if (l == oc.level) {
             if (FILL) { ridx[pos] = (int32_t)r; pidx[pos] = node; depth[2 * pos] = t0; depth[2 * pos + 1] = t1; ++pos; }
+            if (MODE == 2 && cnt < cache.K) { cache.pidx[(int64_t)cnt * R + r] = node; cache.depth[(int64_t)cnt * R + r] = make_float2(t0, t1); }
             ++cnt; continue;
         }
         const uint32_t bits = __ldg(oc.octree + node);
@@ -66,28 +86,53 @@ wb_raytrace_kernel(WbOct oc, const float* __restrict__ origins, const float* __r
     if (!FILL) counts[r] = cnt;
 }
 
-extern "C" int wb_raytrace_count(const wb_octree* oct, int32_t level, const wb_rays* rays, int32_t* counts, wb_stream s)
+static int wb_raytrace_launch(int mode, const wb_octree* oct, int32_t level, const wb_rays* rays, int32_t* counts, const int64_t* offsets,
+                              int32_t* ridx, int32_t* pidx, float* depth, void* cache, int32_t cache_k, wb_stream s)
 {
     WbOct o; int rc = wb_make_oct(oct, level, &o); if (rc) return rc;
     WB_CHECK_ARG(rays != nullptr, "null rays");
     const int64_t R = rays->num_rays;
     if (R == 0) return WB_OK;
-    WB_CHECK_ARG(rays->origins && rays->dirs && counts, "null pointer");
-    wb_raytrace_kernel<false><<<(unsigned)((R + 127) / 128), 128, 0, (cudaStream_t)s>>>(o, rays->origins, rays->dirs, R, counts, nullptr, nullptr, nullptr, nullptr);
+    WB_CHECK_ARG(rays->origins && rays->dirs, "null pointer");
+    WbNugCache nc = { nullptr, nullptr, 0 };
+    if (mode >= 2) {
+        WB_CHECK_ARG(cache != nullptr && cache_k >= 1, "null nugget cache");
+        nc.K = cache_k; nc.depth = reinterpret_cast<float2*>(cache); nc.pidx = reinterpret_cast<int32_t*>(nc.depth + (int64_t)cache_k * R);
+    }
+    const unsigned grid = (unsigned)((R + 127) / 128);
+    cudaStream_t st = (cudaStream_t)s;
+    if (mode == 0) wb_raytrace_kernel<0><<<grid, 128, 0, st>>>(o, rays->origins, rays->dirs, R, counts, nullptr, nullptr, nullptr, nullptr, nc);
+    else if (mode == 1) wb_raytrace_kernel<1><<<grid, 128, 0, st>>>(o, rays->origins, rays->dirs, R, nullptr, offsets, ridx, pidx, depth, nc);
+    else if (mode == 2) wb_raytrace_kernel<2><<<grid, 128, 0, st>>>(o, rays->origins, rays->dirs, R, counts, nullptr, nullptr, nullptr, nullptr, nc);
+    else wb_raytrace_kernel<3><<<grid, 128, 0, st>>>(o, rays->origins, rays->dirs, R, nullptr, offsets, ridx, pidx, depth, nc);
     WB_LAUNCH_CHECK();
     return WB_OK;
+}
+
+extern "C" int wb_raytrace_count(const wb_octree* oct, int32_t level, const wb_rays* rays, int32_t* counts, wb_stream s)
+{
+    WB_CHECK_ARG(counts != nullptr || (rays && rays->num_rays == 0), "null pointer");
+    return wb_raytrace_launch(0, oct, level, rays, counts, nullptr, nullptr, nullptr, nullptr, nullptr, 0, s);
 }
 extern "C" int wb_raytrace_fill(const wb_octree* oct, int32_t level, const wb_rays* rays, const int64_t* offsets,
                                 int32_t* ridx, int32_t* pidx, float* depth, wb_stream s)
 {
-    WbOct o; int rc = wb_make_oct(oct, level, &o); if (rc) return rc;
-    WB_CHECK_ARG(rays != nullptr, "null rays");
-    const int64_t R = rays->num_rays;
-    if (R == 0) return WB_OK;
-    WB_CHECK_ARG(rays->origins && rays->dirs && offsets && ridx && pidx && depth, "null pointer");
-    wb_raytrace_kernel<true><<<(unsigned)((R + 127) / 128), 128, 0, (cudaStream_t)s>>>(o, rays->origins, rays->dirs, R, nullptr, offsets, ridx, pidx, depth);
-    WB_LAUNCH_CHECK();
-    return WB_OK;
+    WB_CHECK_ARG((offsets && ridx && pidx && depth) || (rays && rays->num_rays == 0), "null pointer");
+    return wb_raytrace_launch(1, oct, level, rays, nullptr, offsets, ridx, pidx, depth, nullptr, 0, s);
+}
+// One-traversal form: count + cache of the first cache_k nuggets per ray (cache: wb_raytrace_cache_bytes(R, cache_k) bytes), then the fill
+// that copies from the cache and re-traverses only the rays that overflowed it.  Same outputs as wb_raytrace_count / wb_raytrace_fill.
+extern "C" int64_t wb_raytrace_cache_bytes(int64_t R, int32_t cache_k) { return (R < 0 || cache_k < 1) ? -1 : R * (int64_t)cache_k * 12; }
+extern "C" int wb_raytrace_count_cached(const wb_octree* oct, int32_t level, const wb_rays* rays, int32_t* counts, void* cache, int32_t cache_k, wb_stream s)
+{
+    WB_CHECK_ARG(counts != nullptr || (rays && rays->num_rays == 0), "null pointer");
+    return wb_raytrace_launch(2, oct, level, rays, counts, nullptr, nullptr, nullptr, nullptr, cache, cache_k, s);
+}
+extern "C" int wb_raytrace_fill_cached(const wb_octree* oct, int32_t level, const wb_rays* rays, const int64_t* offsets, const void* cache, int32_t cache_k,
+                                       int32_t* ridx, int32_t* pidx, float* depth, wb_stream s)
+{
+    WB_CHECK_ARG((offsets && ridx && pidx && depth) || (rays && rays->num_rays == 0), "null pointer");
+    return wb_raytrace_launch(3, oct, level, rays, nullptr, offsets, ridx, pidx, depth, const_cast<void*>(cache), cache_k, s);
 }
 
 // ---- 'voxel': n jittered samples per nugget ------------------------------------------------------------------------

@@ -265,6 +265,9 @@ def _scan(counts: torch.Tensor) -> torch.Tensor:
     return offsets
 
 
+RAYTRACE_CACHE_K = 24      # nuggets per ray kept by the counting traversal (0: two traversals, wb_raytrace_count + wb_raytrace_fill)
+
+
 def raytrace(oct: OctreeTensors, origins, dirs, level: int):
     """spc_render.unbatched_raytrace(..., return_depth=True, with_exit=True) (octree_as.py:183-185)
     -> ridx int32 [Ng], pidx int32 [Ng], depth f32 [Ng,2], ray_offsets int64 [R+1]."""
@@ -273,15 +276,26 @@ def raytrace(oct: OctreeTensors, origins, dirs, level: int):
     R, dev, L = rays.num_rays, origins.device, A.lib()
     od = oct.desc()
     counts = torch.empty(R, dtype=torch.int32, device=dev)
+    # one traversal: the count pass caches the first RAYTRACE_CACHE_K nuggets of every ray, the fill copies them (rays with more are
+    # traversed again); the cache is scratch (12 B x K per ray) and is skipped for ray counts where it would be unreasonably large
+    K = RAYTRACE_CACHE_K if (RAYTRACE_CACHE_K > 0 and R * RAYTRACE_CACHE_K * 12 <= (2 << 30)) else 0
+    cache = torch.empty(int(L.wb_raytrace_cache_bytes(C.c_int64(R), C.c_int32(K))), dtype=torch.uint8, device=dev) if K > 0 else None
     with _stage("raytrace_count"):
-        A.check(L.wb_raytrace_count(C.byref(od), C.c_int32(level), C.byref(rays), A.ptr(counts), A.stream()))
+        if K > 0:
+            A.check(L.wb_raytrace_count_cached(C.byref(od), C.c_int32(level), C.byref(rays), A.ptr(counts), A.ptr(cache), C.c_int32(K), A.stream()))
+        else:
+            A.check(L.wb_raytrace_count(C.byref(od), C.c_int32(level), C.byref(rays), A.ptr(counts), A.stream()))
     offsets = _scan(counts)
     Ng = int(offsets[-1].item())
     ridx = torch.empty(Ng, dtype=torch.int32, device=dev); pidx = torch.empty(Ng, dtype=torch.int32, device=dev)
     depth = torch.empty((Ng, 2), dtype=torch.float32, device=dev)
     if Ng > 0:
         with _stage("raytrace_fill"):
-            A.check(L.wb_raytrace_fill(C.byref(od), C.c_int32(level), C.byref(rays), A.ptr(offsets), A.ptr(ridx), A.ptr(pidx), A.ptr(depth), A.stream()))
+            if K > 0:
+                A.check(L.wb_raytrace_fill_cached(C.byref(od), C.c_int32(level), C.byref(rays), A.ptr(offsets), A.ptr(cache), C.c_int32(K),
+                                                  A.ptr(ridx), A.ptr(pidx), A.ptr(depth), A.stream()))
+            else:
+                A.check(L.wb_raytrace_fill(C.byref(od), C.c_int32(level), C.byref(rays), A.ptr(offsets), A.ptr(ridx), A.ptr(pidx), A.ptr(depth), A.stream()))
     return ridx, pidx, depth, offsets
 
 

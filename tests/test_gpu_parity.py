@@ -571,6 +571,25 @@ def test_fused_trace_with_nugget_samplers(W, kind, n):
     np.testing.assert_allclose(a.rgb.detach().cpu().numpy(), exp_rgb, atol=1e-4)
 
 
+def test_raytrace_single_traversal_matches_two_pass(W):
+    """OctreeAS.raytrace with the nugget cache (one depth-first traversal: count + cache, then copy; rays that overflow the cache are
+    traversed again) gives exactly the nuggets of the two-traversal form, for a cache that holds everything, almost nothing, and nothing."""
+    blas = W.OctreeAS.from_quantized_points(torch.from_numpy(O.lego_like_points(6)).cuda(), 6)
+    o, d = O.look_at_rays([-3.0, 0.65, -3.0], [0, 0, 0], 64, 64, 30.0)
+    outs = []
+    old = W.ops.RAYTRACE_CACHE_K
+    try:
+        for K in (0, 24, 2, 1):
+            W.ops.RAYTRACE_CACHE_K = K
+            outs.append(W.ops.raytrace(blas.tensors(), dev(o), dev(d), 6))
+    finally:
+        W.ops.RAYTRACE_CACHE_K = old
+    assert outs[0][0].shape[0] > 2000 and int((outs[0][3][1:] - outs[0][3][:-1]).max()) > 2        # some rays overflow K = 2
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert torch.equal(a, b)
+
+
 def test_raygen_kernels(W, golden_dir):
     """wb_raygen_lookat vs the reference's _look_at (golden from the unmodified source, persp + ortho, wide / tall aspect), and
     wb_raygen_pinhole vs a torch restatement of generate_pinhole_rays (raygen.py:40-85; Kaolin's Camera is absent: unpinned)."""
