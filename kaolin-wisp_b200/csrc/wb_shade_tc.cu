@@ -701,21 +701,11 @@ wb_shade_fwd_tc_kernel(WbGrid g, WbGridX gx, WbTc m, const uint8_t* __restrict__
             else tile_gather_ta(g, c.tmem + ((uint32_t)c.laneq << 16) + (uint32_t)m.work_col[1], c.h, px, py, pz, in.x0_save, in.S, s, valid);
         } else {
             if (!GX) tile_gather(g, t0, c.r, c.h, px, py, pz);
-            else {
-                // the two threads of a row split the LODs (the triplanar gather is 48 texel loads per LOD): 'cat' features go straight into
-                // the tile; 'sum' grids exchange fp32 partial sums through a [2][width][128] scratch behind the dynamic shared memory
-                const int kmid = (gx.nl + 1) >> 1;
-                const int ka = c.h == 0 ? 0 : kmid, kb = c.h == 0 ? kmid : gx.nl;
-                const bool sum = gx.sum && gx.nl > 1;
-                if (!sum) wb_featx_gather(gx, px, py, pz, [&](int f, float v) { tile_store1(t0, c.r, f, v); }, ka, kb);
-                else {
-                    float* scr = reinterpret_cast<float*>(smem + m.smem_bytes);
-                    const int width = gx.kind == 1 ? 3 * gx.C : gx.C;
-                    for (int f = 0; f < width; ++f) scr[(c.h * width + f) * TC_ROWS + c.r] = 0.0f;       // octree: a point may leave the tree early
-                    wb_featx_gather(gx, px, py, pz, [&](int f, float v) { scr[(c.h * width + f) * TC_ROWS + c.r] = v; }, ka, kb);
-                    tc_group_sync(1, TC_GROUP);
-                    for (int f = c.h; f < width; f += 2) tile_store1(t0, c.r, f, scr[f * TC_ROWS + c.r] + scr[(width + f) * TC_ROWS + c.r]);
-                }
+            else if (c.h == 0) {
+                // one thread of the row pair gathers all LODs.  Splitting the LODs over the pair (partial sums through shared memory for 'sum'
+                // grids) was measured SLOWER on config 4 (231 -> 280 ms per 800^2 frame): the gather is latency-bound, the extra group
+                // barrier and scratch traffic cost more than the halved chain saves
+                wb_featx_gather(gx, px, py, pz, [&](int f, float v) { tile_store1(t0, c.r, f, v); });
             }
             if (c.h == 0) {
                 tile_embed(t0, c.r, m.feat_dim, m.pos_mode, m.pos_freq, px, py, pz);
@@ -797,7 +787,7 @@ int wb_tc_shade_fwd(const wb_nef_desc* nef, const float* blob, const wb_rays* ra
     {   // function attributes are driver calls that can wait behind other driver work (e.g. an NVML poll): set them once, not per launch
         static int64_t done_for[16] = { -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1 };
         if (done_for[gx.kind != 0 ? 9 : pipe ? 10 + per_sm : per_sm + (ta ? 5 : 0)] != WB_ATTR_KEY(m.smem_bytes)) {
-            WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, m.smem_bytes + (gx.kind != 0 ? 2 * 32 * TC_ROWS * 4 : 0)));
+            WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, m.smem_bytes));
             WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          min(100, (per_sm * (m.smem_bytes + 4096) * 100) / (228 * 1024) + 1)));
             done_for[gx.kind != 0 ? 9 : pipe ? 10 + per_sm : per_sm + (ta ? 5 : 0)] = WB_ATTR_KEY(m.smem_bytes);
@@ -805,7 +795,7 @@ int wb_tc_shade_fwd(const wb_nef_desc* nef, const float* blob, const wb_rays* ra
     }
     const int64_t ntiles = (S + TC_ROWS - 1) / TC_ROWS;
     int64_t grid = (int64_t)wb_num_sms() * per_sm; if (grid > ntiles) grid = ntiles;
-    const int xscratch = gx.kind != 0 ? 2 * 32 * TC_ROWS * 4 : 0;                   // [2 halves][<= 32 features][128 rows] fp32 partial sums
+    const int xscratch = 0;
     kern<<<(unsigned)grid, TC_GROUP, m.smem_bytes + xscratch, st>>>(g, gx, m, reinterpret_cast<const uint8_t*>(blob), in, reinterpret_cast<float4*>(shaded));
     WB_LAUNCH_CHECK();
     return WB_OK;

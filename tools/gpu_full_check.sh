@@ -1,9 +1,14 @@
-python -m pytest tests -m gpu -q --tb=short 2>&1 | tail -60 > gpurun_out/r02h_pytest.log
-python __graft_entry__.py smoke > gpurun_out/r02h_smoke.log 2>&1
-timeout 300 python bench.py > gpurun_out/r02h_bench2.json 2> gpurun_out/r02h_bench2.err
-WB_TC_FUSE_SCATTER=3 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02h_bench2_fuse3.json 2> gpurun_out/r02h_bench2_fuse3.err
-WB_TC_FWD_PIPE=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02h_bench2_pipe3.json 2> gpurun_out/r02h_bench2_pipe3.err
-WB_TC_FWD_PIPE=1 WB_TC_FWD_CTAS=2 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02h_bench2_pipe2.json 2> gpurun_out/r02h_bench2_pipe2.err
-timeout 300 python bench.py --config 3 > gpurun_out/r02h_bench3.json 2> gpurun_out/r02h_bench3.err
-timeout 400 python bench.py --config 4 > gpurun_out/r02h_bench4.json 2> gpurun_out/r02h_bench4.err
-tail -6 gpurun_out/r02h_pytest.log
+#!/bin/bash
+# One GPU call that checks the whole tree (used during development: bash tools/gpu_full_check.sh TAG under gpurun).
+TAG=${1:-chk}
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q --tb=short > gpurun_out/${TAG}_pytest_full.log 2>&1
+head -c 6000 gpurun_out/${TAG}_pytest_full.log > gpurun_out/${TAG}_pytest_head.log
+tail -60 gpurun_out/${TAG}_pytest_full.log > gpurun_out/${TAG}_pytest.log
+grep -n "Error" gpurun_out/${TAG}_pytest_full.log | sort | uniq -c | sort -rn | head -20 > gpurun_out/${TAG}_pytest_errors.log
+rm -f gpurun_out/${TAG}_pytest_full.log
+python __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.log 2>&1
+timeout 300 python bench.py > gpurun_out/${TAG}_bench2.json 2> gpurun_out/${TAG}_bench2.err
+timeout 300 python bench.py --config 3 > gpurun_out/${TAG}_bench3.json 2> gpurun_out/${TAG}_bench3.err
+timeout 400 python bench.py --config 4 > gpurun_out/${TAG}_bench4.json 2> gpurun_out/${TAG}_bench4.err
+tail -6 gpurun_out/${TAG}_pytest.log
