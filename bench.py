@@ -51,13 +51,32 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = N views per step (1024^2 rays per GPU, the default the driver runs); strong = ONE view per step tiled over "
                          "the N GPUs (rows rank::N each), SURVEY 8(e) inference-style partitioning")
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
-                    help="BASELINE.json config: 2 = HashGrid NeRF fwd+bwd (headline), 3 = nglod OctreeGrid SDF sphere trace, 4 = TriplanarGrid NeRF")
-    return ap.parse_args()
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4],
+                    help="BASELINE.json config: 1 = HashGrid 8-level, 1-layer-32 MLP, 256^2 single view (the reference's CPU-runnable case; same runner as 2), "
+                         "2 = HashGrid NeRF fwd+bwd (headline), 3 = nglod OctreeGrid SDF sphere trace, 4 = TriplanarGrid NeRF")
+    a = ap.parse_args()
+    if a.config == 1 and a.res == 1024:
+        a.res = 256
+    return a
+
+
+def metric_name(args):
+    return METRIC if args.config != 1 else "rays/sec (fwd+bwd) 256^2 single-view NeRF HashGrid 8-level (BASELINE configs[0])"
+
+
+def nef_shape(args):
+    """(num_lods, hidden_dim) of the benched field: configs[1] (headline) unless --config 1 (configs[0])."""
+    return (8, 32) if args.config == 1 else (16, 64)
+
+
+def make_onef(O, args):
+    L, H = nef_shape(args)
+    return O.make_nef(feature_std=1e-4, seed=0, num_lods=L, hidden_dim=H)
 
 
 def workload_config(args):
-    return {"workload": f"app/nerf HashGrid 16-level F=2 T=2^19, 2-layer-64 MLP, {args.res}^2 rays x {args.num_steps} steps ('ray'), "
+    L, H = nef_shape(args)
+    return {"workload": f"app/nerf HashGrid {L}-level F=2 T=2^19, {'2-layer-64' if H == 64 else 'num_layers=1 hidden-32'} MLP, {args.res}^2 rays x {args.num_steps} steps ('ray'), "
                         f"{'lego-like level-7 octree' if args.scene == 'lego' else 'dense level-7 octree'}, fwd+bwd+Adam",
             "rays_per_step_per_gpu": args.res * args.res // (args.gpus if getattr(args, "scaling", "weak") == "strong" else 1), "num_steps": args.num_steps, "scene": args.scene,
             "camera": {"origin": CAM_ORIGIN, "lookat": CAM_LOOKAT, "fov": CAM_FOV, "near": NEAR, "far": FAR},
@@ -84,7 +103,7 @@ def orbit_origin(i: int):
 # ------------------------------------------------------------------------------------------------------------------
 def cpu_scene(args):
     from oracle import oracle as O
-    onef = O.make_nef(feature_std=1e-4, seed=0)                       # config 2 shapes
+    onef = make_onef(O, args)                                         # config 2 shapes (config 1 with --config 1)
     pts = O.lego_like_points(7)
     spc = O.octree_to_spc(O.points_to_octree(pts, 7) if args.scene == "lego" else O.dense_octree(7))
     return O, onef, spc
@@ -134,7 +153,7 @@ def run_reference(args):
     value = nrays / med
     sample = (f"{nrays} rays strided over the {args.res}^2 frame per step, full config (n={args.num_steps}); "
               f"{samples // max(args.steps, 1)} hit samples/step; value = rays / median step time")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    line = {"impl": "reference", "metric": metric_name(args), "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * med, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args),
             "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
@@ -200,12 +219,13 @@ def run_ours(args):
     # ---- model: identical init on every rank, taken from the oracle's seeded numpy init so that the CPU restatement and the GPU
     # model are the SAME network (the parity leg below compares them on the cpu_baseline sample) ----
     torch.manual_seed(0)
-    onef0 = O.make_nef(feature_std=1e-4, seed=0)                      # config 2 shapes; pure numpy (no oracle library call)
+    onef0 = make_onef(O, args)                                        # config 2 shapes; pure numpy (no oracle library call)
+    n_lods, hidden = nef_shape(args)
     pts = torch.from_numpy(O.lego_like_points(7))
     blas = W.OctreeAS.from_quantized_points(pts.to(dev), 7) if args.scene == "lego" else W.OctreeAS.make_dense(7, device=dev)
-    grid = W.HashGrid.from_geometric(blas, feature_dim=2, num_lods=16, multiscale_type='cat', feature_std=1e-4, codebook_bitwidth=19,
+    grid = W.HashGrid.from_geometric(blas, feature_dim=2, num_lods=n_lods, multiscale_type='cat', feature_std=1e-4, codebook_bitwidth=19,
                                      min_grid_res=16, max_grid_res=512)
-    nef = W.NeuralRadianceField(grid, view_embedder='positional', view_multires=4, hidden_dim=64, num_layers=1, bias=True).to(dev)
+    nef = W.NeuralRadianceField(grid, view_embedder='positional', view_multires=4, hidden_dim=hidden, num_layers=1, bias=True).to(dev)
     with torch.no_grad():
         grid.codebook.feats.copy_(torch.from_numpy(onef0.table))
         for dec, Ws, bs in ((nef.decoder_density, onef0.dens_W, onef0.dens_b), (nef.decoder_color, onef0.col_W, onef0.col_b)):
@@ -375,11 +395,14 @@ def run_ours(args):
                 "stage_ms": {k: round(float(np.mean(v)), 4) for k, v in stage_ms.items()}}
         per_rank = [None] * world
         dist.all_gather_object(per_rank, mine)
-    tms = torch.tensor([ms, ms_e2e, float(total_samples)], dtype=torch.float64, device=dev)
+    tms = torch.tensor([ms, ms_e2e, float(total_samples), float((render or {}).get("ms_per_frame", float("nan")))], dtype=torch.float64, device=dev)
     if world > 1:
         mx = tms.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = tms.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         ms, ms_e2e, total_samples = float(mx[0]), float(mx[1]), float(sm[2])
+        if render and "ms_per_frame" in render:        # forward-only at N GPUs: every rank renders its share concurrently, max over ranks
+            render.update(ms_per_frame=float(mx[3]), value=R * world / (float(mx[3]) * 1e-3),
+                          what=f"forward only (march + shade + composite), device-resident rays, aggregate over {world} GPUs, max over ranks (unsynchronised start)")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -405,7 +428,8 @@ def run_ours(args):
     except Exception:
         pass
     e = 4                                                      # fp32 table and fp32 gradients
-    L_eff = 15                                                 # 'cat' zeroes the last LOD (hash_grid.py:228): 15 of 16 levels are live
+    L_eff = n_lods - 1                                         # 'cat' zeroes the last LOD (hash_grid.py:228): 15 of 16 levels are live
+    dec_flop = 2 * (2 * n_lods * hidden + hidden * 16 + (15 + 27) * hidden + hidden * hidden + hidden * 3)   # one forward pass of both decoders (20096 at config 2)
     mean_ms = {k: float(np.mean(v)) for k, v in stage_ms.items()}
     models = {   # stage -> (kernel, bound, algorithmic units per hit sample, unit)
         "shade_fwd": ("wb_shade_fwd_tc_kernel" if args.precision == 1 else "wb_shade_fwd_kernel", "hbm", L_eff * 8 * 2 * e, "B"),
@@ -414,7 +438,7 @@ def run_ours(args):
         # (2 * L * 8 * F * 4 B): that is its SURVEY 8(d) figure; its decoder FLOPs are reported as a second line below
         "shade_bwd": (("wb_mlp_bwd3_tc_kernel<FUSE> (decoder backward + table scatter)", "hbm", 64 + 2 * L_eff * 8 * 2 * e, "B") if args.precision == 1
                       else ("wb_shade_bwd_kernel", "hbm", 2 * L_eff * 8 * 2 * e, "B")),
-        "decoder_bwd": ("wb_mlp_bwd_tc_kernel", "tensor", 3 * 20096, "FLOP"),     # forward recompute + data grad + weight grad of both decoders
+        "decoder_bwd": ("wb_mlp_bwd_tc_kernel", "tensor", 3 * dec_flop, "FLOP"),     # forward recompute + data grad + weight grad of both decoders
     }
     rooflines = []
     for st_name, (kern, bound, per, unit) in models.items():
@@ -432,16 +456,16 @@ def run_ours(args):
             rooflines[-1]["note"] = "algorithmic table bytes; the table is L2-resident, so this is HBM-equivalent and can exceed 1 (see `traffic`)"
     if args.precision == 1 and "shade_bwd" in mean_ms:   # the same launch against the tensor roof: recompute + data grad + weight grad of both decoders
         t_s = mean_ms["shade_bwd"] * 1e-3
-        ach = S_step * (3 * 20096) / t_s / 1e12
+        ach = S_step * (3 * dec_flop) / t_s / 1e12
         rooflines.append({"bound": "tensor", "kernel": "wb_mlp_bwd3_tc_kernel<FUSE> (decoder part)", "achieved": ach, "peak": tfl, "unit": "TFLOP/s", "frac": ach / tfl,
-                          "traffic": traffic.get("wb_mlp_bwd3_tc_kernel"), "kernel_ms": mean_ms["shade_bwd"] - 1e-9, "algorithmic_per_sample": f"{3 * 20096} FLOP",
+                          "traffic": traffic.get("wb_mlp_bwd3_tc_kernel"), "kernel_ms": mean_ms["shade_bwd"] - 1e-9, "algorithmic_per_sample": f"{3 * dec_flop} FLOP",
                           "samples_per_launch": S_step, "note": "same launch as the hbm line of this kernel; the decoder rounds alone take 3.7 of its 7.0 ms (profiles/README.md)"})
     roofline = dict(max(rooflines, key=lambda r: r["kernel_ms"]))
     roofline["peak_source"] = src
     roofline["note"] = ("dominant kernel by time.  hbm-bound kernels: the 41.7 MB table is L2 resident, so `achieved` is HBM-equivalent gather/scatter "
                         "bandwidth and DRAM `traffic` is far below the algorithmic bytes (no wasted re-reads); see DESIGN.md section 4")
 
-    line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": metric_name(args), "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32" if args.precision == 0 else "f16(tensor)+f32 accumulate", "data": "synthetic", "config": workload_config(args),
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": R * (24 + 12), "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,

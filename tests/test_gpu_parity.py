@@ -382,6 +382,34 @@ def test_wide_decoders_under_autocast_stay_native(W):
 
 
 @pytest.mark.parametrize("precision", [0, 1])
+def test_trace_config1_full_frame_vs_oracle(W, precision):
+    """BASELINE configs[0] (the reference's CPU-runnable case): HashGrid 8 levels, hidden 32, the WHOLE 256^2 single view
+    (65 536 rays x 512 steps) forward + backward against the CPU restatement."""
+    from gpu_util import nef_from_oracle, packed_grads
+    tol = TOL[precision]
+    onef = O.make_nef(feature_std=0.2, seed=5, num_lods=8, hidden_dim=32)
+    spc = O.octree_to_spc(O.points_to_octree(O.lego_like_points(7), 7))
+    o, d = O.look_at_rays([-3.0, 0.65, -3.0], [0, 0, 0], 256, 256, 30.0)
+    nef, blas = nef_from_oracle(onef, spc)
+    tracer = W.PackedRFTracer('ray', 512, bg_color=(1.0, 1.0, 1.0)); tracer.seed = 9
+    tracer.precision = precision
+    rb = W.Pipeline(nef, tracer)(rays=W.Rays(dev(o), dev(d), 0.0, 10.0), channels=["rgb", "depth", "alpha", "hit"])
+    f = O.rf_trace_fwd(spc, onef, o, d, 0.0, 10.0, 512, bg=(1, 1, 1), seed=9)
+    assert tracer.get_prev_num_samples() == f["num_samples"] > 100000
+    np.testing.assert_allclose(rb.rgb.detach().cpu().numpy(), f["rgb"], atol=tol["rgb"])
+    np.testing.assert_allclose(rb.alpha.detach().cpu().numpy(), f["alpha"], atol=tol["rgb"])
+    if precision == 0:
+        assert np.array_equal(rb.hit.cpu().numpy(), f["hit"])
+    tgt = torch.sigmoid(torch.randn(o.shape[0], 3, generator=torch.Generator().manual_seed(6)))
+    torch.nn.functional.smooth_l1_loss(rb.rgb, tgt.cuda()).backward()
+    st = O.rf_step(spc, onef, o, d, 0.0, 10.0, 512, tgt.numpy(), bg=(1, 1, 1), seed=9)
+    gt, gd, gc = packed_grads(nef)
+    for got, ref, nm in ((gt, st["table"], "table"), (gd, st["dens"], "dens"), (gc, st["col"], "col")):
+        scale = np.abs(ref).max()
+        assert np.abs(got - ref).max() <= max(2e-3, tol["grad"]) * scale, (nm, np.abs(got - ref).max(), scale)
+
+
+@pytest.mark.parametrize("precision", [0, 1])
 def test_trace_config2_slice_vs_oracle(W, precision):
     """BASELINE config 2 shapes (L=16, F=2, T=2^19, 64-wide decoders, n=2048, level-7 lego-like octree) on a
     32x32-ray slice of the 1024^2 frame; counter-based jitter; fwd + bwd vs the oracle."""
