@@ -436,7 +436,8 @@ def run_ours(args):
         "table_scatter": ("wb_table_scatter_kernel", "hbm", 2 * L_eff * 8 * 2 * e, "B"),
         # the fused backward kernel moves, per hit sample, the 64 B of saved features in and the read-modify-write of the table entries
         # (2 * L * 8 * F * 4 B): that is its SURVEY 8(d) figure; its decoder FLOPs are reported as a second line below
-        "shade_bwd": (("wb_mlp_bwd3_tc_kernel<FUSE> (decoder backward + table scatter)", "hbm", 64 + 2 * L_eff * 8 * 2 * e, "B") if args.precision == 1
+        "shade_bwd": (((("wb_mlp_bwd3_tc_kernel<FUSE> (decoder backward + table scatter)" if hidden == 64 else "wb_mlp_bwd_tc_kernel + wb_table_scatter_kernel (one stage)"),
+                        "hbm", 4 * n_lods + 2 * L_eff * 8 * 2 * e, "B")) if args.precision == 1
                       else ("wb_shade_bwd_kernel", "hbm", 2 * L_eff * 8 * 2 * e, "B")),
         "decoder_bwd": ("wb_mlp_bwd_tc_kernel", "tensor", 3 * dec_flop, "FLOP"),     # forward recompute + data grad + weight grad of both decoders
     }

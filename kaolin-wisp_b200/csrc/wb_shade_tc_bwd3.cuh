@@ -30,20 +30,22 @@
 constexpr int TC_B3_ROUNDS = 11;
 
 // ---- per-CTA issue table: [group][round][chain]  (chain 0, 1: warp 0 in this order; chain 2: warp 1) ----
+template <int NG>
 __device__ __forceinline__ void tc_b3_build_table(const WbTc& m, const TcB3Plan& p, TcRec* tab, uint8_t* smem, uint32_t tmem)
 {
+    constexpr int WC = NG == 3 ? 64 : 128;                        // working-accumulator columns per group
     const int e = threadIdx.x;
     if (e < TC_ROWS) {                                           // Ones[128 x 16] of the bias UMMA
         uint4 one; one.x = 0x00003C00u; one.y = 0; one.z = 0; one.w = 0;
         *reinterpret_cast<uint4*>(smem + p.ones_off + e * 16) = one;
         *reinterpret_cast<uint4*>(smem + p.ones_off + 2048 + e * 16) = make_uint4(0, 0, 0, 0);
     }
-    if (e >= TC_B3_GROUPS * TC_B3_ROUNDS * 3) return;
+    if (e >= NG * TC_B3_ROUNDS * 3) return;
     const int ch = e % 3, rd = (e / 3) % TC_B3_ROUNDS, g = e / (3 * TC_B3_ROUNDS);
     const uint32_t base = tc_smem_u32(smem), gb = base + g * p.GB;
     const uint32_t bP = gb + p.P, bQ = gb + p.Q, bR = gb + p.R, bE = gb + p.E;
     const uint32_t wbase = base + p.blob_off;
-    const uint32_t work = tmem + g * 64;                          // D_work[g]: 64 columns per group, accumulators behind them
+    const uint32_t work = tmem + g * WC;                          // D_work[g]: WC columns per group, accumulators behind them
     // round -> (layer, forward?, X buffer, dY buffer)
     const int  lay[TC_B3_ROUNDS] = { 0, 1, 2, 3, 4, 4, 3, 2, 0, 1, 0 };
     const bool fwd[TC_B3_ROUNDS] = { true, true, true, true, true, false, false, false, true, false, false };
@@ -60,9 +62,15 @@ __device__ __forceinline__ void tc_b3_build_table(const WbTc& m, const TcB3Plan&
             id = tc_idesc(128, Np, 0, 0); d = work; nk = Kp / 16; acc = m.has_bias; aadv = 4096 >> 4; badv = (2 * Np * 16) >> 4;
         }
     } else {
-        if (ch == 0) {            // acc_l[in, out] += X_l^T . dY_l   (K = 128 samples)
+        if (ch == 0 && p.kind[l] != 2) {   // acc_l[in, out] += X_l^T . dY_l   (K = 128 samples); kind 0: row Kp_l = bias gradient (constant-one slab)
             da = tc_desc(X[rd], 128, 2048); db = tc_desc(Y[rd], 128, 2048);
-            id = tc_idesc(128, Np, 1, 1); d = tmem + m.acc_col[l]; nk = 8; acc = 1; aadv = 256 >> 4; badv = 256 >> 4;
+            id = tc_idesc(128, Np, 1, 1); d = tmem + p.acc_col[l]; nk = 8; acc = 1; aadv = 256 >> 4; badv = 256 >> 4;
+        } else if (ch == 0) {              // kind 2: acc_l^T[out, in | 1] += dY_l^T . [X_l | 1]: Kp_l + 16 columns instead of Np_l, column Kp_l = bias gradient
+            da = tc_desc(Y[rd], 128, 2048); db = tc_desc(X[rd], 128, 2048);
+            id = tc_idesc(128, Kp + 16, 1, 1); d = tmem + p.acc_col[l]; nk = 8; acc = 1; aadv = 256 >> 4; badv = 256 >> 4;
+        } else if (ch == 1 && p.kind[l] == 1) {   // kind 1 (X_l is 128 wide: no row left for the bias): bias_l[out, 0] += dY_l^T . Ones, Ones = the tile's constant-one slab
+            da = tc_desc(Y[rd], 128, 2048); db = tc_desc(X[rd] + (uint32_t)(Kp / 8) * 2048u, 128, 2048);
+            id = tc_idesc(128, 16, 1, 1); d = tmem + p.bias_col[l]; nk = m.has_bias ? 8 : 0; acc = 1; aadv = 256 >> 4; badv = 256 >> 4;
         } else if (ch == 2) {     // D_work = dY_l . W_l             (K = out features)
             da = tc_desc(Y[rd], 2048, 128); db = tc_desc(wbase + m.w_off[l], 128, Np * 16);
             id = tc_idesc(128, Kp, 0, 1); d = work; nk = Np / 16; aadv = 4096 >> 4; badv = 256 >> 4;
@@ -227,27 +235,28 @@ __device__ __forceinline__ void tc_scatter_level_f2(const WbGrid& g, int l, floa
 //      them), LOD q of sub-tile i is scattered inside round q of sub-tile i+1 between the issue of that round's UMMAs and the wait for
 //      their completion.  It does not pay: a round's wait is barrier / commit / wake-up latency, not UMMA execution time, so there is
 //      little tensor work to hide behind, and the extra plane traffic comes back.
-template <int FUSE>
-__global__ void __launch_bounds__(TC_B3_GROUPS * TC_GROUP, 1)
+template <int FUSE, int NG = TC_B3_GROUPS>     // NG: sub-tile groups per CTA: 3 (every width <= 64) or 1 (widths up to 128: hidden_dim = 128)
+__global__ void __launch_bounds__(NG * TC_GROUP, 1)
 wb_mlp_bwd3_tc_kernel(WbTc m, TcB3Plan p, const uint8_t* __restrict__ blob, TcIn in, const float4* __restrict__ g_shaded, TcGrads G, WbGrid g, float* __restrict__ gtable)
 {
+    constexpr int WC = NG == 3 ? 64 : 128;
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[TC_B3_GROUPS + 1];
+    __shared__ __align__(8) uint64_t bars[NG + 1];
     __shared__ uint32_t tmem_s;
     __shared__ int scatter_token;                                // FUSE == 3: which group (1..3) is scattering, 0 = nobody
-    __shared__ TcRec tab[TC_B3_GROUPS * TC_B3_ROUNDS * 3];
+    __shared__ TcRec tab[NG * TC_B3_ROUNDS * 3];
     if (threadIdx.x == 0) {
         scatter_token = 0;
-        for (int i = 0; i < TC_B3_GROUPS; ++i) tc_mbar_init(&bars[i], TC_ISSUERS);
-        tc_mbar_init(&bars[TC_B3_GROUPS], 1); tc_mbar_init_fence();
-        tc_mbar_expect_tx(&bars[TC_B3_GROUPS], (uint32_t)m.blob_bytes);
-        tc_bulk_g2s(smem + p.blob_off, blob, (uint32_t)m.blob_bytes, &bars[TC_B3_GROUPS]);
+        for (int i = 0; i < NG; ++i) tc_mbar_init(&bars[i], TC_ISSUERS);
+        tc_mbar_init(&bars[NG], 1); tc_mbar_init_fence();
+        tc_mbar_expect_tx(&bars[NG], (uint32_t)m.blob_bytes);
+        tc_bulk_g2s(smem + p.blob_off, blob, (uint32_t)m.blob_bytes, &bars[NG]);
     }
     if (threadIdx.x < 32) tc_tmem_alloc(&tmem_s, 512u);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    tc_b3_build_table(m, p, tab, smem, tmem_s);
+    tc_b3_build_table<NG>(m, p, tab, smem, tmem_s);
     TcCtx c; tc_ctx_init(c, smem, bars, nullptr, tmem_s, 1);
     uint8_t* gbase = smem + c.g * p.GB;
     uint8_t* bP = gbase + p.P; uint8_t* bQ = gbase + p.Q; uint8_t* bR = gbase + p.R; uint8_t* bE = gbase + p.E;
@@ -256,17 +265,16 @@ wb_mlp_bwd3_tc_kernel(WbTc m, TcB3Plan p, const uint8_t* __restrict__ blob, TcIn
     if (c.h == 0) { tc_b3_one_slab(bP, maxslab, c.r); tc_b3_one_slab(bQ, maxslab, c.r); }
     if (threadIdx.x < 128) {                                     // zero the resident weight-grad accumulators
         const uint32_t tr = c.tmem + ((uint32_t)c.laneq << 16);
-        for (int l = 0; l < 5; ++l)
-            for (int cc = 0; cc < m.Np[l]; cc += 16) tc_st16_zero(tr + m.acc_col[l] + cc);
+        for (int cc = p.acc_begin; cc < p.acc_end; cc += 16) tc_st16_zero(tr + cc);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    tc_mbar_wait(&bars[TC_B3_GROUPS], 0);
+    tc_mbar_wait(&bars[NG], 0);
     const float scale = __ldg(G.scale), inv_scale = 1.0f / scale;
     const int nch0 = m.Kp[0] / 8, nchc = m.Kp[2] / 8;
     const int64_t ntiles = (in.S + TC_ROWS - 1) / TC_ROWS;
-    const uint32_t trow = c.tmem + ((uint32_t)c.laneq << 16) + (uint32_t)c.g * 64u;
+    const uint32_t trow = c.tmem + ((uint32_t)c.laneq << 16) + (uint32_t)(c.g * WC);
     const float z8[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
     // FUSE == 2: the sample of the previous sub-tile whose gradient this thread still has to scatter
     bool have_prev = false, pvalid = false; int64_t ps = 0; float ppx = 0.0f, ppy = 0.0f, ppz = 0.0f;
@@ -281,7 +289,7 @@ wb_mlp_bwd3_tc_kernel(WbTc m, TcB3Plan p, const uint8_t* __restrict__ blob, TcIn
             }
         }
     };
-    for (int64_t tile = (int64_t)blockIdx.x * TC_B3_GROUPS + c.g; tile < ntiles; tile += (int64_t)gridDim.x * TC_B3_GROUPS) {
+    for (int64_t tile = (int64_t)blockIdx.x * NG + c.g; tile < ntiles; tile += (int64_t)gridDim.x * NG) {
         int64_t s = tile * TC_ROWS + c.r;
         const bool valid = s < in.S;
         if (!valid) s = in.S - 1;
@@ -409,7 +417,9 @@ wb_mlp_bwd3_tc_kernel(WbTc m, TcB3Plan p, const uint8_t* __restrict__ blob, TcIn
 #pragma unroll 1
         for (int q = 0; q < 8; ++q) scatter_prev(q);
     }
-    // ---- flush weight / bias gradient accumulators (TMEM rows = input feature, row Kp = bias) ----
+    // ---- flush weight / bias gradient accumulators ----
+    // kind 0: TMEM rows = input feature, row Kp = bias;  kind 1: the same rows, bias in column 0 of its own 16-column accumulator (row = output);
+    // kind 2: TMEM rows = output feature, columns = input features, column Kp = bias
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -420,16 +430,35 @@ wb_mlp_bwd3_tc_kernel(WbTc m, TcB3Plan p, const uint8_t* __restrict__ blob, TcIn
             float* gbase2 = l < m.nl_d ? G.gdens : G.gcol;
             const int I = m.I[l], O = m.O[l];
             const int wrow0 = row & ~31;
+            if (p.kind[l] == 2) {
+                if (wrow0 >= m.Np[l]) continue;
+                for (int cc = 0; cc < m.Kp[l] + 16; cc += 16) {
+                    float v[16]; tc_ld16(tr + p.acc_col[l] + cc, v);
+                    if (row >= O) continue;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int i = cc + j;
+                        const float val = v[j] * inv_scale;
+                        if (i < I) { if (val != 0.0f) atomicAdd(gbase2 + m.src_w[l] + row * I + i, val); }
+                        else if (i == m.Kp[l] && m.src_b[l] >= 0) atomicAdd(gbase2 + m.src_b[l] + row, val);
+                    }
+                }
+                continue;
+            }
+            if (p.kind[l] == 1 && m.src_b[l] >= 0 && wrow0 < m.Np[l]) {
+                float v[16]; tc_ld16(tr + p.bias_col[l], v);
+                if (row < O) atomicAdd(gbase2 + m.src_b[l] + row, v[0] * inv_scale);
+            }
             if (wrow0 > m.Kp[l]) continue;
             for (int cc = 0; cc < m.Np[l]; cc += 16) {
-                float v[16]; tc_ld16(tr + m.acc_col[l] + cc, v);
+                float v[16]; tc_ld16(tr + p.acc_col[l] + cc, v);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int o = cc + j;
                     if (o >= O) continue;
                     const float val = v[j] * inv_scale;
                     if (row < I) { if (val != 0.0f) atomicAdd(gbase2 + m.src_w[l] + o * I + row, val); }
-                    else if (row == m.Kp[l] && m.src_b[l] >= 0) atomicAdd(gbase2 + m.src_b[l] + o, val);
+                    else if (p.kind[l] == 0 && row == m.Kp[l] && m.src_b[l] >= 0) atomicAdd(gbase2 + m.src_b[l] + o, val);
                 }
             }
         }
