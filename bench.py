@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4],
                     help="BASELINE.json config: 1 = HashGrid 8-level, 1-layer-32 MLP, 256^2 single view (the reference's CPU-runnable case; same runner as 2), "
                          "2 = HashGrid NeRF fwd+bwd (headline), 3 = nglod OctreeGrid SDF sphere trace, 4 = TriplanarGrid NeRF")
+    ap.add_argument("--hidden-dim", type=int, default=0, help="configs 1/2: decoder width override (128 = the reference's best published app/nerf setting)")
     a = ap.parse_args()
     if a.config == 1 and a.res == 1024:
         a.res = 256
@@ -66,7 +67,8 @@ def metric_name(args):
 
 def nef_shape(args):
     """(num_lods, hidden_dim) of the benched field: configs[1] (headline) unless --config 1 (configs[0])."""
-    return (8, 32) if args.config == 1 else (16, 64)
+    L, H = (8, 32) if args.config == 1 else (16, 64)
+    return L, (args.hidden_dim or H)
 
 
 def make_onef(O, args):
@@ -76,7 +78,7 @@ def make_onef(O, args):
 
 def workload_config(args):
     L, H = nef_shape(args)
-    return {"workload": f"app/nerf HashGrid {L}-level F=2 T=2^19, {'2-layer-64' if H == 64 else 'num_layers=1 hidden-32'} MLP, {args.res}^2 rays x {args.num_steps} steps ('ray'), "
+    return {"workload": f"app/nerf HashGrid {L}-level F=2 T=2^19, {'2-layer-64' if H == 64 else f'num_layers=1 hidden-{H}'} MLP, {args.res}^2 rays x {args.num_steps} steps ('ray'), "
                         f"{'lego-like level-7 octree' if args.scene == 'lego' else 'dense level-7 octree'}, fwd+bwd+Adam",
             "rays_per_step_per_gpu": args.res * args.res // (args.gpus if getattr(args, "scaling", "weak") == "strong" else 1), "num_steps": args.num_steps, "scene": args.scene,
             "camera": {"origin": CAM_ORIGIN, "lookat": CAM_LOOKAT, "fov": CAM_FOV, "near": NEAR, "far": FAR},
@@ -436,7 +438,7 @@ def run_ours(args):
         "table_scatter": ("wb_table_scatter_kernel", "hbm", 2 * L_eff * 8 * 2 * e, "B"),
         # the fused backward kernel moves, per hit sample, the 64 B of saved features in and the read-modify-write of the table entries
         # (2 * L * 8 * F * 4 B): that is its SURVEY 8(d) figure; its decoder FLOPs are reported as a second line below
-        "shade_bwd": (((("wb_mlp_bwd3_tc_kernel<FUSE> (decoder backward + table scatter)" if hidden == 64 else "wb_mlp_bwd_tc_kernel + wb_table_scatter_kernel (one stage)"),
+        "shade_bwd": (((("wb_mlp_bwd3_tc_kernel<FUSE> (decoder backward + table scatter)" if hidden in (64, 128) else "wb_mlp_bwd_tc_kernel + wb_table_scatter_kernel (one stage)"),
                         "hbm", 4 * n_lods + 2 * L_eff * 8 * 2 * e, "B")) if args.precision == 1
                       else ("wb_shade_bwd_kernel", "hbm", 2 * L_eff * 8 * 2 * e, "B")),
         "decoder_bwd": ("wb_mlp_bwd_tc_kernel", "tensor", 3 * dec_flop, "FLOP"),     # forward recompute + data grad + weight grad of both decoders

@@ -63,27 +63,50 @@ static int tc_round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // ---- three-group decoder backward (wb_shade_tc_bwd3.cuh): shared-memory plan ----
 constexpr int TC_B3_GROUPS = 3;
-struct TcB3Plan { int P, Q, R, E, GB, blob_off, ones_off, smem_bytes; };      // byte offsets (P..E from the group base, GB = group stride)
+struct TcB3Plan {
+    int P, Q, R, E, GB, blob_off, ones_off, smem_bytes;          // byte offsets (P..E from the group base, GB = group stride)
+    int groups;                                                   // 3: every width <= 64;  1: widths up to 128 (hidden_dim = 128)
+    int kind[8], acc_col[8], bias_col[8];                         // weight-grad accumulator of layer l: orientation (see below) and TMEM columns
+    int acc_begin, acc_end;                                       // TMEM column range of all accumulators (zeroed at kernel start)
+};
 
-// host: shared-memory plan; returns false when the configuration is outside the variant's scope
+// host: shared-memory + tensor-memory plan; returns false when the configuration is outside the kernel's scope.
+// Accumulator kinds (one group, 128-wide layers: 416 accumulator columns in the [in, out] orientation + 128 working columns would not
+// fit the 512 TMEM columns, and a 128-row X^T leaves no row for the bias gradient):
+//   0  acc[in, out] += X^T . dY, the tile's constant-one slab makes row Kp the bias gradient             (Np columns;  Kp < 128)
+//   1  the same, bias gradient in a 16-column accumulator of its own: bias[out, 0] += dY^T . Ones         (Np + 16;     Kp == 128)
+//   2  acc^T[out, in | 1] += dY^T . [X | 1]                                                              (Kp + 16;     used when Kp + 16 < Np)
+// hidden_dim 128 on the app/nerf field: 48 + 32 + 64 + 144 + 32 = 320 accumulator columns + 128 working columns.
 static bool tc_b3_plan(const WbTc& m, TcB3Plan* p)
 {
     if (m.nl_d != 2 || m.nl_c != 3) return false;
-    int maxw = 0;
-    for (int l = 0; l < 5; ++l) maxw = max(maxw, max(m.Kp[l], m.Np[l]));
-    if (maxw > 64) return false;
+    int maxw = 0, sumN = 0;
+    for (int l = 0; l < 5; ++l) { maxw = max(maxw, max(m.Kp[l], m.Np[l])); sumN += m.Np[l]; }
+    if (maxw > 128) return false;
     // the hidden activation tiles X1, X3, X4 share the buffers P and Q, whose constant-one slab sits behind a maxw-wide tile: the
     // hidden width must BE the widest tile (true for app/nerf: 64-wide hidden layers over 32 / 42 inputs; a 32-wide decoder over a
     // 42-wide colour input would read its bias-gradient row from a stale slab)
-    if (m.Np[0] + m.Np[1] + m.Np[2] + m.Np[3] + m.Np[4] > 512 - 3 * 64) return false;      // TMEM: 64 working columns per group + the weight-grad accumulators
     if (m.Kp[1] != maxw || m.Kp[3] != maxw || m.Kp[4] != maxw || m.Np[0] != maxw || m.Np[2] != maxw || m.Np[3] != maxw) return false;
+    memset(p, 0, sizeof(*p));
+    p->groups = (maxw <= 64 && sumN <= 512 - 3 * 64) ? 3 : 1;    // TMEM: 64 working columns per group (3 groups) / 128 (1 group) + the accumulators
+    const int wc = p->groups == 3 ? 64 : 128;
+    int col = p->groups * wc;
+    p->acc_begin = col;
+    for (int l = 0; l < 5; ++l) {
+        p->kind[l] = p->groups == 3 ? 0 : (m.Kp[l] + 16 < m.Np[l] ? 2 : (m.Kp[l] >= 128 ? 1 : 0));
+        p->acc_col[l] = col; col += p->kind[l] == 2 ? m.Kp[l] + 16 : m.Np[l];
+        p->bias_col[l] = col; if (p->kind[l] == 1) col += 16;
+    }
+    p->acc_end = col;
+    if (col > 512) return false;
     const int big = (maxw / 8 + 1) * 2048;                       // a maxw-wide tile + its constant-one slab
     const int small = (max(m.Np[1], m.Np[4]) / 8) * 2048;        // dY1 / dY4
     p->P = 0; p->Q = big; p->R = 2 * big; p->E = 3 * big; p->GB = 3 * big + small;
-    p->blob_off = TC_B3_GROUPS * p->GB;
+    p->blob_off = p->groups * p->GB;
     p->ones_off = p->blob_off + m.blob_bytes;
     int end = p->ones_off + 2 * 2048;
-    const int window = (TC_B3_GROUPS - 1) * p->GB + p->R + 16 * 2048;     // 16-slab read window of the weight-grad A operand
+    // 16-slab read windows of the MN-major A operands (M = 128 feature rows): X tiles in R, and (kinds 1, 2) dY tiles in E
+    const int window = (p->groups - 1) * p->GB + (p->groups == 3 ? p->R : p->E) + 16 * 2048;
     if (end < window) end = window;
     p->smem_bytes = end + 64;
     return p->smem_bytes + 6144 <= 227 * 1024;
@@ -146,20 +169,21 @@ int wb_tc_make(const wb_nef_desc* d, bool backward, WbTc* m, bool tmem_a = false
     }
     m->smem_bytes = p + 64;
     // static shared memory of the kernels (issue table, barriers): 3 KB forward, 5 KB backward
-    m->fits2 = (m->smem_bytes + (backward ? 5632 : 3584) <= 227 * 1024) ? 1 : 0;
-    if (!m->fits2) {       // the two-group backward retains every activation tile; the three-group kernel's uniform buffers may still fit
-        TcB3Plan plan3;
-        WB_CHECK_ARG(backward && tc_b3_plan(*m, &plan3),
-                     backward ? "tensor-core path: decoder backward does not fit in shared memory (use precision 0)"
-                              : "tensor-core path: decoder does not fit in shared memory (use precision 0)");
-    }
+    const bool smem2 = m->smem_bytes + (backward ? 5632 : 3584) <= 227 * 1024;
     int col = 0;
     for (int gi = 0; gi < groups; ++gi) { m->work_col[gi] = col; col += maxw; }
     // forward TMEM-A variant (one group): work_col[1] is otherwise unused and holds the first column of the fp16 activation tile
     if (tmem_a && !backward) { m->work_col[1] = col; col += maxw / 2; }  // two halfs per 32-bit column
     if (backward) for (int l = 0; l < nl; ++l) { m->acc_col[l] = col; col += m->Np[l]; }
-    if (backward && !m->fits2) col += 64;      // three-group kernel: a third working accumulator
-    WB_CHECK_ARG(col <= 512, "tensor-core path: accumulators do not fit in TMEM (use precision 0)");
+    m->fits2 = (smem2 && col <= 512) ? 1 : 0;
+    if (!m->fits2) {       // the two-group backward retains every activation tile and keeps all accumulators [in, out]; the kernel of
+        TcB3Plan plan3;    // wb_shade_tc_bwd3.cuh (uniform buffers, three groups or one wide group, mixed accumulator orientation) may still fit
+        WB_CHECK_ARG(backward && tc_b3_plan(*m, &plan3),
+                     !smem2 ? (backward ? "tensor-core path: decoder backward does not fit in shared memory (use precision 0)"
+                                        : "tensor-core path: decoder does not fit in shared memory (use precision 0)")
+                            : "tensor-core path: accumulators do not fit in TMEM (use precision 0)");
+        col = 512;
+    }
     int alloc = 32; while (alloc < col) alloc <<= 1;
     m->tmem_cols = alloc;
     return WB_OK;
@@ -264,6 +288,7 @@ struct TcIn {
     const uint4* ray_embed;      // [R][Kc/8] rows prepared by wb_ray_embed_kernel
     uint4* x0_save;              // forward: optional [Kp0/8][S] copy of the density-decoder input rows
     const uint4* x0_saved;       // backward: the same buffer
+    int64_t s_begin, s_end;      // backward kernels that take a sample range (a multiple of 128 .. s_end; s_end == 0: the whole [0, S)); S stays the plane stride
 };
 
 __device__ __forceinline__ void tile_store1(uint8_t* tile, int r, int f, float v)
@@ -731,6 +756,7 @@ wb_shade_fwd_tc_kernel(WbGrid g, WbGridX gx, WbTc m, const uint8_t* __restrict__
 
 // set by wb_rf_workspace_holds_ray_rows(): the next backward of this thread finds the per-ray colour-input rows in its workspace already
 static thread_local int g_tc_skip_embed = 0;
+static thread_local int64_t g_tc_s_begin = 0, g_tc_s_end = 0;      // sample range of the next backward launches (0, 0 = everything); set by wb_tc_shade_bwd's chunked schedule
 extern "C" int wb_rf_workspace_holds_ray_rows(int32_t yes) { g_tc_skip_embed = yes ? 1 : 0; return WB_OK; }
 
 static int tc_launch_ray_embed(const WbTc& m, const wb_rays* rays, void* workspace, cudaStream_t st)
@@ -750,6 +776,8 @@ static int tc_knob_bwd_groups() { static const int v = tc_env_int("WB_TC_BWD_GRO
 static int tc_knob_fwd_tmema() { static const int v = tc_env_int("WB_TC_FWD_TMEMA", 1); return v; }
 static int tc_knob_fwd_pipe() { static const int v = tc_env_int("WB_TC_FWD_PIPE", 0); return v; }
 static int tc_knob_fwd_ctas() { static const int v = tc_env_int("WB_TC_FWD_CTAS", 3); return v; }
+static int tc_knob_fuse_scatter_wide() { static const int v = tc_env_int("WB_TC_FUSE_SCATTER_WIDE", 0); return v; }
+static int tc_knob_wide_chunks() { static const int v = tc_env_int("WB_TC_WIDE_CHUNKS", 4); return v; }       // 1: no overlap of decoder backward and table scatter
 static int tc_knob_scatter_lpb() { static const int v = tc_env_int("WB_TC_SCATTER_LPB", 16); return v; }
 static int tc_knob_scatter_idx2() { static const int v = tc_env_int("WB_TC_SCATTER_IDX2", 1); return v; }
 static int tc_knob_scatter_ctas() { static const int v = tc_env_int("WB_TC_SCATTER_CTAS", 16); return v; }
@@ -970,9 +998,10 @@ wb_table_scatter_kernel(WbGrid g, TcIn in, const __half* __restrict__ dfeat, int
     const int lane = threadIdx.x & 31;
     const float scale = __ldg(scale_p), inv_scale = 1.0f / scale;
     const int Fr = F > 0 ? F : g.F;
-    const int64_t nwork = (in.S + 31) & ~(int64_t)31;            // whole warps
-    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nwork; s += (int64_t)gridDim.x * blockDim.x) {
-        const bool valid = s < in.S;
+    const int64_t s_end = in.s_end ? in.s_end : in.S;
+    const int64_t nwork = in.s_begin + ((s_end - in.s_begin + 31) & ~(int64_t)31);            // whole warps
+    for (int64_t s = in.s_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nwork; s += (int64_t)gridDim.x * blockDim.x) {
+        const bool valid = s < s_end;
         float px = 0.0f, py = 0.0f, pz = 0.0f;
         if (valid) {
             const int64_t ray = __ldg(in.rec_ray + s);
@@ -1193,27 +1222,30 @@ int wb_tc_decoder_bwd_ex(const wb_nef_desc* nef, const float* blob, const wb_ray
     int planes, width; tc_dfeat_shape(nef, &planes, &width);
     const int64_t R = rays->num_rays;
     __half* dfeat = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(workspace) + tc_align256(R * m.Kp[m.nl_d] * 2));
-    TcIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S, reinterpret_cast<const uint4*>(workspace), nullptr, reinterpret_cast<const uint4*>(feat_saved) };
+    TcIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S, reinterpret_cast<const uint4*>(workspace), nullptr, reinterpret_cast<const uint4*>(feat_saved),
+                g_tc_s_begin, g_tc_s_end };
+    const int64_t S_launch = (g_tc_s_end ? g_tc_s_end : S) - g_tc_s_begin;
     TcGrads G = { grad_dens, grad_col, scale, dfeat, planes, width };
     TcB3Plan plan;
-    if ((tc_knob_bwd_groups() == 3 || !m.fits2) && tc_b3_plan(m, &plan)) {     // three sub-tile groups per SM (wb_shade_tc_bwd3.cuh): 4.53 -> 3.69 ms measured
-        WbTc m3 = m;
-        for (int l = 0; l < m.nl_d + m.nl_c; ++l) m3.acc_col[l] = 3 * 64 + (m.acc_col[l] - m.acc_col[0]);      // work columns 0..191 (64 per group,
-                                                                                            // whatever maxw is), accumulators behind them
-        WbGrid g; memset(&g, 0, sizeof(g));
+    if ((tc_knob_bwd_groups() == 3 || !m.fits2) && tc_b3_plan(m, &plan)) {     // wb_shade_tc_bwd3.cuh: three sub-tile groups per SM (4.53 -> 3.69 ms measured),
+        WbGrid g; memset(&g, 0, sizeof(g));                                     // or one 128-wide group (hidden_dim = 128)
+        const int wide = plan.groups == 1 ? 1 : 0;
+        // one wide group per SM: the fused scatter has only 8 warps to issue from and measured slower than the stand-alone scatter kernel
+        // (16.0 vs 13.7 ms at hidden_dim 128 on the 1024^2 frame), so it is opt-in there (WB_TC_FUSE_SCATTER_WIDE=1)
         const bool fuse = grad_table != nullptr && tc_knob_fuse_scatter() && nef->grid_kind == 0 && nef->feature_dim == 2 && nef->multiscale == 0 &&
-                          planes <= 16;
+                          planes <= 16 && (!wide || tc_knob_fuse_scatter_wide());
         if (fuse) { rc = wb_make_grid(nef, &g); if (rc) return rc; }
-        const int fmode = !fuse ? 0 : (tc_knob_fuse_scatter() == 2 ? 2 : tc_knob_fuse_scatter() == 3 ? 3 : 1);
-        auto kern3 = fmode == 3 ? wb_mlp_bwd3_tc_kernel<3> : fmode == 2 ? wb_mlp_bwd3_tc_kernel<2> : fmode == 1 ? wb_mlp_bwd3_tc_kernel<1> : wb_mlp_bwd3_tc_kernel<0>;
-        static int64_t done3[4] = { -1, -1, -1, -1 };
-        if (done3[fmode] != WB_ATTR_KEY(plan.smem_bytes)) {
+        const int fmode = !fuse ? 0 : (tc_knob_fuse_scatter() == 2 ? 2 : (tc_knob_fuse_scatter() == 3 && !wide) ? 3 : 1);
+        auto kern3 = wide ? (fmode == 2 ? wb_mlp_bwd3_tc_kernel<2, 1> : fmode ? wb_mlp_bwd3_tc_kernel<1, 1> : wb_mlp_bwd3_tc_kernel<0, 1>)
+                          : fmode == 3 ? wb_mlp_bwd3_tc_kernel<3, 3> : fmode == 2 ? wb_mlp_bwd3_tc_kernel<2, 3> : fmode == 1 ? wb_mlp_bwd3_tc_kernel<1, 3> : wb_mlp_bwd3_tc_kernel<0, 3>;
+        static int64_t done3[2][4] = { { -1, -1, -1, -1 }, { -1, -1, -1, -1 } };
+        if (done3[wide][fmode] != WB_ATTR_KEY(plan.smem_bytes)) {
             WB_CUDA(cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
-            done3[fmode] = WB_ATTR_KEY(plan.smem_bytes);
+            done3[wide][fmode] = WB_ATTR_KEY(plan.smem_bytes);
         }
-        const int64_t nctas3 = ((S + TC_ROWS - 1) / TC_ROWS + TC_B3_GROUPS - 1) / TC_B3_GROUPS;
+        const int64_t nctas3 = ((S_launch + TC_ROWS - 1) / TC_ROWS + plan.groups - 1) / plan.groups;
         int64_t grid3 = (int64_t)wb_num_sms(); if (grid3 > nctas3) grid3 = nctas3;
-        kern3<<<(unsigned)grid3, TC_B3_GROUPS * TC_GROUP, plan.smem_bytes, st>>>(m3, plan, reinterpret_cast<const uint8_t*>(blob), in,
+        kern3<<<(unsigned)grid3, plan.groups * TC_GROUP, plan.smem_bytes, st>>>(m, plan, reinterpret_cast<const uint8_t*>(blob), in,
                                                                           reinterpret_cast<const float4*>(g_shaded), G, g, grad_table);
         WB_LAUNCH_CHECK();
         if (fuse && fused_out) *fused_out = 1;
@@ -1245,7 +1277,8 @@ int wb_tc_table_scatter(const wb_nef_desc* nef, const wb_rays* rays, const float
     int planes, width; tc_dfeat_shape(nef, &planes, &width);
     const int64_t R = rays->num_rays;
     const __half* dfeat = reinterpret_cast<const __half*>(reinterpret_cast<const uint8_t*>(workspace) + tc_align256(R * m.Kp[m.nl_d] * 2));
-    TcIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S, nullptr, nullptr, nullptr };
+    TcIn in = { rays->origins, rays->dirs, rec_t, rec_ray, S, nullptr, nullptr, nullptr, gx.kind != 0 ? 0 : g_tc_s_begin, gx.kind != 0 ? 0 : g_tc_s_end };
+    const int64_t S_launch = gx.kind != 0 ? S : (g_tc_s_end ? g_tc_s_end : S) - g_tc_s_begin;
     if (gx.kind != 0) {
         int64_t bx = (S + 255) / 256; const int64_t cap = (int64_t)wb_num_sms() * 16; if (bx > cap) bx = cap;
         wb_featx_scatter_kernel<<<(unsigned)bx, 256, 0, st>>>(gx, in, dfeat, width, scale);
@@ -1256,7 +1289,7 @@ int wb_tc_table_scatter(const wb_nef_desc* nef, const wb_rays* rays, const float
     if (levels > 0) {
         // LODs per CTA row: the sample position / record loads are shared by `lpb` LODs (measured sweep in profiles/README.md)
         const int lpb = max(1, min(levels, tc_knob_scatter_lpb()));
-        int64_t bx = (S + 255) / 256; const int64_t cap = (int64_t)wb_num_sms() * tc_knob_scatter_ctas(); if (bx > cap) bx = cap;
+        int64_t bx = (S_launch + 255) / 256; const int64_t cap = (int64_t)wb_num_sms() * tc_knob_scatter_ctas(); if (bx > cap) bx = cap;
         dim3 grid2((unsigned)bx, (unsigned)((levels + lpb - 1) / lpb));
         const int v4 = tc_knob_scatter_v4();
         if (g.F == 2 && tc_knob_scatter_h2() && tc_knob_scatter_idx2()) wb_table_scatter_kernel<2, true, true><<<grid2, 256, 0, st>>>(g, in, dfeat, planes, levels, lpb, scale, grad_table, v4);
@@ -1268,10 +1301,48 @@ int wb_tc_table_scatter(const wb_nef_desc* nef, const wb_rays* rays, const float
     return WB_OK;
 }
 
+// Wide decoders (one 256-thread group per SM, half the register file and all the other warp slots idle): the sample range is cut
+// into chunks; the decoder backward of chunk c+1 runs on the caller's stream while the table scatter of chunk c (an issue-bound SIMT
+// kernel with 48 registers per thread and no shared memory: two of its CTAs fit beside a decoder CTA) runs on a side stream.
+struct TcSide { cudaStream_t stream; cudaEvent_t ev[17]; bool ok; };
+static TcSide* tc_side_stream()
+{
+    static TcSide side[64];
+    int dev = 0; if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    TcSide& s = side[dev];
+    if (!s.ok) {
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        for (int i = 0; i < 17; ++i) if (cudaEventCreateWithFlags(&s.ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        s.ok = true;
+    }
+    return &s;
+}
+
 int wb_tc_shade_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* rays, const float* rec_t, const int32_t* rec_ray,
                     int64_t S, const float* g_shaded, const float* scale, const void* feat_saved, void* workspace,
                     float* grad_table, float* grad_dens, float* grad_col, cudaStream_t st)
 {
+    {
+        WbTc m; TcB3Plan plan;
+        int chunks = tc_knob_wide_chunks(); if (chunks > 16) chunks = 16;
+        TcSide* side = nullptr;
+        if (chunks > 1 && S >= ((int64_t)1 << 20) && nef->grid_kind == 0 && grad_table && wb_tc_make(nef, true, &m) == WB_OK && !m.fits2 &&
+            tc_b3_plan(m, &plan) && plan.groups == 1 && !tc_knob_fuse_scatter_wide() && (side = tc_side_stream()) != nullptr) {
+            const int64_t per = ((S + chunks - 1) / chunks + TC_ROWS - 1) / TC_ROWS * TC_ROWS;
+            int rc = WB_OK, c = 0;
+            for (int64_t s0 = 0; s0 < S && rc == WB_OK; s0 += per, ++c) {
+                g_tc_s_begin = s0; g_tc_s_end = s0 + per < S ? s0 + per : S;
+                if (c > 0) g_tc_skip_embed = 1;                       // the per-ray rows were written by the first chunk's launch
+                rc = wb_tc_decoder_bwd_ex(nef, blob, rays, rec_t, rec_ray, S, g_shaded, scale, feat_saved, workspace, grad_dens, grad_col, nullptr, nullptr, st);
+                if (rc == WB_OK && (cudaEventRecord(side->ev[c], st) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->ev[c], 0) != cudaSuccess)) rc = WB_ERR_CUDA;
+                if (rc == WB_OK) rc = wb_tc_table_scatter(nef, rays, rec_t, rec_ray, S, scale, workspace, grad_table, side->stream);
+            }
+            g_tc_s_begin = 0; g_tc_s_end = 0;
+            // the caller's stream continues after the last scatter (also on an error path: never leave the side stream unjoined)
+            if (cudaEventRecord(side->ev[16], side->stream) != cudaSuccess || cudaStreamWaitEvent(st, side->ev[16], 0) != cudaSuccess) { if (rc == WB_OK) rc = WB_ERR_CUDA; }
+            return rc;
+        }
+    }
     int fused = 0;
     int rc = wb_tc_decoder_bwd_ex(nef, blob, rays, rec_t, rec_ray, S, g_shaded, scale, feat_saved, workspace, grad_dens, grad_col, grad_table, &fused, st);
     if (rc || fused) return rc;

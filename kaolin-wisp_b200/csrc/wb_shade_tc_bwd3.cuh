@@ -273,7 +273,8 @@ wb_mlp_bwd3_tc_kernel(WbTc m, TcB3Plan p, const uint8_t* __restrict__ blob, TcIn
     tc_mbar_wait(&bars[NG], 0);
     const float scale = __ldg(G.scale), inv_scale = 1.0f / scale;
     const int nch0 = m.Kp[0] / 8, nchc = m.Kp[2] / 8;
-    const int64_t ntiles = (in.S + TC_ROWS - 1) / TC_ROWS;
+    const int64_t s_end = in.s_end ? in.s_end : in.S;             // this launch's sample range (in.S stays the stride of the saved rows / planes)
+    const int64_t tile0 = in.s_begin / TC_ROWS, ntiles = (s_end + TC_ROWS - 1) / TC_ROWS;
     const uint32_t trow = c.tmem + ((uint32_t)c.laneq << 16) + (uint32_t)(c.g * WC);
     const float z8[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
     // FUSE == 2: the sample of the previous sub-tile whose gradient this thread still has to scatter
@@ -289,10 +290,10 @@ wb_mlp_bwd3_tc_kernel(WbTc m, TcB3Plan p, const uint8_t* __restrict__ blob, TcIn
             }
         }
     };
-    for (int64_t tile = (int64_t)blockIdx.x * NG + c.g; tile < ntiles; tile += (int64_t)gridDim.x * NG) {
+    for (int64_t tile = tile0 + (int64_t)blockIdx.x * NG + c.g; tile < ntiles; tile += (int64_t)gridDim.x * NG) {
         int64_t s = tile * TC_ROWS + c.r;
-        const bool valid = s < in.S;
-        if (!valid) s = in.S - 1;
+        const bool valid = s < s_end;
+        if (!valid) s = s_end - 1;
         const int64_t ray = __ldg(in.rec_ray + s);
         // X0 -> P
         for (int ch = c.h; ch < nch0; ch += 2)

@@ -117,7 +117,7 @@ def test_host_prefetcher_cpu_passthrough():
 
 def test_precision_support_query_is_host_side():
     """wb_rf_precision_supported answers without a device: the 64-wide app/nerf decoders fit the tensor-core path forward
-    and backward; wider / deeper decoders fit forward only (their backward stays on the fp32 kernels)."""
+    and backward, so do 128-wide ones of the same depth; deeper decoders fit forward only (their backward stays on the fp32 kernels)."""
     import wisp_b200 as W
     from wisp_b200 import ops
     ans = {}
@@ -130,7 +130,7 @@ def test_precision_support_query_is_host_side():
         ans[(hidden, layers)] = (ops.precision_supported(spec, nef, 1, False), ops.precision_supported(spec, nef, 1, True),
                                  ops.precision_supported(spec, nef, 0, True))
     assert ans[(64, 1)] == (True, True, True)
-    assert ans[(128, 1)] == (True, False, True) and ans[(64, 2)] == (True, False, True)
+    assert ans[(128, 1)] == (True, True, True) and ans[(64, 2)] == (True, False, True)      # hidden 128: one-group tensor-core backward
 
 
 def test_bucketed_capacities():
@@ -228,7 +228,9 @@ assert spec.dens_dims == [8, 64, 16] and spec.col_dims == [42, 64, 64, 3] and sp
 assert ops.precision_supported(spec, nef, 1, True)
 wide = NeuralRadianceField(hg, view_embedder='positional', view_multires=4, hidden_dim=128, num_layers=1, bias=False)
 sw = ops.nef_spec(wide, 3)
-assert sw is not None and not sw.has_bias and ops.precision_supported(sw, wide, 1, False) and not ops.precision_supported(sw, wide, 1, True)
+assert sw is not None and not sw.has_bias and ops.precision_supported(sw, wide, 1, False) and ops.precision_supported(sw, wide, 1, True)
+deep = NeuralRadianceField(hg, view_embedder='positional', view_multires=4, hidden_dim=128, num_layers=2, bias=True)
+assert ops.precision_supported(ops.nef_spec(deep, 3), deep, 1, False) and not ops.precision_supported(ops.nef_spec(deep, 3), deep, 1, True)
 ident = NeuralRadianceField(hg, view_embedder='none', pos_embedder='positional', pos_multires=3, position_input=True, hidden_dim=32)
 si = ops.nef_spec(ident, 3)
 assert si.view_mode == 1 and si.pos_mode == 3 and si.pos_freq == 3 and si.dens_dims[0] == 8 + 3 + 18
