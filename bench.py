@@ -519,8 +519,7 @@ def parity_leg(args, O, W, torch, dev, spc_np, onef, pipe, tracer, nef, stepper=
         torch.cuda.synchronize()
         rgb_gpu = stepper.last_rgb.cpu().numpy()
         g_table, g_dens, g_col = stepper.g_grid[0].cpu().numpy(), stepper.g_dens.cpu().numpy(), stepper.g_col.cpu().numpy()
-        for gbuf in stepper.g_grid + [stepper.g_dens, stepper.g_col]:
-            gbuf.zero_()
+        stepper.zero_grads()
     else:
         rb = pipe(rays=W.Rays(o, d, dist_min=NEAR, dist_max=FAR), lod_idx=None, channels=["rgb"])
         loss = torch.nn.functional.smooth_l1_loss(rb.rgb, tgt, reduction='none').mean()

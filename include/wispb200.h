@@ -74,7 +74,10 @@ typedef struct wb_nef_desc {
      * grid_kind 2 = OctreeGrid (octree_grid.py:24-226): num_lods = LODs used, feature_dim = F, grid_ptrs = features[0..num_lods)
      *   each [pyramid_dual[0,l]+1, F] fp32; oct/points/trinkets/base_lod/half_round as in wb_octree_interp_fwd.
      * For both: lod_idx = num_lods (nothing is zeroed), table / resolutions-as-hash / begin_idxes / codebook_size unused.
-     * grid_grads: same shapes as grid_ptrs, accumulated into by the backward entry points (their grad_table may be NULL). */
+     * grid_grads: same shapes as grid_ptrs, accumulated into by the backward entry points (their grad_table may be NULL).
+     * grid_layout (grid_kind 1 only): 0 = the reference's plane layout [1, fdim, res+1, res+1]; 1 = channel-last [res+1, res+1, fdim]
+     *   for grid_ptrs AND grid_grads (fdim == 4: one 16-byte load / one 16-byte reduction per texel instead of four 4-byte ones;
+     *   wb_triplane_relayout converts between the two). */
     int32_t grid_kind;
     int32_t base_lod, half_round;
     const float* const* grid_ptrs;          /* HOST array of device pointers */
@@ -82,6 +85,7 @@ typedef struct wb_nef_desc {
     const struct wb_octree* oct;            /* grid_kind 2 */
     const int16_t* points;
     const int32_t* trinkets;
+    int32_t grid_layout;
 } wb_nef_desc;
 
 /* Rays (wisp/core/rays.py:19-36).  near/far: scalars, or per-ray arrays when near_v != NULL. */
@@ -193,6 +197,11 @@ int wb_triplane_fwd(const float* coords, int64_t N, int32_t num_lods, int32_t fd
                     const float* const* planes, float* feats, wb_stream s);
 int wb_triplane_bwd(const float* coords, int64_t N, int32_t num_lods, int32_t fdim, const int32_t* res,
                     const float* const* planes, const float* grad_feats, float* const* grad_planes, wb_stream s);
+/* Plane layout conversion for the fused path (wb_nef_desc.grid_layout = 1), all planes in ONE launch: src / dst are HOST arrays of
+ * n_planes device pointers, sizes[i] = plane side (res + 1).  to_channel_last != 0: [fdim, size, size] -> [size, size, fdim];
+ * 0: the inverse (gradients back into the layout of the reference's nn.Parameter, triplanar_grid.py:178-180).  dst is overwritten. */
+int wb_triplane_relayout(const float* const* src, float* const* dst, const int32_t* sizes, int32_t n_planes, int32_t fdim,
+                         int32_t to_channel_last, wb_stream s);
 
 /* ------------------------------------------------------------------------------------------------
  * OctreeGrid.interpolate (wisp/models/grids/octree_grid.py:130-219): replaces blas.query(with_parents=True) + one

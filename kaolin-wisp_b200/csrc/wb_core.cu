@@ -87,6 +87,8 @@ int wb_make_gridx(const wb_nef_desc* d, bool backward, WbGridX* x) {
     if (d->grid_kind == 1) {
         WB_CHECK_ARG(d->feature_dim % 3 == 0 && d->feature_dim / 3 <= WB_X_MAX_C, "triplanar: feature_dim = 3 * fdim, fdim <= 8");
         x->C = d->feature_dim / 3;
+        WB_CHECK_ARG(d->grid_layout == 0 || (d->grid_layout == 1 && x->C == 4), "triplanar: channel-last planes need fdim == 4");
+        x->chlast = d->grid_layout;
         for (int l = 0; l < d->num_lods; ++l) { WB_CHECK_ARG(d->resolutions[l] >= 1, "plane resolution must be >= 1"); x->res[l] = d->resolutions[l]; }
     } else {
         WB_CHECK_ARG(d->feature_dim <= WB_X_MAX_F, "octree: feature_dim <= 32 on the fused path");

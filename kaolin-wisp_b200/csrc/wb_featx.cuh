@@ -24,6 +24,7 @@ struct WbGridX {
     // octree
     const uint8_t* octree; const int32_t* prefix; const int16_t* points; const int32_t* trinkets;
     int base_lod, half_round;
+    int chlast;                            // triplanar, C == 4: planes and plane gradients are [H, W, 4] (one float4 per texel)
 };
 
 // ---- ATen grid sampler coordinate handling (GridSampler.h), align_corners=True, padding_mode='reflection' ----
@@ -114,6 +115,17 @@ __device__ __forceinline__ void wb_featx_gather(const WbGridX& x, float cx, floa
             for (int p = 0; p < 3; ++p) {
                 const WbBilinear b = wb_tp_setup(cx, cy, cz, p, size);
                 const float* pl = x.ptr[l * 3 + p];
+                if (x.chlast) {                                  // one 16-byte load per texel
+                    const float4* t4 = reinterpret_cast<const float4*>(pl);
+                    float4 a = __ldg(t4 + b.o00);
+                    float v0 = a.x * b.nw, v1 = a.y * b.nw, v2 = a.z * b.nw, v3 = a.w * b.nw;
+                    if (b.bx1) { a = __ldg(t4 + b.o01); v0 += a.x * b.ne; v1 += a.y * b.ne; v2 += a.z * b.ne; v3 += a.w * b.ne; }
+                    if (b.by1) { a = __ldg(t4 + b.o10); v0 += a.x * b.sw; v1 += a.y * b.sw; v2 += a.z * b.sw; v3 += a.w * b.sw; }
+                    if (b.bx1 && b.by1) { a = __ldg(t4 + b.o11); v0 += a.x * b.se; v1 += a.y * b.se; v2 += a.z * b.se; v3 += a.w * b.se; }
+                    if (x.sum) { acc[p][0] += v0; acc[p][1] += v1; acc[p][2] += v2; acc[p][3] += v3; }
+                    else { const int f = (l * 3 + p) * 4; emit(f, v0); emit(f + 1, v1); emit(f + 2, v2); emit(f + 3, v3); }
+                    continue;
+                }
 #pragma unroll
                 for (int c = 0; c < WB_X_MAX_C; ++c) {
                     if (c < C) {
@@ -184,6 +196,17 @@ __device__ __forceinline__ void wb_featx_scatter(const WbGridX& x, float cx, flo
             for (int p = 0; p < 3; ++p) {
                 const WbBilinear b = wb_tp_setup(cx, cy, cz, p, size);
                 float* pl = x.gptr[l * 3 + p];
+                if (x.chlast) {                                  // one 16-byte reduction per texel
+                    const int f = x.sum ? p * 4 : (l * 3 + p) * 4;
+                    const float g0 = grad(f), g1 = grad(f + 1), g2 = grad(f + 2), g3 = grad(f + 3);
+                    if (g0 == 0.0f && g1 == 0.0f && g2 == 0.0f && g3 == 0.0f) continue;
+                    float4* t4 = reinterpret_cast<float4*>(pl);
+                    atomicAdd(t4 + b.o00, make_float4(g0 * b.nw, g1 * b.nw, g2 * b.nw, g3 * b.nw));
+                    if (b.bx1) atomicAdd(t4 + b.o01, make_float4(g0 * b.ne, g1 * b.ne, g2 * b.ne, g3 * b.ne));
+                    if (b.by1) atomicAdd(t4 + b.o10, make_float4(g0 * b.sw, g1 * b.sw, g2 * b.sw, g3 * b.sw));
+                    if (b.bx1 && b.by1) atomicAdd(t4 + b.o11, make_float4(g0 * b.se, g1 * b.se, g2 * b.se, g3 * b.se));
+                    continue;
+                }
                 for (int c = 0; c < C; ++c) {
                     const float g = grad(x.sum ? p * C + c : (l * 3 + p) * C + c);
                     if (g == 0.0f) continue;

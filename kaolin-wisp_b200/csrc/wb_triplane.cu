@@ -100,3 +100,42 @@ extern "C" int wb_triplane_bwd(const float* coords, int64_t N, int32_t num_lods,
     WB_LAUNCH_CHECK();
     return WB_OK;
 }
+
+// ---- plane layout conversion for the fused path (wb_nef_desc.grid_layout = 1) ------------------------------------
+struct WbRelayout { const float* src[3 * WB_X_MAX_LODS]; float* dst[3 * WB_X_MAX_LODS]; int64_t start[3 * WB_X_MAX_LODS + 1]; int n, C, to_cl; };
+
+__global__ void __launch_bounds__(256)
+wb_triplane_relayout_kernel(WbRelayout r)
+{
+    const int64_t total = r.start[r.n];
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        int i = 0;
+        while (i + 1 < r.n && t >= r.start[i + 1]) ++i;           // <= 36 planes
+        const int64_t e = t - r.start[i], hw = r.start[i + 1] - r.start[i];
+        const float* s = r.src[i]; float* d = r.dst[i];
+        if (r.C == 4) {
+            if (r.to_cl) reinterpret_cast<float4*>(d)[e] = make_float4(__ldg(s + e), __ldg(s + hw + e), __ldg(s + 2 * hw + e), __ldg(s + 3 * hw + e));
+            else { const float4 v = __ldg(reinterpret_cast<const float4*>(s) + e); d[e] = v.x; d[hw + e] = v.y; d[2 * hw + e] = v.z; d[3 * hw + e] = v.w; }
+        } else {
+            for (int c = 0; c < r.C; ++c) { if (r.to_cl) d[e * r.C + c] = __ldg(s + c * hw + e); else d[c * hw + e] = __ldg(s + e * r.C + c); }
+        }
+    }
+}
+
+extern "C" int wb_triplane_relayout(const float* const* src, float* const* dst, const int32_t* sizes, int32_t n_planes, int32_t fdim,
+                                    int32_t to_channel_last, wb_stream s)
+{
+    WB_CHECK_ARG(src && dst && sizes && n_planes >= 1 && n_planes <= 3 * WB_X_MAX_LODS && fdim >= 1 && fdim <= WB_X_MAX_C, "bad plane list");
+    WbRelayout r; memset(&r, 0, sizeof(r));
+    r.n = n_planes; r.C = fdim; r.to_cl = to_channel_last ? 1 : 0;
+    int64_t at = 0;
+    for (int i = 0; i < n_planes; ++i) {
+        WB_CHECK_ARG(src[i] && dst[i] && sizes[i] >= 1, "null plane / bad size");
+        r.src[i] = src[i]; r.dst[i] = dst[i]; r.start[i] = at; at += (int64_t)sizes[i] * sizes[i];
+    }
+    r.start[n_planes] = at;
+    int64_t bx = (at + 255) / 256; const int64_t cap = (int64_t)wb_num_sms() * 8; if (bx > cap) bx = cap;
+    wb_triplane_relayout_kernel<<<(unsigned)bx, 256, 0, (cudaStream_t)s>>>(r);
+    WB_LAUNCH_CHECK();
+    return WB_OK;
+}

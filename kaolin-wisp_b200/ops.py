@@ -753,8 +753,9 @@ class NefSpec:
     half_round: bool = True
 
     def desc(self, grid: Sequence[torch.Tensor], dens_flat: torch.Tensor, col_flat: torch.Tensor, oct: Optional[OctreeTensors] = None,
-             trinkets: Optional[torch.Tensor] = None, grads: Optional[Sequence[torch.Tensor]] = None):
-        """-> (NefDesc, keepalive).  grid: [table] | planes (fmx, fmy, fmz per LOD) | feature levels."""
+             trinkets: Optional[torch.Tensor] = None, grads: Optional[Sequence[torch.Tensor]] = None, layout: int = 0):
+        """-> (NefDesc, keepalive).  grid: [table] | planes (fmx, fmy, fmz per LOD) | feature levels.  layout 1 (triplanar): `grid`
+        and `grads` are channel-last copies (triplane_channel_last)."""
         keep = []
         if self.kind == "hash":
             d = A.make_grid_desc(grid[0], self.resolutions, self.begin_idxes, self.codebook_size, self.multiscale, self.lod_idx)
@@ -763,6 +764,7 @@ class NefSpec:
             d.grid_kind = GRID_KINDS[self.kind]
             d.num_lods, d.feature_dim, d.codebook_size = self.num_lods, self.feature_dim, 0
             d.multiscale, d.lod_idx = (0 if self.multiscale == "cat" else 1), self.num_lods
+            d.grid_layout = int(layout)
             for i, r in enumerate(self.resolutions):
                 d.resolutions[i] = int(r)
             ptrs = (C.c_void_p * len(grid))(*[t.data_ptr() for t in grid])
@@ -787,6 +789,29 @@ class NefSpec:
             d.col_dims[i] = v
         d.dens_params, d.col_params = dens_flat.data_ptr(), col_flat.data_ptr()
         return d, keep
+
+
+def triplane_wants_channel_last(spec: "NefSpec") -> bool:
+    """The fused kernels read a 4-channel texel as one 16-byte load (and reduce its gradient with one 16-byte red) when the planes
+    are channel-last; the reference's nn.Parameter layout [1, fdim, H, W] (triplanar_grid.py:178-180) costs four 4-byte accesses."""
+    return spec.kind == "triplanar" and spec.feature_dim == 12
+
+
+def triplane_relayout(src: Sequence[torch.Tensor], to_channel_last: bool, out: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
+    """All planes in one native launch (wb_triplane_relayout): [1, C, H, W] -> [H, W, C] fp32 copies, or back (into `out` if given)."""
+    src = [A.f32c(t) for t in src]
+    A.require_device(src[0])
+    if to_channel_last:
+        Cc = int(src[0].shape[1]); sizes = [int(t.shape[2]) for t in src]
+        dst = [torch.empty((n, n, Cc), dtype=torch.float32, device=t.device) for n, t in zip(sizes, src)] if out is None else list(out)
+    else:
+        Cc = int(src[0].shape[2]); sizes = [int(t.shape[0]) for t in src]
+        dst = [torch.empty((1, Cc, n, n), dtype=torch.float32, device=t.device) for n, t in zip(sizes, src)] if out is None else list(out)
+    n = len(src)
+    sp = (C.c_void_p * n)(*[t.data_ptr() for t in src]); dp = (C.c_void_p * n)(*[t.data_ptr() for t in dst])
+    sz = (C.c_int32 * n)(*sizes)
+    A.check(A.lib().wb_triplane_relayout(sp, dp, sz, C.c_int32(n), C.c_int32(Cc), C.c_int32(1 if to_channel_last else 0), A.stream()))
+    return dst
 
 
 def _flatten(params: Sequence[torch.Tensor]) -> torch.Tensor:
@@ -942,9 +967,12 @@ class RFTraceFn(torch.autograd.Function):
         L = A.lib()
         dev = grid[0].device
         gt = [A.f32c(t.detach()) for t in grid]
+        layout = 1 if triplane_wants_channel_last(spec) else 0
+        if layout:                                          # channel-last copies of the planes (one launch, 17 MB at config 4)
+            gt = triplane_relayout(gt, True)
         dens_flat, col_flat = _flatten(params[:n_dens]), _flatten(params[n_dens:])
         oct, trinkets = octctx if octctx is not None else (None, None)
-        desc, keep = spec.desc(gt, dens_flat, col_flat, oct, trinkets)
+        desc, keep = spec.desc(gt, dens_flat, col_flat, oct, trinkets, layout=layout)
         nblob = int(L.wb_rf_param_blob_floats(C.byref(desc), C.c_int32(precision)))
         if nblob < 0:
             raise A.WispB200Error(L.wb_last_error().decode())
@@ -975,6 +1003,7 @@ class RFTraceFn(torch.autograd.Function):
             A.check(L.wb_composite_fwd(A.ptr(shaded), A.ptr(rec_t), A.ptr(rec_delta), A.ptr(ms.offsets), C.c_int64(R), bgv,
                                        A.ptr(rgb), A.ptr(depth), A.ptr(alpha), A.ptr(hit), A.stream()))
         ctx.ms, ctx.spec, ctx.n_grid, ctx.n_dens, ctx.bg, ctx.precision, ctx.octctx = ms, spec, n_grid, n_dens, bgv, precision, octctx
+        ctx.layout = layout
         ctx.param_shapes = [p.shape for p in params]
         ctx.feat = feat
         ctx.save_for_backward(dens_flat, col_flat, blob, rec_t, rec_delta, rec_ray, shaded, *gt)
@@ -989,7 +1018,7 @@ class RFTraceFn(torch.autograd.Function):
         S, R = ms.total, ms.rays.num_rays
         oct, trinkets = ctx.octctx if ctx.octctx is not None else (None, None)
         g_grid = [torch.zeros_like(t) for t in gt]
-        desc, keep = spec.desc(gt, dens_flat, col_flat, oct, trinkets, grads=g_grid)
+        desc, keep = spec.desc(gt, dens_flat, col_flat, oct, trinkets, grads=g_grid, layout=ctx.layout)
         g_table = g_grid[0] if spec.kind == "hash" else None
         g_sh = _empty_s(S, (4,), torch.float32, shaded.device)
         gd = A.f32c(g_depth).reshape(-1) if g_depth is not None else None
@@ -1025,6 +1054,8 @@ class RFTraceFn(torch.autograd.Function):
             for shp in shapes:
                 n = int(torch.Size(shp).numel())
                 grads.append(flat[o:o + n].reshape(shp)); o += n
+        if ctx.layout:                                      # gradients back into the layout of the plane parameters
+            g_grid = triplane_relayout(g_grid, False)
         return (None, None, None, None, None, None, None, None, *g_grid, *grads)
 
 

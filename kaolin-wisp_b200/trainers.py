@@ -99,6 +99,7 @@ class MultiviewStep:
         self.loss_buf, self.absmax = self._scalars[0:1], self._scalars[1:2]
         self.scale = torch.ones(1, dtype=torch.float32, device=dev)
         self.last_stage = {}
+        self._cl = None                                                        # triplanar planes: channel-last copies + gradient accumulators
 
     # ---- helpers -------------------------------------------------------------------------------------------------------
     def _world(self) -> int:
@@ -147,8 +148,15 @@ class MultiviewStep:
         precision = self._precision()
         gt = [t.data for t in self.grid]
         g_used = self.g_grid
+        layout = 1 if ops.triplane_wants_channel_last(spec) else 0
+        if layout:          # channel-last copies of the planes for this step; their gradients are accumulated channel-last and converted back below
+            if self._cl is None:
+                self._cl = ([torch.empty((t.shape[2], t.shape[3], t.shape[1]), dtype=torch.float32, device=dev) for t in gt],
+                            [torch.zeros((t.shape[2], t.shape[3], t.shape[1]), dtype=torch.float32, device=dev) for t in gt])
+            gt = ops.triplane_relayout(gt, True, out=self._cl[0])
+            g_used = self._cl[1]
         oct, trinkets = ops._grid_context(nef, spec)
-        desc, keep = spec.desc(gt, self.dens_flat, self.col_flat, oct, trinkets, grads=g_used)
+        desc, keep = spec.desc(gt, self.dens_flat, self.col_flat, oct, trinkets, grads=g_used, layout=layout)
         blob = torch.empty(int(L.wb_rf_param_blob_floats(C.byref(desc), C.c_int32(precision))), dtype=torch.float32, device=dev)
         A.check(L.wb_rf_pack_params(C.byref(desc), C.c_int32(precision), A.ptr(blob), A.stream()))
         rec_t, rec_delta, rec_ray = ops.march_fill_records(ms, dev)
@@ -187,6 +195,8 @@ class MultiviewStep:
             with ops._stage("shade_bwd"):      # precision 1: decoder backward + table scatter in one kernel where the shape allows
                 A.check(L.wb_rf_shade_bwd(C.byref(desc), A.ptr(blob), C.c_int32(precision), C.byref(ms.rays), A.ptr(rec_t), A.ptr(rec_ray), C.c_int64(S), A.ptr(g_sh),
                                           A.ptr(self.scale) if precision == 1 else None, A.ptr(feat), A.ptr(ws), A.ptr(g_table), A.ptr(self.g_dens), A.ptr(self.g_col), A.stream()))
+        if layout:          # -> self.g_grid (reference layout, overwritten with the accumulated channel-last gradients)
+            ops.triplane_relayout(g_used, False, out=self.g_grid)
         self.last_rgb, self.last_alpha, self.last_hit = rgb, alpha, hit
         loss = self.loss_buf.clone()
         if world > 1:
@@ -195,7 +205,14 @@ class MultiviewStep:
         if update:
             with ops._stage("adam"):
                 self.opt.step(self.g_grid + [self.g_dens, self.g_col] + self.g_rest, grad_scale=1.0, zero_grad=zero_grad)
+            if layout and zero_grad:
+                torch._foreach_zero_(g_used)
         return loss[0]
+
+    def zero_grads(self) -> None:
+        """Clear every gradient accumulator (after a step(update=False) whose gradients were only inspected)."""
+        for g in self.g_grid + [self.g_dens, self.g_col] + self.g_rest + (self._cl[1] if self._cl is not None else []):
+            g.zero_()
 
     def _all_reduce(self, loss):
         """Gradient exchange of data-parallel training: sum over ranks (the mean's 1/world is already in the loss
