@@ -181,6 +181,12 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            # nvidia-smi's start-up (driver enumeration, seconds on a fresh box) stalls kernel launches of this process for tens of ms:
+            # wait for its first row here, outside every timed region (seen as a 14 ms "step" in a 1.5 ms-per-step configuration)
+            t0 = time.perf_counter()
+            while not self.rows and time.perf_counter() - t0 < 8.0 and self.proc.poll() is None:
+                time.sleep(0.02)
+            self.idle_rows = len(self.rows)
         except Exception:
             self.proc = None
 
@@ -195,6 +201,8 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except Exception:
                 pass
+        if len(self.rows) > getattr(self, "idle_rows", 0):       # rows read before the warm-up started describe an idle GPU
+            self.rows = self.rows[self.idle_rows:]
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
