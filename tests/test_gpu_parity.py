@@ -1041,3 +1041,15 @@ def test_full_frame_properties(W):
     for a, b in zip(grads[0], grads[1]):
         assert float((2 * a - b).abs().max()) <= 2e-2 * float(b.abs().max()) + 1e-12
     assert float(grads[0][0][int(grid.codebook.begin_idxes[15]):].abs().sum()) == 0.0      # the zeroed last LOD receives no gradient
+
+
+def test_triplane_relayout_roundtrip(W):
+    """wb_triplane_relayout: [1, C, H, W] -> [H, W, C] is torch's permute, and back is the identity (C = 4 vector path and C = 3 scalar path)."""
+    for Cc in (4, 3):
+        planes = [torch.randn(1, Cc, n, n, device="cuda") for n in (5, 17, 33, 65, 9, 129)]
+        cl = W.ops.triplane_relayout(planes, True)
+        for p, q in zip(planes, cl):
+            assert q.shape == (p.shape[2], p.shape[3], Cc) and torch.equal(q, p[0].permute(1, 2, 0).contiguous())
+        back = W.ops.triplane_relayout(cl, False)
+        for p, q in zip(planes, back):
+            assert torch.equal(p, q)

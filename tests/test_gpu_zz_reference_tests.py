@@ -162,3 +162,48 @@ def test_multiview_step_matches_autograd_step(precision):
     assert len(tr_b._pending) == 0 and torch.isfinite(loss_c) and float(ms.g_grid[0].abs().max()) == 0.0
     # decoder parameters are views of the flat buffers the optimiser updates
     assert nef_b.decoder_density.layers[0].weight.data_ptr() == ms.dens_flat.data_ptr()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", [0, 1])
+def test_multiview_step_on_triplanar_grid_channel_last(precision):
+    """MultiviewStep over a TriplanarGrid(feature_dim=4): the kernels read channel-last copies of the planes and accumulate
+    channel-last gradients (wb_nef_desc.grid_layout = 1); what the step leaves in g_grid is in the layout of the reference's
+    plane parameters and equals the autograd route's .grad; two accumulating steps double it; the optimiser clears everything."""
+    import wisp_b200 as W
+    from oracle import oracle as O
+    torch.manual_seed(4)
+    o, d = O.look_at_rays([-3.0, 0.65, -3.0], [0, 0, 0], 32, 32, 30.0)
+    rays = W.Rays(torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda(), 0.0, 10.0)
+    tgt = torch.sigmoid(torch.randn(o.shape[0], 3, generator=torch.Generator().manual_seed(3))).cuda()
+
+    def make():
+        torch.manual_seed(7)
+        grid = W.TriplanarGrid(W.AxisAlignedBBoxAS(device="cuda"), feature_dim=4, log_base_resolution=4, num_lods=3, multiscale_type='sum', feature_std=0.3)
+        nef = W.NeuralRadianceField(grid, view_embedder='positional', view_multires=4, hidden_dim=64, num_layers=1, bias=True).cuda()
+        tr = W.PackedRFTracer('voxel', 32, bg_color=(1.0, 1.0, 1.0)); tr.precision = precision
+        return nef, tr
+    nef_a, tr_a = make(); tr_a.seed = 5
+    rb = W.Pipeline(nef_a, tr_a)(rays=rays, channels=["rgb"])
+    loss_a = torch.nn.functional.smooth_l1_loss(rb.rgb, tgt, reduction='none').mean()
+    loss_a.backward()
+    ga = [p.grad.detach().clone() for p in W.ops.grid_tensors(nef_a, W.ops.nef_spec(nef_a, None))]
+    nef_b, tr_b = make()
+    ms = W.MultiviewStep(W.Pipeline(nef_b, tr_b), lr=1e-3, eps=1e-8)
+    assert W.ops.triplane_wants_channel_last(ms.spec)
+    loss_b = ms.step(rays, tgt, seed=5, zero_grad=False, update=False)
+    assert abs(float(loss_b) - float(loss_a)) <= (1e-6 if precision == 0 else 1e-5) * max(1.0, abs(float(loss_a)))
+    gtol = 2e-3 if precision == 0 else 0.2          # fp16 'sum' grids: see test_fused_triplanar_octree_nerf
+    for mine, ref in zip(ms.g_grid, ga):
+        assert mine.shape == ref.shape
+        assert float((mine - ref).abs().max()) <= gtol * float(ref.abs().max())
+    first = [g.clone() for g in ms.g_grid]
+    ms.step(rays, tgt, seed=5, zero_grad=False, update=False)                # accumulates: exactly twice the first gradient at precision 0
+    if precision == 0:
+        for g2, g1 in zip(ms.g_grid, first):
+            assert float((g2 - 2 * g1).abs().max()) <= 1e-4 * float(g1.abs().max())
+    ms.zero_grads()
+    before = [p.detach().clone() for p in ms.grid]
+    ms.step(rays, tgt, seed=5)                                               # a real update: planes move, every accumulator is cleared
+    assert all(float((p.detach() - b).abs().max()) > 0 for p, b in zip(ms.grid, before))
+    assert all(float(g.abs().max()) == 0.0 for g in ms.g_grid + ms._cl[1])
