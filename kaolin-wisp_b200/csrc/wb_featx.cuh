@@ -116,12 +116,17 @@ __device__ __forceinline__ void wb_featx_gather(const WbGridX& x, float cx, floa
                 const WbBilinear b = wb_tp_setup(cx, cy, cz, p, size);
                 const float* pl = x.ptr[l * 3 + p];
                 if (x.chlast) {                                  // one 16-byte load per texel
+                    // The four loads are unconditional (out-of-range neighbours fold onto the cell's own texel, where their weight is
+                    // exactly 0: x0 == size-1 only after the clip, i.e. tx == 0), so that the loads of all planes and LODs can be in
+                    // flight together instead of waiting behind the bounds branches; v + a*0 == v for the finite plane values.
                     const float4* t4 = reinterpret_cast<const float4*>(pl);
-                    float4 a = __ldg(t4 + b.o00);
-                    float v0 = a.x * b.nw, v1 = a.y * b.nw, v2 = a.z * b.nw, v3 = a.w * b.nw;
-                    if (b.bx1) { a = __ldg(t4 + b.o01); v0 += a.x * b.ne; v1 += a.y * b.ne; v2 += a.z * b.ne; v3 += a.w * b.ne; }
-                    if (b.by1) { a = __ldg(t4 + b.o10); v0 += a.x * b.sw; v1 += a.y * b.sw; v2 += a.z * b.sw; v3 += a.w * b.sw; }
-                    if (b.bx1 && b.by1) { a = __ldg(t4 + b.o11); v0 += a.x * b.se; v1 += a.y * b.se; v2 += a.z * b.se; v3 += a.w * b.se; }
+                    const float4 a00 = __ldg(t4 + b.o00), a01 = __ldg(t4 + (b.bx1 ? b.o01 : b.o00));
+                    const float4 a10 = __ldg(t4 + (b.by1 ? b.o10 : b.o00)), a11 = __ldg(t4 + ((b.bx1 && b.by1) ? b.o11 : b.o00));
+                    const float ne = b.bx1 ? b.ne : 0.0f, sw = b.by1 ? b.sw : 0.0f, se = (b.bx1 && b.by1) ? b.se : 0.0f;
+                    float v0 = a00.x * b.nw, v1 = a00.y * b.nw, v2 = a00.z * b.nw, v3 = a00.w * b.nw;
+                    v0 += a01.x * ne; v1 += a01.y * ne; v2 += a01.z * ne; v3 += a01.w * ne;
+                    v0 += a10.x * sw; v1 += a10.y * sw; v2 += a10.z * sw; v3 += a10.w * sw;
+                    v0 += a11.x * se; v1 += a11.y * se; v2 += a11.z * se; v3 += a11.w * se;
                     if (x.sum) { acc[p][0] += v0; acc[p][1] += v1; acc[p][2] += v2; acc[p][3] += v3; }
                     else { const int f = (l * 3 + p) * 4; emit(f, v0); emit(f + 1, v1); emit(f + 2, v2); emit(f + 3, v3); }
                     continue;

@@ -1150,6 +1150,11 @@ wb_featx_scatter_kernel(WbGridX gx, TcIn in, const __half* __restrict__ dfeat, i
             continue;
         }
         const int C = gx.C;
+        float gsum[3][4];                                         // 'sum' grids: every LOD receives the same dL/dfeat -> loaded once per sample
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) gsum[p][c] = (gx.sum && valid && c < C) ? grad(p * C + c) : 0.0f;
         for (int l = 0; l < gx.nl; ++l) {
             const int size = gx.res[l] + 1; const int64_t hw = (int64_t)size * size;
 #pragma unroll
@@ -1158,7 +1163,7 @@ wb_featx_scatter_kernel(WbGridX gx, TcIn in, const __half* __restrict__ dfeat, i
                 float v[4][4];                                    // [texel nw, ne, sw, se][channel]
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const float g = (valid && c < C) ? grad(gx.sum ? p * C + c : (l * 3 + p) * C + c) : 0.0f;
+                    const float g = gx.sum ? gsum[p][c] : ((valid && c < C) ? grad((l * 3 + p) * C + c) : 0.0f);
                     v[0][c] = g * b.nw; v[1][c] = g * b.ne; v[2][c] = g * b.sw; v[3][c] = g * b.se;
                 }
                 const int key = valid ? b.o00 : -1 - lane;        // invalid lanes never merge
