@@ -777,6 +777,7 @@ static int tc_knob_fwd_tmema() { static const int v = tc_env_int("WB_TC_FWD_TMEM
 static int tc_knob_fwd_pipe() { static const int v = tc_env_int("WB_TC_FWD_PIPE", 0); return v; }
 static int tc_knob_fwd_ctas() { static const int v = tc_env_int("WB_TC_FWD_CTAS", 3); return v; }
 static int tc_knob_fuse_scatter_wide() { static const int v = tc_env_int("WB_TC_FUSE_SCATTER_WIDE", 0); return v; }
+static int64_t tc_knob_wide_min_s() { static const int v = tc_env_int("WB_TC_WIDE_MIN_S", 1 << 20); return v; }      // below this many samples the chunked schedule is not worth its launches
 static int tc_knob_wide_chunks() { static const int v = tc_env_int("WB_TC_WIDE_CHUNKS", 4); return v; }       // 1: no overlap of decoder backward and table scatter
 static int tc_knob_scatter_lpb() { static const int v = tc_env_int("WB_TC_SCATTER_LPB", 16); return v; }
 static int tc_knob_scatter_idx2() { static const int v = tc_env_int("WB_TC_SCATTER_IDX2", 1); return v; }
@@ -1338,7 +1339,7 @@ int wb_tc_shade_bwd(const wb_nef_desc* nef, const float* blob, const wb_rays* ra
         WbTc m; TcB3Plan plan;
         int chunks = tc_knob_wide_chunks(); if (chunks > 16) chunks = 16;
         TcSide* side = nullptr;
-        if (chunks > 1 && S >= ((int64_t)1 << 20) && nef->grid_kind == 0 && grad_table && wb_tc_make(nef, true, &m) == WB_OK && !m.fits2 &&
+        if (chunks > 1 && S >= tc_knob_wide_min_s() && nef->grid_kind == 0 && grad_table && wb_tc_make(nef, true, &m) == WB_OK && !m.fits2 &&
             tc_b3_plan(m, &plan) && plan.groups == 1 && !tc_knob_fuse_scatter_wide() && (side = tc_side_stream()) != nullptr) {
             const int64_t per = ((S + chunks - 1) / chunks + TC_ROWS - 1) / TC_ROWS * TC_ROWS;
             int rc = WB_OK, c = 0;

@@ -37,11 +37,13 @@ def test_extra_channels():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("knob", ["WB_TC_FWD_TMEMA=0", "WB_TC_BWD_GROUPS=2"])
+@pytest.mark.parametrize("knob", ["WB_TC_FWD_TMEMA=0", "WB_TC_BWD_GROUPS=2", "WB_TC_WIDE_MIN_S=1000:128", "WB_TC_FUSE_SCATTER_WIDE=1:128"])
 def test_kernel_variant_matches_default(knob):
     """Default kernels (TMEM-A forward, three-group decoder backward: validated and faster on B200 in round 2) against the
     round-1 kernels they replaced, which stay selectable through the knobs.  The knobs are read once per process, hence the
-    subprocesses: same samples, rgb within fp16 round-off of each other, gradients within the precision-1 tolerance."""
+    subprocesses: same samples, rgb within fp16 round-off of each other, gradients within the precision-1 tolerance.
+    ':128' runs the case with hidden_dim = 128 (the one-group backward): its chunked schedule (decoder backward of chunk c+1 beside
+    the table scatter of chunk c, normally only above 2^20 samples) against the single launch pair, and its fused-scatter variant."""
     import os
     import subprocess
     import sys
@@ -53,7 +55,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import wisp_b200 as W
 from oracle import oracle as O
 from gpu_util import nef_from_oracle, packed_grads
-onef = O.make_nef(feature_std=0.2, seed=3)
+onef = O.make_nef(feature_std=0.2, seed=3, hidden_dim=int(os.environ.get("WB_TEST_HIDDEN", "64")))
 spc = O.octree_to_spc(O.points_to_octree(O.lego_like_points(6), 6))
 o, d = O.look_at_rays([-3.0, 0.65, -3.0], [0, 0, 0], 48, 48, 30.0)
 nef, blas = nef_from_oracle(onef, spc)
@@ -65,12 +67,15 @@ gt, gd, gc = packed_grads(nef)
 np.savez(OUT, rgb=rb.rgb.detach().cpu().numpy(), gt=gt, gd=gd, gc=gc, n=tracer.get_prev_num_samples())
 '''
     import tempfile
+    knob, _, hidden = knob.partition(":")
     name, value = knob.split("=")
     outs = []
     tmp = tempfile.mkdtemp(prefix="wb_variant_")          # NOT under gpurun_out/: two 42 MB gradient tables per run would blow its 64 MiB cap
     for on in (False, True):
         out = os.path.join(tmp, f"exp_{name}_{int(on)}.npz")
         env = dict(os.environ)
+        if hidden:
+            env["WB_TEST_HIDDEN"] = hidden
         if on:
             env[name] = value
         r = subprocess.run([sys.executable, "-c", code.replace("ROOT", repr(root)).replace("OUT", repr(out))], env=env, capture_output=True, text=True, timeout=600)
