@@ -463,6 +463,12 @@ def run_ours(args):
         tr = traffic.get(kern)
         rooflines.append({"bound": bound, "kernel": kern, "achieved": ach, "peak": peak, "unit": u, "frac": ach / peak,
                           "traffic": tr, "kernel_ms": mean_ms[st_name], "algorithmic_per_sample": f"{per} {unit}", "samples_per_launch": S_step})
+        kshort = kern.split("<")[0].split(" ")[0]
+        if traffic.get(kshort + "__l2_pct") is not None:       # the table is L2-resident: where the launch sits against the L2 roof (ncu, same command)
+            rooflines[-1]["l2_frac"] = traffic[kshort + "__l2_pct"] / 100.0
+            rooflines[-1]["l2_source"] = f"ncu lts__throughput.avg.pct_of_peak_sustained_elapsed, profiles/{traffic.get('tag', '')}_{kshort}.txt"
+            if tr is None:
+                rooflines[-1]["traffic"] = traffic.get(kshort)
         if bound == "hbm":
             rooflines[-1]["note"] = "algorithmic table bytes; the table is L2-resident, so this is HBM-equivalent and can exceed 1 (see `traffic`)"
     if args.precision == 1 and "shade_bwd" in mean_ms:   # the same launch against the tensor roof: recompute + data grad + weight grad of both decoders
@@ -569,6 +575,20 @@ def _peaks():
         return float(pk.get("hbm_gbs", 6650.0)), "MEASURED_PEAKS.json (measured)"
     except Exception:
         return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
+def _ncu_facts(roof: dict, key: str) -> dict:
+    """DRAM bytes per launch and L2 utilisation of kernel `key` from the last ncu capture of the same command (profiles/traffic.json)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return roof
+    if t.get(key) is not None:
+        roof["traffic"] = t[key]
+    if t.get(key + "__l2_pct") is not None:
+        roof["l2_frac"] = t[key + "__l2_pct"] / 100.0
+        roof["l2_source"] = f"ncu lts__throughput.avg.pct_of_peak_sustained_elapsed, profiles/{t.get('tag', '')}_{key}.txt"
+    return roof
 
 
 def _finish_line(args, torch, dist, world, rank, dev, line_fn, ms, ms_e2e, extra):
@@ -693,9 +713,10 @@ def run_config3(args):
                 "e2e": {"value": R * args.steps * world / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": R * 24, "d2h_bytes_per_step": R * 13,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks,
-                "roofline": {"bound": "hbm", "kernel": "wb_sdf_trace_kernel", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                "roofline": _ncu_facts({"bound": "hbm", "kernel": "wb_sdf_trace_kernel", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
                              "kernel_ms": t_trace, "algorithmic_per_eval": f"{per_eval} B", "evals_per_launch": ev / (args.steps * world), "peak_source": src,
                              "note": "HBM-equivalent: the feature levels are L2 resident; the kernel is a latency chain of <= 33 dependent field evaluations per ray"},
+                                       "wb_sdf_trace_kernel"),
                 "stage_ms": {k: float(np.mean(v)) for k, v in stage.items()}, "hits_last_frame": hits, "field_evals_per_frame": ev / (args.steps * world),
                 "cpu_baseline": cpu_base, "parity": parity}
     _finish_line(args, torch, dist, world, rank, dev, line, ms, ms_e2e, [n_evals])
@@ -830,6 +851,7 @@ def run_config4(args):
         if roof:
             roof["peak_source"] = src
             roof["note"] = "HBM-equivalent: the planes (12.6 MB) are L2 resident"
+            _ncu_facts(roof, "wb_shade_fwd_tc_kernel_cfg4" if roof["kernel"].startswith("wb_shade_fwd_tc") else "wb_featx_scatter_kernel_cfg4")
         return {"metric": "rays/sec (fwd+bwd) 800^2 TriplanarGrid NeRF (BASELINE config 4)", "value": R * args.steps * world / (ms * 1e-3), "unit": "rays/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32" if args.precision == 0 else "f16(tensor)+f32 accumulate", "data": "synthetic",

@@ -54,6 +54,11 @@ def main(tag):
                     traffic[name] = float(v[ir].replace(',', '')) * UNIT[units[ir]] + float(v[iw].replace(',', '')) * UNIT[units[iw]]
                 except (ValueError, KeyError):
                     pass
+                try:     # L2 utilisation of the launch as ncu reports it -> `l2_frac` of bench.py's roofline entries
+                    il = hdr.index('lts__throughput.avg.pct_of_peak_sustained_elapsed')
+                    traffic[name + "__l2_pct"] = float(v[il].replace(',', ''))
+                except (ValueError, KeyError):
+                    pass
                 for w in WANT:
                     if w in hdr:
                         f.write(f"  {w:72s} {v[hdr.index(w)]:>18s} {units[hdr.index(w)]}\n")
