@@ -4,6 +4,7 @@ wisp_b200.install()) call.  Each one names the reference operator it stands in f
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -36,7 +37,7 @@ class _stage:
 # --------------------------------------------------------------------------------------------------------------
 # octree handle: the SPC tensors the reference's OctreeAS keeps (octree_as.py:58-62) + the optional dense bitmask
 # --------------------------------------------------------------------------------------------------------------
-COARSE_LEVEL = 5      # level of the dilated mask the marcher uses to skip empty 32-candidate words (0 disables it)
+COARSE_LEVEL = int(os.environ.get("WB_COARSE_LEVEL", "6"))      # level of the dilated mask the marcher uses to skip empty 32-candidate words (0 disables it)
 
 
 @dataclass
@@ -78,7 +79,7 @@ class OctreeTensors:
         A.check(A.lib().wb_octree_build_bits(A.ptr(lvl), C.c_int64(cnt), C.c_int32(level), A.ptr(bits), A.stream()))
         self.bits, self.bits_level = bits, level
         self.coarse, self.coarse_level = None, 0
-        cl = min(level - 2, COARSE_LEVEL)
+        cl = min(level - 1, COARSE_LEVEL)
         if cl >= 2 and cnt > 0:
             coarse = torch.zeros((8 ** cl + 31) // 32, dtype=torch.int32, device=self.octree.device)
             A.check(A.lib().wb_octree_build_coarse(A.ptr(lvl), C.c_int64(cnt), C.c_int32(level), C.c_int32(cl), A.ptr(coarse), A.stream()))

@@ -119,7 +119,7 @@ def test_raymarch_seeded_vs_oracle(W, n, level, pernear):
     assert np.array_equal(mr.boundary.cpu().numpy(), ref["boundary"])
 
 
-@pytest.mark.parametrize("level,coarse,n", [(7, 5, 2048), (7, 3, 512), (6, 2, 100), (5, 3, 33)])
+@pytest.mark.parametrize("level,coarse,n", [(7, 6, 2048), (7, 5, 2048), (7, 3, 512), (6, 2, 100), (5, 3, 33), (5, 4, 64)])
 def test_raymarch_word_skipping_is_exact(W, level, coarse, n):
     """The dilated coarse mask only skips 32-candidate words that cannot hold a sample: hit masks are identical with and
     without it, for camera rays, rays starting inside the volume, axis-aligned / grazing rays and unnormalised directions."""
