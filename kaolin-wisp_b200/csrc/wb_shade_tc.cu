@@ -807,19 +807,21 @@ int wb_tc_shade_fwd(const wb_nef_desc* nef, const float* blob, const wb_rays* ra
     // profiles/README.md).  The register bound of the instantiation must match, or the hardware silently runs fewer.
     int per_sm = (227 * 1024) / (m.smem_bytes + 4096); per_sm = max(1, min(per_sm, 512 / m.tmem_cols));
     per_sm = max(2, min(min(per_sm, 4), tc_knob_fwd_ctas()));
-    if (gx.kind != 0) per_sm = 2;                   // the generic grids keep more state per thread: 128 registers, 2 CTAs per SM
+    // the generic grids keep more state per thread.  Triplanar (12 planes x 4 texel loads in flight): 3 CTAs per SM at 80 registers beat 2 at 128
+    // despite 144 B of spills (config 4 forward 105 -> 88 ms measured); the octree gather (up to 32 accumulators) stays at 2
+    if (gx.kind != 0) per_sm = max(2, min(min(per_sm, 4), tc_env_int("WB_TC_GX_CTAS", gx.kind == 1 ? 3 : 2)));
     const bool pipe = ta && tc_knob_fwd_pipe() != 0 && per_sm <= 3;
-    auto kern = gx.kind != 0 ? wb_shade_fwd_tc_kernel<2, false, true>
+    auto kern = gx.kind != 0 ? (per_sm == 4 ? wb_shade_fwd_tc_kernel<4, false, true> : per_sm == 3 ? wb_shade_fwd_tc_kernel<3, false, true> : wb_shade_fwd_tc_kernel<2, false, true>)
               : pipe ? (per_sm == 2 ? wb_shade_fwd_tc_kernel<2, true, false, true> : wb_shade_fwd_tc_kernel<3, true, false, true>)
               : ta ? (per_sm == 2 ? wb_shade_fwd_tc_kernel<2, true> : per_sm == 3 ? wb_shade_fwd_tc_kernel<3, true> : wb_shade_fwd_tc_kernel<4, true>)
                    : (per_sm == 2 ? wb_shade_fwd_tc_kernel<2, false> : per_sm == 3 ? wb_shade_fwd_tc_kernel<3, false> : wb_shade_fwd_tc_kernel<4, false>);
     {   // function attributes are driver calls that can wait behind other driver work (e.g. an NVML poll): set them once, not per launch
-        static int64_t done_for[16] = { -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1 };
-        if (done_for[gx.kind != 0 ? 9 : pipe ? 10 + per_sm : per_sm + (ta ? 5 : 0)] != WB_ATTR_KEY(m.smem_bytes)) {
+        static int64_t done_for[24] = { -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1 };
+        if (done_for[gx.kind != 0 ? 16 + per_sm : pipe ? 10 + per_sm : per_sm + (ta ? 5 : 0)] != WB_ATTR_KEY(m.smem_bytes)) {
             WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, m.smem_bytes));
             WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          min(100, (per_sm * (m.smem_bytes + 4096) * 100) / (228 * 1024) + 1)));
-            done_for[gx.kind != 0 ? 9 : pipe ? 10 + per_sm : per_sm + (ta ? 5 : 0)] = WB_ATTR_KEY(m.smem_bytes);
+            done_for[gx.kind != 0 ? 16 + per_sm : pipe ? 10 + per_sm : per_sm + (ta ? 5 : 0)] = WB_ATTR_KEY(m.smem_bytes);
         }
     }
     const int64_t ntiles = (S + TC_ROWS - 1) / TC_ROWS;
