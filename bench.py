@@ -177,6 +177,8 @@ class ClockSampler:
         self.rows, self.proc, self.index = [], None, index
 
     def start(self):
+        if os.environ.get("WB_BENCH_NO_SAMPLER"):      # diagnostics: is a stall caused by the nvidia-smi poll?
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -660,23 +662,36 @@ def run_config3(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+    # untimed setup: size the per-nugget buffers for the largest nugget count of this run's cameras (as reserve_samples does for the
+    # radiance-field configurations); without it the caching allocator goes to cudaMalloc whenever a camera beats the previous maximum
+    W.ops.reserve_nuggets(max(int(W.ops.raytrace(nef.grid.blas.tensors(), o_, d_, nef.grid.active_lods[-1])[0].shape[0]) for o_, d_ in devr))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     with torch.no_grad():
-        for i in range(args.warmup):
-            pipe(rays=W.Rays(*devr[i], 0.0, 6.0), channels=chans)
+        evals = []
+        for i in range(args.warmup):       # same body as the timed loop (the previous frame's outputs stay alive while the next one renders): the
+            rb = pipe(rays=W.Rays(*devr[i], 0.0, 6.0), channels=chans)       # caching allocator reaches its steady state before the timed region
+            evals.append(tracer.prev_num_evals.clone())
         barrier()
         W.ops.PROFILE = []
         l0 = W._cabi.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         evals, hits = [], 0
-        e0.record()
+        sev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        dev_allocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
+        e0.record(); sev[0].record()
         for k in range(args.steps):
             rb = pipe(rays=W.Rays(*devr[args.warmup + k], 0.0, 6.0), channels=chans)
             evals.append(tracer.prev_num_evals.clone())
+            sev[k + 1].record()
+            if args.trace_host:
+                ms_ = torch.cuda.memory_stats(dev)
+                print("step", k, "device allocs", ms_.get("num_device_alloc", 0), "reserved MB", ms_.get("reserved_bytes.all.current", 0) / 1e6, file=sys.stderr)
         e1.record()
         barrier()
+        step_ms3 = [sev[k].elapsed_time(sev[k + 1]) for k in range(args.steps)]
+        dev_allocs3 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - dev_allocs0
         launches = W._cabi.launch_count() - l0
         prof, W.ops.PROFILE = W.ops.PROFILE, None
         hits = int(rb.hit.sum())
@@ -723,6 +738,7 @@ def run_config3(args):
                              "note": "HBM-equivalent: the feature levels are L2 resident; the kernel is a latency chain of <= 33 dependent field evaluations per ray"},
                                        "wb_sdf_trace_kernel"),
                 "stage_ms": {k: float(np.mean(v)) for k, v in stage.items()}, "hits_last_frame": hits, "field_evals_per_frame": ev / (args.steps * world),
+                "step_ms": step_ms3, "cudaMalloc_calls_in_timed_region": int(dev_allocs3),
                 "cpu_baseline": cpu_base, "parity": parity}
     _finish_line(args, torch, dist, world, rank, dev, line, ms, ms_e2e, [n_evals])
 

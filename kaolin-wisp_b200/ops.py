@@ -233,6 +233,28 @@ def _bucket(S: int) -> int:
     return _CAP_FLOOR
 
 
+_NUG_FLOOR = 0
+
+
+def reserve_nuggets(n: int) -> int:
+    """Pre-size the per-nugget buffers of raytrace() (render loops over many cameras: the largest nugget count of the orbit)."""
+    global _NUG_FLOOR
+    _NUG_FLOOR = max(_NUG_FLOOR, _bucket_raw(int(n)))
+    return _NUG_FLOOR
+
+
+def _empty_n(n: int, tail: tuple, dtype, device):
+    """Per-nugget buffer (raytrace outputs) with its own high-water capacity: the nugget count changes with every camera, and an
+    exact-size torch.empty sent the caching allocator to cudaMalloc inside render loops (2 per frame in bench.py --config 3)."""
+    global _NUG_FLOOR
+    if n <= 0:
+        return torch.empty((0,) + tuple(tail), dtype=dtype, device=device)
+    b = _bucket_raw(n)
+    if b > _NUG_FLOOR:
+        _NUG_FLOOR = _bucket_raw(n + n // 4)
+    return torch.empty((_NUG_FLOOR,) + tuple(tail), dtype=dtype, device=device)[:n]
+
+
 def _empty_s(S: int, tail: tuple, dtype, device):
     """torch.empty((S, *tail)) carved from a bucketed allocation."""
     return torch.empty((_bucket(S),) + tuple(tail), dtype=dtype, device=device)[:S]
@@ -269,6 +291,21 @@ def _scan(counts: torch.Tensor) -> torch.Tensor:
 RAYTRACE_CACHE_K = 24      # nuggets per ray kept by the counting traversal (0: two traversals, wb_raytrace_count + wb_raytrace_fill)
 
 
+_RT_SCRATCH: dict = {}
+
+
+def _raytrace_scratch(nbytes: int, dev) -> torch.Tensor:
+    """The nugget cache of raytrace() (12 B x K per ray, 75 MB for a 512^2 frame) is kept per (device, stream) instead of being
+    allocated per call: returned to the caching allocator between frames, the block was carved up for the frame's output buffers
+    and the next frame went to cudaMalloc for a new one (1-7 ms inside a 1.5 ms render, seen as outliers of bench.py --config 3)."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), int(torch.cuda.current_stream(dev).cuda_stream))
+    buf = _RT_SCRATCH.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _RT_SCRATCH[key] = buf
+    return buf
+
+
 def raytrace(oct: OctreeTensors, origins, dirs, level: int):
     """spc_render.unbatched_raytrace(..., return_depth=True, with_exit=True) (octree_as.py:183-185)
     -> ridx int32 [Ng], pidx int32 [Ng], depth f32 [Ng,2], ray_offsets int64 [R+1]."""
@@ -280,7 +317,7 @@ def raytrace(oct: OctreeTensors, origins, dirs, level: int):
     # one traversal: the count pass caches the first RAYTRACE_CACHE_K nuggets of every ray, the fill copies them (rays with more are
     # traversed again); the cache is scratch (12 B x K per ray) and is skipped for ray counts where it would be unreasonably large
     K = RAYTRACE_CACHE_K if (RAYTRACE_CACHE_K > 0 and R * RAYTRACE_CACHE_K * 12 <= (2 << 30)) else 0
-    cache = torch.empty(int(L.wb_raytrace_cache_bytes(C.c_int64(R), C.c_int32(K))), dtype=torch.uint8, device=dev) if K > 0 else None
+    cache = _raytrace_scratch(int(L.wb_raytrace_cache_bytes(C.c_int64(R), C.c_int32(K))), dev) if K > 0 else None
     with _stage("raytrace_count"):
         if K > 0:
             A.check(L.wb_raytrace_count_cached(C.byref(od), C.c_int32(level), C.byref(rays), A.ptr(counts), A.ptr(cache), C.c_int32(K), A.stream()))
@@ -288,8 +325,8 @@ def raytrace(oct: OctreeTensors, origins, dirs, level: int):
             A.check(L.wb_raytrace_count(C.byref(od), C.c_int32(level), C.byref(rays), A.ptr(counts), A.stream()))
     offsets = _scan(counts)
     Ng = int(offsets[-1].item())
-    ridx = torch.empty(Ng, dtype=torch.int32, device=dev); pidx = torch.empty(Ng, dtype=torch.int32, device=dev)
-    depth = torch.empty((Ng, 2), dtype=torch.float32, device=dev)
+    ridx = _empty_n(Ng, (), torch.int32, dev); pidx = _empty_n(Ng, (), torch.int32, dev)
+    depth = _empty_n(Ng, (2,), torch.float32, dev)
     if Ng > 0:
         with _stage("raytrace_fill"):
             if K > 0:
