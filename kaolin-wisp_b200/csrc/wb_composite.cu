@@ -8,11 +8,12 @@
 #include "wb_common.cuh"
 
 constexpr int WB_COMP_THREADS = 256;
+constexpr int WB_COMP_BATCH = 4;        // rays whose first chunk is in flight together (per warp)
 
 // A warp owns 32 CONSECUTIVE rays: lane i reads the sample range of ray r0 + i (one coalesced load instead of a dependent broadcast load
 // per ray), rays without samples are finished by their lane alone, the others are composited one after the other by the whole warp
 // (lane = sample, warp-shuffle scan with a running carry); every lane then writes its own ray's outputs (coalesced).
-__global__ void __launch_bounds__(WB_COMP_THREADS, 5)
+__global__ void __launch_bounds__(WB_COMP_THREADS, 4)
 wb_composite_fwd_kernel(const float4* __restrict__ shaded, const float* __restrict__ depth, const float* __restrict__ deltas,
                         const int64_t* __restrict__ offsets, int64_t R, float bgr, float bgg, float bgb,
                         float* __restrict__ rgb, float* __restrict__ depth_out, float* __restrict__ alpha, uint8_t* __restrict__ hit)
@@ -25,41 +26,44 @@ wb_composite_fwd_kernel(const float4* __restrict__ shaded, const float* __restri
         const int64_t mb = rm < R ? __ldg(offsets + rm) : 0, me = rm < R ? __ldg(offsets + rm + 1) : 0;
         float o_r = bgr, o_g = bgg, o_b = bgb, o_d = 0.0f, o_a = 0.0f;           // rgb = zeros + bg for rays without samples (:143)
         uint32_t todo = __ballot_sync(0xffffffffu, me > mb);
-        // the first chunk of the NEXT ray is loaded before the current ray is composited: the kernel is a chain of dependent
-        // DRAM-latency loads per warp (ncu r02u: long_scoreboard 9.4 per issue), one ray's samples after the other
-        int jn = todo ? __ffs(todo) - 1 : 0;
-        int64_t bn = 0, en = 0; float4 shn = make_float4(0, 0, 0, 0); float dln = 0.0f, tn = 0.0f;
-        if (todo) {
-            bn = __shfl_sync(0xffffffffu, mb, jn); en = __shfl_sync(0xffffffffu, me, jn);
-            if (bn + lane < en) { shn = __ldg(shaded + bn + lane); dln = __ldg(deltas + bn + lane); tn = __ldg(depth + bn + lane); }
-        }
+        // Rays are taken in batches of WB_COMP_BATCH: the first 32-sample chunk of every ray of the batch is requested before any of them is
+        // composited, so four DRAM-latency loads overlap instead of one ray's samples waiting after the other (the kernel is a chain of
+        // dependent loads per warp: ncu r02u long_scoreboard 9.4 per issue).  The arithmetic of a ray is unchanged.
         while (todo) {
-            const int j = jn; todo &= todo - 1;
-            const int64_t b = bn, e = en;
-            float4 sh = shn; float dl = dln, t = tn;
-            if (todo) {
-                jn = __ffs(todo) - 1;
-                bn = __shfl_sync(0xffffffffu, mb, jn); en = __shfl_sync(0xffffffffu, me, jn);
-                shn = make_float4(0, 0, 0, 0); dln = 0.0f; tn = 0.0f;
-                if (bn + lane < en) { shn = __ldg(shaded + bn + lane); dln = __ldg(deltas + bn + lane); tn = __ldg(depth + bn + lane); }
-            }
-            float cr = 0, cg = 0, cb = 0, dd = 0, aa = 0, carry = 0;
-            for (int64_t k0 = b; k0 < e; k0 += 32) {
-                const int64_t k = k0 + lane;
-                if (k0 != b) {
-                    sh = make_float4(0, 0, 0, 0); dl = 0.0f; t = 0.0f;
-                    if (k < e) { sh = __ldg(shaded + k); dl = __ldg(deltas + k); t = __ldg(depth + k); }
+            int js[WB_COMP_BATCH]; float4 shs[WB_COMP_BATCH]; float dls[WB_COMP_BATCH], ts[WB_COMP_BATCH];
+#pragma unroll
+            for (int q = 0; q < WB_COMP_BATCH; ++q) {
+                js[q] = -1; shs[q] = make_float4(0, 0, 0, 0); dls[q] = 0.0f; ts[q] = 0.0f;
+                if (todo) {
+                    js[q] = __ffs(todo) - 1; todo &= todo - 1;
+                    const int64_t b = __shfl_sync(0xffffffffu, mb, js[q]), e = __shfl_sync(0xffffffffu, me, js[q]);
+                    if (b + lane < e) { shs[q] = __ldg(shaded + b + lane); dls[q] = __ldg(deltas + b + lane); ts[q] = __ldg(depth + b + lane); }
                 }
-                const float tau = (k < e) ? sh.w * dl : 0.0f;
-                const float incl = wb_warp_incl_scan(tau, lane);
-                const float T = expf(-(carry + (incl - tau)));
-                const float w = (k < e) ? T * (1.0f - expf(-tau)) : 0.0f;
-                cr = fmaf(w, sh.x, cr); cg = fmaf(w, sh.y, cg); cb = fmaf(w, sh.z, cb); dd = fmaf(w, t, dd); aa += w;
-                carry += __shfl_sync(0xffffffffu, incl, 31);
             }
-            cr = wb_warp_sum(cr); cg = wb_warp_sum(cg); cb = wb_warp_sum(cb); dd = wb_warp_sum(dd); aa = wb_warp_sum(aa);
-            if (lane == j) {     // rgb[ridx_hit] = bg*(1-alpha) + ray_colors (:165)
-                o_r = bgr * (1.0f - aa) + cr; o_g = bgg * (1.0f - aa) + cg; o_b = bgb * (1.0f - aa) + cb; o_d = dd; o_a = aa;
+#pragma unroll
+            for (int q = 0; q < WB_COMP_BATCH; ++q) {
+                if (js[q] < 0) continue;                             // warp-uniform
+                const int j = js[q];
+                const int64_t b = __shfl_sync(0xffffffffu, mb, j), e = __shfl_sync(0xffffffffu, me, j);
+                float4 sh = shs[q]; float dl = dls[q], t = ts[q];
+                float cr = 0, cg = 0, cb = 0, dd = 0, aa = 0, carry = 0;
+                for (int64_t k0 = b; k0 < e; k0 += 32) {
+                    const int64_t k = k0 + lane;
+                    if (k0 != b) {
+                        sh = make_float4(0, 0, 0, 0); dl = 0.0f; t = 0.0f;
+                        if (k < e) { sh = __ldg(shaded + k); dl = __ldg(deltas + k); t = __ldg(depth + k); }
+                    }
+                    const float tau = (k < e) ? sh.w * dl : 0.0f;
+                    const float incl = wb_warp_incl_scan(tau, lane);
+                    const float T = expf(-(carry + (incl - tau)));
+                    const float w = (k < e) ? T * (1.0f - expf(-tau)) : 0.0f;
+                    cr = fmaf(w, sh.x, cr); cg = fmaf(w, sh.y, cg); cb = fmaf(w, sh.z, cb); dd = fmaf(w, t, dd); aa += w;
+                    carry += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                cr = wb_warp_sum(cr); cg = wb_warp_sum(cg); cb = wb_warp_sum(cb); dd = wb_warp_sum(dd); aa = wb_warp_sum(aa);
+                if (lane == j) {     // rgb[ridx_hit] = bg*(1-alpha) + ray_colors (:165)
+                    o_r = bgr * (1.0f - aa) + cr; o_g = bgg * (1.0f - aa) + cg; o_b = bgb * (1.0f - aa) + cb; o_d = dd; o_a = aa;
+                }
             }
         }
         if (rm < R) {
@@ -127,80 +131,82 @@ wb_composite_bwd_kernel(const float4* __restrict__ shaded, const float* __restri
             }
         }
         uint32_t todo = __ballot_sync(0xffffffffu, me > mb);
-        int jn = todo ? __ffs(todo) - 1 : 0;                               // next ray's first chunk is in flight while this one is processed
-        int64_t bn = 0, en = 0; float4 shn = make_float4(0, 0, 0, 0); float dln = 0.0f, tn = 0.0f;
-        if (todo) {
-            bn = __shfl_sync(0xffffffffu, mb, jn); en = __shfl_sync(0xffffffffu, me, jn);
-            if (bn + lane < en) { shn = __ldg(shaded + bn + lane); dln = __ldg(deltas + bn + lane); tn = __ldg(depth + bn + lane); }
-        }
-        while (todo) {
-            const int j = jn; todo &= todo - 1;
-            const int64_t b = bn, e = en;
-            const float4 sh0 = shn; const float dl0 = dln, t0 = tn;
-            if (todo) {
-                jn = __ffs(todo) - 1;
-                bn = __shfl_sync(0xffffffffu, mb, jn); en = __shfl_sync(0xffffffffu, me, jn);
-                shn = make_float4(0, 0, 0, 0); dln = 0.0f; tn = 0.0f;
-                if (bn + lane < en) { shn = __ldg(shaded + bn + lane); dln = __ldg(deltas + bn + lane); tn = __ldg(depth + bn + lane); }
-            }
-            const float gr = __shfl_sync(0xffffffffu, mgr, j), gg = __shfl_sync(0xffffffffu, mgg, j), gb = __shfl_sync(0xffffffffu, mgb, j);
-            const float gd = __shfl_sync(0xffffffffu, mgd, j);
-            const float ga = __shfl_sync(0xffffffffu, mga, j) - (gr * bgr + gg * bgg + gb * bgb);
-            if (e - b <= 32) {
-                // the whole ray is in registers: both passes without a second read (same arithmetic as the two-pass form with carry = 0)
-                const int64_t k = b + lane;
-                const bool in = k < e;
-                const float tau = in ? sh0.w * dl0 : 0.0f;
-                const float gk = in ? gr * sh0.x + gg * sh0.y + gb * sh0.z + gd * t0 + ga : 0.0f;
-                const float incl = wb_warp_incl_scan(tau, lane);
-                const float T = expf(-(0.0f + (incl - tau)));
-                const float Tn = expf(-(0.0f + incl));
-                const float w = in ? T * (1.0f - expf(-tau)) : 0.0f;
-                const float G = wb_warp_sum(fmaf(gk, w, 0.0f));
-                const float gw = gk * w;
-                const float gw_incl = wb_warp_incl_scan(gw, lane);
-                const float suffix = G - (0.0f + gw_incl);
-                const float gtau = gk * Tn - suffix;
-                if (in) {
-                    const float4 gs = make_float4(gr * w, gg * w, gb * w, gtau * dl0);
-                    g_shaded[k] = gs;
-                    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(gs.x), fabsf(gs.y)), fmaxf(fabsf(gs.z), fabsf(gs.w))));
+        while (todo) {                                                    // batches of WB_COMP_BATCH rays, first chunks requested together (see the forward)
+            int js[WB_COMP_BATCH]; float4 shs[WB_COMP_BATCH]; float dls[WB_COMP_BATCH], ts[WB_COMP_BATCH];
+#pragma unroll
+            for (int q = 0; q < WB_COMP_BATCH; ++q) {
+                js[q] = -1; shs[q] = make_float4(0, 0, 0, 0); dls[q] = 0.0f; ts[q] = 0.0f;
+                if (todo) {
+                    js[q] = __ffs(todo) - 1; todo &= todo - 1;
+                    const int64_t b = __shfl_sync(0xffffffffu, mb, js[q]), e = __shfl_sync(0xffffffffu, me, js[q]);
+                    if (b + lane < e) { shs[q] = __ldg(shaded + b + lane); dls[q] = __ldg(deltas + b + lane); ts[q] = __ldg(depth + b + lane); }
                 }
-                continue;
             }
-            float G = 0, carry = 0;
-            for (int64_t k0 = b; k0 < e; k0 += 32) {
-                const int64_t k = k0 + lane;
-                float tau = 0, gk = 0; float4 sh = sh0; float dl = dl0, t = t0;
-                if (k0 != b && k < e) { sh = __ldg(shaded + k); dl = __ldg(deltas + k); t = __ldg(depth + k); }
-                if (k < e) { tau = sh.w * dl; gk = gr * sh.x + gg * sh.y + gb * sh.z + gd * t + ga; }
-                const float incl = wb_warp_incl_scan(tau, lane);
-                const float T = expf(-(carry + (incl - tau)));
-                const float w = (k < e) ? T * (1.0f - expf(-tau)) : 0.0f;
-                G = fmaf(gk, w, G);
-                carry += __shfl_sync(0xffffffffu, incl, 31);
-            }
-            G = wb_warp_sum(G);
-            carry = 0; float gw_carry = 0;
-            for (int64_t k0 = b; k0 < e; k0 += 32) {
-                const int64_t k = k0 + lane;
-                float tau = 0, gk = 0, dl = 0; float4 sh = make_float4(0, 0, 0, 0);
-                if (k < e) { sh = __ldg(shaded + k); dl = __ldg(deltas + k); tau = sh.w * dl; gk = gr * sh.x + gg * sh.y + gb * sh.z + gd * __ldg(depth + k) + ga; }
-                const float incl = wb_warp_incl_scan(tau, lane);
-                const float T = expf(-(carry + (incl - tau)));
-                const float Tn = expf(-(carry + incl));                 // T_{k+1}
-                const float w = (k < e) ? T * (1.0f - expf(-tau)) : 0.0f;
-                const float gw = gk * w;
-                const float gw_incl = wb_warp_incl_scan(gw, lane);
-                const float suffix = G - (gw_carry + gw_incl);          // sum_{j>k} g_j w_j
-                const float gtau = gk * Tn - suffix;
-                if (k < e) {
-                    const float4 gs = make_float4(gr * w, gg * w, gb * w, gtau * dl);
-                    g_shaded[k] = gs;
-                    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(gs.x), fabsf(gs.y)), fmaxf(fabsf(gs.z), fabsf(gs.w))));
+#pragma unroll
+            for (int q = 0; q < WB_COMP_BATCH; ++q) {
+                if (js[q] < 0) continue;                                  // warp-uniform
+                const int j = js[q];
+                const int64_t b = __shfl_sync(0xffffffffu, mb, j), e = __shfl_sync(0xffffffffu, me, j);
+                const float4 sh0 = shs[q]; const float dl0 = dls[q], t0 = ts[q];
+                const float gr = __shfl_sync(0xffffffffu, mgr, j), gg = __shfl_sync(0xffffffffu, mgg, j), gb = __shfl_sync(0xffffffffu, mgb, j);
+                const float gd = __shfl_sync(0xffffffffu, mgd, j);
+                const float ga = __shfl_sync(0xffffffffu, mga, j) - (gr * bgr + gg * bgg + gb * bgb);
+                if (e - b <= 32) {
+                    // the whole ray is in registers: both passes without a second read (same arithmetic as the two-pass form with carry = 0)
+                    const int64_t k = b + lane;
+                    const bool in = k < e;
+                    const float tau = in ? sh0.w * dl0 : 0.0f;
+                    const float gk = in ? gr * sh0.x + gg * sh0.y + gb * sh0.z + gd * t0 + ga : 0.0f;
+                    const float incl = wb_warp_incl_scan(tau, lane);
+                    const float T = expf(-(0.0f + (incl - tau)));
+                    const float Tn = expf(-(0.0f + incl));
+                    const float w = in ? T * (1.0f - expf(-tau)) : 0.0f;
+                    const float G = wb_warp_sum(fmaf(gk, w, 0.0f));
+                    const float gw = gk * w;
+                    const float gw_incl = wb_warp_incl_scan(gw, lane);
+                    const float suffix = G - (0.0f + gw_incl);
+                    const float gtau = gk * Tn - suffix;
+                    if (in) {
+                        const float4 gs = make_float4(gr * w, gg * w, gb * w, gtau * dl0);
+                        g_shaded[k] = gs;
+                        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(gs.x), fabsf(gs.y)), fmaxf(fabsf(gs.z), fabsf(gs.w))));
+                    }
+                    continue;
                 }
-                carry += __shfl_sync(0xffffffffu, incl, 31);
-                gw_carry += __shfl_sync(0xffffffffu, gw_incl, 31);
+                float G = 0, carry = 0;
+                for (int64_t k0 = b; k0 < e; k0 += 32) {
+                    const int64_t k = k0 + lane;
+                    float tau = 0, gk = 0; float4 sh = sh0; float dl = dl0, t = t0;
+                    if (k0 != b && k < e) { sh = __ldg(shaded + k); dl = __ldg(deltas + k); t = __ldg(depth + k); }
+                    if (k < e) { tau = sh.w * dl; gk = gr * sh.x + gg * sh.y + gb * sh.z + gd * t + ga; }
+                    const float incl = wb_warp_incl_scan(tau, lane);
+                    const float T = expf(-(carry + (incl - tau)));
+                    const float w = (k < e) ? T * (1.0f - expf(-tau)) : 0.0f;
+                    G = fmaf(gk, w, G);
+                    carry += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                G = wb_warp_sum(G);
+                carry = 0; float gw_carry = 0;
+                for (int64_t k0 = b; k0 < e; k0 += 32) {
+                    const int64_t k = k0 + lane;
+                    float tau = 0, gk = 0, dl = 0; float4 sh = make_float4(0, 0, 0, 0);
+                    if (k < e) { sh = __ldg(shaded + k); dl = __ldg(deltas + k); tau = sh.w * dl; gk = gr * sh.x + gg * sh.y + gb * sh.z + gd * __ldg(depth + k) + ga; }
+                    const float incl = wb_warp_incl_scan(tau, lane);
+                    const float T = expf(-(carry + (incl - tau)));
+                    const float Tn = expf(-(carry + incl));                 // T_{k+1}
+                    const float w = (k < e) ? T * (1.0f - expf(-tau)) : 0.0f;
+                    const float gw = gk * w;
+                    const float gw_incl = wb_warp_incl_scan(gw, lane);
+                    const float suffix = G - (gw_carry + gw_incl);          // sum_{j>k} g_j w_j
+                    const float gtau = gk * Tn - suffix;
+                    if (k < e) {
+                        const float4 gs = make_float4(gr * w, gg * w, gb * w, gtau * dl);
+                        g_shaded[k] = gs;
+                        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(gs.x), fabsf(gs.y)), fmaxf(fabsf(gs.z), fabsf(gs.w))));
+                    }
+                    carry += __shfl_sync(0xffffffffu, incl, 31);
+                    gw_carry += __shfl_sync(0xffffffffu, gw_incl, 31);
+                }
             }
         }
     }
