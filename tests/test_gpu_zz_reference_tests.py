@@ -36,19 +36,7 @@ def test_extra_channels():
     assert gb is not None and torch.isfinite(gb).all()
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("knob", ["WB_TC_FWD_TMEMA=0", "WB_TC_BWD_GROUPS=2", "WB_TC_WIDE_MIN_S=1000:128", "WB_TC_FUSE_SCATTER_WIDE=1:128"])
-def test_kernel_variant_matches_default(knob):
-    """Default kernels (TMEM-A forward, three-group decoder backward: validated and faster on B200 in round 2) against the
-    round-1 kernels they replaced, which stay selectable through the knobs.  The knobs are read once per process, hence the
-    subprocesses: same samples, rgb within fp16 round-off of each other, gradients within the precision-1 tolerance.
-    ':128' runs the case with hidden_dim = 128 (the one-group backward): its chunked schedule (decoder backward of chunk c+1 beside
-    the table scatter of chunk c, normally only above 2^20 samples) against the single launch pair, and its fused-scatter variant."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = r'''
+_VARIANT_CODE = r'''
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -66,23 +54,41 @@ torch.nn.functional.smooth_l1_loss(rb.rgb, tgt).backward()
 gt, gd, gc = packed_grads(nef)
 np.savez(OUT, rgb=rb.rgb.detach().cpu().numpy(), gt=gt, gd=gd, gc=gc, n=tracer.get_prev_num_samples())
 '''
+_VARIANT_DEFAULTS = {}          # hidden width -> outputs of the default kernels (one subprocess per width, shared by the variants)
+
+
+def _run_variant(hidden: str, knobs: dict):
+    import os
+    import subprocess
+    import sys
     import tempfile
-    knob, _, hidden = knob.partition(":")
-    name, value = knob.split("=")
-    outs = []
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     tmp = tempfile.mkdtemp(prefix="wb_variant_")          # NOT under gpurun_out/: two 42 MB gradient tables per run would blow its 64 MiB cap
-    for on in (False, True):
-        out = os.path.join(tmp, f"exp_{name}_{int(on)}.npz")
-        env = dict(os.environ)
-        if hidden:
-            env["WB_TEST_HIDDEN"] = hidden
-        if on:
-            env[name] = value
-        r = subprocess.run([sys.executable, "-c", code.replace("ROOT", repr(root)).replace("OUT", repr(out))], env=env, capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0, r.stderr[-800:]
-        outs.append({k: v for k, v in np.load(out).items()})
-        os.remove(out)
-    os.rmdir(tmp)
+    out = os.path.join(tmp, "out.npz")
+    env = dict(os.environ)
+    if hidden:
+        env["WB_TEST_HIDDEN"] = hidden
+    env.update(knobs)
+    r = subprocess.run([sys.executable, "-c", _VARIANT_CODE.replace("ROOT", repr(root)).replace("OUT", repr(out))], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-800:]
+    res = {k: v for k, v in np.load(out).items()}
+    os.remove(out); os.rmdir(tmp)
+    return res
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("knob", ["WB_TC_FWD_TMEMA=0,WB_TC_BWD_GROUPS=2", "WB_TC_WIDE_MIN_S=1000:128", "WB_TC_FUSE_SCATTER_WIDE=1:128"])
+def test_kernel_variant_matches_default(knob):
+    """Default kernels (TMEM-A forward, three-group decoder backward: validated and faster on B200 in round 2) against the
+    round-1 kernels they replaced, which stay selectable through the knobs (forward and backward variant in ONE run: they are
+    different kernels).  The knobs are read once per process, hence the subprocesses: same samples, rgb within fp16 round-off of
+    each other, gradients within the precision-1 tolerance.
+    ':128' runs the case with hidden_dim = 128 (the one-group backward): its chunked schedule (decoder backward of chunk c+1 beside
+    the table scatter of chunk c, normally only above 2^20 samples) against the single launch pair, and its fused-scatter variant."""
+    knob, _, hidden = knob.partition(":")
+    if hidden not in _VARIANT_DEFAULTS:
+        _VARIANT_DEFAULTS[hidden] = _run_variant(hidden, {})
+    outs = [_VARIANT_DEFAULTS[hidden], _run_variant(hidden, dict(kv.split("=") for kv in knob.split(",")))]
     a, b = outs
     assert int(a["n"]) == int(b["n"]) > 1000
     np.testing.assert_allclose(b["rgb"], a["rgb"], atol=2e-3)
