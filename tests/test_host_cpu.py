@@ -156,6 +156,42 @@ def test_bucketed_capacities():
         ops._CAP_FLOOR = old
 
 
+def test_nugget_capacities_and_bench_shapes():
+    """Raytrace outputs come from their own high-water capacity (a render loop over many cameras must not reach cudaMalloc), and
+    bench.py's --config 1 / --hidden-dim select the documented shapes."""
+    import importlib.util
+    import torch
+    from wisp_b200 import ops
+    old = ops._NUG_FLOOR
+    try:
+        ops._NUG_FLOOR = 0
+        a = ops._empty_n(1_000_000, (2,), torch.float32, "cpu")
+        cap = ops._NUG_FLOOR
+        assert a.shape == (1_000_000, 2) and 1_000_000 <= cap <= 1_400_000
+        assert ops._empty_n(1_100_000, (), torch.int32, "cpu").shape == (1_100_000,) and ops._NUG_FLOOR == cap       # within the headroom: same capacity
+        assert ops._empty_n(0, (2,), torch.float32, "cpu").shape == (0, 2)
+        assert ops.reserve_nuggets(5_000_000) >= 5_000_000 and ops._empty_n(10, (), torch.int32, "cpu").untyped_storage().nbytes() >= 5_000_000 * 4
+    finally:
+        ops._NUG_FLOOR = old
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("wb_bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    import sys
+    argv = sys.argv
+    try:
+        sys.argv = ["bench.py", "--config", "1"]
+        a1 = bench.parse()
+        assert a1.res == 256 and bench.nef_shape(a1) == (8, 32) and "256^2" in bench.metric_name(a1)
+        sys.argv = ["bench.py", "--hidden-dim", "128"]
+        a2 = bench.parse()
+        assert a2.res == 1024 and bench.nef_shape(a2) == (16, 128) and bench.metric_name(a2) == bench.METRIC
+        assert "hidden-128" in bench.workload_config(a2)["workload"]
+        sys.argv = ["bench.py"]
+        assert "2-layer-64" in bench.workload_config(bench.parse())["workload"]
+    finally:
+        sys.argv = argv
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` needs no GPU: it times the CPU oracle on a bounded sample and prints ONE JSON line carrying
     the contract keys with impl = reference, zero-byte e2e and a cpu_baseline that repeats the line's value."""
