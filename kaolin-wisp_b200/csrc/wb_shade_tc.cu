@@ -83,6 +83,8 @@ static bool tc_b3_plan(const WbTc& m, TcB3Plan* p)
     int maxw = 0, sumN = 0;
     for (int l = 0; l < 5; ++l) { maxw = max(maxw, max(m.Kp[l], m.Np[l])); sumN += m.Np[l]; }
     if (maxw > 128) return false;
+    if (maxw > 64 && maxw != 128) return false;      // the one-group layout has been validated on B200 for 128-wide decoders only (hidden_dim 128);
+                                                     // widths in between keep training on the fp32 kernels, as before
     // the hidden activation tiles X1, X3, X4 share the buffers P and Q, whose constant-one slab sits behind a maxw-wide tile: the
     // hidden width must BE the widest tile (true for app/nerf: 64-wide hidden layers over 32 / 42 inputs; a 32-wide decoder over a
     // 42-wide colour input would read its bias-gradient row from a stale slab)
